@@ -1,0 +1,191 @@
+/*
+ * reid_b200.h -- C ABI of libreid_b200.so: the B200 (sm_100a) implementation of the
+ * pseudo-label hot path of cluster-contrast-reid (daemon-219/ReID-GAN).
+ *
+ * The reference is 100% Python and has no FFI of its own; each entry point below
+ * replaces the Python statement(s) cited next to it (paths relative to
+ * cluster-contrast-reid-main/).  INTEGRATION.md shows the ctypes binding a
+ * maintainer of the reference would add.
+ *
+ * Conventions
+ *   - every pointer is a DEVICE pointer unless the name ends in _host;
+ *   - `stream` is a cudaStream_t passed as void* (NULL = legacy default stream);
+ *   - every call is asynchronous on `stream` unless stated; no call allocates
+ *     device memory: the caller owns inputs, outputs and scratch;
+ *   - indices are int32, CSR row pointers int64, sets are sorted ascending;
+ *   - rows [row_begin, row_end) are the caller's shard of the N query rows;
+ *     "local" arrays are indexed by (row - row_begin), "global" arrays by row;
+ *   - return value: REID_OK or a negative code; reid_last_error() (thread local)
+ *     describes the last failure.  No exception crosses this boundary and there
+ *     is no CPU fallback behind any entry.
+ */
+#ifndef REID_B200_H_
+#define REID_B200_H_
+
+#include <stddef.h>
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define REID_OK 0
+#define REID_ERR_INVALID_ARG (-1)
+#define REID_ERR_CUDA (-2)
+#define REID_ERR_NCCL (-3)
+#define REID_ERR_CERTIFICATE (-4)
+#define REID_ERR_UNSUPPORTED (-5)
+
+#define REID_MAX_K1 64 /* rank positions are kept in 64-bit masks */
+
+int reid_abi_version(void);
+const char* reid_last_error(void);
+
+/* ---- utilities ---------------------------------------------------------- */
+
+/* ptr_out[0..n] = exclusive prefix sum of cnt[0..n-1] (ptr_out[n] = total);
+ * stats_out (optional, 2 x int64) = {total, max(cnt)}. */
+int reid_scan_counts(const int32_t* cnt, int64_t n, int64_t* ptr_out, int64_t* stats_out, void* stream);
+
+/* ---- a1: kNN search  (utils/faiss_rerank.py:58-62, faiss IndexFlatL2.search) ----
+ * Exact top-k of  key(i,j) = fp32( sum_d x[i,d]*x[j,d] accumulated in fp64 ),
+ * ordered by (key descending, j ascending) -- for unit-norm rows the L2-ascending
+ * order faiss returns.  Query rows are rows_list[0..n_rows) (or row_begin + r when
+ * rows_list is NULL); all N rows are searched, self included.
+ * scratch: at least reid_knn_exact_scratch_bytes(N, 1) bytes; more lets more query
+ * rows go per pass. */
+size_t reid_knn_exact_scratch_bytes(int64_t N, int64_t n_rows);
+int reid_knn_exact(const float* x, int64_t N, int64_t D, const int32_t* rows_list, int64_t row_begin,
+                   int64_t n_rows, int k, int32_t* out_idx, float* out_key, void* scratch,
+                   size_t scratch_bytes, void* stream);
+
+/* Tensor-core candidate search: fp16 tcgen05 GEMM (TMA-fed, TMEM accumulators) of
+ * query rows [row_begin,row_end) against all N rows with a fused per-row running
+ * top-kc selection in the epilogue.  xh = fp16(x * 2^scale_log2), row-major N x D,
+ * D % 64 == 0.  cand_idx/cand_val: (row_end-row_begin) x kc, unordered; cand_val is the
+ * approximate dot product (already un-scaled).  See reid_knn_rescore. */
+int reid_knn_candidates_tc(const void* xh, int64_t N, int64_t D, int scale_log2, int64_t row_begin,
+                           int64_t row_end, int kc, int32_t* cand_idx, float* cand_val, void* stream);
+/* Convert fp32 features to the scaled fp16 operand of reid_knn_candidates_tc. */
+int reid_features_to_half(const float* x, int64_t n_elems, int scale_log2, void* xh, void* stream);
+
+/* Exact re-score of the candidates with the canonical key, certificate, final order.
+ * A row is certified when every column whose approximate score lies within 2*err_bound of
+ * the k-th best approximate score is among its kc candidates (then the exact top-k is
+ * provably inside the candidate set).  Uncertified rows get uncertified_flag[row]=1 and
+ * must be redone with reid_knn_exact.  max_err_out (1 float) receives the largest
+ * |approx - exact| seen, to audit err_bound. */
+int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, int64_t row_end, int kc,
+                     const int32_t* cand_idx, const float* cand_val, int k, float err_bound,
+                     int32_t* out_idx, float* out_key, int32_t* uncertified_flag, float* max_err_out,
+                     void* stream);
+
+/* ---- a2: reciprocal sets  (faiss_rerank.py:23-27, 65-69) -----------------------
+ * mask_out[row - row_begin] bit r  <=>  row in rank[rank[row,r], :cols], cols = min(k+1, ncols).
+ * R_k(row) = { rank[row, r] : bit r set }, in rank order. */
+int reid_reciprocal_masks(const int32_t* rank, int64_t N, int ncols, int k, int64_t row_begin,
+                          int64_t row_end, uint64_t* mask_out, void* stream);
+
+/* ---- a3: expansion  (faiss_rerank.py:72-80) ------------------------------------
+ * E(row) = sort_unique( R(row) + all R_half(c), c in R(row), 3*|R_half(c) & R(row)| > 2*|R_half(c)| ).
+ * Two passes: E_ptr == NULL -> writes E_cnt (local); else writes E_idx at E_ptr (local CSR).
+ * Rmask is local, Rhalf_mask is global (all N rows). */
+int reid_expand(const int32_t* rank, int64_t N, int ncols, const uint64_t* Rmask, const uint64_t* Rhalf_mask,
+                int64_t row_begin, int64_t row_end, const int64_t* E_ptr, int32_t* E_cnt, int32_t* E_idx,
+                void* stream);
+
+/* ---- a4: Gaussian weights  (faiss_rerank.py:81-85) ------------------------------
+ * V_val[p] = softmax over the row of -(2 - 2 x_row.x_e), e = E_idx[p]; fp32.
+ * rank/rank_key (optional, global rank rows of the shard, local indexing) let the kernel reuse
+ * the search keys for members that are among the row's k1 neighbours. */
+int reid_v_weights(const float* x, int64_t N, int64_t D, const int64_t* E_ptr, const int32_t* E_idx,
+                   int64_t row_begin, int64_t row_end, const int32_t* rank_local, const float* rank_key_local,
+                   int ncols, float* V_val, void* stream);
+
+/* ---- a5: k2 query expansion  (faiss_rerank.py:89-94) ----------------------------
+ * Vq[row] = (V[rank[row,0]] + ... + V[rank[row,k2-1]]) / k2, adds in that order, fp32.
+ * V is the GLOBAL CSR (all N rows).  Two passes like reid_expand.  max_row_nnz = max |E|. */
+int reid_query_expand(const int32_t* rank, int64_t N, int ncols, int k2, const int64_t* V_ptr,
+                      const int32_t* V_idx, const float* V_val, int max_row_nnz, int64_t row_begin,
+                      int64_t row_end, const int64_t* Q_ptr, int32_t* Q_cnt, int32_t* Q_idx, float* Q_val,
+                      void* stream);
+
+/* ---- a6: inverted index  (faiss_rerank.py:98-100) -------------------------------
+ * CSC of a CSR with n_rows x n_cols; column lists sorted by row.
+ * Step 1 writes col_cnt; caller scans it into C_ptr; step 2 fills.  cursor: n_cols int32 scratch. */
+int reid_transpose_count(const int32_t* idx, int64_t nnz, int64_t n_cols, int32_t* col_cnt, void* stream);
+int reid_transpose_fill(const int64_t* ptr, const int32_t* idx, const float* val, int64_t n_rows,
+                        int64_t n_cols, const int64_t* C_ptr, int32_t* cursor, int32_t* C_idx, float* C_val,
+                        void* stream);
+
+/* ---- a7: Jaccard min-sum  (faiss_rerank.py:102-119) -----------------------------
+ * t_ij = sum over shared columns c (ascending) of min(Vq[i,c], Vq[j,c]) in sequential fp32;
+ * J = max(0, 1 - t/(2-t)); pairs without a shared column have J == 1 exactly.
+ * Q (CSR) and C (CSC) are global. */
+/* upper bound of the number of distinct j per row: T_cnt[row-row_begin] = sum_c |col(c)| */
+int reid_jaccard_bounds(const int64_t* Q_ptr, const int32_t* Q_idx, const int64_t* C_ptr, int64_t row_begin,
+                        int64_t row_end, int32_t* T_cnt, void* stream);
+/* eps-neighbourhoods { j : J_ij <= eps } (what DBSCAN consumes), written at slot_ptr (local, from a
+ * scan of T_cnt); nbr_cnt[row-row_begin] = size, or -1 when the row overflowed the shared-memory
+ * table (redo those rows with a larger table_slots).  J values optional (nbr_val may be NULL).
+ * rows_list (optional): local row ids to process instead of the whole shard. */
+int reid_jaccard_neighbors(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val,
+                           const int64_t* C_ptr, const int32_t* C_idx, const float* C_val, int64_t N,
+                           int64_t row_begin, int64_t row_end, const int32_t* rows_list, int64_t n_list,
+                           float eps, const int64_t* slot_ptr, int32_t* nbr_idx, float* nbr_val,
+                           int32_t* nbr_cnt, int table_slots, void* stream);
+/* dense rows: out[(row-row_begin)*ld + j] for all j < N  (the reference's return value). */
+int reid_jaccard_dense(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
+                       const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin,
+                       int64_t row_end, float* out, int64_t ld, void* stream);
+
+/* ---- a8: DBSCAN on precomputed distances -----------------------------------------
+ * (examples/cluster_contrast_train_usl.py:160,163; sklearn/cluster/_dbscan.py:397-475)
+ * neighbourhood = { j : d_ij <= eps } in fp32, self included; core <=> |nbr| >= min_samples;
+ * cluster ids 0.. by ascending smallest core index; border -> smallest adjacent core label; noise -1. */
+/* dense input (drop-in class): two passes over rows [row_begin,row_end) of an n x n matrix */
+int reid_dbscan_dense_count(const float* dist, int64_t N, int64_t ld, float eps, int64_t row_begin,
+                            int64_t row_end, int32_t* nbr_cnt, void* stream);
+int reid_dbscan_dense_fill(const float* dist, int64_t N, int64_t ld, float eps, int64_t row_begin,
+                           int64_t row_end, const int64_t* nbr_ptr, int32_t* nbr_idx, void* stream);
+/* labelling from neighbour lists of ALL N rows: list of row i = nbr_idx[nbr_ptr[i] .. +nbr_cnt[i]).
+ * workspace: reid_dbscan_workspace_bytes(N).  labels: int64 (numpy intp); core_mask: uint8 (optional). */
+size_t reid_dbscan_workspace_bytes(int64_t N);
+int reid_dbscan_labels(int64_t N, const int64_t* nbr_ptr, const int32_t* nbr_idx, const int32_t* nbr_cnt,
+                       int min_samples, int64_t* labels, uint8_t* core_mask, int64_t* num_clusters_out,
+                       void* workspace, void* stream);
+
+/* ---- a9: centroid init  (train_usl.py:169-182, 191) -------------------------------
+ * out[k] = mean of x[i] over labels[i] == k, k = 0..C-1 (labels < 0 skipped), members added in
+ * ascending i; normalize != 0 fuses the F.normalize of :191.  workspace: reid_centroids_workspace_bytes(N, C). */
+size_t reid_centroids_workspace_bytes(int64_t N, int64_t C);
+int reid_centroids(const float* x, int64_t N, int64_t D, const int64_t* labels, int64_t C, int normalize,
+                   float* out, void* workspace, void* stream);
+
+/* ---- a10-a12: ClusterMemory  (models/cm.py:9-76, 110-137) --------------------------
+ * forward: xhat = normalize(inputs); z = xhat . F^T / temp; loss_b = logsumexp(z_b) - z_b[y_b].
+ * Saves xhat (B x D), inv_norm (B) and z (B x C) for backward.  (cm.py:125,16/47,134-135)
+ * scratch: reid_cm_forward_scratch_bytes(B, C, D) bytes (split-K partial sums). */
+size_t reid_cm_forward_scratch_bytes(int64_t B, int64_t C, int64_t D);
+int reid_cm_forward(const float* inputs, const int64_t* targets, const float* centroids, int64_t B,
+                    int64_t C, int64_t D, float temp, float* loss, float* xhat, float* inv_norm, float* z,
+                    void* scratch, void* stream);
+/* backward: grad_inputs through CE, /temp, mm with the PRE-update centroids (cm.py:26,56) and normalize. */
+int reid_cm_backward(const float* grad_loss, const float* z, const int64_t* targets, const float* centroids,
+                     const float* xhat, const float* inv_norm, int64_t B, int64_t C, int64_t D, float temp,
+                     float* gz_scratch, float* grad_inputs, void* stream);
+/* plain logits = a . F^T and grad = g . F for the module-level cm()/cm_hard() (cm.py:16,26,47,56) */
+int reid_cm_logits(const float* a, const float* centroids, int64_t B, int64_t C, int64_t D, float* out,
+                   void* stream);
+int reid_cm_grad_inputs(const float* g, const float* centroids, int64_t B, int64_t C, int64_t D, float* out,
+                        void* stream);
+/* momentum update, in place on centroids.  hard = 0: per-sample sequential chain in batch order
+ * (cm.py:29-31); hard = 1: per distinct label the first-argmin member of x.f[label] (cm.py:58-70).
+ * workspace: B int32. */
+int reid_cm_update(const float* xhat, const int64_t* targets, float* centroids, int64_t B, int64_t C,
+                   int64_t D, float momentum, int hard, void* workspace, void* stream);
+
+#ifdef __cplusplus
+}
+#endif
+#endif /* REID_B200_H_ */

@@ -1,0 +1,101 @@
+"""ctypes binding of libreid_b200.so (include/reid_b200.h).
+
+The library is the product: if it is missing or a call fails there is NO fallback --
+`lib()` raises and every wrapper turns a non-zero return code into an exception
+(REID_ERR_INVALID_ARG -> ValueError, everything else -> RuntimeError), mirroring the
+reference's assert/exception-only error convention (utils/faiss_utils.py:7-8,13-14,22-24).
+"""
+import ctypes
+import os
+
+_HERE = os.path.dirname(os.path.abspath(__file__))
+LIB_PATH = os.path.join(_HERE, "libreid_b200.so")
+
+REID_OK = 0
+REID_ERR_INVALID_ARG = -1
+REID_ERR_CUDA = -2
+REID_ERR_NCCL = -3
+REID_ERR_CERTIFICATE = -4
+REID_ERR_UNSUPPORTED = -5
+
+_P = ctypes.c_void_p
+_I = ctypes.c_int
+_L = ctypes.c_int64
+_F = ctypes.c_float
+_Z = ctypes.c_size_t
+
+# name -> (restype, argtypes); must list every symbol declared in include/reid_b200.h
+SIGNATURES = {
+    "reid_abi_version": (_I, []),
+    "reid_last_error": (ctypes.c_char_p, []),
+    "reid_scan_counts": (_I, [_P, _L, _P, _P, _P]),
+    "reid_knn_exact_scratch_bytes": (_Z, [_L, _L]),
+    "reid_knn_exact": (_I, [_P, _L, _L, _P, _L, _L, _I, _P, _P, _P, _Z, _P]),
+    "reid_knn_candidates_tc": (_I, [_P, _L, _L, _I, _L, _L, _I, _P, _P, _P]),
+    "reid_features_to_half": (_I, [_P, _L, _I, _P, _P]),
+    "reid_knn_rescore": (_I, [_P, _L, _L, _L, _L, _I, _P, _P, _I, _F, _P, _P, _P, _P, _P]),
+    "reid_reciprocal_masks": (_I, [_P, _L, _I, _I, _L, _L, _P, _P]),
+    "reid_expand": (_I, [_P, _L, _I, _P, _P, _L, _L, _P, _P, _P, _P]),
+    "reid_v_weights": (_I, [_P, _L, _L, _P, _P, _L, _L, _P, _P, _I, _P, _P]),
+    "reid_query_expand": (_I, [_P, _L, _I, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P]),
+    "reid_transpose_count": (_I, [_P, _L, _L, _P, _P]),
+    "reid_transpose_fill": (_I, [_P, _P, _P, _L, _L, _P, _P, _P, _P, _P]),
+    "reid_jaccard_bounds": (_I, [_P, _P, _P, _L, _L, _P, _P]),
+    "reid_jaccard_neighbors": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _P, _L, _F, _P, _P, _P, _P, _I, _P]),
+    "reid_jaccard_dense": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _P, _L, _P]),
+    "reid_dbscan_dense_count": (_I, [_P, _L, _L, _F, _L, _L, _P, _P]),
+    "reid_dbscan_dense_fill": (_I, [_P, _L, _L, _F, _L, _L, _P, _P, _P]),
+    "reid_dbscan_workspace_bytes": (_Z, [_L]),
+    "reid_dbscan_labels": (_I, [_L, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
+    "reid_centroids_workspace_bytes": (_Z, [_L, _L]),
+    "reid_centroids": (_I, [_P, _L, _L, _P, _L, _I, _P, _P, _P]),
+    "reid_cm_forward_scratch_bytes": (_Z, [_L, _L, _L]),
+    "reid_cm_forward": (_I, [_P, _P, _P, _L, _L, _L, _F, _P, _P, _P, _P, _P, _P]),
+    "reid_cm_backward": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _F, _P, _P, _P]),
+    "reid_cm_logits": (_I, [_P, _P, _L, _L, _L, _P, _P]),
+    "reid_cm_grad_inputs": (_I, [_P, _P, _L, _L, _L, _P, _P]),
+    "reid_cm_update": (_I, [_P, _P, _P, _L, _L, _L, _F, _I, _P, _P]),
+}
+
+_lib = None
+
+
+def lib():
+    """Load libreid_b200.so (once).  Raises if it has not been built -- there is no CPU path."""
+    global _lib
+    if _lib is None:
+        if not os.path.isfile(LIB_PATH):
+            raise RuntimeError(
+                "libreid_b200.so not found at %s: build it with `python -c \"import __graft_entry__ as g; g.build()\"` "
+                "(or reid-gan_b200/csrc/build.sh).  This package has no CPU fallback." % LIB_PATH)
+        handle = ctypes.CDLL(LIB_PATH)
+        for name, (res, args) in SIGNATURES.items():
+            fn = getattr(handle, name)
+            fn.restype = res
+            fn.argtypes = args
+        _lib = handle
+    return _lib
+
+
+def last_error():
+    msg = lib().reid_last_error()
+    return msg.decode("utf-8", "replace") if msg else ""
+
+
+def check(rc, what=""):
+    if rc == REID_OK:
+        return
+    msg = "%s failed (%d): %s" % (what or "libreid_b200 call", rc, last_error())
+    if rc == REID_ERR_INVALID_ARG:
+        raise ValueError(msg)
+    raise RuntimeError(msg)
+
+
+def ptr(t):
+    """Device (or host) address of a torch tensor / None."""
+    return None if t is None else ctypes.c_void_p(t.data_ptr())
+
+
+def stream_ptr():
+    import torch
+    return ctypes.c_void_p(torch.cuda.current_stream().cuda_stream)

@@ -1,0 +1,94 @@
+// a9 -- centroid initialisation (examples/cluster_contrast_train_usl.py:169-182, 191):
+//   centre_k = mean of x[i] over labels[i] == k (members visited in ascending i, like the
+//   reference's enumerate(labels) loop feeding torch.stack(...).mean(0)), then F.normalize.
+// One CTA per cluster; the label vector (N ints, L2-resident) is streamed once per CTA and the
+// member rows are accumulated in registers, so every feature row is read exactly once overall.
+#include "common.cuh"
+
+namespace reid {
+
+constexpr int kCenThreads = 256;
+constexpr int kCenMaxPerThread = 16;  // D <= 4096
+
+__global__ void __launch_bounds__(kCenThreads) centroids_kernel(const float* __restrict__ x, int64_t N, int64_t D,
+                                                                const int64_t* __restrict__ labels, int normalize,
+                                                                float* __restrict__ out) {
+  __shared__ unsigned s_mask[kCenThreads / 32];
+  __shared__ float s_red[kCenThreads / 32];
+  const int64_t k = blockIdx.x;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  float acc[kCenMaxPerThread];
+#pragma unroll
+  for (int u = 0; u < kCenMaxPerThread; ++u) acc[u] = 0.f;
+  int count = 0;
+  for (int64_t base = 0; base < N; base += kCenThreads) {
+    const int64_t i = base + t;
+    const bool hit = i < N && labels[i] == k;
+    const unsigned b = __ballot_sync(kFull, hit);
+    if (lane == 0) s_mask[w] = b;
+    __syncthreads();
+#pragma unroll 1
+    for (int ww = 0; ww < kCenThreads / 32; ++ww) {
+      unsigned m = s_mask[ww];
+      while (m) {
+        const int bit = __ffs(m) - 1;
+        m &= m - 1;
+        const float* row = x + (base + ww * 32 + bit) * D;
+#pragma unroll
+        for (int u = 0; u < kCenMaxPerThread; ++u) {
+          const int64_t d = t + (int64_t)u * kCenThreads;
+          if (d < D) acc[u] = __fadd_rn(acc[u], row[d]);
+        }
+        ++count;
+      }
+    }
+    __syncthreads();
+  }
+  const float inv_cnt = (float)count;
+  float ss = 0.f;
+#pragma unroll
+  for (int u = 0; u < kCenMaxPerThread; ++u) {
+    const int64_t d = t + (int64_t)u * kCenThreads;
+    if (d < D) {
+      acc[u] = count ? __fdiv_rn(acc[u], inv_cnt) : 0.f;
+      ss += acc[u] * acc[u];
+    }
+  }
+  ss = warp_sum(ss);
+  if (lane == 0) s_red[w] = ss;
+  __syncthreads();
+  float tot = 0.f;
+#pragma unroll
+  for (int ww = 0; ww < kCenThreads / 32; ++ww) tot += s_red[ww];
+  const float nrm = normalize ? fmaxf(sqrtf(tot), 1e-12f) : 1.0f;  // F.normalize eps
+#pragma unroll
+  for (int u = 0; u < kCenMaxPerThread; ++u) {
+    const int64_t d = t + (int64_t)u * kCenThreads;
+    if (d < D) out[k * D + d] = __fdiv_rn(acc[u], nrm);
+  }
+}
+
+}  // namespace reid
+
+extern "C" {
+
+size_t reid_centroids_workspace_bytes(int64_t N, int64_t C) {
+  (void)N;
+  (void)C;
+  return 0;
+}
+
+int reid_centroids(const float* x, int64_t N, int64_t D, const int64_t* labels, int64_t C, int normalize, float* out,
+                   void* workspace, void* stream) {
+  using namespace reid;
+  (void)workspace;
+  REID_CHECK_ARG(x && labels && (out || C == 0), "reid_centroids: NULL pointer");
+  REID_CHECK_ARG(N >= 0 && C >= 0 && D > 0 && D <= (int64_t)kCenThreads * kCenMaxPerThread,
+                 "reid_centroids: bad shape N=%lld C=%lld D=%lld (D <= %d)", (long long)N, (long long)C, (long long)D,
+                 kCenThreads * kCenMaxPerThread);
+  if (C == 0) return REID_OK;
+  centroids_kernel<<<(unsigned)C, kCenThreads, 0, (cudaStream_t)stream>>>(x, N, D, labels, normalize, out);
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+}

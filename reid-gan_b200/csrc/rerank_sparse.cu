@@ -1,0 +1,332 @@
+// a4-a6 -- CSR kernels: Gaussian weights V, k2 query expansion V_qe and the inverted index
+// (utils/faiss_rerank.py:81-85, 89-94, 98-100).  No dense N x N matrix is ever formed.
+#include "common.cuh"
+
+namespace reid {
+
+// ---------------------------------------------------------------------------------------
+// a4: one warp per row.  s_e = fp32(fp64 dot(x_row, x_e)) -- the same canonical value the
+// search produces, so members that are among the row's k1 neighbours reuse the search key
+// instead of gathering 4*D bytes.  Then softmax(-(2 - 2 s)) in fp32 exactly as written in
+// faiss_rerank.py:81,85 (max-subtracted, like F.softmax).
+// ---------------------------------------------------------------------------------------
+constexpr int kVWarps = 8;
+constexpr int kVMaxRow = 1024;  // max |E| per row (expand_kernel caps at the same value)
+
+__global__ void __launch_bounds__(kVWarps * 32) v_weights_kernel(
+    const float* __restrict__ x, int64_t D, const int64_t* __restrict__ E_ptr, const int32_t* __restrict__ E_idx,
+    int64_t row_begin, int64_t row_end, const int32_t* __restrict__ rank_local, const float* __restrict__ key_local,
+    int ncols, float* __restrict__ V_val) {
+  __shared__ float s_val[kVWarps][kVMaxRow];
+  const int w = threadIdx.x >> 5, lane = lane_id();
+  const int64_t row = row_begin + (int64_t)blockIdx.x * kVWarps + w;
+  if (row >= row_end) return;
+  const int64_t lr = row - row_begin;
+  const int64_t p0 = E_ptr[lr];
+  const int n = (int)(E_ptr[lr + 1] - p0);
+  if (n == 0) return;
+  const float* xi = x + row * D;
+  float* sv = s_val[w];
+
+  for (int e = 0; e < n; ++e) {
+    const int32_t j = E_idx[p0 + e];
+    float s;
+    bool have = false;
+    if (rank_local) {  // harvest the search key when j is one of the row's stored neighbours
+      float kv = 0.f;
+      bool hit = false;
+      for (int r = lane; r < ncols; r += 32)
+        if (rank_local[lr * ncols + r] == j) {
+          hit = true;
+          kv = key_local[lr * ncols + r];
+        }
+      const unsigned b = __ballot_sync(kFull, hit);
+      if (b) {
+        s = __shfl_sync(kFull, kv, __ffs(b) - 1);
+        have = true;
+      }
+    }
+    if (!have) {
+      const float* xj = x + (int64_t)j * D;
+      double acc = 0.0;
+      if ((D & 3) == 0) {
+        const float4* a4 = reinterpret_cast<const float4*>(xi);
+        const float4* b4 = reinterpret_cast<const float4*>(xj);
+        for (int64_t d = lane; d < (D >> 2); d += 32) {
+          const float4 a = a4[d], b = b4[d];
+          acc = fma((double)a.x, (double)b.x, acc);
+          acc = fma((double)a.y, (double)b.y, acc);
+          acc = fma((double)a.z, (double)b.z, acc);
+          acc = fma((double)a.w, (double)b.w, acc);
+        }
+      } else {
+        for (int64_t d = lane; d < D; d += 32) acc = fma((double)xi[d], (double)xj[d], acc);
+      }
+      acc = warp_sum(acc);
+      s = (float)acc;
+    }
+    if (lane == 0) sv[e] = s;
+  }
+  __syncwarp();
+  // softmax(-dist), dist = 2 - 2 s
+  float mx = -INFINITY;
+  for (int e = lane; e < n; e += 32) {
+    const float neg = -(2.0f - 2.0f * sv[e]);
+    sv[e] = neg;
+    mx = fmaxf(mx, neg);
+  }
+  mx = warp_max(mx);
+  float sum = 0.f;
+  for (int e = lane; e < n; e += 32) {
+    const float ex = expf(sv[e] - mx);
+    sv[e] = ex;
+    sum += ex;
+  }
+  sum = warp_sum(sum);
+  for (int e = lane; e < n; e += 32) V_val[p0 + e] = __fdiv_rn(sv[e], sum);
+}
+
+// ---------------------------------------------------------------------------------------
+// a5: one warp per row.  The k2 neighbour rows of V are concatenated in shared memory with
+// key = col * K2P + r, sorted (warp bitonic network on key/value pairs), and every run of
+// equal columns is summed in r order with sequential fp32 adds, then divided by k2 --
+// the arithmetic of np.mean(V[rank[i,:k2]], axis=0) restricted to the structural non-zeros.
+// ---------------------------------------------------------------------------------------
+constexpr int kQWarps = 4;
+
+__device__ __forceinline__ void warp_bitonic_sort_kv(uint32_t* key, float* val, int n2) {
+  const int lane = lane_id();
+  for (int k = 2; k <= n2; k <<= 1) {
+    for (int j = k >> 1; j > 0; j >>= 1) {
+      for (int t = lane; t < n2; t += 32) {
+        const int p = t ^ j;
+        if (p > t) {
+          const uint32_t a = key[t], b = key[p];
+          const bool up = ((t & k) == 0);
+          if ((a > b) == up) {
+            key[t] = b;
+            key[p] = a;
+            const float va = val[t];
+            val[t] = val[p];
+            val[p] = va;
+          }
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+template <bool kWrite>
+__global__ void __launch_bounds__(kQWarps * 32) query_expand_kernel(
+    const int32_t* __restrict__ rank, int ncols, int k2, int k2p_log2, const int64_t* __restrict__ V_ptr,
+    const int32_t* __restrict__ V_idx, const float* __restrict__ V_val, int cap, int64_t row_begin, int64_t row_end,
+    const int64_t* __restrict__ Q_ptr, int32_t* __restrict__ Q_cnt, int32_t* __restrict__ Q_idx,
+    float* __restrict__ Q_val) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int w = threadIdx.x >> 5, lane = lane_id();
+  uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)w * cap;
+  float* val = reinterpret_cast<float*>(smem_raw + (size_t)kQWarps * cap * sizeof(uint32_t)) + (size_t)w * cap;
+  const int64_t row = row_begin + (int64_t)blockIdx.x * kQWarps + w;
+  if (row >= row_end) return;
+
+  int n = 0;
+  for (int r = 0; r < k2; ++r) {
+    const int64_t j = rank[row * ncols + r];
+    const int64_t a = V_ptr[j];
+    const int m = (int)(V_ptr[j + 1] - a);
+    for (int e = lane; e < m; e += 32) {
+      key[n + e] = ((uint32_t)V_idx[a + e] << k2p_log2) | (uint32_t)r;
+      val[n + e] = V_val[a + e];
+    }
+    n += m;
+  }
+  int n2 = 32;
+  while (n2 < n) n2 <<= 1;
+  for (int t = n + lane; t < n2; t += 32) {
+    key[t] = 0xffffffffu;
+    val[t] = 0.f;
+  }
+  __syncwarp();
+  warp_bitonic_sort_kv(key, val, n2);
+
+  const float k2f = (float)k2;
+  int64_t out = kWrite ? Q_ptr[row - row_begin] : 0;
+  int total = 0;
+  for (int base = 0; base < n; base += 32) {
+    const int t = base + lane;
+    bool head = false;
+    uint32_t col = 0;
+    if (t < n) {
+      col = key[t] >> k2p_log2;
+      head = (t == 0) || ((key[t - 1] >> k2p_log2) != col);
+    }
+    const unsigned b = __ballot_sync(kFull, head);
+    if (kWrite && head) {
+      float acc = val[t];
+      for (int u = t + 1; u < n && (key[u] >> k2p_log2) == col; ++u) acc = __fadd_rn(acc, val[u]);
+      const int64_t p = out + __popc(b & ((1u << lane) - 1u));
+      Q_idx[p] = (int32_t)col;
+      Q_val[p] = __fdiv_rn(acc, k2f);
+    }
+    out += __popc(b);
+    total += __popc(b);
+  }
+  if (!kWrite && lane == 0) Q_cnt[row - row_begin] = total;
+}
+
+// ---------------------------------------------------------------------------------------
+// a6: CSR -> CSC.  Column histogram, (caller scans), atomic-cursor scatter, then each
+// column list is sorted by row so the result does not depend on scheduling.
+// ---------------------------------------------------------------------------------------
+__global__ void col_count_kernel(const int32_t* __restrict__ idx, int64_t nnz, int32_t* __restrict__ cnt) {
+  for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x)
+    atomicAdd(&cnt[idx[p]], 1);
+}
+
+__global__ void __launch_bounds__(256) col_scatter_kernel(const int64_t* __restrict__ ptr,
+                                                          const int32_t* __restrict__ idx,
+                                                          const float* __restrict__ val, int64_t n_rows,
+                                                          const int64_t* __restrict__ C_ptr,
+                                                          int32_t* __restrict__ cursor, int32_t* __restrict__ C_idx,
+                                                          float* __restrict__ C_val) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  for (int64_t p = ptr[row] + lane_id(); p < ptr[row + 1]; p += 32) {
+    const int32_t c = idx[p];
+    const int64_t q = C_ptr[c] + atomicAdd(&cursor[c], 1);
+    C_idx[q] = (int32_t)row;
+    C_val[q] = val[p];
+  }
+}
+
+constexpr int kColSortCap = 2048;
+constexpr int kColSortWarps = 4;
+
+__global__ void __launch_bounds__(kColSortWarps * 32) col_sort_kernel(const int64_t* __restrict__ C_ptr, int64_t n_cols,
+                                                                      int32_t* __restrict__ C_idx,
+                                                                      float* __restrict__ C_val) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  const int w = threadIdx.x >> 5, lane = lane_id();
+  uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)w * kColSortCap;
+  float* val = reinterpret_cast<float*>(smem_raw + (size_t)kColSortWarps * kColSortCap * 4) + (size_t)w * kColSortCap;
+  const int64_t c = (int64_t)blockIdx.x * kColSortWarps + w;
+  if (c >= n_cols) return;
+  const int64_t a = C_ptr[c];
+  const int64_t n = C_ptr[c + 1] - a;
+  if (n <= 1) return;
+  if (n <= kColSortCap) {
+    int n2 = 32;
+    while (n2 < n) n2 <<= 1;
+    for (int t = lane; t < n2; t += 32) {
+      key[t] = t < n ? (uint32_t)C_idx[a + t] : 0xffffffffu;
+      val[t] = t < n ? C_val[a + t] : 0.f;
+    }
+    __syncwarp();
+    warp_bitonic_sort_kv(key, val, n2);
+    for (int t = lane; t < n; t += 32) {
+      C_idx[a + t] = (int32_t)key[t];
+      C_val[a + t] = val[t];
+    }
+  } else {
+    // very long column: odd-even transposition sort in place (rare; correctness path)
+    for (int64_t round = 0; round < n; ++round) {
+      for (int64_t t = (round & 1) + 2 * (int64_t)lane; t + 1 < n; t += 64) {
+        const int32_t x0 = C_idx[a + t], x1 = C_idx[a + t + 1];
+        if (x0 > x1) {
+          C_idx[a + t] = x1;
+          C_idx[a + t + 1] = x0;
+          const float v = C_val[a + t];
+          C_val[a + t] = C_val[a + t + 1];
+          C_val[a + t + 1] = v;
+        }
+      }
+      __syncwarp();
+    }
+  }
+}
+
+}  // namespace reid
+
+extern "C" {
+
+int reid_v_weights(const float* x, int64_t N, int64_t D, const int64_t* E_ptr, const int32_t* E_idx,
+                   int64_t row_begin, int64_t row_end, const int32_t* rank_local, const float* rank_key_local,
+                   int ncols, float* V_val, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(x && E_ptr && E_idx && V_val, "reid_v_weights: NULL pointer");
+  REID_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= N && D > 0, "reid_v_weights: bad shape");
+  REID_CHECK_ARG((rank_local == nullptr) == (rank_key_local == nullptr), "reid_v_weights: rank and keys go together");
+  const int64_t n = row_end - row_begin;
+  if (n == 0) return REID_OK;
+  v_weights_kernel<<<(unsigned)((n + kVWarps - 1) / kVWarps), kVWarps * 32, 0, (cudaStream_t)stream>>>(
+      x, D, E_ptr, E_idx, row_begin, row_end, rank_local, rank_key_local, ncols, V_val);
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+
+int reid_query_expand(const int32_t* rank, int64_t N, int ncols, int k2, const int64_t* V_ptr, const int32_t* V_idx,
+                      const float* V_val, int max_row_nnz, int64_t row_begin, int64_t row_end, const int64_t* Q_ptr,
+                      int32_t* Q_cnt, int32_t* Q_idx, float* Q_val, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(rank && V_ptr && V_idx && V_val, "reid_query_expand: NULL pointer");
+  REID_CHECK_ARG(k2 >= 1 && k2 <= ncols && ncols <= REID_MAX_K1, "reid_query_expand: k2=%d ncols=%d", k2, ncols);
+  REID_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= N, "reid_query_expand: bad row range");
+  REID_CHECK_ARG(Q_ptr ? (Q_idx && Q_val) : (Q_cnt != nullptr), "reid_query_expand: missing output for this pass");
+  REID_CHECK_ARG(max_row_nnz >= 1, "reid_query_expand: max_row_nnz=%d", max_row_nnz);
+  int k2p_log2 = 0;
+  while ((1 << k2p_log2) < k2) ++k2p_log2;
+  REID_CHECK_ARG(((uint64_t)N << k2p_log2) < 0xffffffffull, "reid_query_expand: N * k2 exceeds the 32-bit sort key");
+  int cap = 32;
+  while (cap < k2 * max_row_nnz) cap <<= 1;
+  const size_t smem = (size_t)kQWarps * cap * 8;
+  REID_CHECK_ARG(smem <= 200 * 1024, "reid_query_expand: k2 * max_row_nnz = %d needs %zu B of shared memory",
+                 k2 * max_row_nnz, smem);
+  const int64_t n = row_end - row_begin;
+  if (n == 0) return REID_OK;
+  const unsigned grid = (unsigned)((n + kQWarps - 1) / kQWarps);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (Q_ptr) {
+    REID_CUDA(cudaFuncSetAttribute(query_expand_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    query_expand_kernel<true><<<grid, kQWarps * 32, smem, st>>>(rank, ncols, k2, k2p_log2, V_ptr, V_idx, V_val, cap,
+                                                                row_begin, row_end, Q_ptr, Q_cnt, Q_idx, Q_val);
+  } else {
+    REID_CUDA(cudaFuncSetAttribute(query_expand_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    query_expand_kernel<false><<<grid, kQWarps * 32, smem, st>>>(rank, ncols, k2, k2p_log2, V_ptr, V_idx, V_val, cap,
+                                                                 row_begin, row_end, Q_ptr, Q_cnt, Q_idx, Q_val);
+  }
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+
+int reid_transpose_count(const int32_t* idx, int64_t nnz, int64_t n_cols, int32_t* col_cnt, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(col_cnt && (nnz == 0 || idx) && n_cols > 0, "reid_transpose_count: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  REID_CUDA(cudaMemsetAsync(col_cnt, 0, sizeof(int32_t) * (size_t)n_cols, st));
+  if (nnz == 0) return REID_OK;
+  int64_t blocks = (nnz + 255) / 256;
+  if (blocks > 148 * 16) blocks = 148 * 16;
+  col_count_kernel<<<(unsigned)blocks, 256, 0, st>>>(idx, nnz, col_cnt);
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+
+int reid_transpose_fill(const int64_t* ptr, const int32_t* idx, const float* val, int64_t n_rows, int64_t n_cols,
+                        const int64_t* C_ptr, int32_t* cursor, int32_t* C_idx, float* C_val, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(ptr && idx && val && C_ptr && cursor && C_idx && C_val, "reid_transpose_fill: NULL pointer");
+  REID_CHECK_ARG(n_rows >= 0 && n_cols > 0, "reid_transpose_fill: bad shape");
+  cudaStream_t st = (cudaStream_t)stream;
+  REID_CUDA(cudaMemsetAsync(cursor, 0, sizeof(int32_t) * (size_t)n_cols, st));
+  if (n_rows == 0) return REID_OK;
+  col_scatter_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(ptr, idx, val, n_rows, C_ptr, cursor, C_idx, C_val);
+  REID_LAUNCH_CHECK();
+  const size_t smem = (size_t)kColSortWarps * kColSortCap * 8;
+  REID_CUDA(cudaFuncSetAttribute(col_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  col_sort_kernel<<<(unsigned)((n_cols + kColSortWarps - 1) / kColSortWarps), kColSortWarps * 32, smem, st>>>(
+      C_ptr, n_cols, C_idx, C_val);
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+}

@@ -1,0 +1,339 @@
+"""Drop-in for clustercontrast/utils/faiss_rerank.py (reference lines cited per stage).
+
+    compute_jaccard_distance(target_features, k1=20, k2=6, print_flag=True,
+                             search_option=0, use_float16=False)
+
+Same call surface as faiss_rerank.py:30.  Everything runs on the current CUDA device through
+libreid_b200.so; there is no faiss, no backend dispatch (`search_option` is accepted and
+validated, every value runs the same kernels) and no CPU fallback.
+
+The reference returns a dense host float32 (N, N) matrix (:123).  Here the function returns a
+`JaccardDistance`: a lazy view of that matrix.  `np.asarray(d)`, indexing, `.shape`,
+`.dtype`, arithmetic ... materialise exactly the reference's matrix on first use, while
+`reid_gan_b200.DBSCAN.fit_predict(d)` consumes the device-resident sparse form and never
+builds the N x N matrix (4.26 GB and ~100 ms of PCIe at N = 32,621).
+"""
+import time
+
+import numpy as np
+import torch
+
+from . import _lib
+from ._lib import check, ptr, stream_ptr
+
+
+def half_k(k1):
+    """faiss_rerank.py:69 -- int(np.around(k1/2)): round-half-to-even."""
+    return int(np.around(k1 / 2))
+
+
+def _device_of(t):
+    if not torch.cuda.is_available():
+        raise RuntimeError("reid_gan_b200 needs a CUDA device (sm_100a); there is no CPU fallback")
+    if isinstance(t, torch.Tensor) and t.is_cuda:
+        return t.device
+    return torch.device("cuda", torch.cuda.current_device())
+
+
+def _scan(cnt, n, dev):
+    """counts (int32, device) -> (ptr int64 (n+1), total, max) -- one small host sync."""
+    L = _lib.lib()
+    out = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    stats = torch.empty(2, dtype=torch.int64, device=dev)
+    check(L.reid_scan_counts(ptr(cnt), n, ptr(out), ptr(stats), stream_ptr()), "reid_scan_counts")
+    total, mx = stats.tolist()
+    return out, int(total), int(mx)
+
+
+class RerankState:
+    """Device-resident intermediates of one re-ranking pass (rows [row_begin,row_end) of N)."""
+
+    def __init__(self):
+        self.N = self.D = self.k1 = self.k2 = 0
+        self.row_begin = self.row_end = 0
+        self.rank = self.rank_key = None          # (N, k1) int32 / float32   faiss_rerank.py:62
+        self.R_mask = self.Rh_mask = None         # uint64 bit masks           :65-69
+        self.E_ptr = self.E_idx = self.V_val = None      # CSR of V            :72-85
+        self.Q_ptr = self.Q_idx = self.Q_val = None      # CSR of V_qe         :89-94
+        self.C_ptr = self.C_idx = self.C_val = None      # CSC of V_qe         :98-100
+        self.timings = {}
+        self.knn_info = {}
+
+
+def knn_search(x, k, mode="auto", rows=None):
+    """a1: exact top-k neighbour lists (faiss_rerank.py:58-62).  Returns (idx int32, key fp32).
+    mode "exact": CUDA-core fp64 search for every row; "tc": tensor-core candidates + exact
+    re-score + certificate, uncertified rows redone exactly; "auto": "tc" when the shape allows."""
+    L = _lib.lib()
+    N, D = x.shape
+    dev = x.device
+    if rows is None:
+        r0, r1 = 0, N
+    else:
+        r0, r1 = rows
+    n = r1 - r0
+    idx = torch.empty((n, k), dtype=torch.int32, device=dev)
+    key = torch.empty((n, k), dtype=torch.float32, device=dev)
+    info = {"mode": mode, "uncertified_rows": 0}
+    if mode == "auto":
+        mode = "tc" if (D % 64 == 0 and N >= 256 and k <= 64) else "exact"
+        info["mode"] = mode
+    if mode == "tc":
+        from .knn_tc import knn_search_tc
+        return knn_search_tc(x, k, r0, r1, idx, key, info)
+    if mode != "exact":
+        raise ValueError("unknown kNN mode %r" % (mode,))
+    _knn_exact_rows(x, k, None, r0, n, idx, key)
+    return idx, key, info
+
+
+def _knn_exact_rows(x, k, rows_list, row_begin, n_rows, idx_out, key_out):
+    L = _lib.lib()
+    N, D = x.shape
+    if n_rows == 0:
+        return
+    budget = 1 << 30                                        # ~1 GiB of key rows per pass
+    chunk = max(1, min(n_rows, budget // (4 * N)))
+    scratch = torch.empty(chunk * N, dtype=torch.float32, device=x.device)
+    check(L.reid_knn_exact(ptr(x), N, D, ptr(rows_list), row_begin, n_rows, k, ptr(idx_out), ptr(key_out),
+                           ptr(scratch), scratch.numel() * 4, stream_ptr()), "reid_knn_exact")
+
+
+def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, gather=None):
+    """Run a1-a6 on device for rows `rows` (default all).  `gather` (optional) is a callable
+    all-gathering a per-shard tensor along dim 0 (multi-GPU row sharding, see sharded.py)."""
+    L = _lib.lib()
+    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    N, D = x.shape
+    if not (1 <= k1 <= 64):
+        raise ValueError("k1=%d outside the supported range 1..64" % k1)
+    if k1 > N:
+        raise ValueError("k1=%d exceeds the number of samples N=%d" % (k1, N))
+    if not (1 <= k2 <= k1):
+        raise ValueError("k2=%d must be in 1..k1" % k2)
+    dev = x.device
+    r0, r1 = (0, N) if rows is None else rows
+    n = r1 - r0
+    st = RerankState()
+    st.N, st.D, st.k1, st.k2, st.row_begin, st.row_end = N, D, k1, k2, r0, r1
+    sp = stream_ptr()
+    ev = []
+
+    def mark(name):
+        if timers:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            ev.append((name, e))
+
+    mark("start")
+    # a1 ------------------------------------------------------------------
+    idx, key, info = knn_search(x, k1, knn, rows=(r0, r1))
+    st.knn_info = info
+    rank_local, key_local = idx, key
+    rank = gather(idx) if gather else idx                     # global (N, k1)
+    st.rank, st.rank_key = rank, key_local
+    mark("knn")
+    # a2 ------------------------------------------------------------------
+    h = half_k(k1)
+    R = torch.empty(n, dtype=torch.int64, device=dev)
+    Rh = torch.empty(N, dtype=torch.int64, device=dev)        # every rank needs R_half of all rows
+    check(L.reid_reciprocal_masks(ptr(rank), N, k1, k1, r0, r1, ptr(R), sp), "reid_reciprocal_masks")
+    check(L.reid_reciprocal_masks(ptr(rank), N, k1, h, 0, N, ptr(Rh), sp), "reid_reciprocal_masks")
+    st.R_mask, st.Rh_mask = R, Rh
+    mark("reciprocal")
+    # a3 ------------------------------------------------------------------
+    e_cnt = torch.empty(n, dtype=torch.int32, device=dev)
+    check(L.reid_expand(ptr(rank), N, k1, ptr(R), ptr(Rh), r0, r1, None, ptr(e_cnt), None, sp), "reid_expand")
+    e_ptr, e_total, e_max = _scan(e_cnt, n, dev)
+    e_idx = torch.empty(max(e_total, 1), dtype=torch.int32, device=dev)
+    check(L.reid_expand(ptr(rank), N, k1, ptr(R), ptr(Rh), r0, r1, ptr(e_ptr), None, ptr(e_idx), sp), "reid_expand")
+    mark("expand")
+    # a4 ------------------------------------------------------------------
+    v_val = torch.empty(max(e_total, 1), dtype=torch.float32, device=dev)
+    check(L.reid_v_weights(ptr(x), N, D, ptr(e_ptr), ptr(e_idx), r0, r1, ptr(rank_local), ptr(key_local), k1,
+                           ptr(v_val), sp), "reid_v_weights")
+    mark("v_weights")
+    if gather:                                               # V rows of other shards are read by a5
+        g_cnt = gather(e_cnt)
+        g_ptr, g_total, e_max = _scan(g_cnt, N, dev)
+        g_idx = gather(e_idx[:e_total])
+        g_val = gather(v_val[:e_total])
+    else:
+        g_ptr, g_idx, g_val = e_ptr, e_idx, v_val
+    st.E_ptr, st.E_idx, st.V_val = g_ptr, g_idx, g_val
+    # a5 ------------------------------------------------------------------
+    if k2 != 1:
+        q_cnt = torch.empty(n, dtype=torch.int32, device=dev)
+        check(L.reid_query_expand(ptr(rank), N, k1, k2, ptr(g_ptr), ptr(g_idx), ptr(g_val), max(e_max, 1), r0, r1,
+                                  None, ptr(q_cnt), None, None, sp), "reid_query_expand")
+        q_ptr, q_total, _ = _scan(q_cnt, n, dev)
+        q_idx = torch.empty(max(q_total, 1), dtype=torch.int32, device=dev)
+        q_val = torch.empty(max(q_total, 1), dtype=torch.float32, device=dev)
+        check(L.reid_query_expand(ptr(rank), N, k1, k2, ptr(g_ptr), ptr(g_idx), ptr(g_val), max(e_max, 1), r0, r1,
+                                  ptr(q_ptr), None, ptr(q_idx), ptr(q_val), sp), "reid_query_expand")
+        if gather:
+            gq_cnt = gather(q_cnt)
+            q_ptr, q_total, _ = _scan(gq_cnt, N, dev)
+            q_idx = gather(q_idx[:int(q_cnt.sum())])
+            q_val = gather(q_val[:q_idx.numel()])
+    else:                                                    # faiss_rerank.py:89: skipped when k2 == 1
+        q_ptr, q_idx, q_val, q_total = g_ptr, g_idx, g_val, (e_total if not gather else int(g_ptr[-1]))
+    st.Q_ptr, st.Q_idx, st.Q_val = q_ptr, q_idx, q_val        # global CSR (N + 1)
+    st.q_total = q_total
+    mark("query_expand")
+    # a6 ------------------------------------------------------------------
+    c_cnt = torch.empty(N, dtype=torch.int32, device=dev)
+    check(L.reid_transpose_count(ptr(q_idx), q_total, N, ptr(c_cnt), sp), "reid_transpose_count")
+    c_ptr, _, c_max = _scan(c_cnt, N, dev)
+    c_idx = torch.empty(max(q_total, 1), dtype=torch.int32, device=dev)
+    c_val = torch.empty(max(q_total, 1), dtype=torch.float32, device=dev)
+    check(L.reid_transpose_fill(ptr(q_ptr), ptr(q_idx), ptr(q_val), N, N, ptr(c_ptr), ptr(c_cnt), ptr(c_idx),
+                                ptr(c_val), sp), "reid_transpose_fill")
+    st.C_ptr, st.C_idx, st.C_val = c_ptr, c_idx, c_val
+    st.c_max = c_max
+    mark("transpose")
+    if timers:
+        torch.cuda.synchronize()
+        for (_, a), (nm, b) in zip(ev[:-1], ev[1:]):
+            st.timings[nm] = a.elapsed_time(b) * 1e-3
+    return st
+
+
+def jaccard_neighbors(st, eps, with_values=False):
+    """a7 (sparse form): eps-neighbourhoods of the shard's rows.  Returns (slot_ptr int64 (n+1),
+    nbr_idx int32, nbr_cnt int32 (n), nbr_val or None): row r's list is nbr_idx[slot_ptr[r] : +nbr_cnt[r]]."""
+    L = _lib.lib()
+    dev = st.Q_ptr.device
+    r0, r1 = st.row_begin, st.row_end
+    n = r1 - r0
+    sp = stream_ptr()
+    t_cnt = torch.empty(n, dtype=torch.int32, device=dev)
+    check(L.reid_jaccard_bounds(ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.C_ptr), r0, r1, ptr(t_cnt), sp),
+          "reid_jaccard_bounds")
+    slot_ptr, t_total, t_max = _scan(t_cnt, n, dev)
+    nbr_idx = torch.empty(max(t_total, 1), dtype=torch.int32, device=dev)
+    nbr_val = torch.empty(max(t_total, 1), dtype=torch.float32, device=dev) if with_values else None
+    nbr_cnt = torch.empty(n, dtype=torch.int32, device=dev)
+    eps32 = float(np.float32(eps))
+    slots = 1024
+    rows_list, n_list = None, 0
+    while True:
+        check(L.reid_jaccard_neighbors(ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
+                                       ptr(st.C_val), st.N, r0, r1, ptr(rows_list), n_list, eps32, ptr(slot_ptr),
+                                       ptr(nbr_idx), ptr(nbr_val), ptr(nbr_cnt), slots, sp), "reid_jaccard_neighbors")
+        over = torch.nonzero(nbr_cnt < 0).flatten().to(torch.int32)
+        if over.numel() == 0:
+            break
+        if slots >= 4096:
+            raise RuntimeError("jaccard_neighbors: %d rows exceed the largest shared-memory table "
+                               "(more than 3072 distinct partners)" % over.numel())
+        rows_list, n_list, slots = over.contiguous(), over.numel(), slots * 2
+    return slot_ptr, nbr_idx, nbr_cnt, nbr_val
+
+
+def jaccard_dense_rows(st, out, row_begin, row_end):
+    """a7 (dense form): rows [row_begin,row_end) of the reference's return value into `out` (device, (rows, N))."""
+    L = _lib.lib()
+    check(L.reid_jaccard_dense(ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
+                               ptr(st.C_val), st.N, row_begin, row_end, ptr(out), out.stride(0), stream_ptr()),
+          "reid_jaccard_dense")
+
+
+class JaccardDistance:
+    """Lazy view of the float32 (N, N) Jaccard distance matrix (faiss_rerank.py:123)."""
+
+    __array_priority__ = 100
+
+    def __init__(self, state):
+        self._state = state
+        self._dense = None
+        self.shape = (state.N, state.N)
+        self.dtype = np.dtype(np.float32)
+        self.ndim = 2
+
+    # -- device-side consumers -------------------------------------------------
+    @property
+    def state(self):
+        return self._state
+
+    def dense_device(self, row_begin=0, row_end=None):
+        """Rows of the matrix as a CUDA tensor (no host copy)."""
+        st = self._state
+        row_end = st.N if row_end is None else row_end
+        out = torch.empty((row_end - row_begin, st.N), dtype=torch.float32, device=st.Q_ptr.device)
+        jaccard_dense_rows(st, out, row_begin, row_end)
+        return out
+
+    # -- host-side (reference) view ---------------------------------------------
+    def numpy(self):
+        if self._dense is None:
+            st = self._state
+            N = st.N
+            host = np.empty((N, N), dtype=np.float32)
+            block = max(1, min(N, (256 << 20) // (4 * N)))
+            for a in range(0, N, block):
+                b = min(N, a + block)
+                host[a:b] = self.dense_device(a, b).cpu().numpy()
+            self._dense = host
+        return self._dense
+
+    def __array__(self, dtype=None, copy=None):
+        a = self.numpy()
+        if dtype is not None and np.dtype(dtype) != a.dtype:
+            return a.astype(dtype)
+        return a.copy() if copy else a
+
+    def __len__(self):
+        return self.shape[0]
+
+    def __getitem__(self, item):
+        return self.numpy()[item]
+
+    def __setitem__(self, item, value):
+        self.numpy()[item] = value
+
+    def __getattr__(self, name):                              # min(), max(), mean(), T, astype, ...
+        if name.startswith("_"):
+            raise AttributeError(name)
+        return getattr(self.numpy(), name)
+
+    def _binop(name):
+        def f(self, other):
+            return getattr(self.numpy(), name)(np.asarray(other) if isinstance(other, JaccardDistance) else other)
+        return f
+
+    for _n in ("__add__", "__radd__", "__sub__", "__rsub__", "__mul__", "__rmul__", "__truediv__", "__lt__",
+               "__le__", "__gt__", "__ge__", "__eq__", "__ne__"):
+        locals()[_n] = _binop(_n)
+    del _n, _binop
+
+    def __repr__(self):
+        return "JaccardDistance(N=%d, materialised=%s)" % (self.shape[0], self._dense is not None)
+
+    __hash__ = None
+
+
+def compute_jaccard_distance(target_features, k1=20, k2=6, print_flag=True, search_option=0, use_float16=False,
+                             knn="auto"):
+    """Drop-in for faiss_rerank.py:30.  `target_features`: (N, D) float32 tensor (CPU or CUDA) or ndarray,
+    rows L2-normalised as the reference's backbone emits them (models/resnet.py:90-94)."""
+    end = time.time()
+    if print_flag:
+        print('Computing jaccard distance...')
+    if search_option not in (0, 1, 2, 3):
+        raise ValueError("search_option must be 0..3 (faiss_rerank.py:39-62), got %r" % (search_option,))
+    if use_float16:
+        raise NotImplementedError("use_float16=True (fp16 storage of V, faiss_rerank.py:37) is not implemented")
+    if isinstance(target_features, np.ndarray):
+        target_features = torch.from_numpy(target_features)
+    if target_features.dim() != 2:
+        raise ValueError("target_features must be (N, D)")
+    dev = _device_of(target_features)
+    with torch.cuda.device(dev), torch.no_grad():
+        x = target_features.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+        st = rerank_state(x, k1, k2, knn=knn)
+        out = JaccardDistance(st)
+        torch.cuda.current_stream().synchronize()
+    if print_flag:
+        print("Jaccard distance computing time cost: {}".format(time.time() - end))
+    return out

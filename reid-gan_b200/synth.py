@@ -1,0 +1,46 @@
+"""Synthetic ResNet-50-shaped re-ID features.
+
+The reference extracts (N, 2048) L2-normalised fp32 features with its backbone
+(clustercontrast/models/resnet.py:90-94, evaluators.py:30-68); there are no
+datasets or checkpoints in this environment, so every test and benchmark uses
+the seeded generator below: `n_ids` unit-norm identity centres plus isotropic
+noise, re-normalised.  It is host-side only (CPU torch generator) so the same
+seed gives the same bytes on every box.
+"""
+import torch
+import torch.nn.functional as F
+
+
+def synth(N, D=2048, n_ids=None, noise=0.8, seed=0):
+    """Return (x, ids): x (N, D) fp32 unit-norm CPU tensor, ids (N,) int64."""
+    if n_ids is None:
+        n_ids = max(1, N // 31)
+    g = torch.Generator().manual_seed(int(seed))
+    centres = F.normalize(torch.randn(n_ids, D, generator=g), dim=1)
+    ids = torch.randint(0, n_ids, (N,), generator=g)
+    x = centres[ids] + noise * torch.randn(N, D, generator=g) / (D ** 0.5)
+    x = F.normalize(x, dim=1).contiguous()
+    return x, ids
+
+
+def synth_cm_batch(x, ids, centroid_labels, num_ids=16, num_instances=16, seed=0):
+    """A ClusterMemory batch shaped like the reference's identity sampler
+    (utils/data/sampler.py:69-107): `num_ids` labels x `num_instances` members,
+    features un-normalised by a random positive scale.
+    Returns (inputs (B, D) fp32, targets (B,) int64)."""
+    g = torch.Generator().manual_seed(int(seed) + 7919)
+    labels = torch.unique(centroid_labels[centroid_labels >= 0])
+    pick = labels[torch.randperm(labels.numel(), generator=g)[:num_ids]]
+    rows, tg = [], []
+    for lab in pick.tolist():
+        members = torch.nonzero(centroid_labels == lab).flatten()
+        sel = members[torch.randint(0, members.numel(), (num_instances,), generator=g)]
+        rows.append(sel)
+        tg.append(torch.full((num_instances,), lab, dtype=torch.int64))
+    rows = torch.cat(rows)
+    tg = torch.cat(tg)
+    perm = torch.randperm(rows.numel(), generator=g)
+    rows, tg = rows[perm], tg[perm]
+    scale = 1.0 + 0.1 * torch.randn(rows.numel(), 1, generator=g)
+    inputs = (x[rows] * scale.abs().clamp_min(0.1)).contiguous()
+    return inputs, tg

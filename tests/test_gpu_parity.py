@@ -1,0 +1,183 @@
+"""GPU (-m gpu): the CUDA path, called through the C ABI, against the golden vectors of the
+reference and against the oracle on seeded inputs.  Bars (BASELINE.json north_star):
+neighbour lists / reciprocal sets / expansion sets / DBSCAN labels bit-exact; Jaccard distance
+within 1e-5 absolute; centroids within 1e-4 relative."""
+import glob
+import os
+
+import numpy as np
+import pytest
+import torch
+
+pytestmark = pytest.mark.gpu
+
+GOLD = os.path.join(os.path.dirname(os.path.abspath(__file__)), "golden")
+RERANK = sorted(glob.glob(os.path.join(GOLD, "rerank_*.npz")))
+KNN_MODES = ("exact", "auto")
+J_ATOL = 1e-5
+
+
+def golden_J(g):
+    N = g["x"].shape[0]
+    J = np.ones((N, N), dtype=np.float32)
+    J[g["J_rows"], g["J_cols"]] = g["J_vals"]
+    return J
+
+
+def masks_to_lists(rank, mask):
+    out = []
+    for i in range(rank.shape[0]):
+        m = int(mask[i]) & 0xFFFFFFFFFFFFFFFF
+        out.append(np.array([rank[i, r] for r in range(rank.shape[1]) if (m >> r) & 1], dtype=np.int64))
+    return out
+
+
+@pytest.mark.parametrize("knn", KNN_MODES)
+@pytest.mark.parametrize("path", RERANK, ids=[os.path.basename(p)[:-4] for p in RERANK])
+def test_golden_jaccard_and_labels(path, knn):
+    import reid_gan_b200 as rg
+    g = np.load(path)
+    x, k1, k2 = torch.from_numpy(g["x"]), int(g["k1"]), int(g["k2"])
+    dist = rg.compute_jaccard_distance(x, k1=k1, k2=k2, print_flag=False, search_option=3, knn=knn)
+    J = np.asarray(dist)
+    J_ref = golden_J(g)
+    assert J.dtype == np.float32 and J.shape == J_ref.shape
+    assert np.array_equal(J == 1.0, J_ref == 1.0), "sparsity structure differs from the reference"
+    assert np.abs(J - J_ref).max() <= J_ATOL
+    assert np.array_equal(J, J.T), "J must be bit-symmetric like the reference's"
+    for eps in g["eps_list"]:
+        tag = "eps%02d" % round(float(eps) * 100)
+        if not bool(g["admissible_" + tag]):
+            continue
+        c = rg.DBSCAN(eps=float(eps), min_samples=4, metric="precomputed", n_jobs=-1)
+        assert np.array_equal(c.fit_predict(dist), g["labels_" + tag]), "sparse-path labels"
+        assert c.labels_.dtype == np.intp
+        assert np.array_equal(rg.DBSCAN(eps=float(eps), min_samples=4).fit_predict(J_ref), g["labels_" + tag]), \
+            "dense-path labels on the reference's own matrix"
+        if "centroids_" + tag in g.files:
+            cen = rg.generate_cluster_features(g["labels_" + tag], x, normalize=True).cpu().numpy()
+            np.testing.assert_allclose(cen, g["centroids_" + tag], rtol=1e-4, atol=1e-7)
+
+
+@pytest.mark.parametrize("knn", KNN_MODES)
+@pytest.mark.parametrize("N,D,n_ids,noise,k1,k2,seed", [
+    (2048, 256, 64, 0.8, 30, 6, 0),
+    (1500, 192, 1500, 1.0, 20, 6, 1),      # isotropic: worst case for top-k gaps
+    (700, 64, 10, 0.3, 64, 6, 2),          # k1 at the 64-bit mask limit, tight clusters
+    (300, 64, 10, 0.8, 7, 1, 3),           # k2 == 1, odd k1
+])
+def test_every_stage_against_oracle(N, D, n_ids, noise, k1, k2, seed, knn):
+    import reid_gan_b200 as rg
+    from oracle import rerank as orr
+    x, _ = rg.synth(N, D, n_ids, noise, seed)
+    st = rg.rerank_state(x.cuda(), k1, k2, knn=knn)
+    o = orr.sparse_pipeline(x.numpy(), k1, k2)
+    rank = st.rank.cpu().numpy()
+    assert np.array_equal(rank, o["rank"]), "a1 neighbour lists"
+    # a2: reciprocal sets as rank-position masks
+    R = masks_to_lists(rank, st.R_mask.cpu().numpy())
+    Rh = masks_to_lists(rank, st.Rh_mask.cpu().numpy())
+    R_ref = orr.reciprocal_lists(o["rank"], k1)
+    Rh_ref = orr.reciprocal_lists(o["rank"], orr.half_k(k1))
+    for i in range(N):
+        assert np.array_equal(R[i], R_ref[i]) and np.array_equal(Rh[i], Rh_ref[i]), "a2 row %d" % i
+    # a3: expansion sets
+    assert np.array_equal(st.E_ptr.cpu().numpy(), o["E_ptr"])
+    nE = int(o["E_ptr"][-1])
+    assert np.array_equal(st.E_idx.cpu().numpy()[:nE], o["E_idx"])
+    # a4 / a5: weights
+    np.testing.assert_allclose(st.V_val.cpu().numpy()[:nE], o["V_val"], atol=2e-6, rtol=0)
+    assert np.array_equal(st.Q_ptr.cpu().numpy(), o["Vq_ptr"])
+    nQ = int(o["Vq_ptr"][-1])
+    assert np.array_equal(st.Q_idx.cpu().numpy()[:nQ], o["Vq_idx"])
+    np.testing.assert_allclose(st.Q_val.cpu().numpy()[:nQ], o["Vq_val"], atol=2e-6, rtol=0)
+    # a6: inverted index
+    cp, ci, cv = orr.transpose_csr(st.Q_ptr.cpu().numpy(), st.Q_idx.cpu().numpy()[:nQ], st.Q_val.cpu().numpy()[:nQ], N)
+    assert np.array_equal(st.C_ptr.cpu().numpy(), cp)
+    assert np.array_equal(st.C_idx.cpu().numpy()[:nQ], ci)
+    assert np.array_equal(st.C_val.cpu().numpy()[:nQ], cv)
+    # a7 on the device's own V_qe: bit-exact against the oracle's sequential ascending-column sum
+    jp, jj, jv = orr.jaccard_sparse(st.Q_ptr.cpu().numpy(), st.Q_idx.cpu().numpy()[:nQ],
+                                    st.Q_val.cpu().numpy()[:nQ], N)
+    Jd = rg.JaccardDistance(st).numpy()
+    assert np.array_equal(Jd, orr.jaccard_dense_from_sparse(jp, jj, jv, N)), "a7 must be bit-exact given V_qe"
+
+
+def test_stage_inputs_from_oracle_are_bit_exact():
+    """Integer stages fed with the ORACLE's neighbour lists: outputs must be identical (no tolerance)."""
+    import reid_gan_b200 as rg
+    from reid_gan_b200 import _lib
+    from reid_gan_b200._lib import check, ptr, stream_ptr
+    from oracle import rerank as orr
+    L = _lib.lib()
+    N, D, k1 = 900, 64, 25
+    x, _ = rg.synth(N, D, 30, 0.8, 11)
+    rank = orr.exact_knn(x.numpy(), k1)
+    d_rank = torch.from_numpy(rank.astype(np.int32)).cuda()
+    for k in (k1, orr.half_k(k1)):
+        m = torch.empty(N, dtype=torch.int64, device="cuda")
+        check(L.reid_reciprocal_masks(ptr(d_rank), N, k1, k, 0, N, ptr(m), stream_ptr()))
+        ref = orr.k_reciprocal_masks(rank, k)
+        got = m.cpu().numpy()
+        for i in range(N):
+            bits = [(int(got[i]) >> r) & 1 for r in range(ref.shape[1])]
+            assert bits == list(ref[i].astype(int))
+            assert (int(got[i]) & 0xFFFFFFFFFFFFFFFF) >> ref.shape[1] == 0
+
+
+@pytest.mark.parametrize("eps", [0.3, 0.45, 0.6])
+def test_dbscan_dense_matches_sklearn(eps):
+    import reid_gan_b200 as rg
+    from oracle import cluster as ocl
+    rng = np.random.default_rng(int(eps * 100))
+    pts = np.concatenate([rng.normal(c, 0.08, (60, 2)) for c in ((0, 0), (1, 0), (0, 1), (1, 1))] +
+                         [rng.uniform(-0.5, 1.5, (80, 2))]).astype(np.float32)
+    d = np.sqrt(((pts[:, None] - pts[None]) ** 2).sum(-1)).astype(np.float32)
+    for ms in (2, 4, 9):
+        ref = ocl.sklearn_dbscan(d, eps * 0.3, ms)
+        c = rg.DBSCAN(eps=eps * 0.3, min_samples=ms)
+        assert np.array_equal(c.fit_predict(d), ref)
+        from sklearn.cluster import DBSCAN as SK
+        sk = SK(eps=eps * 0.3, min_samples=ms, metric="precomputed").fit(d)
+        assert np.array_equal(c.core_sample_indices_, sk.core_sample_indices_)
+    # inclusive fp32 threshold: a distance of exactly float32(eps) is a neighbour
+    d2 = np.full((5, 5), 2.0, np.float32)
+    np.fill_diagonal(d2, 0.0)
+    d2[0, 1] = d2[1, 0] = np.float32(0.6)
+    assert np.array_equal(rg.DBSCAN(eps=0.6, min_samples=2).fit_predict(d2), ocl.sklearn_dbscan(d2, 0.6, 2))
+    # all noise
+    assert np.array_equal(rg.DBSCAN(eps=0.1, min_samples=3).fit_predict(d2), np.full(5, -1))
+
+
+def test_full_size_properties():
+    """N = 12,936 x 2048 (Market-1501 shape, BASELINE configs[0]): size-independent properties
+    plus a sampled comparison with the oracle."""
+    import reid_gan_b200 as rg
+    from oracle import rerank as orr
+    N, D, k1, k2 = 12936, 2048, 30, 6
+    x, _ = rg.synth(N, D, 751, 0.8, 0)
+    dist = rg.compute_jaccard_distance(x, k1=k1, k2=k2, print_flag=False)
+    st = dist.state
+    rank = st.rank.cpu().numpy()
+    rows = np.arange(0, N, 97)
+    assert np.array_equal(rank[rows], orr.exact_knn(x.numpy(), k1, rows=rows)), "neighbour lists (sampled rows)"
+    qp = st.Q_ptr.cpu().numpy()
+    qv = st.Q_val.cpu().numpy()[:qp[-1]]
+    sums = np.add.reduceat(qv.astype(np.float64), qp[:-1])
+    np.testing.assert_allclose(sums, 1.0, atol=1e-5)            # rows of V_qe sum to 1
+    assert np.all(np.diff(qp) > 0)
+    blk = dist.dense_device(0, 512).cpu().numpy()
+    blk_t = torch.stack([dist.dense_device(i, i + 1)[0, :512] for i in range(0, 512, 64)]).cpu().numpy()
+    assert np.array_equal(blk[:512:64, :512].T[:, :] if False else blk[0:512:64, :512], blk_t)
+    assert blk.min() >= 0.0 and blk.max() <= 1.0
+    assert np.abs(np.diag(blk[:, :512])).max() <= 2e-6          # J_ii ~ 0
+    sub = blk[:, :512]
+    assert np.array_equal(sub, sub.T)                           # symmetric bit for bit
+    labels = rg.DBSCAN(eps=0.6, min_samples=4, metric="precomputed", n_jobs=-1).fit_predict(dist)
+    assert labels.shape == (N,) and labels.min() >= -1
+    # labels from the sparse path == labels from the dense path on the same matrix block structure
+    ncl = labels.max() + 1
+    assert 300 < ncl < 1500
+    # idempotence / determinism
+    labels2 = rg.DBSCAN(eps=0.6, min_samples=4).fit_predict(rg.compute_jaccard_distance(x, k1, k2, print_flag=False))
+    assert np.array_equal(labels, labels2)
