@@ -59,26 +59,38 @@ int reid_knn_exact(const float* x, int64_t N, int64_t D, const int32_t* rows_lis
                    int64_t n_rows, int k, int32_t* out_idx, float* out_key, void* scratch,
                    size_t scratch_bytes, void* stream);
 
-/* Tensor-core candidate search: fp16 tcgen05 GEMM (TMA-fed, TMEM accumulators) of
- * query rows [row_begin,row_end) against all N rows with a fused per-row running
- * top-kc selection in the epilogue.  xh = fp16(x * 2^scale_log2), row-major N x D,
- * D % 64 == 0.  cand_idx/cand_val: (row_end-row_begin) x kc, unordered; cand_val is the
- * approximate dot product (already un-scaled).  See reid_knn_rescore. */
+/* Tensor-core candidate search: fp16 tcgen05 GEMM (TMA-fed, TMEM accumulators) of query rows
+ * [row_begin,row_end) against all N rows with a fused per-row running top-`keep` selection in the
+ * epilogue.  xh = fp16(x * 2^scale_log2), row-major N x D, D % 64 == 0, 16-byte aligned.
+ * The N columns are cut into n_splits ranges (reid_knn_tc_plan picks the count that fills the SMs);
+ * every (row, range) keeps its own list:
+ *   cand[((row-row_begin)*n_splits + q)*REID_TC_CAP + p] = (fp32 score bits << 32) | column,
+ *   p < cand_cnt[(row-row_begin)*n_splits + q] <= keep.  A list with fewer than `keep` entries holds
+ *   every column of its range.  Scores are approximate (fp16 inputs); see reid_knn_rescore. */
+#define REID_TC_CAP 128
+#define REID_TC_MAX_SPLITS 4
+int reid_knn_tc_plan(int64_t N, int64_t n_rows, int* n_splits_out);
 int reid_knn_candidates_tc(const void* xh, int64_t N, int64_t D, int scale_log2, int64_t row_begin,
-                           int64_t row_end, int kc, int32_t* cand_idx, float* cand_val, void* stream);
-/* Convert fp32 features to the scaled fp16 operand of reid_knn_candidates_tc. */
-int reid_features_to_half(const float* x, int64_t n_elems, int scale_log2, void* xh, void* stream);
+                           int64_t row_end, int keep, int n_splits, uint64_t* cand, int32_t* cand_cnt,
+                           void* stream);
+/* fp32 features -> scaled fp16 operand; max_sqnorm_out (optional, 1 float) = max_i ||x_i||^2, which
+ * scales the fp16 rounding bound  |approx - exact| <= 2^-10 ||x_i|| ||x_j||. */
+int reid_features_to_half(const float* x, int64_t n_rows, int64_t D, int scale_log2, void* xh,
+                          float* max_sqnorm_out, void* stream);
 
 /* Exact re-score of the candidates with the canonical key, certificate, final order.
- * A row is certified when every column whose approximate score lies within 2*err_bound of
- * the k-th best approximate score is among its kc candidates (then the exact top-k is
- * provably inside the candidate set).  Uncertified rows get uncertified_flag[row]=1 and
- * must be redone with reid_knn_exact.  max_err_out (1 float) receives the largest
- * |approx - exact| seen, to audit err_bound. */
-int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, int64_t row_end, int kc,
-                     const int32_t* cand_idx, const float* cand_val, int k, float err_bound,
-                     int32_t* out_idx, float* out_key, int32_t* uncertified_flag, float* max_err_out,
-                     void* stream);
+ * Let a_(k) be the k-th best approximate score of a row.  Every member of the exact top-k has an
+ * approximate score >= a_(k) - 2*err_bound (the "window").  The row is certified when, for every
+ * column range whose list is full, the weakest retained score is below the window -- then the window,
+ * hence the exact top-k, is entirely among the candidates.  Window members are re-scored with
+ * fp32(fp64 dot) and ordered by (key desc, index asc): bit-identical to reid_knn_exact.
+ * |approx - exact| is audited against err_bound; a violation un-certifies the row.
+ * uncertified_flag[row-row_begin] = 1 marks rows the caller must redo with reid_knn_exact;
+ * max_err_out (1 float) = largest |approx - exact| seen. */
+int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, int64_t row_end,
+                     const uint64_t* cand, const int32_t* cand_cnt, int n_splits, int keep, int k,
+                     float err_bound, int32_t* out_idx, float* out_key, int32_t* uncertified_flag,
+                     float* max_err_out, void* stream);
 
 /* ---- a2: reciprocal sets  (faiss_rerank.py:23-27, 65-69) -----------------------
  * mask_out[row - row_begin] bit r  <=>  row in rank[rank[row,r], :cols], cols = min(k+1, ncols).
@@ -134,6 +146,13 @@ int reid_jaccard_neighbors(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
                            int64_t row_begin, int64_t row_end, const int32_t* rows_list, int64_t n_list,
                            float eps, const int64_t* slot_ptr, int32_t* nbr_idx, float* nbr_val,
                            int32_t* nbr_cnt, int table_slots, void* stream);
+/* same contract for the rows of rows_list that overflowed every table ("hub" rows): dense accumulator
+ * rows in `scratch` (n_list x N floats), neighbours written in ascending j. */
+int reid_jaccard_neighbors_heavy(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val,
+                                 const int64_t* C_ptr, const int32_t* C_idx, const float* C_val, int64_t N,
+                                 int64_t row_begin, const int32_t* rows_list, int64_t n_list, float eps,
+                                 const int64_t* slot_ptr, int32_t* nbr_idx, float* nbr_val, int32_t* nbr_cnt,
+                                 float* scratch, void* stream);
 /* dense rows: out[(row-row_begin)*ld + j] for all j < N  (the reference's return value). */
 int reid_jaccard_dense(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
                        const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin,

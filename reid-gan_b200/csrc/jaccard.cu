@@ -151,6 +151,60 @@ __global__ void __launch_bounds__(256) jaccard_dense_kernel(
   }
 }
 
+// Rows whose partner set does not fit any shared-memory table ("hub" rows): one CTA per row, dense
+// accumulator row in global scratch (L2-resident), same ascending-column order, then an ordered
+// block-wide compaction of { j : J_ij <= eps }.
+__global__ void __launch_bounds__(256) jaccard_neighbors_heavy_kernel(
+    const int64_t* __restrict__ Q_ptr, const int32_t* __restrict__ Q_idx, const float* __restrict__ Q_val,
+    const int64_t* __restrict__ C_ptr, const int32_t* __restrict__ C_idx, const float* __restrict__ C_val, int64_t N,
+    int64_t row_begin, const int32_t* __restrict__ rows_list, float eps, const int64_t* __restrict__ slot_ptr,
+    int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_val, int32_t* __restrict__ nbr_cnt,
+    float* __restrict__ scratch) {
+  __shared__ int s_warp[8];
+  __shared__ int s_base;
+  const int64_t lr = rows_list[blockIdx.x];
+  const int64_t row = row_begin + lr;
+  float* acc = scratch + (int64_t)blockIdx.x * N;
+  for (int64_t j = threadIdx.x; j < N; j += blockDim.x) __stcg(&acc[j], 0.f);
+  if (threadIdx.x == 0) s_base = 0;
+  __syncthreads();
+  for (int64_t p = Q_ptr[row]; p < Q_ptr[row + 1]; ++p) {
+    const int32_t c = Q_idx[p];
+    const float vic = Q_val[p];
+    for (int64_t q = C_ptr[c] + threadIdx.x; q < C_ptr[c + 1]; q += blockDim.x) {
+      const int32_t j = C_idx[q];
+      __stcg(&acc[j], __fadd_rn(__ldcg(&acc[j]), fminf(vic, C_val[q])));
+    }
+    __syncthreads();
+  }
+  const int64_t o = slot_ptr[lr];
+  const int lane = lane_id(), w = threadIdx.x >> 5;
+  for (int64_t base = 0; base < N; base += blockDim.x) {
+    const int64_t j = base + threadIdx.x;
+    float jd = 2.f;
+    if (j < N) jd = jaccard_from_t(__ldcg(&acc[j]));
+    const bool keep = j < N && jd <= eps;
+    const unsigned b = __ballot_sync(kFull, keep);
+    if (lane == 0) s_warp[w] = __popc(b);
+    __syncthreads();
+    int before = s_base;
+    for (int ww = 0; ww < w; ++ww) before += s_warp[ww];
+    if (keep) {
+      const int64_t dst = o + before + __popc(b & ((1u << lane) - 1u));
+      nbr_idx[dst] = (int32_t)j;
+      if (nbr_val) nbr_val[dst] = jd;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+      int tot = 0;
+      for (int ww = 0; ww < 8; ++ww) tot += s_warp[ww];
+      s_base += tot;
+    }
+    __syncthreads();
+  }
+  if (threadIdx.x == 0) nbr_cnt[lr] = s_base;
+}
+
 }  // namespace reid
 
 extern "C" {
@@ -208,6 +262,22 @@ int reid_jaccard_dense(const int64_t* Q_ptr, const int32_t* Q_idx, const float* 
     jaccard_dense_kernel<false><<<(unsigned)n, 256, 0, st>>>(Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin,
                                                             out, ld);
   }
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+int reid_jaccard_neighbors_heavy(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
+                                 const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin,
+                                 const int32_t* rows_list, int64_t n_list, float eps, const int64_t* slot_ptr,
+                                 int32_t* nbr_idx, float* nbr_val, int32_t* nbr_cnt, float* scratch, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(Q_ptr && Q_idx && Q_val && C_ptr && C_idx && C_val && rows_list && slot_ptr && nbr_idx && nbr_cnt &&
+                     scratch,
+                 "reid_jaccard_neighbors_heavy: NULL pointer");
+  REID_CHECK_ARG(N > 0 && n_list >= 0, "reid_jaccard_neighbors_heavy: bad shape");
+  if (n_list == 0) return REID_OK;
+  jaccard_neighbors_heavy_kernel<<<(unsigned)n_list, 256, 0, (cudaStream_t)stream>>>(
+      Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin, rows_list, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt,
+      scratch);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

@@ -1,12 +1,483 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// a1 (first half) -- the N x N similarity contraction on the 5th-generation tensor cores, fused
+// with a per-row running top-K selection (replaces the SGEMM + block-select inside faiss
+// IndexFlatL2 / GpuIndexFlatL2.search, utils/faiss_rerank.py:39-62).
+//
+//   S = Xh . Xh^T,  Xh = fp16(2^s X)  (N x D, K-major for both operands)
+//
+// One persistent CTA per SM, warp-specialised:
+//   warp 0      TMA producer : cp.async.bulk.tensor 128B-swizzled 64-wide K slices of a 128-row query
+//                              tile (A) and a 256-row column tile (B) into a 4-stage shared-memory ring
+//   warp 1      MMA issuer   : one elected lane issues tcgen05.mma (M=128, N=256, K=16, fp16 -> fp32)
+//                              into one of two 256-column TMEM accumulators; tcgen05.commit frees the
+//                              ring slot / publishes the accumulator
+//   warps 2..5  epilogue     : tcgen05.ld 32 columns at a time; thread <-> query row; every score is
+//                              compared with the row's running threshold tau and survivors are appended
+//                              to the row's candidate list (global scratch, L2 resident).  When a list
+//                              nears capacity the warp compacts it cooperatively to the best K
+//                              (bitwise binary search for the K-th value, ballot prefix sums) and raises
+//                              tau, so after warm-up almost every score dies on a single compare.
+// A work unit is (128-row query tile) x (one of n_splits column ranges); units are dealt round-robin,
+// column-range major so that concurrently running CTAs stream the same B tiles out of L2.
+// The scores are only candidates: knn_rescore.cu re-scores them exactly and certifies the result.
+#include <cuda.h>
+#include <cuda_fp16.h>
+
 #include "common.cuh"
-extern "C" {
-int reid_knn_candidates_tc(const void*, int64_t, int64_t, int, int64_t, int64_t, int, int32_t*, float*, void*) {
-  reid::set_error("reid_knn_candidates_tc: not built yet");
-  return REID_ERR_UNSUPPORTED;
+
+namespace reid {
+namespace tc {
+
+constexpr int BM = 128, BN = 256, BK = 64;   // tile; BK * 2 B = 128 B = one swizzle atom row
+constexpr int UMMA_K = 16;
+constexpr int kStages = 4;
+constexpr int kATileBytes = BM * BK * 2;     // 16 KB
+constexpr int kBTileBytes = BN * BK * 2;     // 32 KB
+constexpr int kStageBytes = kATileBytes + kBTileBytes;
+constexpr int kThreads = 192;
+constexpr int kCap = REID_TC_CAP;            // per (row, split) candidate list capacity
+constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
+
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
 }
-int reid_features_to_half(const float*, int64_t, int, void*, void*) {
-  reid::set_error("reid_features_to_half: not built yet");
-  return REID_ERR_UNSUPPORTED;
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+  uint32_t ok;
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
+      "selp.u32 %0, 1, 0, p;\n"
+      "}\n"
+      : "=r"(ok)
+      : "r"(smem_u32(bar)), "r"(parity)
+      : "memory");
+  return ok != 0;
+}
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+  while (!mbar_try_wait(bar, parity)) {
+  }
+}
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
+      : "memory");
+}
+
+__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+// K-major operand tile, 128-byte swizzle: rows are 128 B apart inside an 8-row / 1024 B atom (SBO = 1024 B)
+__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
+  uint64_t d = 0;
+  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);        // start address
+  d |= (uint64_t)1 << 16;                             // leading byte offset (unused with swizzle; canonical 1)
+  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset
+  d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
+  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
+  return d;
+}
+
+// kind::f16 instruction descriptor: fp16 A/B (K-major), fp32 accumulate, M x N
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
+  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                         uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_c),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+               : "memory");
+}
+
+__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
+  asm volatile(
+      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
+      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
+      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
+      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
+        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
+        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
+        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
+      : "r"(taddr));
+  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+}
+
+// Cooperative compaction of one row's candidate list (n entries at `list`, n <= kCap) to its best
+// `keep` entries (by score; ties by list position).  Returns the keep-th best score (the new tau).
+// Entry = (score bits << 32) | column.
+__device__ __forceinline__ float warp_compact(unsigned long long* list, int n, int keep) {
+  const int lane = lane_id();
+  constexpr int kPer = kCap / 32;
+  unsigned long long e[kPer];
+  uint32_t o[kPer];
+  __syncwarp();  // the owner lane's appends must be visible to the whole warp
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const int i = j * 32 + lane;
+    e[j] = i < n ? list[i] : 0ull;
+    o[j] = i < n ? float_ord(__uint_as_float((uint32_t)(e[j] >> 32))) : 0u;  // 0 sorts below every real score
+  }
+  __syncwarp();
+  // largest T with #{o >= T} >= keep  == the keep-th largest ordered score
+  uint32_t T = 0;
+#pragma unroll 1
+  for (int bit = 31; bit >= 0; --bit) {
+    const uint32_t cand = T | (1u << bit);
+    int c = 0;
+#pragma unroll
+    for (int j = 0; j < kPer; ++j) c += o[j] >= cand;
+    c = __reduce_add_sync(kFull, c);
+    if (c >= keep) T = cand;
+  }
+  int n_gt = 0;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) n_gt += o[j] > T;
+  n_gt = __reduce_add_sync(kFull, n_gt);
+  const int quota = keep - n_gt;  // how many of the entries equal to T stay
+  int eq_seen = 0, kept_seen = 0;
+  const unsigned lt = (1u << lane) - 1u;
+#pragma unroll
+  for (int j = 0; j < kPer; ++j) {
+    const bool gt = o[j] > T, eq = o[j] == T && (j * 32 + lane) < n;
+    const unsigned beq = __ballot_sync(kFull, eq);
+    const bool keep_me = gt || (eq && eq_seen + __popc(beq & lt) < quota);
+    const unsigned bk = __ballot_sync(kFull, keep_me);
+    if (keep_me) list[kept_seen + __popc(bk & lt)] = e[j];
+    eq_seen += __popc(beq);
+    kept_seen += __popc(bk);
+  }
+  __syncwarp();
+  return ord_float(T);
+}
+
+struct Params {
+  int64_t N;
+  int64_t row_begin, row_end;
+  int num_k_blocks;     // D / 64
+  int n_mblk;           // query tiles in the shard
+  int n_splits;
+  int n_tiles;          // ceil(N / 256) column tiles
+  int keep;             // K: entries kept per (row, split)
+  float descale;        // 2^(-2 s)
+  unsigned long long* cand;   // [(rows) x n_splits x kCap]
+  int32_t* cand_cnt;          // [(rows) x n_splits]
+};
+
+__global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+  extern __shared__ __align__(1024) uint8_t smem_raw[];
+  uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
+  uint64_t* full_bar = (uint64_t*)(smem + kStages * kStageBytes);
+  uint64_t* empty_bar = full_bar + kStages;
+  uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained
+  uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+
+  const int warp = threadIdx.x >> 5, lane = lane_id();
+
+  if (warp == 0 && lane == 0) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    for (int s = 0; s < kStages; ++s) {
+      mbar_init(&full_bar[s], 1);
+      mbar_init(&empty_bar[s], 1);
+    }
+    for (int a = 0; a < 2; ++a) {
+      mbar_init(&tfull_bar[a], 1);
+      mbar_init(&tempty_bar[a], 4);
+    }
+    asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
+  }
+  if (warp == 1) {  // TMEM: all 512 columns = two 128 x 256 fp32 accumulators
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  }
+  tcgen05_fence_before();
+  __syncthreads();
+  tcgen05_fence_after();
+  const uint32_t tmem_base = *tmem_slot;
+
+  const int n_units = p.n_mblk * p.n_splits;
+
+  if (warp == 0) {
+    // ------------------------------ TMA producer ------------------------------
+    if (lane == 0) {
+      int stage = 0;
+      uint32_t phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int split = u / p.n_mblk, mblk = u % p.n_mblk;
+        const int t0 = (int)((int64_t)p.n_tiles * split / p.n_splits), t1 = (int)((int64_t)p.n_tiles * (split + 1) / p.n_splits);
+        const int m_row = (int)p.row_begin + mblk * BM;
+        for (int t = t0; t < t1; ++t) {
+          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+            mbar_wait(&empty_bar[stage], phase ^ 1);
+            uint8_t* a_dst = smem + stage * kStageBytes;
+            uint8_t* b_dst = a_dst + kATileBytes;
+            mbar_expect_tx(&full_bar[stage], kStageBytes);
+            tma_load_2d(a_dst, &tmap, &full_bar[stage], kb * BK, m_row);
+            tma_load_2d(b_dst, &tmap, &full_bar[stage], kb * BK, t * BN);
+            tma_load_2d(b_dst + kATileBytes, &tmap, &full_bar[stage], kb * BK, t * BN + 128);
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+        }
+      }
+    }
+  } else if (warp == 1) {
+    // ------------------------------ MMA issuer --------------------------------
+    if (lane == 0) {
+      constexpr uint32_t idesc = make_idesc(BM, BN);
+      int stage = 0;
+      uint32_t phase = 0;
+      int acc = 0;
+      uint32_t acc_phase = 0;
+      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+        const int split = u / p.n_mblk;
+        const int t0 = (int)((int64_t)p.n_tiles * split / p.n_splits), t1 = (int)((int64_t)p.n_tiles * (split + 1) / p.n_splits);
+        for (int t = t0; t < t1; ++t) {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+          tcgen05_fence_after();
+          const uint32_t tmem_c = tmem_base + (uint32_t)(acc * BN);
+          for (int kb = 0; kb < p.num_k_blocks; ++kb) {
+            mbar_wait(&full_bar[stage], phase);
+            tcgen05_fence_after();
+            const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+            const uint32_t b_addr = a_addr + kATileBytes;
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = make_smem_desc(a_addr + k * UMMA_K * 2);
+              const uint64_t db = make_smem_desc(b_addr + k * UMMA_K * 2);
+              umma_f16(tmem_c, da, db, idesc, (kb | k) != 0);
+            }
+            umma_commit(&empty_bar[stage]);             // slot free once these MMAs have read it
+            if (++stage == kStages) {
+              stage = 0;
+              phase ^= 1;
+            }
+          }
+          umma_commit(&tfull_bar[acc]);                 // accumulator complete
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
+        }
+      }
+    }
+  } else {
+    // ------------------------------ epilogue: fused running top-K ----------------
+    const int quarter = warp & 3;                       // TMEM lanes this warp may read
+    const int r_in_tile = quarter * 32 + lane;
+    int acc = 0;
+    uint32_t acc_phase = 0;
+    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      const int split = u / p.n_mblk, mblk = u % p.n_mblk;
+      const int t0 = (int)((int64_t)p.n_tiles * split / p.n_splits), t1 = (int)((int64_t)p.n_tiles * (split + 1) / p.n_splits);
+      const int64_t lrow = (int64_t)mblk * BM + r_in_tile;               // local row in the shard
+      const bool row_ok = p.row_begin + lrow < p.row_end;
+      unsigned long long* list = p.cand + (((row_ok ? lrow : 0) * p.n_splits + split) * (int64_t)kCap);
+      float tau = row_ok ? -INFINITY : INFINITY;
+      int cnt = 0;
+      for (int t = t0; t < t1; ++t) {
+        mbar_wait(&tfull_bar[acc], acc_phase);
+        tcgen05_fence_after();
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+#pragma unroll 1
+        for (int ch = 0; ch < BN / 32; ++ch) {
+          uint32_t v[32];
+          tmem_ld_32x32b_x32(taddr + ch * 32, v);
+          const int col0 = t * BN + ch * 32;
+          if (col0 + 32 <= p.N) {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float s = __uint_as_float(v[c]) * p.descale;
+              if (s > tau) list[cnt++] = ((unsigned long long)__float_as_uint(s) << 32) | (uint32_t)(col0 + c);
+            }
+          } else {
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              const float s = __uint_as_float(v[c]) * p.descale;
+              if (s > tau && col0 + c < p.N) list[cnt++] = ((unsigned long long)__float_as_uint(s) << 32) | (uint32_t)(col0 + c);
+            }
+          }
+          // lists that could overflow during the next 32 columns are compacted now, one row at a time
+          unsigned need = __ballot_sync(kFull, cnt > kCap - 32);
+          while (need) {
+            const int src = __ffs(need) - 1;
+            need &= need - 1;
+            unsigned long long* l = (unsigned long long*)__shfl_sync(kFull, (unsigned long long)list, src);
+            const int n = __shfl_sync(kFull, cnt, src);
+            const float nt = warp_compact(l, n, p.keep);
+            if (lane == src) {
+              tau = nt;
+              cnt = p.keep;
+            }
+          }
+        }
+        tcgen05_fence_before();
+        __syncwarp();
+        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
+        if (++acc == 2) {
+          acc = 0;
+          acc_phase ^= 1;
+        }
+      }
+      // unit done: trim every list to `keep` and publish the counts
+      unsigned need = __ballot_sync(kFull, cnt > p.keep);
+      while (need) {
+        const int src = __ffs(need) - 1;
+        need &= need - 1;
+        unsigned long long* l = (unsigned long long*)__shfl_sync(kFull, (unsigned long long)list, src);
+        const int n = __shfl_sync(kFull, cnt, src);
+        warp_compact(l, n, p.keep);
+        if (lane == src) cnt = p.keep;
+      }
+      if (row_ok) p.cand_cnt[lrow * p.n_splits + split] = cnt;
+    }
+  }
+
+  tcgen05_fence_before();
+  __syncthreads();
+  if (warp == 1) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  }
+}
+
+__global__ void __launch_bounds__(256) to_half_kernel(const float* __restrict__ x, int64_t n_rows, int64_t D, float scale,
+                                                      __half* __restrict__ xh, float* __restrict__ max_sqnorm) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  float ss = 0.f;
+  for (int64_t d = lane_id(); d < D; d += 32) {
+    const float v = x[row * D + d];
+    ss = fmaf(v, v, ss);
+    xh[row * D + d] = __float2half_rn(v * scale);
+  }
+  ss = warp_sum(ss);
+  if (lane_id() == 0 && max_sqnorm) atomicMax((unsigned*)max_sqnorm, __float_as_uint(ss));
+}
+
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
+                                  const cuuint64_t*, const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave,
+                                  CUtensorMapSwizzle, CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+
+static EncodeTiledFn get_encode_fn() {
+  static EncodeTiledFn fn = nullptr;
+  if (!fn) {
+    void* p = nullptr;
+    cudaDriverEntryPointQueryResult q;
+    if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+        q == cudaDriverEntryPointSuccess)
+      fn = (EncodeTiledFn)p;
+  }
+  return fn;
+}
+
+}  // namespace tc
+}  // namespace reid
+
+extern "C" {
+
+int reid_knn_tc_plan(int64_t N, int64_t n_rows, int* n_splits_out) {
+  using namespace reid;
+  REID_CHECK_ARG(N > 0 && n_rows > 0 && n_splits_out, "reid_knn_tc_plan: bad arguments");
+  const int sms = num_sms();
+  const int64_t n_mblk = (n_rows + tc::BM - 1) / tc::BM;
+  const int64_t n_tiles = (N + tc::BN - 1) / tc::BN;
+  int best = 1;
+  double best_eff = -1.0;
+  for (int s = 1; s <= REID_TC_MAX_SPLITS; ++s) {
+    if (s > n_tiles) break;
+    const int64_t units = n_mblk * s;
+    const int64_t waves = (units + sms - 1) / sms;
+    const double eff = (double)units / (double)(waves * sms);
+    if (eff > best_eff + 0.02) {  // prefer fewer splits unless the gain is real
+      best_eff = eff;
+      best = s;
+    }
+  }
+  *n_splits_out = best;
+  return REID_OK;
+}
+
+int reid_features_to_half(const float* x, int64_t n_rows, int64_t D, int scale_log2, void* xh, float* max_sqnorm_out,
+                          void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(x && xh && n_rows >= 0 && D > 0, "reid_features_to_half: bad arguments");
+  REID_CHECK_ARG(scale_log2 >= -8 && scale_log2 <= 12, "reid_features_to_half: scale_log2=%d out of range", scale_log2);
+  cudaStream_t st = (cudaStream_t)stream;
+  if (max_sqnorm_out) REID_CUDA(cudaMemsetAsync(max_sqnorm_out, 0, sizeof(float), st));
+  if (n_rows == 0) return REID_OK;
+  tc::to_half_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(x, n_rows, D, ldexpf(1.0f, scale_log2), (__half*)xh,
+                                                                  max_sqnorm_out);
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+
+int reid_knn_candidates_tc(const void* xh, int64_t N, int64_t D, int scale_log2, int64_t row_begin, int64_t row_end,
+                           int keep, int n_splits, uint64_t* cand, int32_t* cand_cnt, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(xh && cand && cand_cnt, "reid_knn_candidates_tc: NULL pointer");
+  REID_CHECK_ARG(N > 0 && N < (1ll << 31) && D > 0 && D % tc::BK == 0, "reid_knn_candidates_tc: need D %% 64 == 0 (D=%lld)",
+                 (long long)D);
+  REID_CHECK_ARG(((uintptr_t)xh & 15) == 0, "reid_knn_candidates_tc: xh must be 16-byte aligned");
+  REID_CHECK_ARG(0 <= row_begin && row_begin < row_end && row_end <= N, "reid_knn_candidates_tc: bad row range");
+  REID_CHECK_ARG(keep >= 1 && keep <= tc::kCap - 32, "reid_knn_candidates_tc: keep=%d not in 1..%d", keep, tc::kCap - 32);
+  const int64_t n_tiles = (N + tc::BN - 1) / tc::BN;
+  REID_CHECK_ARG(n_splits >= 1 && n_splits <= REID_TC_MAX_SPLITS && n_splits <= n_tiles,
+                 "reid_knn_candidates_tc: n_splits=%d", n_splits);
+  tc::EncodeTiledFn encode = tc::get_encode_fn();
+  if (!encode) {
+    set_error("reid_knn_candidates_tc: cuTensorMapEncodeTiled is not available from the driver");
+    return REID_ERR_CUDA;
+  }
+  CUtensorMap tmap;
+  const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)N};
+  const cuuint64_t gstride[1] = {(cuuint64_t)D * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)tc::BK, 128u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(xh), gdim, gstride, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("reid_knn_candidates_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    return REID_ERR_CUDA;
+  }
+  tc::Params p;
+  p.N = N;
+  p.row_begin = row_begin;
+  p.row_end = row_end;
+  p.num_k_blocks = (int)(D / tc::BK);
+  p.n_mblk = (int)((row_end - row_begin + tc::BM - 1) / tc::BM);
+  p.n_splits = n_splits;
+  p.n_tiles = (int)n_tiles;
+  p.keep = keep;
+  p.descale = ldexpf(1.0f, -2 * scale_log2);
+  p.cand = (unsigned long long*)cand;
+  p.cand_cnt = cand_cnt;
+  REID_CUDA(cudaFuncSetAttribute(tc::simtopk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+  const int units = p.n_mblk * n_splits;
+  const int grid = units < num_sms() ? units : num_sms();
+  tc::simtopk_kernel<<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>(tmap, p);
+  REID_LAUNCH_CHECK();
+  return REID_OK;
 }
 }

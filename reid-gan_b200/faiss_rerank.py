@@ -22,6 +22,9 @@ from . import _lib
 from ._lib import check, ptr, stream_ptr
 
 
+TC_AVAILABLE = True      # the tcgen05 candidate kernel (csrc/simgemm_tc.cu) is part of the library
+
+
 def half_k(k1):
     """faiss_rerank.py:69 -- int(np.around(k1/2)): round-half-to-even."""
     return int(np.around(k1 / 2))
@@ -76,7 +79,7 @@ def knn_search(x, k, mode="auto", rows=None):
     key = torch.empty((n, k), dtype=torch.float32, device=dev)
     info = {"mode": mode, "uncertified_rows": 0}
     if mode == "auto":
-        mode = "tc" if (D % 64 == 0 and N >= 256 and k <= 64) else "exact"
+        mode = "tc" if (TC_AVAILABLE and D % 64 == 0 and N >= 256 and k <= 64) else "exact"
         info["mode"] = mode
     if mode == "tc":
         from .knn_tc import knn_search_tc
@@ -225,8 +228,16 @@ def jaccard_neighbors(st, eps, with_values=False):
         if over.numel() == 0:
             break
         if slots >= 4096:
-            raise RuntimeError("jaccard_neighbors: %d rows exceed the largest shared-memory table "
-                               "(more than 3072 distinct partners)" % over.numel())
+            # hub rows: dense accumulator rows in global scratch, in batches of <= 256 MiB
+            per = max(1, (256 << 20) // (4 * st.N))
+            for a in range(0, over.numel(), per):
+                part = over[a:a + per].contiguous()
+                scratch = torch.empty(part.numel() * st.N, dtype=torch.float32, device=dev)
+                check(L.reid_jaccard_neighbors_heavy(ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr),
+                                                     ptr(st.C_idx), ptr(st.C_val), st.N, r0, ptr(part), part.numel(),
+                                                     eps32, ptr(slot_ptr), ptr(nbr_idx), ptr(nbr_val), ptr(nbr_cnt),
+                                                     ptr(scratch), sp), "reid_jaccard_neighbors_heavy")
+            break
         rows_list, n_list, slots = over.contiguous(), over.numel(), slots * 2
     return slot_ptr, nbr_idx, nbr_cnt, nbr_val
 
