@@ -40,6 +40,8 @@ extern "C" {
 
 int reid_abi_version(void);
 const char* reid_last_error(void);
+/* kernels launched by the library in this process (bench.py's gpu_launches) */
+uint64_t reid_launch_count(void);
 
 /* ---- utilities ---------------------------------------------------------- */
 

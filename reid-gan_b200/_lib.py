@@ -28,6 +28,7 @@ _Z = ctypes.c_size_t
 SIGNATURES = {
     "reid_abi_version": (_I, []),
     "reid_last_error": (ctypes.c_char_p, []),
+    "reid_launch_count": (ctypes.c_uint64, []),
     "reid_scan_counts": (_I, [_P, _L, _P, _P, _P]),
     "reid_knn_exact_scratch_bytes": (_Z, [_L, _L]),
     "reid_knn_exact": (_I, [_P, _L, _L, _P, _L, _L, _I, _P, _P, _P, _Z, _P]),
@@ -91,6 +92,54 @@ def check(rc, what=""):
     if rc == REID_ERR_INVALID_ARG:
         raise ValueError(msg)
     raise RuntimeError(msg)
+
+
+class Profiler:
+    """Optional per-entry-point device timing (CUDA events on the launching stream) and launch
+    counting, used by bench.py for the roofline / gpu_launches fields.  Off by default."""
+
+    def __init__(self):
+        self.enabled = False
+        self.records = []          # (name, start_event, end_event)
+
+    def start(self):
+        self.records = []
+        self.enabled = True
+
+    def stop(self):
+        self.enabled = False
+
+    def summary(self):
+        """{name: (calls, total_ms)} -- call after a device synchronize."""
+        out = {}
+        for name, e0, e1 in self.records:
+            c, t = out.get(name, (0, 0.0))
+            out[name] = (c + 1, t + e0.elapsed_time(e1))
+        return out
+
+
+profiler = Profiler()
+
+
+def call(name, *args):
+    """Invoke one C-ABI entry point and raise on a non-zero return code."""
+    fn = getattr(lib(), name)
+    if profiler.enabled:
+        import torch
+        e0 = torch.cuda.Event(enable_timing=True)
+        e1 = torch.cuda.Event(enable_timing=True)
+        e0.record()
+        rc = fn(*args)
+        e1.record()
+        profiler.records.append((name, e0, e1))
+    else:
+        rc = fn(*args)
+    check(rc, name)
+
+
+def launch_count():
+    """Number of kernels libreid_b200.so has launched in this process."""
+    return int(lib().reid_launch_count())
 
 
 def ptr(t):

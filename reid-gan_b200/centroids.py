@@ -11,7 +11,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import check, ptr, stream_ptr
+from ._lib import call, check, ptr, stream_ptr
 from .faiss_rerank import _device_of
 
 
@@ -36,6 +36,5 @@ def generate_cluster_features(labels, features, normalize=False, num_clusters=No
             raise RuntimeError("generate_cluster_features: no clusters (all labels are -1); "
                                "the reference fails at torch.stack of an empty list here too")
         out = torch.empty((C, D), dtype=torch.float32, device=dev)
-        check(L.reid_centroids(ptr(x), N, D, ptr(lab), C, 1 if normalize else 0, ptr(out), None, stream_ptr()),
-              "reid_centroids")
+        call("reid_centroids", ptr(x), N, D, ptr(lab), C, 1 if normalize else 0, ptr(out), None, stream_ptr())
         return out

@@ -19,7 +19,7 @@ import torch
 from torch import nn, autograd
 
 from . import _lib
-from ._lib import check, ptr, stream_ptr
+from ._lib import call, check, ptr, stream_ptr
 
 
 def _need_cuda(*ts):
@@ -37,8 +37,8 @@ def _update(xhat, targets, features, momentum, hard):
     B, D = xhat.shape
     if not features.is_contiguous():
         raise ValueError("the centroid buffer must be contiguous (it is updated in place)")
-    check(L.reid_cm_update(ptr(xhat), ptr(targets), ptr(features), B, features.shape[0], D, momentum, int(hard), None,
-                           stream_ptr()), "reid_cm_update")
+    call("reid_cm_update", ptr(xhat), ptr(targets), ptr(features), B, features.shape[0], D, momentum, int(hard), None,
+                           stream_ptr())
 
 
 class _CMBase(autograd.Function):
@@ -57,7 +57,7 @@ class _CMBase(autograd.Function):
         C = features.shape[0]
         out = torch.empty((B, C), dtype=torch.float32, device=x.device)
         with torch.cuda.device(x.device):
-            check(L.reid_cm_logits(ptr(x), ptr(features), B, C, D, ptr(out), stream_ptr()), "reid_cm_logits")
+            call("reid_cm_logits", ptr(x), ptr(features), B, C, D, ptr(out), stream_ptr())
         return out                                   # inputs.mm(features.t())  (cm.py:16,47)
 
     @staticmethod
@@ -73,8 +73,7 @@ class _CMBase(autograd.Function):
                 g = grad_outputs.to(torch.float32).contiguous()
                 grad_inputs = torch.empty((B, D), dtype=torch.float32, device=x.device)
                 # grad_outputs.mm(features) with the PRE-update centroids (cm.py:26,56)
-                check(L.reid_cm_grad_inputs(ptr(g), ptr(f), B, C, D, ptr(grad_inputs), stream_ptr()),
-                      "reid_cm_grad_inputs")
+                call("reid_cm_grad_inputs", ptr(g), ptr(f), B, C, D, ptr(grad_inputs), stream_ptr())
             _update(x, t, f, ctx.momentum, hard)     # cm.py:29-31 / 58-70
         return grad_inputs, None, None, None
 
@@ -126,8 +125,8 @@ class _FusedClusterLoss(autograd.Function):
         z = torch.empty((B, C), dtype=torch.float32, device=dev)
         scratch = torch.empty(max(1, L.reid_cm_forward_scratch_bytes(B, C, D)), dtype=torch.uint8, device=dev)
         with torch.cuda.device(dev):
-            check(L.reid_cm_forward(ptr(x), ptr(t), ptr(features), B, C, D, float(temp), ptr(loss), ptr(xhat),
-                                    ptr(inv_norm), ptr(z), ptr(scratch), stream_ptr()), "reid_cm_forward")
+            call("reid_cm_forward", ptr(x), ptr(t), ptr(features), B, C, D, float(temp), ptr(loss), ptr(xhat),
+                                    ptr(inv_norm), ptr(z), ptr(scratch), stream_ptr())
         ctx.features = features
         ctx.momentum = float(momentum)
         ctx.temp = float(temp)
@@ -149,8 +148,8 @@ class _FusedClusterLoss(autograd.Function):
                 g = grad_loss.to(torch.float32).contiguous()
                 gz = torch.empty((B, C), dtype=torch.float32, device=dev)
                 grad_inputs = torch.empty((B, D), dtype=torch.float32, device=dev)
-                check(L.reid_cm_backward(ptr(g), ptr(z), ptr(t), ptr(f), ptr(xhat), ptr(inv_norm), B, C, D, ctx.temp,
-                                         ptr(gz), ptr(grad_inputs), stream_ptr()), "reid_cm_backward")
+                call("reid_cm_backward", ptr(g), ptr(z), ptr(t), ptr(f), ptr(xhat), ptr(inv_norm), B, C, D, ctx.temp,
+                                         ptr(gz), ptr(grad_inputs), stream_ptr())
             _update(xhat, t, f, ctx.momentum, ctx.hard)
         return grad_inputs, None, None, None, None, None
 

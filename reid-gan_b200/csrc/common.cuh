@@ -28,7 +28,13 @@ void set_error(const char* fmt, ...);
     }                                                                                \
   } while (0)
 
-#define REID_LAUNCH_CHECK() REID_CUDA(cudaGetLastError())
+extern unsigned long long g_launches;  // kernels launched by this library in this process
+
+#define REID_LAUNCH_CHECK()        \
+  do {                             \
+    ++::reid::g_launches;          \
+    REID_CUDA(cudaGetLastError()); \
+  } while (0)
 
 constexpr int kWarp = 32;
 constexpr unsigned kFull = 0xffffffffu;

@@ -6,6 +6,7 @@
 namespace reid {
 
 static thread_local char g_err[512] = "";
+unsigned long long g_launches = 0;
 
 void set_error(const char* fmt, ...) {
   va_list ap;
@@ -61,6 +62,7 @@ extern "C" {
 
 int reid_abi_version(void) { return 1; }
 const char* reid_last_error(void) { return reid::g_err; }
+uint64_t reid_launch_count(void) { return reid::g_launches; }
 
 int reid_scan_counts(const int32_t* cnt, int64_t n, int64_t* ptr_out, int64_t* stats_out, void* stream) {
   REID_CHECK_ARG(n >= 0 && ptr_out, "reid_scan_counts: bad arguments");

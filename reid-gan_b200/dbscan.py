@@ -15,7 +15,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import check, ptr, stream_ptr
+from ._lib import call, check, ptr, stream_ptr
 from .faiss_rerank import JaccardDistance, _device_of, _scan, jaccard_neighbors
 
 
@@ -27,8 +27,8 @@ def dbscan_from_neighbors(N, nbr_ptr, nbr_idx, nbr_cnt, min_samples):
     core = torch.empty(N, dtype=torch.uint8, device=dev)
     ncl = torch.zeros(1, dtype=torch.int64, device=dev)
     ws = torch.empty(max(1, L.reid_dbscan_workspace_bytes(N)), dtype=torch.uint8, device=dev)
-    check(L.reid_dbscan_labels(N, ptr(nbr_ptr), ptr(nbr_idx), ptr(nbr_cnt), int(min_samples), ptr(labels), ptr(core),
-                               ptr(ncl), ptr(ws), stream_ptr()), "reid_dbscan_labels")
+    call("reid_dbscan_labels", N, ptr(nbr_ptr), ptr(nbr_idx), ptr(nbr_cnt), int(min_samples), ptr(labels), ptr(core),
+                               ptr(ncl), ptr(ws), stream_ptr())
     return labels, core, ncl
 
 
@@ -101,12 +101,10 @@ class DBSCAN:
                 b = min(N, a + block)
                 blk = X[a:b].to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
                 cnt = torch.empty(b - a, dtype=torch.int32, device=dev)
-                check(L.reid_dbscan_dense_count(ptr(blk), N, blk.stride(0), eps32, 0, b - a, ptr(cnt), sp),
-                      "reid_dbscan_dense_count")
+                call("reid_dbscan_dense_count", ptr(blk), N, blk.stride(0), eps32, 0, b - a, ptr(cnt), sp)
                 p_loc, total, _ = _scan(cnt, b - a, dev)
                 idx = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
-                check(L.reid_dbscan_dense_fill(ptr(blk), N, blk.stride(0), eps32, 0, b - a, ptr(p_loc), ptr(idx), sp),
-                      "reid_dbscan_dense_fill")
+                call("reid_dbscan_dense_fill", ptr(blk), N, blk.stride(0), eps32, 0, b - a, ptr(p_loc), ptr(idx), sp)
                 cnts.append(cnt)
                 idxs.append(idx[:total])
             cnt = torch.cat(cnts) if len(cnts) > 1 else cnts[0]

@@ -19,7 +19,7 @@ import numpy as np
 import torch
 
 from . import _lib
-from ._lib import check, ptr, stream_ptr
+from ._lib import call, check, ptr, stream_ptr
 
 
 TC_AVAILABLE = True      # the tcgen05 candidate kernel (csrc/simgemm_tc.cu) is part of the library
@@ -43,7 +43,7 @@ def _scan(cnt, n, dev):
     L = _lib.lib()
     out = torch.empty(n + 1, dtype=torch.int64, device=dev)
     stats = torch.empty(2, dtype=torch.int64, device=dev)
-    check(L.reid_scan_counts(ptr(cnt), n, ptr(out), ptr(stats), stream_ptr()), "reid_scan_counts")
+    call("reid_scan_counts", ptr(cnt), n, ptr(out), ptr(stats), stream_ptr())
     total, mx = stats.tolist()
     return out, int(total), int(mx)
 
@@ -98,13 +98,15 @@ def _knn_exact_rows(x, k, rows_list, row_begin, n_rows, idx_out, key_out):
     budget = 1 << 30                                        # ~1 GiB of key rows per pass
     chunk = max(1, min(n_rows, budget // (4 * N)))
     scratch = torch.empty(chunk * N, dtype=torch.float32, device=x.device)
-    check(L.reid_knn_exact(ptr(x), N, D, ptr(rows_list), row_begin, n_rows, k, ptr(idx_out), ptr(key_out),
-                           ptr(scratch), scratch.numel() * 4, stream_ptr()), "reid_knn_exact")
+    call("reid_knn_exact", ptr(x), N, D, ptr(rows_list), row_begin, n_rows, k, ptr(idx_out), ptr(key_out),
+                           ptr(scratch), scratch.numel() * 4, stream_ptr())
 
 
-def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, gather=None):
-    """Run a1-a6 on device for rows `rows` (default all).  `gather` (optional) is a callable
-    all-gathering a per-shard tensor along dim 0 (multi-GPU row sharding, see sharded.py)."""
+def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None):
+    """Run a1-a6 on device.  Single GPU: all rows.  Row-sharded (comm = sharded.RowComm): this rank
+    computes rows [comm.r0, comm.r1) of every per-row stage and the stages' outputs are all-gathered
+    (neighbour lists, V rows, V_qe rows), so the returned state always holds GLOBAL rank / V / V_qe /
+    inverted index while `row_begin:row_end` remembers the rank's own rows."""
     L = _lib.lib()
     assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
     N, D = x.shape
@@ -115,7 +117,10 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, gather=None):
     if not (1 <= k2 <= k1):
         raise ValueError("k2=%d must be in 1..k1" % k2)
     dev = x.device
-    r0, r1 = (0, N) if rows is None else rows
+    if comm is not None:
+        r0, r1 = comm.r0, comm.r1
+    else:
+        r0, r1 = (0, N) if rows is None else rows
     n = r1 - r0
     st = RerankState()
     st.N, st.D, st.k1, st.k2, st.row_begin, st.row_end = N, D, k1, k2, r0, r1
@@ -130,68 +135,59 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, gather=None):
 
     mark("start")
     # a1 ------------------------------------------------------------------
-    idx, key, info = knn_search(x, k1, knn, rows=(r0, r1))
+    rank_local, key_local, info = knn_search(x, k1, knn, rows=(r0, r1))
     st.knn_info = info
-    rank_local, key_local = idx, key
-    rank = gather(idx) if gather else idx                     # global (N, k1)
+    rank = comm.gather_rows(rank_local) if comm is not None else rank_local      # global (N, k1)
     st.rank, st.rank_key = rank, key_local
     mark("knn")
     # a2 ------------------------------------------------------------------
     h = half_k(k1)
-    R = torch.empty(n, dtype=torch.int64, device=dev)
+    R = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
     Rh = torch.empty(N, dtype=torch.int64, device=dev)        # every rank needs R_half of all rows
-    check(L.reid_reciprocal_masks(ptr(rank), N, k1, k1, r0, r1, ptr(R), sp), "reid_reciprocal_masks")
-    check(L.reid_reciprocal_masks(ptr(rank), N, k1, h, 0, N, ptr(Rh), sp), "reid_reciprocal_masks")
+    call("reid_reciprocal_masks", ptr(rank), N, k1, k1, r0, r1, ptr(R), sp)
+    call("reid_reciprocal_masks", ptr(rank), N, k1, h, 0, N, ptr(Rh), sp)
     st.R_mask, st.Rh_mask = R, Rh
     mark("reciprocal")
     # a3 ------------------------------------------------------------------
-    e_cnt = torch.empty(n, dtype=torch.int32, device=dev)
-    check(L.reid_expand(ptr(rank), N, k1, ptr(R), ptr(Rh), r0, r1, None, ptr(e_cnt), None, sp), "reid_expand")
+    e_cnt = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    call("reid_expand", ptr(rank), N, k1, ptr(R), ptr(Rh), r0, r1, None, ptr(e_cnt), None, sp)
     e_ptr, e_total, e_max = _scan(e_cnt, n, dev)
     e_idx = torch.empty(max(e_total, 1), dtype=torch.int32, device=dev)
-    check(L.reid_expand(ptr(rank), N, k1, ptr(R), ptr(Rh), r0, r1, ptr(e_ptr), None, ptr(e_idx), sp), "reid_expand")
+    call("reid_expand", ptr(rank), N, k1, ptr(R), ptr(Rh), r0, r1, ptr(e_ptr), None, ptr(e_idx), sp)
     mark("expand")
     # a4 ------------------------------------------------------------------
     v_val = torch.empty(max(e_total, 1), dtype=torch.float32, device=dev)
-    check(L.reid_v_weights(ptr(x), N, D, ptr(e_ptr), ptr(e_idx), r0, r1, ptr(rank_local), ptr(key_local), k1,
-                           ptr(v_val), sp), "reid_v_weights")
+    call("reid_v_weights", ptr(x), N, D, ptr(e_ptr), ptr(e_idx), r0, r1, ptr(rank_local), ptr(key_local), k1,
+         ptr(v_val), sp)
     mark("v_weights")
-    if gather:                                               # V rows of other shards are read by a5
-        g_cnt = gather(e_cnt)
-        g_ptr, g_total, e_max = _scan(g_cnt, N, dev)
-        g_idx = gather(e_idx[:e_total])
-        g_val = gather(v_val[:e_total])
-    else:
-        g_ptr, g_idx, g_val = e_ptr, e_idx, v_val
-    st.E_ptr, st.E_idx, st.V_val = g_ptr, g_idx, g_val
+    if comm is not None:                                     # V rows of other shards are read by a5
+        e_ptr, e_idx, v_val, e_total, e_max = comm.gather_csr(e_cnt[:n], e_idx[:e_total], v_val[:e_total])
+    st.E_ptr, st.E_idx, st.V_val = e_ptr, e_idx, v_val       # global CSR when sharded
     # a5 ------------------------------------------------------------------
     if k2 != 1:
-        q_cnt = torch.empty(n, dtype=torch.int32, device=dev)
-        check(L.reid_query_expand(ptr(rank), N, k1, k2, ptr(g_ptr), ptr(g_idx), ptr(g_val), max(e_max, 1), r0, r1,
-                                  None, ptr(q_cnt), None, None, sp), "reid_query_expand")
+        q_cnt = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        call("reid_query_expand", ptr(rank), N, k1, k2, ptr(e_ptr), ptr(e_idx), ptr(v_val), max(e_max, 1), r0, r1,
+             None, ptr(q_cnt), None, None, sp)
         q_ptr, q_total, _ = _scan(q_cnt, n, dev)
         q_idx = torch.empty(max(q_total, 1), dtype=torch.int32, device=dev)
         q_val = torch.empty(max(q_total, 1), dtype=torch.float32, device=dev)
-        check(L.reid_query_expand(ptr(rank), N, k1, k2, ptr(g_ptr), ptr(g_idx), ptr(g_val), max(e_max, 1), r0, r1,
-                                  ptr(q_ptr), None, ptr(q_idx), ptr(q_val), sp), "reid_query_expand")
-        if gather:
-            gq_cnt = gather(q_cnt)
-            q_ptr, q_total, _ = _scan(gq_cnt, N, dev)
-            q_idx = gather(q_idx[:int(q_cnt.sum())])
-            q_val = gather(q_val[:q_idx.numel()])
+        call("reid_query_expand", ptr(rank), N, k1, k2, ptr(e_ptr), ptr(e_idx), ptr(v_val), max(e_max, 1), r0, r1,
+             ptr(q_ptr), None, ptr(q_idx), ptr(q_val), sp)
+        if comm is not None:
+            q_ptr, q_idx, q_val, q_total, _ = comm.gather_csr(q_cnt[:n], q_idx[:q_total], q_val[:q_total])
     else:                                                    # faiss_rerank.py:89: skipped when k2 == 1
-        q_ptr, q_idx, q_val, q_total = g_ptr, g_idx, g_val, (e_total if not gather else int(g_ptr[-1]))
+        q_ptr, q_idx, q_val, q_total = e_ptr, e_idx, v_val, e_total
     st.Q_ptr, st.Q_idx, st.Q_val = q_ptr, q_idx, q_val        # global CSR (N + 1)
     st.q_total = q_total
     mark("query_expand")
-    # a6 ------------------------------------------------------------------
+    # a6 (replicated on every rank: it needs every row of V_qe and is tiny) ---------------------
     c_cnt = torch.empty(N, dtype=torch.int32, device=dev)
-    check(L.reid_transpose_count(ptr(q_idx), q_total, N, ptr(c_cnt), sp), "reid_transpose_count")
+    call("reid_transpose_count", ptr(q_idx), q_total, N, ptr(c_cnt), sp)
     c_ptr, _, c_max = _scan(c_cnt, N, dev)
     c_idx = torch.empty(max(q_total, 1), dtype=torch.int32, device=dev)
     c_val = torch.empty(max(q_total, 1), dtype=torch.float32, device=dev)
-    check(L.reid_transpose_fill(ptr(q_ptr), ptr(q_idx), ptr(q_val), N, N, ptr(c_ptr), ptr(c_cnt), ptr(c_idx),
-                                ptr(c_val), sp), "reid_transpose_fill")
+    call("reid_transpose_fill", ptr(q_ptr), ptr(q_idx), ptr(q_val), N, N, ptr(c_ptr), ptr(c_cnt), ptr(c_idx),
+         ptr(c_val), sp)
     st.C_ptr, st.C_idx, st.C_val = c_ptr, c_idx, c_val
     st.c_max = c_max
     mark("transpose")
@@ -211,8 +207,7 @@ def jaccard_neighbors(st, eps, with_values=False):
     n = r1 - r0
     sp = stream_ptr()
     t_cnt = torch.empty(n, dtype=torch.int32, device=dev)
-    check(L.reid_jaccard_bounds(ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.C_ptr), r0, r1, ptr(t_cnt), sp),
-          "reid_jaccard_bounds")
+    call("reid_jaccard_bounds", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.C_ptr), r0, r1, ptr(t_cnt), sp)
     slot_ptr, t_total, t_max = _scan(t_cnt, n, dev)
     nbr_idx = torch.empty(max(t_total, 1), dtype=torch.int32, device=dev)
     nbr_val = torch.empty(max(t_total, 1), dtype=torch.float32, device=dev) if with_values else None
@@ -221,9 +216,9 @@ def jaccard_neighbors(st, eps, with_values=False):
     slots = 1024
     rows_list, n_list = None, 0
     while True:
-        check(L.reid_jaccard_neighbors(ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
+        call("reid_jaccard_neighbors", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
                                        ptr(st.C_val), st.N, r0, r1, ptr(rows_list), n_list, eps32, ptr(slot_ptr),
-                                       ptr(nbr_idx), ptr(nbr_val), ptr(nbr_cnt), slots, sp), "reid_jaccard_neighbors")
+                                       ptr(nbr_idx), ptr(nbr_val), ptr(nbr_cnt), slots, sp)
         over = torch.nonzero(nbr_cnt < 0).flatten().to(torch.int32)
         if over.numel() == 0:
             break
@@ -233,10 +228,10 @@ def jaccard_neighbors(st, eps, with_values=False):
             for a in range(0, over.numel(), per):
                 part = over[a:a + per].contiguous()
                 scratch = torch.empty(part.numel() * st.N, dtype=torch.float32, device=dev)
-                check(L.reid_jaccard_neighbors_heavy(ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr),
+                call("reid_jaccard_neighbors_heavy", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr),
                                                      ptr(st.C_idx), ptr(st.C_val), st.N, r0, ptr(part), part.numel(),
                                                      eps32, ptr(slot_ptr), ptr(nbr_idx), ptr(nbr_val), ptr(nbr_cnt),
-                                                     ptr(scratch), sp), "reid_jaccard_neighbors_heavy")
+                                                     ptr(scratch), sp)
             break
         rows_list, n_list, slots = over.contiguous(), over.numel(), slots * 2
     return slot_ptr, nbr_idx, nbr_cnt, nbr_val
@@ -245,9 +240,8 @@ def jaccard_neighbors(st, eps, with_values=False):
 def jaccard_dense_rows(st, out, row_begin, row_end):
     """a7 (dense form): rows [row_begin,row_end) of the reference's return value into `out` (device, (rows, N))."""
     L = _lib.lib()
-    check(L.reid_jaccard_dense(ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
-                               ptr(st.C_val), st.N, row_begin, row_end, ptr(out), out.stride(0), stream_ptr()),
-          "reid_jaccard_dense")
+    call("reid_jaccard_dense", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
+                               ptr(st.C_val), st.N, row_begin, row_end, ptr(out), out.stride(0), stream_ptr())
 
 
 class JaccardDistance:

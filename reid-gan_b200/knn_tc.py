@@ -10,7 +10,7 @@ import ctypes
 import torch
 
 from . import _lib
-from ._lib import check, ptr, stream_ptr
+from ._lib import call, check, ptr, stream_ptr
 
 TC_CAP = 128
 SCALE_LOG2 = 4          # features are scaled by 2^4 before rounding to fp16 (keeps them out of the subnormals)
@@ -33,25 +33,24 @@ def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None):
     if xh is None:
         xh = torch.empty((N, D), dtype=torch.float16, device=dev)
         msq = torch.zeros(1, dtype=torch.float32, device=dev)
-        check(L.reid_features_to_half(ptr(x), N, D, SCALE_LOG2, ptr(xh), ptr(msq), sp), "reid_features_to_half")
+        call("reid_features_to_half", ptr(x), N, D, SCALE_LOG2, ptr(xh), ptr(msq), sp)
         max_sqnorm = None
     else:
         msq = None
     n_splits = ctypes.c_int(1)
-    check(L.reid_knn_tc_plan(N, n, ctypes.byref(n_splits)), "reid_knn_tc_plan")
+    call("reid_knn_tc_plan", N, n, ctypes.byref(n_splits))
     s = n_splits.value
     keep = max(k, min(k + SLACK, 256 // s, TC_CAP - 32))
     cand = torch.empty(n * s * TC_CAP, dtype=torch.int64, device=dev)
     cand_cnt = torch.zeros(n * s, dtype=torch.int32, device=dev)
-    check(L.reid_knn_candidates_tc(ptr(xh), N, D, SCALE_LOG2, r0, r1, keep, s, ptr(cand), ptr(cand_cnt), sp),
-          "reid_knn_candidates_tc")
+    call("reid_knn_candidates_tc", ptr(xh), N, D, SCALE_LOG2, r0, r1, keep, s, ptr(cand), ptr(cand_cnt), sp)
     if max_sqnorm is None:
         max_sqnorm = float(msq.item())                     # one scalar read-back, after the GEMM is queued
     eps = err_bound(max_sqnorm)
     flag = torch.empty(n, dtype=torch.int32, device=dev)
     max_err = torch.zeros(1, dtype=torch.float32, device=dev)
-    check(L.reid_knn_rescore(ptr(x), N, D, r0, r1, ptr(cand), ptr(cand_cnt), s, keep, k, eps, ptr(idx), ptr(key),
-                             ptr(flag), ptr(max_err), sp), "reid_knn_rescore")
+    call("reid_knn_rescore", ptr(x), N, D, r0, r1, ptr(cand), ptr(cand_cnt), s, keep, k, eps, ptr(idx), ptr(key),
+                             ptr(flag), ptr(max_err), sp)
     bad = torch.nonzero(flag).flatten().to(torch.int32)
     n_bad = bad.numel()
     if n_bad:

@@ -107,7 +107,7 @@ def test_stage_inputs_from_oracle_are_bit_exact():
     """Integer stages fed with the ORACLE's neighbour lists: outputs must be identical (no tolerance)."""
     import reid_gan_b200 as rg
     from reid_gan_b200 import _lib
-    from reid_gan_b200._lib import check, ptr, stream_ptr
+    from reid_gan_b200._lib import call, ptr, stream_ptr
     from oracle import rerank as orr
     L = _lib.lib()
     N, D, k1 = 900, 64, 25
@@ -116,7 +116,7 @@ def test_stage_inputs_from_oracle_are_bit_exact():
     d_rank = torch.from_numpy(rank.astype(np.int32)).cuda()
     for k in (k1, orr.half_k(k1)):
         m = torch.empty(N, dtype=torch.int64, device="cuda")
-        check(L.reid_reciprocal_masks(ptr(d_rank), N, k1, k, 0, N, ptr(m), stream_ptr()))
+        call("reid_reciprocal_masks", ptr(d_rank), N, k1, k, 0, N, ptr(m), stream_ptr())
         ref = orr.k_reciprocal_masks(rank, k)
         got = m.cpu().numpy()
         for i in range(N):
