@@ -214,9 +214,9 @@ def main():
     if rank == 0:                       # nvidia-smi needs a few hundred ms to start: begin before the warm-up and
         sampler.start()                 # keep the GPU busy until the first sample has arrived
         t_wait = time.time()
-        while not sampler.rows and time.time() - t_wait < 3.0:
+        while world == 1 and not sampler.rows and time.time() - t_wait < 3.0:
             one_pass()
-    for _ in range(max(args.warmup, 3)):
+    for _ in range(max(args.warmup, 3) + (10 if world > 1 else 0)):
         out = one_pass()
     barrier()
     l0 = _lib.launch_count()

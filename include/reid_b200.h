@@ -64,17 +64,23 @@ int reid_knn_exact(const float* x, int64_t N, int64_t D, const int32_t* rows_lis
 /* Tensor-core candidate search: fp16 tcgen05 GEMM (TMA-fed, TMEM accumulators) of query rows
  * [row_begin,row_end) against all N rows with a fused per-row running top-`keep` selection in the
  * epilogue.  xh = fp16(x * 2^scale_log2), row-major N x D, D % 64 == 0, 16-byte aligned.
- * The N columns are cut into n_splits ranges (reid_knn_tc_plan picks the count that fills the SMs);
- * every (row, range) keeps its own list:
- *   cand[((row-row_begin)*n_splits + q)*REID_TC_CAP + p] = (fp32 score bits << 32) | column,
- *   p < cand_cnt[(row-row_begin)*n_splits + q] <= keep.  A list with fewer than `keep` entries holds
- *   every column of its range.  Scores are approximate (fp16 inputs); see reid_knn_rescore. */
-#define REID_TC_CAP 128
+ * The N columns are cut into n_splits ranges (reid_knn_tc_plan picks the count that fills the SMs) and
+ * inside a range the 256-column tiles alternate between the two epilogue groups of the kernel, so every
+ * row owns n_lists = 2 * n_splits candidate lists:
+ *   cand[((row-row_begin)*n_lists + l)*REID_TC_CAP + p] = (fp32 score bits << 32) | column,
+ *   p < cand_cnt[(row-row_begin)*n_lists + l] <= REID_TC_CAP.
+ * row_tau[row-row_begin] (order-preserving integer image of a float, 0 = none) is the row's final
+ * rejection threshold: every column that is in none of the row's lists scored <= that value, and at
+ * least `keep` listed columns score >= it.  Scores are approximate (fp16 inputs); see reid_knn_rescore.
+ * cta_group = 1: one CTA per 128-row tile; 2: a CTA pair per 256-row tile (tcgen05 cta_group::2,
+ * the column tile is fetched once per pair). */
+#define REID_TC_CAP 512
+#define REID_TC_KEEP_MAX 64
 #define REID_TC_MAX_SPLITS 4
-int reid_knn_tc_plan(int64_t N, int64_t n_rows, int* n_splits_out);
+int reid_knn_tc_plan(int64_t N, int64_t n_rows, int cta_group, int* n_splits_out);
 int reid_knn_candidates_tc(const void* xh, int64_t N, int64_t D, int scale_log2, int64_t row_begin,
-                           int64_t row_end, int keep, int n_splits, uint64_t* cand, int32_t* cand_cnt,
-                           void* stream);
+                           int64_t row_end, int keep, int n_splits, int cta_group, uint64_t* cand,
+                           int32_t* cand_cnt, uint32_t* row_tau, void* stream);
 /* fp32 features -> scaled fp16 operand; max_sqnorm_out (optional, 1 float) = max_i ||x_i||^2, which
  * scales the fp16 rounding bound  |approx - exact| <= 2^-10 ||x_i|| ||x_j||. */
 int reid_features_to_half(const float* x, int64_t n_rows, int64_t D, int scale_log2, void* xh,
@@ -82,15 +88,15 @@ int reid_features_to_half(const float* x, int64_t n_rows, int64_t D, int scale_l
 
 /* Exact re-score of the candidates with the canonical key, certificate, final order.
  * Let a_(k) be the k-th best approximate score of a row.  Every member of the exact top-k has an
- * approximate score >= a_(k) - 2*err_bound (the "window").  The row is certified when, for every
- * column range whose list is full, the weakest retained score is below the window -- then the window,
- * hence the exact top-k, is entirely among the candidates.  Window members are re-scored with
+ * approximate score >= a_(k) - 2*err_bound (the "window").  The row is certified when its rejection
+ * threshold row_tau lies below the window -- then the window, hence the exact top-k, is entirely among
+ * the listed candidates.  Window members are re-scored with
  * fp32(fp64 dot) and ordered by (key desc, index asc): bit-identical to reid_knn_exact.
  * |approx - exact| is audited against err_bound; a violation un-certifies the row.
  * uncertified_flag[row-row_begin] = 1 marks rows the caller must redo with reid_knn_exact;
  * max_err_out (1 float) = largest |approx - exact| seen. */
 int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, int64_t row_end,
-                     const uint64_t* cand, const int32_t* cand_cnt, int n_splits, int keep, int k,
+                     const uint64_t* cand, const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists, int k,
                      float err_bound, int32_t* out_idx, float* out_key, int32_t* uncertified_flag,
                      float* max_err_out, void* stream);
 

@@ -21,6 +21,7 @@
 // The scores are only candidates: knn_rescore.cu re-scores them exactly and certifies the result.
 #include <cuda.h>
 #include <cuda_fp16.h>
+#include <stdlib.h>
 
 #include "common.cuh"
 
@@ -29,13 +30,10 @@ namespace tc {
 
 constexpr int BM = 128, BN = 256, BK = 64;   // tile; BK * 2 B = 128 B = one swizzle atom row
 constexpr int UMMA_K = 16;
-constexpr int kStages = 4;
 constexpr int kATileBytes = BM * BK * 2;     // 16 KB
 constexpr int kBTileBytes = BN * BK * 2;     // 32 KB
-constexpr int kStageBytes = kATileBytes + kBTileBytes;
-constexpr int kThreads = 192;
+constexpr int kThreads = 320;               // TMA warp, MMA warp, 2 x 4 epilogue warps
 constexpr int kCap = REID_TC_CAP;            // per (row, split) candidate list capacity
-constexpr int kSmemBytes = kStages * kStageBytes + 1024 /*align*/ + 256 /*barriers*/;
 
 __device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
 
@@ -121,10 +119,14 @@ __device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)
   asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
 }
 
-// Cooperative compaction of one row's candidate list (n entries at `list`, n <= kCap) to its best
-// `keep` entries (by score; ties by list position).  Returns the keep-th best score (the new tau).
-// Entry = (score bits << 32) | column.
-__device__ __forceinline__ float warp_compact(unsigned long long* list, int n, int keep) {
+// Cooperative compaction of one row's candidate list (n entries at `list`, n <= kCap) to (at least) its
+// best `keep` entries.  Entry = (score bits << 32) | column.  The threshold is found by a bitwise binary
+// search on the order-preserving integer image of the scores.  kBits = 32 resolves it exactly (exactly
+// `keep` survivors, ties by list position); kBits = 16 stops at the top 16 bits, which can only LOWER the
+// threshold: a few more than `keep` survive, never fewer -- half the dependent REDUX chain, used for the
+// in-flight compactions where only the trend of tau matters.  Returns the new tau and the survivor count.
+template <int kBits>
+__device__ __forceinline__ float warp_compact(unsigned long long* list, int n, int keep, int& n_out) {
   const int lane = lane_id();
   constexpr int kPer = kCap / 32;
   unsigned long long e[kPer];
@@ -137,10 +139,10 @@ __device__ __forceinline__ float warp_compact(unsigned long long* list, int n, i
     o[j] = i < n ? float_ord(__uint_as_float((uint32_t)(e[j] >> 32))) : 0u;  // 0 sorts below every real score
   }
   __syncwarp();
-  // largest T with #{o >= T} >= keep  == the keep-th largest ordered score
+  // largest T (on the searched bits) with #{o >= T} >= keep
   uint32_t T = 0;
 #pragma unroll 1
-  for (int bit = 31; bit >= 0; --bit) {
+  for (int bit = 31; bit >= 32 - kBits; --bit) {
     const uint32_t cand = T | (1u << bit);
     int c = 0;
 #pragma unroll
@@ -152,7 +154,8 @@ __device__ __forceinline__ float warp_compact(unsigned long long* list, int n, i
 #pragma unroll
   for (int j = 0; j < kPer; ++j) n_gt += o[j] > T;
   n_gt = __reduce_add_sync(kFull, n_gt);
-  const int quota = keep - n_gt;  // how many of the entries equal to T stay
+  // exact search: n_gt < keep and the ties at T fill the quota; coarse search: everything >= T stays
+  const int quota = kBits == 32 ? keep - n_gt : 0x7fffffff;
   int eq_seen = 0, kept_seen = 0;
   const unsigned lt = (1u << lane) - 1u;
 #pragma unroll
@@ -166,6 +169,7 @@ __device__ __forceinline__ float warp_compact(unsigned long long* list, int n, i
     kept_seen += __popc(bk);
   }
   __syncwarp();
+  n_out = kept_seen;
   return ord_float(T);
 }
 
@@ -180,61 +184,146 @@ struct Params {
   float descale;        // 2^(-2 s)
   unsigned long long* cand;   // [(rows) x n_splits x kCap]
   int32_t* cand_cnt;          // [(rows) x n_splits]
+  uint32_t* row_tau;          // [rows] shared rejection threshold per query row (order-preserving image), 0 = none
+  int dbg;                    // developer switch (REID_TC_DEBUG): 1 = epilogue skips TMEM reads, 2 = reads but no selection, 4 = no TMA
 };
 
+// ---- cta_group::2 flavours of the PTX wrappers (CTA pair = one 256-row MMA tile) ---------------------
+__device__ __forceinline__ uint32_t cluster_ctarank() {
+  uint32_t r;
+  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
+  return r;
+}
+__device__ __forceinline__ void cluster_sync_all() {
+  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
+  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
+}
+// address of this CTA's shared object inside CTA `rank` of the cluster (shared::cluster window)
+__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
+  uint32_t r;
+  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
+  return r;
+}
+__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
+  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
+}
+// TMA load whose completion is signalled on the LEADER CTA's barrier (cluster address)
+__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, uint32_t leader_bar, int c0,
+                                                 int c1) {
+  asm volatile(
+      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
+      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1)
+      : "memory");
+}
+__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
+                                              uint32_t accumulate) {
+  asm volatile(
+      "{\n"
+      ".reg .pred p;\n"
+      "setp.ne.b32 p, %4, 0;\n"
+      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
+      "}\n" ::"r"(tmem_c),
+      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
+      : "memory");
+}
+// commit arriving on the barrier at the same offset in BOTH CTAs of the pair
+__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
+  asm volatile(
+      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
+          smem_u32(bar)),
+      "h"((uint16_t)3)
+      : "memory");
+}
+
+template <int kCtas>
+struct Cfg {
+  // per-CTA bytes of one pipeline stage: its 128 query rows of A + its share of the 256-row B tile
+  static constexpr int kBRows = BN / kCtas;
+  static constexpr int kBBytes = kBRows * BK * 2;
+  static constexpr int kStage = kATileBytes + kBBytes;      // 48 KB (1 CTA) / 32 KB (pair)
+  static constexpr int kNumStages = kCtas == 1 ? 4 : 6;
+  static constexpr int kSmem = kNumStages * kStage + 1024 /*align*/ + 256 /*barriers*/;
+};
+
+// kCtas = 1: one CTA per 128-row tile (tcgen05.mma.cta_group::1, M = 128).
+// kCtas = 2: a CTA pair per 256-row tile (cta_group::2, M = 256): each CTA stages its own 128 query rows
+//            and HALF of the column tile, so the B operand is fetched from L2 once per pair; the leader
+//            CTA issues the MMAs, both CTAs run a TMA producer and the top-K epilogue on their own
+//            128 accumulator lanes.
+template <int kCtas>
 __global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+  using C = Cfg<kCtas>;
+  constexpr int kNumStages = C::kNumStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
-  uint64_t* full_bar = (uint64_t*)(smem + kStages * kStageBytes);
-  uint64_t* empty_bar = full_bar + kStages;
-  uint64_t* tfull_bar = empty_bar + kStages;   // [2] accumulator ready
-  uint64_t* tempty_bar = tfull_bar + 2;        // [2] accumulator drained
+  uint64_t* full_bar = (uint64_t*)(smem + kNumStages * C::kStage);
+  uint64_t* empty_bar = full_bar + kNumStages;
+  uint64_t* tfull_bar = empty_bar + kNumStages;   // [2] accumulator ready
+  uint64_t* tempty_bar = tfull_bar + 2;           // [2] accumulator drained (lives in the leader CTA)
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
 
   const int warp = threadIdx.x >> 5, lane = lane_id();
+  const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;
+  const bool leader = cta_rank == 0;
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
-    for (int s = 0; s < kStages; ++s) {
+    for (int s = 0; s < kNumStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
     }
     for (int a = 0; a < 2; ++a) {
       mbar_init(&tfull_bar[a], 1);
-      mbar_init(&tempty_bar[a], 4);
+      mbar_init(&tempty_bar[a], 4 * kCtas);   // the 4 warps of the owning epilogue group, in every CTA of the pair
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: all 512 columns = two 128 x 256 fp32 accumulators
-    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
-    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+  if (warp == 1) {  // TMEM: all 512 columns = two 128 x 256 fp32 accumulators (per CTA)
+    if (kCtas == 1) {
+      asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;");
+    } else {
+      asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
+      asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
+    }
   }
   tcgen05_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   tcgen05_fence_after();
   const uint32_t tmem_base = *tmem_slot;
 
-  const int n_units = p.n_mblk * p.n_splits;
+  const int n_units = p.n_mblk * p.n_splits;         // n_mblk counts (128 * kCtas)-row tiles
+  const int unit0 = blockIdx.x / kCtas, unit_step = gridDim.x / kCtas;
 
   if (warp == 0) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int stage = 0;
       uint32_t phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      for (int u = unit0; u < n_units; u += unit_step) {
         const int split = u / p.n_mblk, mblk = u % p.n_mblk;
         const int t0 = (int)((int64_t)p.n_tiles * split / p.n_splits), t1 = (int)((int64_t)p.n_tiles * (split + 1) / p.n_splits);
-        const int m_row = (int)p.row_begin + mblk * BM;
+        const int m_row = (int)p.row_begin + mblk * (BM * kCtas) + (int)cta_rank * BM;
         for (int t = t0; t < t1; ++t) {
           for (int kb = 0; kb < p.num_k_blocks; ++kb) {
             mbar_wait(&empty_bar[stage], phase ^ 1);
-            uint8_t* a_dst = smem + stage * kStageBytes;
+            uint8_t* a_dst = smem + stage * C::kStage;
             uint8_t* b_dst = a_dst + kATileBytes;
-            mbar_expect_tx(&full_bar[stage], kStageBytes);
-            tma_load_2d(a_dst, &tmap, &full_bar[stage], kb * BK, m_row);
-            tma_load_2d(b_dst, &tmap, &full_bar[stage], kb * BK, t * BN);
-            tma_load_2d(b_dst + kATileBytes, &tmap, &full_bar[stage], kb * BK, t * BN + 128);
-            if (++stage == kStages) {
+            if (p.dbg & 4) {
+              if (kCtas == 1 || leader) mbar_arrive(&full_bar[stage]);
+            } else if (kCtas == 1) {
+              mbar_expect_tx(&full_bar[stage], C::kStage);
+              tma_load_2d(a_dst, &tmap, &full_bar[stage], kb * BK, m_row);
+              tma_load_2d(b_dst, &tmap, &full_bar[stage], kb * BK, t * BN);
+              tma_load_2d(b_dst + kATileBytes, &tmap, &full_bar[stage], kb * BK, t * BN + 128);
+            } else {
+              // all bytes of the pair are accounted on the leader's barrier
+              if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::kStage);
+              const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+              tma_load_2d_pair(a_dst, &tmap, lbar, kb * BK, m_row);
+              tma_load_2d_pair(b_dst, &tmap, lbar, kb * BK, t * BN + (int)cta_rank * 128);
+            }
+            if (++stage == kNumStages) {
               stage = 0;
               phase ^= 1;
             }
@@ -243,38 +332,39 @@ __global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_const
       }
     }
   } else if (warp == 1) {
-    // ------------------------------ MMA issuer --------------------------------
-    if (lane == 0) {
-      constexpr uint32_t idesc = make_idesc(BM, BN);
+    // ------------------------------ MMA issuer (leader CTA only) ----------------
+    if (lane == 0 && leader) {
+      constexpr uint32_t idesc = make_idesc(BM * kCtas, BN);
       int stage = 0;
       uint32_t phase = 0;
       int acc = 0;
       uint32_t acc_phase = 0;
-      for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+      for (int u = unit0; u < n_units; u += unit_step) {
         const int split = u / p.n_mblk;
         const int t0 = (int)((int64_t)p.n_tiles * split / p.n_splits), t1 = (int)((int64_t)p.n_tiles * (split + 1) / p.n_splits);
         for (int t = t0; t < t1; ++t) {
-          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // epilogue has drained this accumulator
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // every epilogue warp of the pair has drained this accumulator
           tcgen05_fence_after();
           const uint32_t tmem_c = tmem_base + (uint32_t)(acc * BN);
           for (int kb = 0; kb < p.num_k_blocks; ++kb) {
             mbar_wait(&full_bar[stage], phase);
             tcgen05_fence_after();
-            const uint32_t a_addr = smem_u32(smem + stage * kStageBytes);
+            const uint32_t a_addr = smem_u32(smem + stage * C::kStage);
             const uint32_t b_addr = a_addr + kATileBytes;
 #pragma unroll
             for (int k = 0; k < BK / UMMA_K; ++k) {
               const uint64_t da = make_smem_desc(a_addr + k * UMMA_K * 2);
               const uint64_t db = make_smem_desc(b_addr + k * UMMA_K * 2);
-              umma_f16(tmem_c, da, db, idesc, (kb | k) != 0);
+              if (kCtas == 1) umma_f16(tmem_c, da, db, idesc, (kb | k) != 0);
+              else umma_f16_pair(tmem_c, da, db, idesc, (kb | k) != 0);
             }
-            umma_commit(&empty_bar[stage]);             // slot free once these MMAs have read it
-            if (++stage == kStages) {
+            if (kCtas == 1) umma_commit(&empty_bar[stage]); else umma_commit_pair(&empty_bar[stage]);
+            if (++stage == kNumStages) {
               stage = 0;
               phase ^= 1;
             }
           }
-          umma_commit(&tfull_bar[acc]);                 // accumulator complete
+          if (kCtas == 1) umma_commit(&tfull_bar[acc]); else umma_commit_pair(&tfull_bar[acc]);
           if (++acc == 2) {
             acc = 0;
             acc_phase ^= 1;
@@ -284,28 +374,50 @@ __global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_const
     }
   } else {
     // ------------------------------ epilogue: fused running top-K ----------------
+    // Two epilogue warpgroups: group g drains accumulator g (every other column tile), so each has two
+    // MMA tile periods for its drain + list maintenance.  Every (row, column range, group) owns a list.
+    const int wg = (warp - 2) >> 2;
     const int quarter = warp & 3;                       // TMEM lanes this warp may read
-    const int r_in_tile = quarter * 32 + lane;
-    int acc = 0;
+    const int r_in_tile = (int)cta_rank * BM + quarter * 32 + lane;
+    const uint32_t tempty_remote = kCtas == 2 ? mapa_u32(smem_u32(&tempty_bar[wg]), 0) : 0u;
+    const int n_lists = p.n_splits * 2;
     uint32_t acc_phase = 0;
-    for (int u = blockIdx.x; u < n_units; u += gridDim.x) {
+    int tile_ctr = 0;                                   // running tile count of this CTA == the MMA warp's
+    for (int u = unit0; u < n_units; u += unit_step) {
       const int split = u / p.n_mblk, mblk = u % p.n_mblk;
       const int t0 = (int)((int64_t)p.n_tiles * split / p.n_splits), t1 = (int)((int64_t)p.n_tiles * (split + 1) / p.n_splits);
-      const int64_t lrow = (int64_t)mblk * BM + r_in_tile;               // local row in the shard
+      const int64_t lrow = (int64_t)mblk * (BM * kCtas) + r_in_tile;     // local row in the shard
       const bool row_ok = p.row_begin + lrow < p.row_end;
-      unsigned long long* list = p.cand + (((row_ok ? lrow : 0) * p.n_splits + split) * (int64_t)kCap);
+      const int64_t list_id = (row_ok ? lrow : 0) * n_lists + split * 2 + wg;
+      unsigned long long* list = p.cand + list_id * (int64_t)kCap;
       float tau = row_ok ? -INFINITY : INFINITY;
       int cnt = 0;
-      for (int t = t0; t < t1; ++t) {
-        mbar_wait(&tfull_bar[acc], acc_phase);
+      volatile uint32_t* my_tau = p.row_tau + (row_ok ? lrow : 0);
+      for (int t = t0; t < t1; ++t, ++tile_ctr) {
+        if ((tile_ctr & 1) != wg) continue;
+        // Any threshold published for this row -- by the other epilogue group, or by a CTA that already
+        // swept another column range -- is a valid rejection threshold here too: `keep` columns with a
+        // higher score are known to exist somewhere.  Picking it up removes most of the warm-up.
+        {
+          const uint32_t g = *my_tau;
+          if (g && row_ok) tau = fmaxf(tau, ord_float(g));
+        }
+        mbar_wait(&tfull_bar[wg], acc_phase);
+        acc_phase ^= 1;
         tcgen05_fence_after();
-        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(acc * BN);
+        const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wg * BN);
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
+          if (p.dbg & 1) break;
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + ch * 32, v);
           const int col0 = t * BN + ch * 32;
-          if (col0 + 32 <= p.N) {
+          if (p.dbg & 2) {
+            float m = 0.f;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) m = fmaxf(m, __uint_as_float(v[c]));
+            if (m == 123.456f) list[cnt++] = 1ull;
+          } else if (col0 + 32 <= p.N) {
 #pragma unroll
             for (int c = 0; c < 32; ++c) {
               const float s = __uint_as_float(v[c]) * p.descale;
@@ -318,46 +430,43 @@ __global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_const
               if (s > tau && col0 + c < p.N) list[cnt++] = ((unsigned long long)__float_as_uint(s) << 32) | (uint32_t)(col0 + c);
             }
           }
-          // lists that could overflow during the next 32 columns are compacted now, one row at a time
-          unsigned need = __ballot_sync(kFull, cnt > kCap - 32);
-          while (need) {
-            const int src = __ffs(need) - 1;
-            need &= need - 1;
-            unsigned long long* l = (unsigned long long*)__shfl_sync(kFull, (unsigned long long)list, src);
-            const int n = __shfl_sync(kFull, cnt, src);
-            const float nt = warp_compact(l, n, p.keep);
-            if (lane == src) {
-              tau = nt;
-              cnt = p.keep;
-            }
-          }
         }
+        // the accumulator is drained: hand it back to the MMA warp before doing any list maintenance
         tcgen05_fence_before();
         __syncwarp();
-        if (lane == 0) mbar_arrive(&tempty_bar[acc]);
-        if (++acc == 2) {
-          acc = 0;
-          acc_phase ^= 1;
+        if (lane == 0) {
+          if (kCtas == 1 || leader) mbar_arrive(&tempty_bar[wg]);
+          else mbar_arrive_cluster(tempty_remote);
+        }
+        // a tile appends at most BN entries: lists that could overflow during the next tile are compacted
+        // now (coarse threshold), one row at a time, while the tensor core works on the other accumulator
+        unsigned need = __ballot_sync(kFull, cnt > kCap - BN);
+        while (need) {
+          const int src = __ffs(need) - 1;
+          need &= need - 1;
+          unsigned long long* l = (unsigned long long*)__shfl_sync(kFull, (unsigned long long)list, src);
+          const int n = __shfl_sync(kFull, cnt, src);
+          int kept;
+          float nt = warp_compact<16>(l, n, p.keep, kept);
+          if (kept > kCap - BN) nt = warp_compact<32>(l, kept, p.keep, kept);  // a flood of near-ties: resolve exactly
+          if (lane == src) {
+            tau = fmaxf(tau, nt);
+            cnt = kept;
+            atomicMax(p.row_tau + lrow, float_ord(tau));
+          }
         }
       }
-      // unit done: trim every list to `keep` and publish the counts
-      unsigned need = __ballot_sync(kFull, cnt > p.keep);
-      while (need) {
-        const int src = __ffs(need) - 1;
-        need &= need - 1;
-        unsigned long long* l = (unsigned long long*)__shfl_sync(kFull, (unsigned long long)list, src);
-        const int n = __shfl_sync(kFull, cnt, src);
-        warp_compact(l, n, p.keep);
-        if (lane == src) cnt = p.keep;
-      }
-      if (row_ok) p.cand_cnt[lrow * p.n_splits + split] = cnt;
+      // unit done: publish the count; the list is left untrimmed (<= kCap entries) -- knn_rescore.cu only
+      // looks at entries above the row's final threshold
+      if (row_ok) p.cand_cnt[list_id] = cnt;
     }
   }
 
   tcgen05_fence_before();
-  __syncthreads();
+  if (kCtas == 2) cluster_sync_all(); else __syncthreads();
   if (warp == 1) {
-    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    if (kCtas == 1) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+    else asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
   }
 }
 
@@ -396,19 +505,20 @@ static EncodeTiledFn get_encode_fn() {
 
 extern "C" {
 
-int reid_knn_tc_plan(int64_t N, int64_t n_rows, int* n_splits_out) {
+int reid_knn_tc_plan(int64_t N, int64_t n_rows, int cta_group, int* n_splits_out) {
   using namespace reid;
-  REID_CHECK_ARG(N > 0 && n_rows > 0 && n_splits_out, "reid_knn_tc_plan: bad arguments");
-  const int sms = num_sms();
-  const int64_t n_mblk = (n_rows + tc::BM - 1) / tc::BM;
+  REID_CHECK_ARG(N > 0 && n_rows > 0 && n_splits_out && (cta_group == 1 || cta_group == 2),
+                 "reid_knn_tc_plan: bad arguments");
+  const int slots = num_sms() / cta_group;             // concurrently running work units
+  const int64_t n_mblk = (n_rows + tc::BM * cta_group - 1) / (tc::BM * cta_group);
   const int64_t n_tiles = (N + tc::BN - 1) / tc::BN;
   int best = 1;
   double best_eff = -1.0;
   for (int s = 1; s <= REID_TC_MAX_SPLITS; ++s) {
     if (s > n_tiles) break;
     const int64_t units = n_mblk * s;
-    const int64_t waves = (units + sms - 1) / sms;
-    const double eff = (double)units / (double)(waves * sms);
+    const int64_t waves = (units + slots - 1) / slots;
+    const double eff = (double)units / (double)(waves * slots);
     if (eff > best_eff + 0.02) {  // prefer fewer splits unless the gain is real
       best_eff = eff;
       best = s;
@@ -433,14 +543,17 @@ int reid_features_to_half(const float* x, int64_t n_rows, int64_t D, int scale_l
 }
 
 int reid_knn_candidates_tc(const void* xh, int64_t N, int64_t D, int scale_log2, int64_t row_begin, int64_t row_end,
-                           int keep, int n_splits, uint64_t* cand, int32_t* cand_cnt, void* stream) {
+                           int keep, int n_splits, int cta_group, uint64_t* cand, int32_t* cand_cnt, uint32_t* row_tau,
+                           void* stream) {
   using namespace reid;
-  REID_CHECK_ARG(xh && cand && cand_cnt, "reid_knn_candidates_tc: NULL pointer");
+  REID_CHECK_ARG(xh && cand && cand_cnt && row_tau, "reid_knn_candidates_tc: NULL pointer");
   REID_CHECK_ARG(N > 0 && N < (1ll << 31) && D > 0 && D % tc::BK == 0, "reid_knn_candidates_tc: need D %% 64 == 0 (D=%lld)",
                  (long long)D);
   REID_CHECK_ARG(((uintptr_t)xh & 15) == 0, "reid_knn_candidates_tc: xh must be 16-byte aligned");
   REID_CHECK_ARG(0 <= row_begin && row_begin < row_end && row_end <= N, "reid_knn_candidates_tc: bad row range");
-  REID_CHECK_ARG(keep >= 1 && keep <= tc::kCap - 32, "reid_knn_candidates_tc: keep=%d not in 1..%d", keep, tc::kCap - 32);
+  REID_CHECK_ARG(keep >= 1 && keep <= REID_TC_KEEP_MAX, "reid_knn_candidates_tc: keep=%d not in 1..%d", keep,
+                 REID_TC_KEEP_MAX);
+  REID_CHECK_ARG(cta_group == 1 || cta_group == 2, "reid_knn_candidates_tc: cta_group=%d must be 1 or 2", cta_group);
   const int64_t n_tiles = (N + tc::BN - 1) / tc::BN;
   REID_CHECK_ARG(n_splits >= 1 && n_splits <= REID_TC_MAX_SPLITS && n_splits <= n_tiles,
                  "reid_knn_candidates_tc: n_splits=%d", n_splits);
@@ -466,17 +579,42 @@ int reid_knn_candidates_tc(const void* xh, int64_t N, int64_t D, int scale_log2,
   p.row_begin = row_begin;
   p.row_end = row_end;
   p.num_k_blocks = (int)(D / tc::BK);
-  p.n_mblk = (int)((row_end - row_begin + tc::BM - 1) / tc::BM);
+  p.n_mblk = (int)((row_end - row_begin + tc::BM * cta_group - 1) / (tc::BM * cta_group));
   p.n_splits = n_splits;
   p.n_tiles = (int)n_tiles;
   p.keep = keep;
   p.descale = ldexpf(1.0f, -2 * scale_log2);
   p.cand = (unsigned long long*)cand;
   p.cand_cnt = cand_cnt;
-  REID_CUDA(cudaFuncSetAttribute(tc::simtopk_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSmemBytes));
+  p.row_tau = row_tau;
+  REID_CUDA(cudaMemsetAsync(row_tau, 0, sizeof(uint32_t) * (size_t)(row_end - row_begin), (cudaStream_t)stream));
+  {
+    const char* e = getenv("REID_TC_DEBUG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   const int units = p.n_mblk * n_splits;
-  const int grid = units < num_sms() ? units : num_sms();
-  tc::simtopk_kernel<<<grid, tc::kThreads, tc::kSmemBytes, (cudaStream_t)stream>>>(tmap, p);
+  const int slots = num_sms() / cta_group;
+  const int grid = (units < slots ? units : slots) * cta_group;
+  cudaLaunchConfig_t cfg = {};
+  cfg.gridDim = dim3((unsigned)grid);
+  cfg.blockDim = dim3(tc::kThreads);
+  cfg.stream = (cudaStream_t)stream;
+  cudaLaunchAttribute attr[1];
+  attr[0].id = cudaLaunchAttributeClusterDimension;
+  attr[0].val.clusterDim.x = (unsigned)cta_group;
+  attr[0].val.clusterDim.y = 1;
+  attr[0].val.clusterDim.z = 1;
+  cfg.attrs = attr;
+  cfg.numAttrs = 1;
+  if (cta_group == 1) {
+    cfg.dynamicSmemBytes = tc::Cfg<1>::kSmem;
+    REID_CUDA(cudaFuncSetAttribute(tc::simtopk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<1>::kSmem));
+    REID_CUDA(cudaLaunchKernelEx(&cfg, tc::simtopk_kernel<1>, tmap, p));
+  } else {
+    cfg.dynamicSmemBytes = tc::Cfg<2>::kSmem;
+    REID_CUDA(cudaFuncSetAttribute(tc::simtopk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<2>::kSmem));
+    REID_CUDA(cudaLaunchKernelEx(&cfg, tc::simtopk_kernel<2>, tmap, p));
+  }
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

@@ -15,44 +15,55 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-// One CTA scans up to a few hundred thousand counts: every thread owns a contiguous
-// chunk, the 1024 chunk totals are scanned in shared memory, the chunk is re-walked.
+// One CTA scans up to a few hundred thousand counts: every thread owns a contiguous chunk, the 1024
+// chunk totals are scanned with warp shuffles (two levels), then the chunk is re-walked.
 __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ cnt, int64_t n,
                                                            int64_t* __restrict__ ptr, int64_t* __restrict__ stats) {
-  __shared__ int64_t part[1024];
-  __shared__ int32_t pmax[1024];
-  const int t = threadIdx.x;
+  __shared__ int64_t warp_tot[32];
+  __shared__ int32_t warp_max_s[32];
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const int64_t chunk = (n + 1023) / 1024;
   const int64_t a = min(n, (int64_t)t * chunk), b = min(n, a + chunk);
   int64_t s = 0;
   int32_t mx = 0;
   for (int64_t i = a; i < b; ++i) {
-    int32_t c = cnt[i];
+    const int32_t c = cnt[i];
     s += c;
     mx = max(mx, c);
   }
-  part[t] = s;
-  pmax[t] = mx;
-  __syncthreads();
-  for (int o = 1; o < 1024; o <<= 1) {  // Hillis-Steele inclusive scan
-    int64_t v = t >= o ? part[t - o] : 0;
-    int32_t m = t >= o ? pmax[t - o] : 0;
-    __syncthreads();
-    part[t] += v;
-    pmax[t] = max(pmax[t], m);
-    __syncthreads();
+  int64_t inc = s;  // inclusive scan inside the warp
+#pragma unroll
+  for (int o = 1; o < 32; o <<= 1) {
+    const int64_t v = __shfl_up_sync(kFull, inc, o);
+    if (lane >= o) inc += v;
   }
-  int64_t run = part[t] - s;
+  mx = warp_max(mx);
+  if (lane == 31) warp_tot[w] = inc;
+  if (lane == 0) warp_max_s[w] = mx;
+  __syncthreads();
+  if (w == 0) {
+    int64_t v = warp_tot[lane];
+    int64_t iv = v;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int64_t u = __shfl_up_sync(kFull, iv, o);
+      if (lane >= o) iv += u;
+    }
+    warp_tot[lane] = iv - v;  // exclusive offset of each warp
+    const int32_t m = warp_max(warp_max_s[lane]);
+    if (lane == 31) {
+      ptr[n] = iv;
+      if (stats) {
+        stats[0] = iv;
+        stats[1] = m;
+      }
+    }
+  }
+  __syncthreads();
+  int64_t run = warp_tot[w] + inc - s;
   for (int64_t i = a; i < b; ++i) {
     ptr[i] = run;
     run += cnt[i];
-  }
-  if (t == 1023) {
-    ptr[n] = part[1023];
-    if (stats) {
-      stats[0] = part[1023];
-      stats[1] = pmax[1023];
-    }
   }
 }
 

@@ -12,9 +12,11 @@ import torch
 from . import _lib
 from ._lib import call, check, ptr, stream_ptr
 
-TC_CAP = 128
+TC_CAP = 512
+KEEP_MAX = 64
 SCALE_LOG2 = 4          # features are scaled by 2^4 before rounding to fp16 (keeps them out of the subnormals)
-SLACK = 18              # K = k + SLACK candidates are kept per (row, column range)
+CTA_GROUP = int(__import__("os").environ.get("REID_TC_CTA_GROUP", "2"))   # 2 = CTA pairs (tcgen05 cta_group::2)
+SLACK = 34              # K = k + SLACK candidates are kept per (row, column range)
 
 
 def err_bound(max_sqnorm):
@@ -38,18 +40,20 @@ def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None):
     else:
         msq = None
     n_splits = ctypes.c_int(1)
-    call("reid_knn_tc_plan", N, n, ctypes.byref(n_splits))
+    call("reid_knn_tc_plan", N, n, CTA_GROUP, ctypes.byref(n_splits))
     s = n_splits.value
-    keep = max(k, min(k + SLACK, 256 // s, TC_CAP - 32))
-    cand = torch.empty(n * s * TC_CAP, dtype=torch.int64, device=dev)
-    cand_cnt = torch.zeros(n * s, dtype=torch.int32, device=dev)
-    call("reid_knn_candidates_tc", ptr(xh), N, D, SCALE_LOG2, r0, r1, keep, s, ptr(cand), ptr(cand_cnt), sp)
+    keep = max(k, min(k + SLACK, KEEP_MAX))
+    n_lists = 2 * s                                        # two epilogue groups per column range
+    cand = torch.empty(n * n_lists * TC_CAP, dtype=torch.int64, device=dev)
+    cand_cnt = torch.zeros(n * n_lists, dtype=torch.int32, device=dev)
+    row_tau = torch.empty(n, dtype=torch.int32, device=dev)
+    call("reid_knn_candidates_tc", ptr(xh), N, D, SCALE_LOG2, r0, r1, keep, s, CTA_GROUP, ptr(cand), ptr(cand_cnt), ptr(row_tau), sp)
     if max_sqnorm is None:
         max_sqnorm = float(msq.item())                     # one scalar read-back, after the GEMM is queued
     eps = err_bound(max_sqnorm)
     flag = torch.empty(n, dtype=torch.int32, device=dev)
     max_err = torch.zeros(1, dtype=torch.float32, device=dev)
-    call("reid_knn_rescore", ptr(x), N, D, r0, r1, ptr(cand), ptr(cand_cnt), s, keep, k, eps, ptr(idx), ptr(key),
+    call("reid_knn_rescore", ptr(x), N, D, r0, r1, ptr(cand), ptr(cand_cnt), ptr(row_tau), n_lists, k, eps, ptr(idx), ptr(key),
                              ptr(flag), ptr(max_err), sp)
     bad = torch.nonzero(flag).flatten().to(torch.int32)
     n_bad = bad.numel()
@@ -60,6 +64,6 @@ def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None):
         _knn_exact_rows(x, k, rows, 0, n_bad, bi, bk)
         idx[bad.long()] = bi
         key[bad.long()] = bk
-    info.update(mode="tc", n_splits=s, keep=keep, err_bound=eps, uncertified_rows=int(n_bad),
+    info.update(mode="tc", cta_group=CTA_GROUP, n_splits=s, keep=keep, err_bound=eps, uncertified_rows=int(n_bad),
                 max_abs_err=max_err, xh=xh)
     return idx, key, info
