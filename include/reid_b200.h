@@ -94,11 +94,18 @@ int reid_features_to_half(const float* x, int64_t n_rows, int64_t D, int scale_l
  * fp32(fp64 dot) and ordered by (key desc, index asc): bit-identical to reid_knn_exact.
  * |approx - exact| is audited against err_bound; a violation un-certifies the row.
  * uncertified_flag[row-row_begin] = 1 marks rows the caller must redo with reid_knn_exact;
- * max_err_out (1 float) = largest |approx - exact| seen. */
+ * max_err_out (1 float) = largest |approx - exact| seen.
+ * max_sqnorm (optional device scalar from reid_features_to_half): when given, err_bound is derived on the
+ * device as 1.02 * 2^-10 * max_sqnorm + 2^-14 and the err_bound argument is ignored (no host round trip).
+ * locality_order != 0: the exact stage gathers ~36 feature rows per query row and is HBM bound; rows of one
+ * identity cluster share their candidates, so they are visited back to back (counting sort on the smallest
+ * index among a row's strong candidates) and repeats become L2 hits.
+ * workspace: reid_knn_rescore_workspace_bytes(N, row_end - row_begin). */
 int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, int64_t row_end,
                      const uint64_t* cand, const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists, int k,
-                     float err_bound, int32_t* out_idx, float* out_key, int32_t* uncertified_flag,
-                     float* max_err_out, void* stream);
+                     float err_bound, const float* max_sqnorm, int locality_order, int32_t* out_idx, float* out_key,
+                     int32_t* uncertified_flag, float* max_err_out, void* workspace, void* stream);
+size_t reid_knn_rescore_workspace_bytes(int64_t N, int64_t n_rows);
 
 /* ---- a2: reciprocal sets  (faiss_rerank.py:23-27, 65-69) -----------------------
  * mask_out[row - row_begin] bit r  <=>  row in rank[rank[row,r], :cols], cols = min(k+1, ncols).
@@ -108,27 +115,31 @@ int reid_reciprocal_masks(const int32_t* rank, int64_t N, int ncols, int k, int6
 
 /* ---- a3: expansion  (faiss_rerank.py:72-80) ------------------------------------
  * E(row) = sort_unique( R(row) + all R_half(c), c in R(row), 3*|R_half(c) & R(row)| > 2*|R_half(c)| ).
- * Two passes: E_ptr == NULL -> writes E_cnt (local); else writes E_idx at E_ptr (local CSR).
- * Rmask is local, Rhalf_mask is global (all N rows). */
+ * One pass into padded rows: E_pad[(row-row_begin)*stride + t], t < E_cnt[row-row_begin].  A row that does
+ * not fit reports E_cnt = stride + 1 (stride >= k1 + k1*(k1/2 + 1) always fits).  Rmask is local,
+ * Rhalf_mask is global (all N rows). */
 int reid_expand(const int32_t* rank, int64_t N, int ncols, const uint64_t* Rmask, const uint64_t* Rhalf_mask,
-                int64_t row_begin, int64_t row_end, const int64_t* E_ptr, int32_t* E_cnt, int32_t* E_idx,
-                void* stream);
+                int64_t row_begin, int64_t row_end, int stride, int32_t* E_pad, int32_t* E_cnt, void* stream);
 
 /* ---- a4: Gaussian weights  (faiss_rerank.py:81-85) ------------------------------
- * V_val[p] = softmax over the row of -(2 - 2 x_row.x_e), e = E_idx[p]; fp32.
- * rank/rank_key (optional, global rank rows of the shard, local indexing) let the kernel reuse
- * the search keys for members that are among the row's k1 neighbours. */
-int reid_v_weights(const float* x, int64_t N, int64_t D, const int64_t* E_ptr, const int32_t* E_idx,
+ * V_val[p] = softmax over the row of -(2 - 2 x_row.x_e), e in E(row); fp32.  Reads the padded sets of
+ * reid_expand and writes the CSR (E_idx, V_val) at E_ptr (local, from a scan of E_cnt) in the same pass.
+ * rank/rank_key (optional, the shard's rows of the search result) let the kernel reuse the search keys
+ * for members that are among the row's k1 neighbours instead of gathering 4*D bytes. */
+int reid_v_weights(const float* x, int64_t N, int64_t D, const int32_t* E_pad, int stride, const int64_t* E_ptr,
                    int64_t row_begin, int64_t row_end, const int32_t* rank_local, const float* rank_key_local,
-                   int ncols, float* V_val, void* stream);
+                   int ncols, int32_t* E_idx, float* V_val, void* stream);
 
 /* ---- a5: k2 query expansion  (faiss_rerank.py:89-94) ----------------------------
  * Vq[row] = (V[rank[row,0]] + ... + V[rank[row,k2-1]]) / k2, adds in that order, fp32.
- * V is the GLOBAL CSR (all N rows).  Two passes like reid_expand.  max_row_nnz = max |E|. */
+ * V is the GLOBAL CSR (all N rows); max_row_nnz = max |E|.  One pass into padded rows of
+ * reid_query_expand_stride(k2, max_row_nnz) slots; reid_csr_compact packs them into a CSR. */
+int reid_query_expand_stride(int k2, int max_row_nnz);
 int reid_query_expand(const int32_t* rank, int64_t N, int ncols, int k2, const int64_t* V_ptr,
                       const int32_t* V_idx, const float* V_val, int max_row_nnz, int64_t row_begin,
-                      int64_t row_end, const int64_t* Q_ptr, int32_t* Q_cnt, int32_t* Q_idx, float* Q_val,
-                      void* stream);
+                      int64_t row_end, int32_t* Q_cnt, int32_t* Q_pad_idx, float* Q_pad_val, void* stream);
+int reid_csr_compact(const int32_t* pad_idx, const float* pad_val, int64_t stride, const int32_t* cnt,
+                     const int64_t* ptr, int64_t n_rows, int32_t* out_idx, float* out_val, void* stream);
 
 /* ---- a6: inverted index  (faiss_rerank.py:98-100) -------------------------------
  * CSC of a CSR with n_rows x n_cols; column lists sorted by row.

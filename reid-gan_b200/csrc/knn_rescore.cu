@@ -14,25 +14,35 @@
 namespace reid {
 
 constexpr int kRsWarps = 4;
-constexpr int kRsMaxC = 2 * REID_TC_MAX_SPLITS * REID_TC_KEEP_MAX;  // 512 candidates per row at most
+constexpr int kRsMaxC = 2 * REID_TC_MAX_SPLITS * REID_TC_KEEP_MAX;  // 512 candidates per row held at most
 constexpr int kRsPer = kRsMaxC / 32;
+constexpr int kWinMax = 128;                                         // window members per row at most
 
-__global__ void __launch_bounds__(kRsWarps * 32) rescore_kernel(
-    const float* __restrict__ x, int64_t N, int64_t D, int64_t row_begin, int64_t row_end,
-    const unsigned long long* __restrict__ cand, const int32_t* __restrict__ cand_cnt,
-    const uint32_t* __restrict__ row_tau, int n_lists, int k,
-    float eps, int32_t* __restrict__ out_idx, float* __restrict__ out_key, int32_t* __restrict__ uncert,
-    unsigned* __restrict__ max_err_bits) {
+// |fp16-GEMM score - exact dot| <= 2^-10 ||x_i|| ||x_j||  (both operands rounded to 11 significant bits,
+// Cauchy-Schwarz) with 2% head-room, + 2^-14 for the fp32 accumulation.  max_sqnorm = max_i ||x_i||^2.
+__host__ __device__ inline float reid_tc_err_bound(float max_sqnorm) {
+  return max_sqnorm * (1.02f / 1024.0f) + (1.0f / 16384.0f);
+}
+
+// ---- stage 1: selection (no feature traffic) ----------------------------------------------------
+// Sweeps the row's candidate lists, finds the k-th best approximate score, checks the certificate and
+// writes the window members.  It also emits a locality key for stage 2: the smallest column index among
+// the members that score at least half of the best non-self score -- for a row inside an identity cluster
+// that is the cluster's smallest index, so cluster mates (who share their candidates) get the same key.
+__global__ void __launch_bounds__(kRsWarps * 32) rescore_select_kernel(
+    int64_t row_begin, int64_t n_rows, const unsigned long long* __restrict__ cand,
+    const int32_t* __restrict__ cand_cnt, const uint32_t* __restrict__ row_tau, int n_lists, int k, float eps_in,
+    const float* __restrict__ max_sqnorm, int32_t* __restrict__ win_cnt, int32_t* __restrict__ win_idx, float* __restrict__ win_a,
+    int32_t* __restrict__ uncert, int32_t* __restrict__ key_out, int32_t* __restrict__ hist) {
   __shared__ float s_a[kRsWarps][kRsMaxC];
   __shared__ int32_t s_j[kRsWarps][kRsMaxC];
-  __shared__ uint64_t s_key[kRsWarps][kRsMaxC];
   const int w = threadIdx.x >> 5, lane = lane_id();
-  const int64_t row = row_begin + (int64_t)blockIdx.x * kRsWarps + w;
-  if (row >= row_end) return;
-  const int64_t lr = row - row_begin;
+  const int64_t lr = (int64_t)blockIdx.x * kRsWarps + w;
+  if (lr >= n_rows) return;
+  const int32_t self = (int32_t)(row_begin + lr);
+  const float eps = max_sqnorm ? reid_tc_err_bound(*max_sqnorm) : eps_in;
   float* a = s_a[w];
   int32_t* jj = s_j[w];
-  uint64_t* key = s_key[w];
 
   // Every column outside the row's lists scored <= bound.  The window [a_(k) - 2 eps, inf) starts at or
   // above bound - 2 eps (a_(k) >= bound because at least `keep` >= k listed columns score >= bound), so a
@@ -40,7 +50,6 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_kernel(
   const uint32_t tq = row_tau[lr];
   const float bound = tq ? ord_float(tq) : -INFINITY;
 
-  // sweep the row's lists, keeping entries with score >= thr (at most kRsMaxC are stored; all are counted)
   auto collect = [&](float thr) {
     int cnt = 0;
     for (int q = 0; q < n_lists; ++q) {
@@ -67,7 +76,6 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_kernel(
     __syncwarp();
     return cnt;
   };
-  // k-th largest of a[0..m): bitwise binary search on the order-preserving integer image
   auto kth_largest = [&](int m) {
     uint32_t o[kRsPer];
 #pragma unroll
@@ -102,50 +110,113 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_kernel(
   const float lo = a_k - 2.0f * eps;
   bool certified = !overflow && n >= k && bound < lo;
 
-  // window members, compacted to the front of key[] (as indices into a/jj for now)
-  int n_w = 0;
+  // best non-self score -> locality threshold
+  float best = -INFINITY;
+  for (int t = lane; t < n; t += 32)
+    if (jj[t] != self) best = fmaxf(best, a[t]);
+  best = warp_max(best);
+  const float near = 0.5f * best;
+  // window members -> global lists
+  int n_w = 0, kmin = 0x7fffffff;
 #pragma unroll 1
   for (int base = 0; base < n; base += 32) {
     const int t = base + lane;
     const bool in = t < n && a[t] >= lo;
     const unsigned b = __ballot_sync(kFull, in);
-    if (in) key[n_w + __popc(b & ((1u << lane) - 1u))] = (uint64_t)t;
+    const int pos = n_w + __popc(b & ((1u << lane) - 1u));
+    if (in && pos < kWinMax) {
+      win_idx[lr * kWinMax + pos] = jj[t];
+      win_a[lr * kWinMax + pos] = a[t];
+    }
+    if (in && a[t] >= near) kmin = min(kmin, jj[t]);
     n_w += __popc(b);
   }
-  __syncwarp();
-  // exact keys of the window members
-  float worst = 0.f;
+  kmin = warp_min(kmin);
+  if (n_w > kWinMax || n_w < k) certified = false;
+  if (lane == 0) {
+    win_cnt[lr] = min(n_w, kWinMax);
+    uncert[lr] = certified ? 0 : 1;
+    if (key_out) {
+      if (kmin == 0x7fffffff) kmin = self;
+      key_out[lr] = kmin;
+      atomicAdd(&hist[kmin], 1);
+    }
+  }
+}
+
+__global__ void order_scatter_kernel(const int32_t* __restrict__ key, int64_t n_rows, const int64_t* __restrict__ ptr,
+                                     int32_t* __restrict__ cursor, int32_t* __restrict__ perm) {
+  const int64_t lr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lr >= n_rows) return;
+  const int k = key[lr];
+  perm[ptr[k] + atomicAdd(&cursor[k], 1)] = (int32_t)lr;
+}
+
+// ---- stage 2: exact keys of the window members, audit, final order --------------------------------
+// HBM bound: ~36 feature rows of 4*D bytes per query row.  Rows are visited in `perm` order so that
+// the rows of one identity cluster, which share most candidates, run back to back and hit in L2.
+// kChunks > 0: D == kChunks * 128 and the query row lives in registers (one float4 per lane and chunk), so
+// each candidate costs one pass over ITS row only; kChunks == 0: generic D, both rows are streamed.
+template <int kChunks>
+__global__ void __launch_bounds__(kRsWarps * 32) rescore_exact_kernel(
+    const float* __restrict__ x, int64_t D, int64_t row_begin, int64_t n_rows, const int32_t* __restrict__ perm,
+    const int32_t* __restrict__ win_cnt, const int32_t* __restrict__ win_idx, const float* __restrict__ win_a, int k,
+    float eps_in, const float* __restrict__ max_sqnorm, int32_t* __restrict__ out_idx, float* __restrict__ out_key,
+    int32_t* __restrict__ uncert, unsigned* __restrict__ max_err_bits) {
+  __shared__ uint64_t s_key[kRsWarps][kWinMax];
+  const int w = threadIdx.x >> 5, lane = lane_id();
+  const int64_t slot = (int64_t)blockIdx.x * kRsWarps + w;
+  if (slot >= n_rows) return;
+  const int64_t lr = perm ? perm[slot] : slot;
+  const int64_t row = row_begin + lr;
+  uint64_t* key = s_key[w];
+  const float eps = max_sqnorm ? reid_tc_err_bound(*max_sqnorm) : eps_in;
+  const int n_w = win_cnt[lr];
   const float* xi = x + row * D;
+  constexpr int kRegs = kChunks > 0 ? kChunks : 1;
+  float4 q[kRegs];
+  if (kChunks > 0) {
+#pragma unroll
+    for (int c = 0; c < kRegs; ++c) q[c] = reinterpret_cast<const float4*>(xi)[c * 32 + lane];
+  }
+  float worst = 0.f;
   for (int wi = 0; wi < n_w; ++wi) {
-    const int t = (int)key[wi];
-    const int32_t j = jj[t];
+    const int32_t j = win_idx[lr * kWinMax + wi];
     const float* xj = x + (int64_t)j * D;
-    double acc = 0.0;
-    if ((D & 3) == 0) {
+    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+    if (kChunks > 0) {
+      float4 r[kRegs];
+#pragma unroll
+      for (int c = 0; c < kRegs; ++c) r[c] = reinterpret_cast<const float4*>(xj)[c * 32 + lane];
+#pragma unroll
+      for (int c = 0; c < kRegs; ++c) {
+        acc0 = fma((double)q[c].x, (double)r[c].x, acc0);
+        acc1 = fma((double)q[c].y, (double)r[c].y, acc1);
+        acc2 = fma((double)q[c].z, (double)r[c].z, acc2);
+        acc3 = fma((double)q[c].w, (double)r[c].w, acc3);
+      }
+    } else if ((D & 3) == 0) {
       const float4* a4 = reinterpret_cast<const float4*>(xi);
       const float4* b4 = reinterpret_cast<const float4*>(xj);
       for (int64_t d = lane; d < (D >> 2); d += 32) {
-        const float4 p = a4[d], q = b4[d];
-        acc = fma((double)p.x, (double)q.x, acc);
-        acc = fma((double)p.y, (double)q.y, acc);
-        acc = fma((double)p.z, (double)q.z, acc);
-        acc = fma((double)p.w, (double)q.w, acc);
+        const float4 p = a4[d], r = b4[d];
+        acc0 = fma((double)p.x, (double)r.x, acc0);
+        acc1 = fma((double)p.y, (double)r.y, acc1);
+        acc2 = fma((double)p.z, (double)r.z, acc2);
+        acc3 = fma((double)p.w, (double)r.w, acc3);
       }
     } else {
-      for (int64_t d = lane; d < D; d += 32) acc = fma((double)xi[d], (double)xj[d], acc);
+      for (int64_t d = lane; d < D; d += 32) acc0 = fma((double)xi[d], (double)xj[d], acc0);
     }
-    acc = warp_sum(acc);
+    const double acc = warp_sum((acc0 + acc1) + (acc2 + acc3));
     const float s = (float)acc;
-    worst = fmaxf(worst, fabsf(s - a[t]));
-    __syncwarp();
+    worst = fmaxf(worst, fabsf(s - win_a[lr * kWinMax + wi]));
     if (lane == 0) key[wi] = sel_key(s, j);
   }
   __syncwarp();
-  if (!(worst <= eps)) certified = false;  // the error model was violated (or NaN): do not trust the window
-  if (n_w < k) certified = false;
   if (lane == 0) {
     atomicMax(max_err_bits, __float_as_uint(worst));
-    uncert[lr] = certified ? 0 : 1;
+    if (!(worst <= eps)) uncert[lr] = 1;  // the error model was violated (or NaN): do not trust the window
   }
   // order by (key desc, idx asc); the first k go out
   for (int t = lane; t < n_w; t += 32) {
@@ -159,15 +230,55 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_kernel(
   }
 }
 
+struct RescoreWs {
+  int64_t* ptr;      // N + 1
+  int32_t* hist;     // N
+  int32_t* cursor;   // N
+  int32_t* key;      // n
+  int32_t* perm;     // n
+  int32_t* win_cnt;  // n
+  int32_t* win_idx;  // n * kWinMax
+  float* win_a;      // n * kWinMax
+};
+
+inline size_t rs_align(size_t v) { return (v + 255) / 256 * 256; }
+
+inline size_t rescore_carve(void* base, int64_t N, int64_t n, RescoreWs* w) {
+  unsigned char* p = (unsigned char*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* r = p ? (void*)(p + off) : nullptr;
+    off += rs_align(bytes);
+    return r;
+  };
+  RescoreWs t;
+  t.ptr = (int64_t*)take(sizeof(int64_t) * (size_t)(N + 1));
+  t.hist = (int32_t*)take(sizeof(int32_t) * (size_t)N);
+  t.cursor = (int32_t*)take(sizeof(int32_t) * (size_t)N);
+  t.key = (int32_t*)take(sizeof(int32_t) * (size_t)n);
+  t.perm = (int32_t*)take(sizeof(int32_t) * (size_t)n);
+  t.win_cnt = (int32_t*)take(sizeof(int32_t) * (size_t)n);
+  t.win_idx = (int32_t*)take(sizeof(int32_t) * (size_t)n * kWinMax);
+  t.win_a = (float*)take(sizeof(float) * (size_t)n * kWinMax);
+  if (w) *w = t;
+  return off;
+}
+
 }  // namespace reid
 
 extern "C" {
 
+size_t reid_knn_rescore_workspace_bytes(int64_t N, int64_t n_rows) {
+  if (N < 0 || n_rows < 0) return 0;
+  return reid::rescore_carve(nullptr, N, n_rows, nullptr);
+}
+
 int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, int64_t row_end, const uint64_t* cand,
                      const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists, int k, float err_bound,
-                     int32_t* out_idx, float* out_key, int32_t* uncertified_flag, float* max_err_out, void* stream) {
+                     const float* max_sqnorm, int locality_order, int32_t* out_idx, float* out_key, int32_t* uncertified_flag,
+                     float* max_err_out, void* workspace, void* stream) {
   using namespace reid;
-  REID_CHECK_ARG(x && cand && cand_cnt && row_tau && out_idx && uncertified_flag && max_err_out,
+  REID_CHECK_ARG(x && cand && cand_cnt && row_tau && out_idx && uncertified_flag && max_err_out && workspace,
                  "reid_knn_rescore: NULL pointer");
   REID_CHECK_ARG(N > 0 && D > 0 && 0 <= row_begin && row_begin <= row_end && row_end <= N, "reid_knn_rescore: bad shape");
   REID_CHECK_ARG(n_lists >= 1 && n_lists <= 2 * REID_TC_MAX_SPLITS, "reid_knn_rescore: n_lists=%d (max %d)", n_lists,
@@ -177,10 +288,32 @@ int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, in
   const int64_t n = row_end - row_begin;
   if (n == 0) return REID_OK;
   cudaStream_t st = (cudaStream_t)stream;
+  RescoreWs w;
+  rescore_carve(workspace, N, n, &w);
   REID_CUDA(cudaMemsetAsync(max_err_out, 0, sizeof(float), st));
-  rescore_kernel<<<(unsigned)((n + kRsWarps - 1) / kRsWarps), kRsWarps * 32, 0, st>>>(
-      x, N, D, row_begin, row_end, (const unsigned long long*)cand, cand_cnt, row_tau, n_lists, k, err_bound, out_idx,
-      out_key, uncertified_flag, (unsigned*)max_err_out);
+  if (locality_order) REID_CUDA(cudaMemsetAsync(w.hist, 0, rs_align(sizeof(int32_t) * (size_t)N) * 2, st));  // hist + cursor
+  const unsigned grid = (unsigned)((n + kRsWarps - 1) / kRsWarps);
+  rescore_select_kernel<<<grid, kRsWarps * 32, 0, st>>>(row_begin, n, (const unsigned long long*)cand, cand_cnt, row_tau,
+                                                        n_lists, k, err_bound, max_sqnorm, w.win_cnt, w.win_idx, w.win_a,
+                                                        uncertified_flag, locality_order ? w.key : nullptr, w.hist);
+  REID_LAUNCH_CHECK();
+  if (locality_order) {
+    int rc = reid_scan_counts(w.hist, N, w.ptr, nullptr, stream);
+    if (rc != REID_OK) return rc;
+    order_scatter_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(w.key, n, w.ptr, w.cursor, w.perm);
+    REID_LAUNCH_CHECK();
+  }
+#define REID_RS_LAUNCH(CH)                                                                                          \
+  rescore_exact_kernel<CH><<<grid, kRsWarps * 32, 0, st>>>(x, D, row_begin, n, locality_order ? w.perm : nullptr,     \
+                                                           w.win_cnt, w.win_idx, w.win_a, k, err_bound, max_sqnorm,  \
+                                                           out_idx, out_key, uncertified_flag, (unsigned*)max_err_out)
+  const bool aligned = (((uintptr_t)x) & 15) == 0;
+  if (aligned && D == 2048) REID_RS_LAUNCH(16);
+  else if (aligned && D == 1024) REID_RS_LAUNCH(8);
+  else if (aligned && D == 512) REID_RS_LAUNCH(4);
+  else if (aligned && D == 256) REID_RS_LAUNCH(2);
+  else REID_RS_LAUNCH(0);
+#undef REID_RS_LAUNCH
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

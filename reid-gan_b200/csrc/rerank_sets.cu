@@ -66,11 +66,10 @@ struct ExpandSmem {
   int32_t list[kListCap];
 };
 
-template <bool kWrite>
 __global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(
     const int32_t* __restrict__ rank, int ncols, const uint64_t* __restrict__ Rmask,
-    const uint64_t* __restrict__ Rhmask, int64_t row_begin, int64_t row_end, const int64_t* __restrict__ E_ptr,
-    int32_t* __restrict__ E_cnt, int32_t* __restrict__ E_idx, int* __restrict__ err_flag) {
+    const uint64_t* __restrict__ Rhmask, int64_t row_begin, int64_t row_end, int stride,
+    int32_t* __restrict__ E_pad, int32_t* __restrict__ E_cnt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   ExpandSmem& sm = reinterpret_cast<ExpandSmem*>(smem_raw)[threadIdx.x >> 5];
   const int64_t row = row_begin + (int64_t)blockIdx.x * kExpandWarps + (threadIdx.x >> 5);
@@ -90,6 +89,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(
   }
   __syncwarp();
 
+  bool lost = false;  // the hash set filled up: reported through an impossible count
   auto insert = [&](int32_t g) {
     uint32_t h = hash32((uint32_t)g) & (kSetSlots - 1);
     for (int probe = 0; probe < kSetSlots; ++probe) {
@@ -97,7 +97,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(
       if (old == -1 || old == g) return;
       h = (h + 1) & (kSetSlots - 1);
     }
-    atomicExch(err_flag, 1);
+    lost = true;
   };
 
   // lane <-> candidate c = R(row)[lane (+32)]
@@ -131,21 +131,17 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(
     }
     nE += __popc(b);
   }
-  if (nE > kListCap) {
-    if (lane == 0) atomicExch(err_flag, 2);
-    nE = kListCap;
-  }
-  if (!kWrite) {
-    if (lane == 0) E_cnt[row - row_begin] = nE;
-    return;
-  }
+  const int cap = stride < kListCap ? stride : kListCap;
+  const bool overflow = __any_sync(kFull, lost) || nE > cap;
+  if (nE > cap) nE = cap;
   int n2 = 32;
   while (n2 < nE) n2 <<= 1;
   for (int t = nE + lane; t < n2; t += 32) sm.list[t] = 0x7fffffff;
   __syncwarp();
   warp_bitonic_sort(sm.list, n2);
-  int32_t* dst = E_idx + E_ptr[row - row_begin];
+  int32_t* dst = E_pad + (row - row_begin) * (int64_t)stride;
   for (int t = lane; t < nE; t += 32) dst[t] = sm.list[t];
+  if (lane == 0) E_cnt[row - row_begin] = overflow ? stride + 1 : nE;  // stride + 1 = "did not fit"
 }
 
 }  // namespace reid
@@ -169,43 +165,20 @@ int reid_reciprocal_masks(const int32_t* rank, int64_t N, int ncols, int k, int6
 }
 
 int reid_expand(const int32_t* rank, int64_t N, int ncols, const uint64_t* Rmask, const uint64_t* Rhalf_mask,
-                int64_t row_begin, int64_t row_end, const int64_t* E_ptr, int32_t* E_cnt, int32_t* E_idx,
-                void* stream) {
+                int64_t row_begin, int64_t row_end, int stride, int32_t* E_pad, int32_t* E_cnt, void* stream) {
   using namespace reid;
-  REID_CHECK_ARG(rank && Rmask && Rhalf_mask, "reid_expand: NULL pointer");
+  REID_CHECK_ARG(rank && Rmask && Rhalf_mask && E_pad && E_cnt, "reid_expand: NULL pointer");
   REID_CHECK_ARG(ncols >= 1 && ncols <= REID_MAX_K1, "reid_expand: ncols=%d not in 1..%d", ncols, REID_MAX_K1);
   REID_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= N, "reid_expand: bad row range");
-  REID_CHECK_ARG(E_ptr ? (E_idx != nullptr) : (E_cnt != nullptr), "reid_expand: missing output for this pass");
+  REID_CHECK_ARG(stride >= 1, "reid_expand: stride=%d", stride);
   const int64_t n = row_end - row_begin;
   if (n == 0) return REID_OK;
-  cudaStream_t st = (cudaStream_t)stream;
-  static int* d_flag = nullptr;  // one int, lives for the process
-  if (!d_flag) {
-    REID_CUDA(cudaMalloc(&d_flag, sizeof(int)));
-    REID_CUDA(cudaMemset(d_flag, 0, sizeof(int)));
-  }
   const size_t smem = sizeof(ExpandSmem) * kExpandWarps;
   const unsigned grid = (unsigned)((n + kExpandWarps - 1) / kExpandWarps);
-  if (E_ptr) {
-    REID_CUDA(cudaFuncSetAttribute(expand_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    expand_kernel<true><<<grid, kExpandWarps * 32, smem, st>>>(rank, ncols, Rmask, Rhalf_mask, row_begin, row_end,
-                                                               E_ptr, E_cnt, E_idx, d_flag);
-  } else {
-    REID_CUDA(cudaFuncSetAttribute(expand_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    expand_kernel<false><<<grid, kExpandWarps * 32, smem, st>>>(rank, ncols, Rmask, Rhalf_mask, row_begin, row_end,
-                                                                E_ptr, E_cnt, E_idx, d_flag);
-  }
+  REID_CUDA(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  expand_kernel<<<grid, kExpandWarps * 32, smem, (cudaStream_t)stream>>>(rank, ncols, Rmask, Rhalf_mask, row_begin,
+                                                                         row_end, stride, E_pad, E_cnt);
   REID_LAUNCH_CHECK();
-  if (!E_ptr) {  // the count pass reports capacity errors (one small synchronising copy)
-    int flag = 0;
-    REID_CUDA(cudaMemcpyAsync(&flag, d_flag, sizeof(int), cudaMemcpyDeviceToHost, st));
-    REID_CUDA(cudaStreamSynchronize(st));
-    if (flag) {
-      cudaMemsetAsync(d_flag, 0, sizeof(int), st);
-      set_error("reid_expand: expansion set exceeded kernel capacity (code %d)", flag);
-      return REID_ERR_UNSUPPORTED;
-    }
-  }
   return REID_OK;
 }
 }

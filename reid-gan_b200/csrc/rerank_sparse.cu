@@ -13,10 +13,12 @@ namespace reid {
 constexpr int kVWarps = 8;
 constexpr int kVMaxRow = 1024;  // max |E| per row (expand_kernel caps at the same value)
 
+// kChunks > 0: D == kChunks * 128, the query row is held in registers (see knn_rescore.cu).
+template <int kChunks>
 __global__ void __launch_bounds__(kVWarps * 32) v_weights_kernel(
-    const float* __restrict__ x, int64_t D, const int64_t* __restrict__ E_ptr, const int32_t* __restrict__ E_idx,
-    int64_t row_begin, int64_t row_end, const int32_t* __restrict__ rank_local, const float* __restrict__ key_local,
-    int ncols, float* __restrict__ V_val) {
+    const float* __restrict__ x, int64_t D, const int32_t* __restrict__ E_pad, int stride,
+    const int64_t* __restrict__ E_ptr, int64_t row_begin, int64_t row_end, const int32_t* __restrict__ rank_local,
+    const float* __restrict__ key_local, int ncols, int32_t* __restrict__ E_idx, float* __restrict__ V_val) {
   __shared__ float s_val[kVWarps][kVMaxRow];
   const int w = threadIdx.x >> 5, lane = lane_id();
   const int64_t row = row_begin + (int64_t)blockIdx.x * kVWarps + w;
@@ -27,45 +29,75 @@ __global__ void __launch_bounds__(kVWarps * 32) v_weights_kernel(
   if (n == 0) return;
   const float* xi = x + row * D;
   float* sv = s_val[w];
+  const int32_t* erow = E_pad + lr * (int64_t)stride;   // padded expansion set of this row (sorted)
 
-  for (int e = 0; e < n; ++e) {
-    const int32_t j = E_idx[p0 + e];
-    float s;
-    bool have = false;
-    if (rank_local) {  // harvest the search key when j is one of the row's stored neighbours
-      float kv = 0.f;
-      bool hit = false;
-      for (int r = lane; r < ncols; r += 32)
-        if (rank_local[lr * ncols + r] == j) {
-          hit = true;
-          kv = key_local[lr * ncols + r];
-        }
-      const unsigned b = __ballot_sync(kFull, hit);
-      if (b) {
-        s = __shfl_sync(kFull, kv, __ffs(b) - 1);
-        have = true;
-      }
+  // the row's neighbour list and search keys, two entries per lane (ncols <= 64)
+  int32_t rk0 = -1, rk1 = -1;
+  float kv0 = 0.f, kv1 = 0.f;
+  if (rank_local) {
+    if (lane < ncols) {
+      rk0 = rank_local[lr * ncols + lane];
+      kv0 = key_local[lr * ncols + lane];
     }
-    if (!have) {
-      const float* xj = x + (int64_t)j * D;
-      double acc = 0.0;
-      if ((D & 3) == 0) {
-        const float4* a4 = reinterpret_cast<const float4*>(xi);
-        const float4* b4 = reinterpret_cast<const float4*>(xj);
-        for (int64_t d = lane; d < (D >> 2); d += 32) {
-          const float4 a = a4[d], b = b4[d];
-          acc = fma((double)a.x, (double)b.x, acc);
-          acc = fma((double)a.y, (double)b.y, acc);
-          acc = fma((double)a.z, (double)b.z, acc);
-          acc = fma((double)a.w, (double)b.w, acc);
-        }
+    if (lane + 32 < ncols) {
+      rk1 = rank_local[lr * ncols + lane + 32];
+      kv1 = key_local[lr * ncols + lane + 32];
+    }
+  }
+  constexpr int kRegs = kChunks > 0 ? kChunks : 1;
+  float4 q[kRegs];
+  bool q_loaded = false;
+
+  for (int e0 = 0; e0 < n; e0 += 32) {
+    const int e = e0 + lane;
+    const int32_t mine = e < n ? erow[e] : -1;
+    if (e < n) E_idx[p0 + e] = mine;                      // compacted into the CSR on the way
+    const int m = min(32, n - e0);
+    for (int u = 0; u < m; ++u) {
+      const int32_t j = __shfl_sync(kFull, mine, u);
+      // reuse the search key when j is one of the row's stored neighbours
+      const unsigned b0 = __ballot_sync(kFull, rk0 == j), b1 = __ballot_sync(kFull, rk1 == j);
+      float s;
+      if (b0) {
+        s = __shfl_sync(kFull, kv0, __ffs(b0) - 1);
+      } else if (b1) {
+        s = __shfl_sync(kFull, kv1, __ffs(b1) - 1);
       } else {
-        for (int64_t d = lane; d < D; d += 32) acc = fma((double)xi[d], (double)xj[d], acc);
+        const float* xj = x + (int64_t)j * D;
+        double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+        if (kChunks > 0) {
+          if (!q_loaded) {
+#pragma unroll
+            for (int c = 0; c < kRegs; ++c) q[c] = reinterpret_cast<const float4*>(xi)[c * 32 + lane];
+            q_loaded = true;
+          }
+          float4 r[kRegs];
+#pragma unroll
+          for (int c = 0; c < kRegs; ++c) r[c] = reinterpret_cast<const float4*>(xj)[c * 32 + lane];
+#pragma unroll
+          for (int c = 0; c < kRegs; ++c) {
+            acc0 = fma((double)q[c].x, (double)r[c].x, acc0);
+            acc1 = fma((double)q[c].y, (double)r[c].y, acc1);
+            acc2 = fma((double)q[c].z, (double)r[c].z, acc2);
+            acc3 = fma((double)q[c].w, (double)r[c].w, acc3);
+          }
+        } else if ((D & 3) == 0) {
+          const float4* a4 = reinterpret_cast<const float4*>(xi);
+          const float4* b4 = reinterpret_cast<const float4*>(xj);
+          for (int64_t d = lane; d < (D >> 2); d += 32) {
+            const float4 a = a4[d], r = b4[d];
+            acc0 = fma((double)a.x, (double)r.x, acc0);
+            acc1 = fma((double)a.y, (double)r.y, acc1);
+            acc2 = fma((double)a.z, (double)r.z, acc2);
+            acc3 = fma((double)a.w, (double)r.w, acc3);
+          }
+        } else {
+          for (int64_t d = lane; d < D; d += 32) acc0 = fma((double)xi[d], (double)xj[d], acc0);
+        }
+        s = (float)warp_sum((acc0 + acc1) + (acc2 + acc3));
       }
-      acc = warp_sum(acc);
-      s = (float)acc;
+      if (lane == 0) sv[e0 + u] = s;
     }
-    if (lane == 0) sv[e] = s;
   }
   __syncwarp();
   // softmax(-dist), dist = 2 - 2 s
@@ -117,12 +149,10 @@ __device__ __forceinline__ void warp_bitonic_sort_kv(uint32_t* key, float* val, 
   }
 }
 
-template <bool kWrite>
 __global__ void __launch_bounds__(kQWarps * 32) query_expand_kernel(
     const int32_t* __restrict__ rank, int ncols, int k2, int k2p_log2, const int64_t* __restrict__ V_ptr,
     const int32_t* __restrict__ V_idx, const float* __restrict__ V_val, int cap, int64_t row_begin, int64_t row_end,
-    const int64_t* __restrict__ Q_ptr, int32_t* __restrict__ Q_cnt, int32_t* __restrict__ Q_idx,
-    float* __restrict__ Q_val) {
+    int32_t* __restrict__ Q_cnt, int32_t* __restrict__ Q_idx, float* __restrict__ Q_val) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = lane_id();
   uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)w * cap;
@@ -151,7 +181,7 @@ __global__ void __launch_bounds__(kQWarps * 32) query_expand_kernel(
   warp_bitonic_sort_kv(key, val, n2);
 
   const float k2f = (float)k2;
-  int64_t out = kWrite ? Q_ptr[row - row_begin] : 0;
+  int64_t out = (row - row_begin) * (int64_t)cap;   // padded output: `cap` slots per row
   int total = 0;
   for (int base = 0; base < n; base += 32) {
     const int t = base + lane;
@@ -162,7 +192,7 @@ __global__ void __launch_bounds__(kQWarps * 32) query_expand_kernel(
       head = (t == 0) || ((key[t - 1] >> k2p_log2) != col);
     }
     const unsigned b = __ballot_sync(kFull, head);
-    if (kWrite && head) {
+    if (head) {
       float acc = val[t];
       for (int u = t + 1; u < n && (key[u] >> k2p_log2) == col; ++u) acc = __fadd_rn(acc, val[u]);
       const int64_t p = out + __popc(b & ((1u << lane) - 1u));
@@ -172,7 +202,23 @@ __global__ void __launch_bounds__(kQWarps * 32) query_expand_kernel(
     out += __popc(b);
     total += __popc(b);
   }
-  if (!kWrite && lane == 0) Q_cnt[row - row_begin] = total;
+  if (lane == 0) Q_cnt[row - row_begin] = total;
+}
+
+// padded rows (stride slots, cnt valid) -> CSR at ptr
+__global__ void __launch_bounds__(256) csr_compact_kernel(const int32_t* __restrict__ pad_idx,
+                                                          const float* __restrict__ pad_val, int64_t stride,
+                                                          const int32_t* __restrict__ cnt,
+                                                          const int64_t* __restrict__ ptr, int64_t n_rows,
+                                                          int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int c = cnt[row];
+  const int64_t src = row * stride, dst = ptr[row];
+  for (int t = lane_id(); t < c; t += 32) {
+    out_idx[dst + t] = pad_idx[src + t];
+    out_val[dst + t] = pad_val[src + t];
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -250,51 +296,70 @@ __global__ void __launch_bounds__(kColSortWarps * 32) col_sort_kernel(const int6
 
 extern "C" {
 
-int reid_v_weights(const float* x, int64_t N, int64_t D, const int64_t* E_ptr, const int32_t* E_idx,
+int reid_v_weights(const float* x, int64_t N, int64_t D, const int32_t* E_pad, int stride, const int64_t* E_ptr,
                    int64_t row_begin, int64_t row_end, const int32_t* rank_local, const float* rank_key_local,
-                   int ncols, float* V_val, void* stream) {
+                   int ncols, int32_t* E_idx, float* V_val, void* stream) {
   using namespace reid;
-  REID_CHECK_ARG(x && E_ptr && E_idx && V_val, "reid_v_weights: NULL pointer");
-  REID_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= N && D > 0, "reid_v_weights: bad shape");
+  REID_CHECK_ARG(x && E_pad && E_ptr && E_idx && V_val, "reid_v_weights: NULL pointer");
+  REID_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= N && D > 0 && stride >= 1,
+                 "reid_v_weights: bad shape");
+  REID_CHECK_ARG(stride <= kVMaxRow, "reid_v_weights: stride=%d exceeds %d", stride, kVMaxRow);
   REID_CHECK_ARG((rank_local == nullptr) == (rank_key_local == nullptr), "reid_v_weights: rank and keys go together");
   const int64_t n = row_end - row_begin;
   if (n == 0) return REID_OK;
-  v_weights_kernel<<<(unsigned)((n + kVWarps - 1) / kVWarps), kVWarps * 32, 0, (cudaStream_t)stream>>>(
-      x, D, E_ptr, E_idx, row_begin, row_end, rank_local, rank_key_local, ncols, V_val);
+#define REID_V_LAUNCH(CH)                                                                                          \
+  v_weights_kernel<CH><<<(unsigned)((n + kVWarps - 1) / kVWarps), kVWarps * 32, 0, (cudaStream_t)stream>>>(          \
+      x, D, E_pad, stride, E_ptr, row_begin, row_end, rank_local, rank_key_local, ncols, E_idx, V_val)
+  const bool aligned = (((uintptr_t)x) & 15) == 0;
+  if (aligned && D == 2048) REID_V_LAUNCH(16);
+  else if (aligned && D == 1024) REID_V_LAUNCH(8);
+  else if (aligned && D == 512) REID_V_LAUNCH(4);
+  else if (aligned && D == 256) REID_V_LAUNCH(2);
+  else REID_V_LAUNCH(0);
+#undef REID_V_LAUNCH
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
 
+int reid_query_expand_stride(int k2, int max_row_nnz) {
+  int cap = 32;
+  while (cap < k2 * max_row_nnz) cap <<= 1;
+  return cap;
+}
+
 int reid_query_expand(const int32_t* rank, int64_t N, int ncols, int k2, const int64_t* V_ptr, const int32_t* V_idx,
-                      const float* V_val, int max_row_nnz, int64_t row_begin, int64_t row_end, const int64_t* Q_ptr,
-                      int32_t* Q_cnt, int32_t* Q_idx, float* Q_val, void* stream) {
+                      const float* V_val, int max_row_nnz, int64_t row_begin, int64_t row_end, int32_t* Q_cnt,
+                      int32_t* Q_pad_idx, float* Q_pad_val, void* stream) {
   using namespace reid;
-  REID_CHECK_ARG(rank && V_ptr && V_idx && V_val, "reid_query_expand: NULL pointer");
+  REID_CHECK_ARG(rank && V_ptr && V_idx && V_val && Q_cnt && Q_pad_idx && Q_pad_val, "reid_query_expand: NULL pointer");
   REID_CHECK_ARG(k2 >= 1 && k2 <= ncols && ncols <= REID_MAX_K1, "reid_query_expand: k2=%d ncols=%d", k2, ncols);
   REID_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= N, "reid_query_expand: bad row range");
-  REID_CHECK_ARG(Q_ptr ? (Q_idx && Q_val) : (Q_cnt != nullptr), "reid_query_expand: missing output for this pass");
   REID_CHECK_ARG(max_row_nnz >= 1, "reid_query_expand: max_row_nnz=%d", max_row_nnz);
   int k2p_log2 = 0;
   while ((1 << k2p_log2) < k2) ++k2p_log2;
   REID_CHECK_ARG(((uint64_t)N << k2p_log2) < 0xffffffffull, "reid_query_expand: N * k2 exceeds the 32-bit sort key");
-  int cap = 32;
-  while (cap < k2 * max_row_nnz) cap <<= 1;
+  const int cap = reid_query_expand_stride(k2, max_row_nnz);
   const size_t smem = (size_t)kQWarps * cap * 8;
   REID_CHECK_ARG(smem <= 200 * 1024, "reid_query_expand: k2 * max_row_nnz = %d needs %zu B of shared memory",
                  k2 * max_row_nnz, smem);
   const int64_t n = row_end - row_begin;
   if (n == 0) return REID_OK;
   const unsigned grid = (unsigned)((n + kQWarps - 1) / kQWarps);
-  cudaStream_t st = (cudaStream_t)stream;
-  if (Q_ptr) {
-    REID_CUDA(cudaFuncSetAttribute(query_expand_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    query_expand_kernel<true><<<grid, kQWarps * 32, smem, st>>>(rank, ncols, k2, k2p_log2, V_ptr, V_idx, V_val, cap,
-                                                                row_begin, row_end, Q_ptr, Q_cnt, Q_idx, Q_val);
-  } else {
-    REID_CUDA(cudaFuncSetAttribute(query_expand_kernel<false>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-    query_expand_kernel<false><<<grid, kQWarps * 32, smem, st>>>(rank, ncols, k2, k2p_log2, V_ptr, V_idx, V_val, cap,
-                                                                 row_begin, row_end, Q_ptr, Q_cnt, Q_idx, Q_val);
-  }
+  REID_CUDA(cudaFuncSetAttribute(query_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  query_expand_kernel<<<grid, kQWarps * 32, smem, (cudaStream_t)stream>>>(
+      rank, ncols, k2, k2p_log2, V_ptr, V_idx, V_val, cap, row_begin, row_end, Q_cnt, Q_pad_idx, Q_pad_val);
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+
+int reid_csr_compact(const int32_t* pad_idx, const float* pad_val, int64_t stride, const int32_t* cnt,
+                     const int64_t* ptr, int64_t n_rows, int32_t* out_idx, float* out_val, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(pad_idx && pad_val && cnt && ptr && out_idx && out_val && stride >= 1 && n_rows >= 0,
+                 "reid_csr_compact: bad arguments");
+  if (n_rows == 0) return REID_OK;
+  csr_compact_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(pad_idx, pad_val, stride, cnt, ptr,
+                                                                                    n_rows, out_idx, out_val);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

@@ -149,30 +149,35 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None):
     st.R_mask, st.Rh_mask = R, Rh
     mark("reciprocal")
     # a3 ------------------------------------------------------------------
+    e_stride = min(k1 + k1 * (h + 1), 1024)                  # |E| <= |R| + |R| * |R_half|
+    e_pad = torch.empty(max(n, 1) * e_stride, dtype=torch.int32, device=dev)
     e_cnt = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-    call("reid_expand", ptr(rank), N, k1, ptr(R), ptr(Rh), r0, r1, None, ptr(e_cnt), None, sp)
+    call("reid_expand", ptr(rank), N, k1, ptr(R), ptr(Rh), r0, r1, e_stride, ptr(e_pad), ptr(e_cnt), sp)
     e_ptr, e_total, e_max = _scan(e_cnt, n, dev)
-    e_idx = torch.empty(max(e_total, 1), dtype=torch.int32, device=dev)
-    call("reid_expand", ptr(rank), N, k1, ptr(R), ptr(Rh), r0, r1, ptr(e_ptr), None, ptr(e_idx), sp)
+    if e_max > e_stride:
+        raise RuntimeError("reid_expand: an expansion set exceeded %d entries" % e_stride)
     mark("expand")
     # a4 ------------------------------------------------------------------
+    e_idx = torch.empty(max(e_total, 1), dtype=torch.int32, device=dev)
     v_val = torch.empty(max(e_total, 1), dtype=torch.float32, device=dev)
-    call("reid_v_weights", ptr(x), N, D, ptr(e_ptr), ptr(e_idx), r0, r1, ptr(rank_local), ptr(key_local), k1,
-         ptr(v_val), sp)
+    call("reid_v_weights", ptr(x), N, D, ptr(e_pad), e_stride, ptr(e_ptr), r0, r1, ptr(rank_local), ptr(key_local),
+         k1, ptr(e_idx), ptr(v_val), sp)
     mark("v_weights")
     if comm is not None:                                     # V rows of other shards are read by a5
         e_ptr, e_idx, v_val, e_total, e_max = comm.gather_csr(e_cnt[:n], e_idx[:e_total], v_val[:e_total])
     st.E_ptr, st.E_idx, st.V_val = e_ptr, e_idx, v_val       # global CSR when sharded
     # a5 ------------------------------------------------------------------
     if k2 != 1:
+        q_stride = L.reid_query_expand_stride(k2, max(e_max, 1))
         q_cnt = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+        qp_idx = torch.empty(max(n, 1) * q_stride, dtype=torch.int32, device=dev)
+        qp_val = torch.empty(max(n, 1) * q_stride, dtype=torch.float32, device=dev)
         call("reid_query_expand", ptr(rank), N, k1, k2, ptr(e_ptr), ptr(e_idx), ptr(v_val), max(e_max, 1), r0, r1,
-             None, ptr(q_cnt), None, None, sp)
+             ptr(q_cnt), ptr(qp_idx), ptr(qp_val), sp)
         q_ptr, q_total, _ = _scan(q_cnt, n, dev)
         q_idx = torch.empty(max(q_total, 1), dtype=torch.int32, device=dev)
         q_val = torch.empty(max(q_total, 1), dtype=torch.float32, device=dev)
-        call("reid_query_expand", ptr(rank), N, k1, k2, ptr(e_ptr), ptr(e_idx), ptr(v_val), max(e_max, 1), r0, r1,
-             ptr(q_ptr), None, ptr(q_idx), ptr(q_val), sp)
+        call("reid_csr_compact", ptr(qp_idx), ptr(qp_val), q_stride, ptr(q_cnt), ptr(q_ptr), n, ptr(q_idx), ptr(q_val), sp)
         if comm is not None:
             q_ptr, q_idx, q_val, q_total, _ = comm.gather_csr(q_cnt[:n], q_idx[:q_total], q_val[:q_total])
     else:                                                    # faiss_rerank.py:89: skipped when k2 == 1

@@ -16,6 +16,7 @@ TC_CAP = 512
 KEEP_MAX = 64
 SCALE_LOG2 = 4          # features are scaled by 2^4 before rounding to fp16 (keeps them out of the subnormals)
 CTA_GROUP = int(__import__("os").environ.get("REID_TC_CTA_GROUP", "2"))   # 2 = CTA pairs (tcgen05 cta_group::2)
+ORDER_ROWS = __import__("os").environ.get("REID_RESCORE_ORDER", "1") != "0"   # cluster-locality visiting order
 SLACK = 34              # K = k + SLACK candidates are kept per (row, column range)
 
 
@@ -48,13 +49,12 @@ def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None):
     cand_cnt = torch.zeros(n * n_lists, dtype=torch.int32, device=dev)
     row_tau = torch.empty(n, dtype=torch.int32, device=dev)
     call("reid_knn_candidates_tc", ptr(xh), N, D, SCALE_LOG2, r0, r1, keep, s, CTA_GROUP, ptr(cand), ptr(cand_cnt), ptr(row_tau), sp)
-    if max_sqnorm is None:
-        max_sqnorm = float(msq.item())                     # one scalar read-back, after the GEMM is queued
-    eps = err_bound(max_sqnorm)
+    eps = err_bound(max_sqnorm) if max_sqnorm is not None else 0.0   # else derived on device from msq
     flag = torch.empty(n, dtype=torch.int32, device=dev)
     max_err = torch.zeros(1, dtype=torch.float32, device=dev)
-    call("reid_knn_rescore", ptr(x), N, D, r0, r1, ptr(cand), ptr(cand_cnt), ptr(row_tau), n_lists, k, eps, ptr(idx), ptr(key),
-                             ptr(flag), ptr(max_err), sp)
+    ws = torch.empty(L.reid_knn_rescore_workspace_bytes(N, n), dtype=torch.uint8, device=dev)
+    call("reid_knn_rescore", ptr(x), N, D, r0, r1, ptr(cand), ptr(cand_cnt), ptr(row_tau), n_lists, k, eps,
+         ptr(msq), 1 if ORDER_ROWS else 0, ptr(idx), ptr(key), ptr(flag), ptr(max_err), ptr(ws), sp)
     bad = torch.nonzero(flag).flatten().to(torch.int32)
     n_bad = bad.numel()
     if n_bad:
@@ -64,6 +64,6 @@ def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None):
         _knn_exact_rows(x, k, rows, 0, n_bad, bi, bk)
         idx[bad.long()] = bi
         key[bad.long()] = bk
-    info.update(mode="tc", cta_group=CTA_GROUP, n_splits=s, keep=keep, err_bound=eps, uncertified_rows=int(n_bad),
+    info.update(mode="tc", cta_group=CTA_GROUP, n_splits=s, keep=keep, err_bound=eps if msq is None else None, max_sqnorm=msq, uncertified_rows=int(n_bad),
                 max_abs_err=max_err, xh=xh)
     return idx, key, info

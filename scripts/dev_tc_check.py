@@ -12,8 +12,8 @@ def run(N, D, n_ids, k, noise=0.8, seed=0):
     t = time.time(); ie, ke, _ = fr.knn_search(xd, k, "exact"); torch.cuda.synchronize(); te = time.time() - t
     t = time.time(); it, kt, info = fr.knn_search(xd, k, "tc"); torch.cuda.synchronize(); tt = time.time() - t
     same = bool(torch.equal(ie, it)); samek = bool(torch.equal(ke, kt))
-    print("N=%d D=%d k=%d: idx equal %s, keys equal %s, uncertified %d/%d, splits %d keep %d, eps %.2e, max_err %.3e, exact %.3fs tc %.3fs"
-          % (N, D, k, same, samek, info["uncertified_rows"], N, info["n_splits"], info["keep"], info["err_bound"],
+    print("N=%d D=%d k=%d: idx equal %s, keys equal %s, uncertified %d/%d, splits %d keep %d, max_err %.3e, exact %.3fs tc %.3fs"
+          % (N, D, k, same, samek, info["uncertified_rows"], N, info["n_splits"], info["keep"],
              float(info["max_abs_err"]), te, tt), flush=True)
     if not same:
         bad = torch.nonzero((ie != it).any(dim=1)).flatten()
