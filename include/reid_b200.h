@@ -141,6 +141,10 @@ int reid_query_expand(const int32_t* rank, int64_t N, int ncols, int k2, const i
 int reid_csr_compact(const int32_t* pad_idx, const float* pad_val, int64_t stride, const int32_t* cnt,
                      const int64_t* ptr, int64_t n_rows, int32_t* out_idx, float* out_val, void* stream);
 
+/* neighbour lists kept in upper-bound slots (reid_jaccard_neighbors) -> packed at ptr (before an all-gather) */
+int reid_lists_compact(const int64_t* slot_ptr, const int32_t* idx, const int32_t* cnt, const int64_t* ptr,
+                       int64_t n_rows, int32_t* out, void* stream);
+
 /* ---- a6: inverted index  (faiss_rerank.py:98-100) -------------------------------
  * CSC of a CSR with n_rows x n_cols; column lists sorted by row.
  * Step 1 writes col_cnt; caller scans it into C_ptr; step 2 fills.  cursor: n_cols int32 scratch. */

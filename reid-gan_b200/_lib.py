@@ -43,6 +43,7 @@ SIGNATURES = {
     "reid_query_expand_stride": (_I, [_I, _I]),
     "reid_query_expand": (_I, [_P, _L, _I, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P]),
     "reid_csr_compact": (_I, [_P, _P, _L, _P, _P, _L, _P, _P, _P]),
+    "reid_lists_compact": (_I, [_P, _P, _P, _P, _L, _P, _P]),
     "reid_transpose_count": (_I, [_P, _L, _L, _P, _P]),
     "reid_transpose_fill": (_I, [_P, _P, _P, _L, _L, _P, _P, _P, _P, _P]),
     "reid_jaccard_bounds": (_I, [_P, _P, _P, _L, _L, _P, _P]),

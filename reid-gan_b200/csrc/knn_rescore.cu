@@ -155,15 +155,20 @@ __global__ void order_scatter_kernel(const int32_t* __restrict__ key, int64_t n_
 // ---- stage 2: exact keys of the window members, audit, final order --------------------------------
 // HBM bound: ~36 feature rows of 4*D bytes per query row.  Rows are visited in `perm` order so that
 // the rows of one identity cluster, which share most candidates, run back to back and hit in L2.
-// kChunks > 0: D == kChunks * 128 and the query row lives in registers (one float4 per lane and chunk), so
-// each candidate costs one pass over ITS row only; kChunks == 0: generic D, both rows are streamed.
+// kChunks > 0: D == kChunks * 128.  The query row is parked in shared memory (one float4 per lane and chunk,
+// conflict-free), candidate rows are streamed half a row at a time through two register buffers so that the
+// loads of the next half are in flight while the current one is multiplied and reduced (the kernel is
+// latency bound: ~36 dependent gathers per query row).  kChunks == 0: generic D, both rows are streamed.
 template <int kChunks>
 __global__ void __launch_bounds__(kRsWarps * 32) rescore_exact_kernel(
     const float* __restrict__ x, int64_t D, int64_t row_begin, int64_t n_rows, const int32_t* __restrict__ perm,
     const int32_t* __restrict__ win_cnt, const int32_t* __restrict__ win_idx, const float* __restrict__ win_a, int k,
     float eps_in, const float* __restrict__ max_sqnorm, int32_t* __restrict__ out_idx, float* __restrict__ out_key,
     int32_t* __restrict__ uncert, unsigned* __restrict__ max_err_bits) {
+  constexpr int kQ = kChunks > 0 ? kChunks : 1;
+  constexpr int kH = kChunks > 1 ? kChunks / 2 : 1;
   __shared__ uint64_t s_key[kRsWarps][kWinMax];
+  __shared__ float4 s_q[kRsWarps][kQ * 32];
   const int w = threadIdx.x >> 5, lane = lane_id();
   const int64_t slot = (int64_t)blockIdx.x * kRsWarps + w;
   if (slot >= n_rows) return;
@@ -173,45 +178,72 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_exact_kernel(
   const float eps = max_sqnorm ? reid_tc_err_bound(*max_sqnorm) : eps_in;
   const int n_w = win_cnt[lr];
   const float* xi = x + row * D;
-  constexpr int kRegs = kChunks > 0 ? kChunks : 1;
-  float4 q[kRegs];
-  if (kChunks > 0) {
-#pragma unroll
-    for (int c = 0; c < kRegs; ++c) q[c] = reinterpret_cast<const float4*>(xi)[c * 32 + lane];
-  }
+  const int32_t* wj = win_idx + lr * kWinMax;
   float worst = 0.f;
-  for (int wi = 0; wi < n_w; ++wi) {
-    const int32_t j = win_idx[lr * kWinMax + wi];
-    const float* xj = x + (int64_t)j * D;
-    double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
-    if (kChunks > 0) {
-      float4 r[kRegs];
+
+  if (kChunks > 1) {
+    float4* q = s_q[w];
 #pragma unroll
-      for (int c = 0; c < kRegs; ++c) r[c] = reinterpret_cast<const float4*>(xj)[c * 32 + lane];
+    for (int c = 0; c < kQ; ++c) q[c * 32 + lane] = reinterpret_cast<const float4*>(xi)[c * 32 + lane];
+    float4 ra[kH], rb[kH];
+    if (n_w > 0) {
+      const float4* xj = reinterpret_cast<const float4*>(x + (int64_t)wj[0] * D);
 #pragma unroll
-      for (int c = 0; c < kRegs; ++c) {
-        acc0 = fma((double)q[c].x, (double)r[c].x, acc0);
-        acc1 = fma((double)q[c].y, (double)r[c].y, acc1);
-        acc2 = fma((double)q[c].z, (double)r[c].z, acc2);
-        acc3 = fma((double)q[c].w, (double)r[c].w, acc3);
-      }
-    } else if ((D & 3) == 0) {
-      const float4* a4 = reinterpret_cast<const float4*>(xi);
-      const float4* b4 = reinterpret_cast<const float4*>(xj);
-      for (int64_t d = lane; d < (D >> 2); d += 32) {
-        const float4 p = a4[d], r = b4[d];
-        acc0 = fma((double)p.x, (double)r.x, acc0);
-        acc1 = fma((double)p.y, (double)r.y, acc1);
-        acc2 = fma((double)p.z, (double)r.z, acc2);
-        acc3 = fma((double)p.w, (double)r.w, acc3);
-      }
-    } else {
-      for (int64_t d = lane; d < D; d += 32) acc0 = fma((double)xi[d], (double)xj[d], acc0);
+      for (int c = 0; c < kH; ++c) ra[c] = xj[c * 32 + lane];
     }
-    const double acc = warp_sum((acc0 + acc1) + (acc2 + acc3));
-    const float s = (float)acc;
-    worst = fmaxf(worst, fabsf(s - win_a[lr * kWinMax + wi]));
-    if (lane == 0) key[wi] = sel_key(s, j);
+    for (int wi = 0; wi < n_w; ++wi) {
+      const int32_t j = wj[wi];
+      const float4* xj = reinterpret_cast<const float4*>(x + (int64_t)j * D);
+#pragma unroll
+      for (int c = 0; c < kH; ++c) rb[c] = xj[(kH + c) * 32 + lane];
+      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+#pragma unroll
+      for (int c = 0; c < kH; ++c) {
+        const float4 qq = q[c * 32 + lane];
+        acc0 = fma((double)qq.x, (double)ra[c].x, acc0);
+        acc1 = fma((double)qq.y, (double)ra[c].y, acc1);
+        acc2 = fma((double)qq.z, (double)ra[c].z, acc2);
+        acc3 = fma((double)qq.w, (double)ra[c].w, acc3);
+      }
+      if (wi + 1 < n_w) {
+        const float4* xn = reinterpret_cast<const float4*>(x + (int64_t)wj[wi + 1] * D);
+#pragma unroll
+        for (int c = 0; c < kH; ++c) ra[c] = xn[c * 32 + lane];
+      }
+#pragma unroll
+      for (int c = 0; c < kH; ++c) {
+        const float4 qq = q[(kH + c) * 32 + lane];
+        acc0 = fma((double)qq.x, (double)rb[c].x, acc0);
+        acc1 = fma((double)qq.y, (double)rb[c].y, acc1);
+        acc2 = fma((double)qq.z, (double)rb[c].z, acc2);
+        acc3 = fma((double)qq.w, (double)rb[c].w, acc3);
+      }
+      const float s = (float)warp_sum((acc0 + acc1) + (acc2 + acc3));
+      worst = fmaxf(worst, fabsf(s - win_a[lr * kWinMax + wi]));
+      if (lane == 0) key[wi] = sel_key(s, j);
+    }
+  } else {
+    for (int wi = 0; wi < n_w; ++wi) {
+      const int32_t j = wj[wi];
+      const float* xj = x + (int64_t)j * D;
+      double acc0 = 0.0, acc1 = 0.0, acc2 = 0.0, acc3 = 0.0;
+      if ((D & 3) == 0 && ((((uintptr_t)x) & 15) == 0)) {
+        const float4* a4 = reinterpret_cast<const float4*>(xi);
+        const float4* b4 = reinterpret_cast<const float4*>(xj);
+        for (int64_t d = lane; d < (D >> 2); d += 32) {
+          const float4 p = a4[d], r = b4[d];
+          acc0 = fma((double)p.x, (double)r.x, acc0);
+          acc1 = fma((double)p.y, (double)r.y, acc1);
+          acc2 = fma((double)p.z, (double)r.z, acc2);
+          acc3 = fma((double)p.w, (double)r.w, acc3);
+        }
+      } else {
+        for (int64_t d = lane; d < D; d += 32) acc0 = fma((double)xi[d], (double)xj[d], acc0);
+      }
+      const float s = (float)warp_sum((acc0 + acc1) + (acc2 + acc3));
+      worst = fmaxf(worst, fabsf(s - win_a[lr * kWinMax + wi]));
+      if (lane == 0) key[wi] = sel_key(s, j);
+    }
   }
   __syncwarp();
   if (lane == 0) {

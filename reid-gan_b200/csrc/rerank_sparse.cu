@@ -221,6 +221,19 @@ __global__ void __launch_bounds__(256) csr_compact_kernel(const int32_t* __restr
   }
 }
 
+// lists in upper-bound slots (slot_ptr, cnt) -> packed at ptr (indices only)
+__global__ void __launch_bounds__(256) lists_compact_kernel(const int64_t* __restrict__ slot_ptr,
+                                                            const int32_t* __restrict__ idx,
+                                                            const int32_t* __restrict__ cnt,
+                                                            const int64_t* __restrict__ ptr, int64_t n_rows,
+                                                            int32_t* __restrict__ out) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows) return;
+  const int c = cnt[row];
+  const int64_t src = slot_ptr[row], dst = ptr[row];
+  for (int t = lane_id(); t < c; t += 32) out[dst + t] = idx[src + t];
+}
+
 // ---------------------------------------------------------------------------------------
 // a6: CSR -> CSC.  Column histogram, (caller scans), atomic-cursor scatter, then each
 // column list is sorted by row so the result does not depend on scheduling.
@@ -360,6 +373,17 @@ int reid_csr_compact(const int32_t* pad_idx, const float* pad_val, int64_t strid
   if (n_rows == 0) return REID_OK;
   csr_compact_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(pad_idx, pad_val, stride, cnt, ptr,
                                                                                     n_rows, out_idx, out_val);
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+
+int reid_lists_compact(const int64_t* slot_ptr, const int32_t* idx, const int32_t* cnt, const int64_t* ptr,
+                       int64_t n_rows, int32_t* out, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(slot_ptr && idx && cnt && ptr && out && n_rows >= 0, "reid_lists_compact: bad arguments");
+  if (n_rows == 0) return REID_OK;
+  lists_compact_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(slot_ptr, idx, cnt, ptr, n_rows,
+                                                                                      out);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
