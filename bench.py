@@ -154,6 +154,81 @@ def run_reference(args):
     print(json.dumps(out))
 
 
+
+# ------------------------------------------------------------------ per-stage roofline -------
+def stage_rooflines(out, W, prof, steps, peaks, world):
+    """algorithmic bytes (or flops) of every stage, counted from THIS run's sparse structures,
+    over the stage's CUDA-event time inside the timed region.  Stages that are not the dominant kernel are
+    gather / scan / sparse work: the bound is HBM bandwidth; several work out of L2 at this N (flagged)."""
+    import torch
+    st = out["state"]
+    N, D, k1, k2 = st.N, st.D, st.k1, st.k2
+    n = st.row_end - st.row_begin
+    from reid_gan_b200.faiss_rerank import half_k
+    h = half_k(k1)
+    dev = st.rank.device
+
+    def popc(m):
+        m = m.clone()
+        c = torch.zeros_like(m)
+        for _ in range(64):
+            c += m & 1
+            m >>= 1
+        return c
+
+    r_cnt, rh_cnt = popc(st.R_mask[:n]), popc(st.Rh_mask)
+    sum_R, sum_Rh = int(r_cnt.sum()), int(rh_cnt[st.row_begin:st.row_end].sum())
+    e_cnt = (st.E_ptr[1:] - st.E_ptr[:-1])
+    sum_E = int(e_cnt[st.row_begin:st.row_end].sum()) if e_cnt.numel() == N else int(e_cnt.sum())
+    rank_local = st.rank[st.row_begin:st.row_end].long()
+    # sum_i sum_{c in R(i)} |R_half(c)|  (R(i) as bit positions into rank[i,:])
+    bits = ((st.R_mask[:n].unsqueeze(1) >> torch.arange(k1, device=dev)) & 1).bool()
+    sum_RRh = int((rh_cnt[rank_local] * bits).sum())
+    e_all = e_cnt if e_cnt.numel() == N else None
+    sum_qe_in = int(e_all[rank_local[:, :k2]].sum()) if (e_all is not None and k2 != 1) else 0
+    nnz_q = int(st.q_total)
+    q_cnt = st.Q_ptr[1:] - st.Q_ptr[:-1]
+    nnz_q_local = int(q_cnt[st.row_begin:st.row_end].sum())
+    col_cnt = st.C_ptr[1:] - st.C_ptr[:-1]
+    qa, qb = int(st.Q_ptr[st.row_begin]), int(st.Q_ptr[st.row_end])
+    T = int(col_cnt[st.Q_idx[qa:qb].long()].sum())
+    edges = int(out["nbr_cnt"].sum()) if "nbr_cnt" in out else 0
+    win = out["state"].knn_info.get("window_total")
+    win = int(win) if win is not None else n * k1
+    hbm = peaks["hbm_gbs"]
+
+    def ms(*names):
+        return sum(prof[nm][1] for nm in names if nm in prof) / steps
+
+    rows = [
+        ("features_to_half", ("reid_features_to_half",), 6.0 * N * D, "4ND read + 2ND write"),
+        ("K2 re-score", ("reid_knn_rescore",), 4.0 * D * (win + n) + 4.0 * n * k1,
+         "4D*(window members + rows) + 4*rows*k1; window total %d (%.1f/row)" % (win, win / max(n, 1))),
+        ("K3 reciprocal+expand", ("reid_reciprocal_masks", "reid_expand"),
+         4.0 * (n * k1 * k1 + N * (h + 1) * (h + 1) + sum_RRh + sum_R + sum_Rh + sum_E),
+         "4*[rows*k1^2 + N*(h+1)^2 + sum|R_half(c)| over c in R(i) + sum|R| + sum|R_half| + sum|E|]; L2-resident"),
+        ("K4 V weights", ("reid_v_weights",), 4.0 * D * (n + sum_E) + 8.0 * sum_E,
+         "4D*(rows + sum|E|) + 8*sum|E| (SURVEY formula; the kernel re-uses search keys and gathers less)"),
+        ("K5 query expansion", ("reid_query_expand", "reid_csr_compact"), 8.0 * (sum_qe_in + nnz_q_local),
+         "8*(sum_i sum_{r<k2}|E(rank[i,r])| + nnz(V_qe)); L2-resident"),
+        ("K6 inverted index", ("reid_transpose_count", "reid_transpose_fill"), 16.0 * nnz_q, "2*8*nnz(V_qe); L2-resident"),
+        ("K7 Jaccard eps-graph", ("reid_jaccard_bounds", "reid_jaccard_neighbors", "reid_jaccard_neighbors_heavy",
+                                  "reid_jaccard_classify"),
+         8.0 * T + 8.0 * edges, "8*T + 8*edges, T=%d (%.0f/row), edges=%d; L2-resident" % (T, T / max(n, 1), edges)),
+        ("K8 DBSCAN", ("reid_dbscan_labels",), 8.0 * edges + 16.0 * N, "8*edges + 16N; L2-resident"),
+        ("scans", ("reid_scan_counts",), 0.0, "count->pointer scans between count/fill passes (latency bound)"),
+    ]
+    table = []
+    for name, entries, nbytes, note in rows:
+        t = ms(*entries)
+        if t <= 0:
+            continue
+        gbs = nbytes / (t * 1e-3) / 1e9 if nbytes else None
+        table.append({"stage": name, "ms": round(t, 4), "bound": "hbm", "bytes": int(nbytes),
+                      "achieved_gbs": None if gbs is None else round(gbs, 1), "peak_gbs": hbm,
+                      "frac": None if gbs is None else round(gbs / hbm, 4), "note": note})
+    return table
+
 # ------------------------------------------------------------------ GPU arm ------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -286,6 +361,10 @@ def main():
                 "traffic": None, "ms_per_launch": k_ms, "flops_per_launch": flops,
                 "peak_source": peaks["source"] + " cuBLAS bf16 burst (kernel lasts a few ms)"}
     stage_ms = {k: round(v[1] / args.steps, 4) for k, v in sorted(prof.items(), key=lambda kv: -kv[1][1])}
+    try:
+        stages = stage_rooflines(out, W, prof, args.steps, peaks, world)
+    except Exception as e:                                   # reporting only: never fail the bench line on it
+        stages = [{"error": repr(e)}]
 
     cpu = None
     if not args.no_cpu_baseline and world == 1:
@@ -303,7 +382,7 @@ def main():
                        "uncertified_rows": info.get("uncertified_rows"), "clusters": ncl,
                        "noise_points": int((labels < 0).sum().item())},
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
-            "stage_ms": stage_ms}
+            "stage_ms": stage_ms, "stages": stages}
     print(json.dumps(line))
     if dist is not None:
         dist.destroy_process_group()

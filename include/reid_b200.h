@@ -176,6 +176,15 @@ int reid_jaccard_neighbors_heavy(const int64_t* Q_ptr, const int32_t* Q_idx, con
                                  int64_t row_begin, const int32_t* rows_list, int64_t n_list, float eps,
                                  const int64_t* slot_ptr, int32_t* nbr_idx, float* nbr_val, int32_t* nbr_cnt,
                                  float* scratch, void* stream);
+/* The whole eps-graph of the shard in one call, no host round trip: rows are dealt to shared-memory table
+ * classes (512 .. 8192 slots) on the device from T_cnt (reid_jaccard_bounds), overflowing rows move up a
+ * class, the last resort is the dense-accumulator kernel.  nbr_cnt is never -1 on return.
+ * workspace: reid_jaccard_eps_graph_workspace_bytes(N, row_end - row_begin). */
+size_t reid_jaccard_eps_graph_workspace_bytes(int64_t N, int64_t n_rows);
+int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
+                           const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin,
+                           int64_t row_end, float eps, const int32_t* T_cnt, const int64_t* slot_ptr,
+                           int32_t* nbr_idx, float* nbr_val, int32_t* nbr_cnt, void* workspace, void* stream);
 /* dense rows: out[(row-row_begin)*ld + j] for all j < N  (the reference's return value). */
 int reid_jaccard_dense(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
                        const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin,

@@ -33,87 +33,175 @@ __device__ __forceinline__ float jaccard_from_t(float t) {
   return j < 0.f ? 0.f : j;
 }
 
-// One warp per row; per-warp open-addressing table (j -> running t) in shared memory.
-// Columns are consumed one after another (ascending), the rows of one column in parallel:
-// a column holds each j at most once, so lanes never collide on a slot inside a step.
+// eps-neighbourhoods, one warp per row, per-warp open-addressing table (j -> running t) in shared memory.
+//
+// The reference's inner loop is "for each non-zero column c of row i (ascending): temp_min[rows of c] += min(..)"
+// (:109-110).  Here the (column, row-of-column) pairs of a row form ONE flat sequence in that same order and the
+// warp consumes it 32 entries at a time (load-balanced search over the scanned column lengths), so short columns
+// no longer cost a dependent round trip each.  Two entries of a batch that hit the same j come from different
+// columns; __match_any_sync finds them and their adds are replayed in lane (= column) order, which keeps every
+// t_ij the exact sequential fp32 sum of the reference, bit-symmetric and independent of sharding.
+//
+// Rows are dealt to table-size classes on the device (jaccard_classify_kernel); a row that overflows its table
+// is pushed to the next class's queue, the last resort being the dense-accumulator kernel further down.  Each
+// class is one persistent launch that reads its queue length from device memory: no host round trip.
 constexpr int kJWarps = 4;
+constexpr int kJClasses = 5;                 // 512, 1024, 2048, 4096, 8192 slots
+constexpr int kJHeavyCtas = 64;              // dense-accumulator rows processed at a time by the last resort
 
-__global__ void __launch_bounds__(kJWarps * 32) jaccard_neighbors_kernel(
+__host__ __device__ constexpr int jclass_slots(int c) { return 512 << c; }
+
+template <int kWarps>
+__global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
     const int64_t* __restrict__ Q_ptr, const int32_t* __restrict__ Q_idx, const float* __restrict__ Q_val,
     const int64_t* __restrict__ C_ptr, const int32_t* __restrict__ C_idx, const float* __restrict__ C_val,
-    int64_t row_begin, int64_t n_rows, const int32_t* __restrict__ rows_list, float eps,
+    int64_t row_begin, int64_t n_rows_host, const int32_t* __restrict__ queue, const int32_t* __restrict__ queue_len,
+    int32_t* __restrict__ next_queue, int32_t* __restrict__ next_len, float eps,
     const int64_t* __restrict__ slot_ptr, int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_val,
     int32_t* __restrict__ nbr_cnt, int slots) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = lane_id();
   int32_t* tkey = reinterpret_cast<int32_t*>(smem_raw) + (size_t)w * slots;
-  float* tval = reinterpret_cast<float*>(smem_raw + (size_t)kJWarps * slots * 4) + (size_t)w * slots;
-  const int64_t li = (int64_t)blockIdx.x * kJWarps + w;
-  if (li >= n_rows) return;
-  const int64_t lr = rows_list ? rows_list[li] : li;  // local row id
-  const int64_t row = row_begin + lr;
+  float* tval = reinterpret_cast<float*>(smem_raw + (size_t)kWarps * slots * 4) + (size_t)w * slots;
   const uint32_t smask = (uint32_t)slots - 1u;
+  const unsigned lt = (1u << lane) - 1u;
+  const int64_t n_rows = queue_len ? (int64_t)*queue_len : n_rows_host;
+  const int limit = (slots >> 1) + (slots >> 2);      // load factor < 3/4 so probing terminates
 
-  for (int s = lane; s < slots; s += 32) tkey[s] = -1;
-  __syncwarp();
+  for (int64_t li = (int64_t)blockIdx.x * kWarps + w; li < n_rows; li += (int64_t)gridDim.x * kWarps) {
+    const int64_t lr = queue ? queue[li] : li;        // local row id
+    const int64_t row = row_begin + lr;
+    for (int s = lane; s < slots; s += 32) tkey[s] = -1;
+    __syncwarp();
 
-  int used = 0;
-  bool overflow = false;
-  const int64_t qa = Q_ptr[row], qb = Q_ptr[row + 1];
-  for (int64_t p = qa; p < qb && !overflow; ++p) {
-    const int32_t c = Q_idx[p];
-    const float vic = Q_val[p];
-    const int64_t ca = C_ptr[c], cb = C_ptr[c + 1];
-    for (int64_t q0 = ca; q0 < cb; q0 += 32) {
-      const int64_t q = q0 + lane;
-      bool fresh = false;
-      if (q < cb) {
-        const int32_t j = C_idx[q];
-        const float m = fminf(vic, C_val[q]);
-        uint32_t h = jhash((uint32_t)j) & smask;
-        while (true) {
-          const int32_t old = atomicCAS(&tkey[h], -1, j);
-          if (old == -1) {
-            tval[h] = m;  // 0 + m
-            fresh = true;
-            break;
+    int used = 0;
+    bool overflow = false;
+    const int64_t qa = Q_ptr[row], qb = Q_ptr[row + 1];
+    for (int64_t pc = qa; pc < qb && !overflow; pc += 32) {   // up to 32 columns of the row at a time
+      const int64_t p = pc + lane;
+      const bool has = p < qb;
+      const int32_t c = has ? Q_idx[p] : 0;
+      const float vic = has ? Q_val[p] : 0.f;
+      const int64_t ca = has ? C_ptr[c] : 0;
+      const int len = has ? (int)(C_ptr[c + 1] - ca) : 0;
+      int inc = len;                                            // inclusive scan of the column lengths
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int v = __shfl_up_sync(kFull, inc, o);
+        if (lane >= o) inc += v;
+      }
+      const int total = __shfl_sync(kFull, inc, 31);
+      const int excl = inc - len;
+      // entry f of the chunk's flat sequence -> (j, min(V_ic, V_jc), column slot); loads only, so the next
+      // batch's loads are in flight while the current one goes through the table
+      auto fetch = [&](int base, int32_t& j, float& m, int& col) {
+        const int f = base + lane;
+        const bool act = f < total;
+        col = 0;                                                // number of columns that end at or before f
+#pragma unroll
+        for (int step = 16; step >= 1; step >>= 1) {
+          const int iv = __shfl_sync(kFull, inc, col + step - 1);
+          if (iv <= f) col += step;
+        }
+        col = act ? col : 32;
+        const int src = col & 31;
+        const int e0 = __shfl_sync(kFull, excl, src);
+        const int64_t cb = __shfl_sync(kFull, ca, src);
+        const float vv = __shfl_sync(kFull, vic, src);
+        j = -1;
+        m = 0.f;
+        if (act) {
+          const int64_t q = cb + (f - e0);
+          j = C_idx[q];
+          m = fminf(vv, C_val[q]);
+        }
+      };
+      int32_t j;
+      float m;
+      int col;
+      fetch(0, j, m, col);
+      for (int base = 0; base < total; base += 32) {
+        int32_t jn = -1;
+        float mn = 0.f;
+        int coln = 32;
+        if (base + 32 < total) fetch(base + 32, jn, mn, coln);
+        // a batch spans a few columns; inside one column every j is distinct, so the columns of the batch are
+        // replayed one after the other (ascending) and lanes never meet on a slot
+        const int c_lo = __shfl_sync(kFull, col, 0);
+        const int c_hi = __reduce_max_sync(kFull, col < 32 ? col : 0);
+        int fresh_n = 0;
+        for (int cc = c_lo; cc <= c_hi; ++cc) {
+          bool fresh = false;
+          if (col == cc) {
+            uint32_t h = jhash((uint32_t)j) & smask;
+            while (true) {
+              const int32_t old = atomicCAS(&tkey[h], -1, j);
+              if (old == -1) {
+                tval[h] = m;                                    // 0 + m
+                fresh = true;
+                break;
+              }
+              if (old == j) {
+                tval[h] = __fadd_rn(tval[h], m);
+                break;
+              }
+              h = (h + 1) & smask;
+            }
           }
-          if (old == j) {
-            tval[h] = __fadd_rn(tval[h], m);
-            break;
-          }
-          h = (h + 1) & smask;
+          fresh_n += __popc(__ballot_sync(kFull, fresh));
+          __syncwarp();                                         // this column's adds land before the next column's
+        }
+        used += fresh_n;
+        j = jn;
+        m = mn;
+        col = coln;
+        if (used > limit) {
+          overflow = true;
+          break;
         }
       }
-      used += __popc(__ballot_sync(kFull, fresh));
-      if (used > (slots >> 1) + (slots >> 2)) {  // keep the load factor under 3/4 so probing terminates
-        overflow = true;
-        break;
-      }
     }
+    if (overflow) {
+      if (lane == 0) {
+        if (next_queue) next_queue[atomicAdd(next_len, 1)] = (int32_t)lr;
+        else nbr_cnt[lr] = -1;
+      }
+      __syncwarp();
+      continue;
+    }
+    const int64_t o = slot_ptr[lr];
+    int cnt = 0;
+    for (int base = 0; base < slots; base += 32) {
+      const int32_t j = tkey[base + lane];
+      float jd = 2.f;
+      if (j >= 0) jd = jaccard_from_t(tval[base + lane]);
+      const bool keep = j >= 0 && jd <= eps;
+      const unsigned b = __ballot_sync(kFull, keep);
+      if (keep) {
+        const int64_t dst = o + cnt + __popc(b & lt);
+        nbr_idx[dst] = j;
+        if (nbr_val) nbr_val[dst] = jd;
+      }
+      cnt += __popc(b);
+    }
+    if (lane == 0) nbr_cnt[lr] = cnt;
     __syncwarp();
   }
-  if (overflow) {
-    if (lane == 0) nbr_cnt[lr] = -1;
-    return;
-  }
-  __syncwarp();
-  const int64_t o = slot_ptr[lr];
-  int cnt = 0;
-  for (int base = 0; base < slots; base += 32) {
-    const int32_t j = tkey[base + lane];
-    float jd = 2.f;
-    if (j >= 0) jd = jaccard_from_t(tval[base + lane]);
-    const bool keep = j >= 0 && jd <= eps;
-    const unsigned b = __ballot_sync(kFull, keep);
-    if (keep) {
-      const int64_t dst = o + cnt + __popc(b & ((1u << lane) - 1u));
-      nbr_idx[dst] = j;
-      if (nbr_val) nbr_val[dst] = jd;
-    }
-    cnt += __popc(b);
-  }
-  if (lane == 0) nbr_cnt[lr] = cnt;
+}
+
+// T_cnt (upper bound of the partner count) -> table class.  T counts every (column, row) pair; the number of
+// DISTINCT partners is a small fraction of it (a partner shares many columns with the row), and the latency-bound
+// table kernel lives on occupancy, so the first guess is optimistic -- the class that holds T/4 -- and rows that
+// do overflow move up one class at a time.
+__global__ void __launch_bounds__(256) jaccard_classify_kernel(const int32_t* __restrict__ T_cnt, int64_t n_rows,
+                                                               int32_t* __restrict__ queues, int32_t* __restrict__ qlen) {
+  const int64_t lr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (lr >= n_rows) return;
+  const int t = T_cnt[lr];
+  const int need = t < 2048 ? t >> 2 : t >> 1;           // a retry of a long row is expensive: less optimism there
+  int c = 0;
+  while (c < kJClasses && need > ((jclass_slots(c) >> 1) + (jclass_slots(c) >> 2))) ++c;   // c == kJClasses: heavy
+  queues[(int64_t)c * n_rows + atomicAdd(&qlen[c], 1)] = (int32_t)lr;
 }
 
 // Dense rows for the drop-in return value.  One CTA per row; the accumulator row lives in
@@ -157,14 +245,18 @@ __global__ void __launch_bounds__(256) jaccard_dense_kernel(
 __global__ void __launch_bounds__(256) jaccard_neighbors_heavy_kernel(
     const int64_t* __restrict__ Q_ptr, const int32_t* __restrict__ Q_idx, const float* __restrict__ Q_val,
     const int64_t* __restrict__ C_ptr, const int32_t* __restrict__ C_idx, const float* __restrict__ C_val, int64_t N,
-    int64_t row_begin, const int32_t* __restrict__ rows_list, float eps, const int64_t* __restrict__ slot_ptr,
+    int64_t row_begin, const int32_t* __restrict__ rows_list, int64_t n_list_host,
+    const int32_t* __restrict__ list_len, float eps, const int64_t* __restrict__ slot_ptr,
     int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_val, int32_t* __restrict__ nbr_cnt,
     float* __restrict__ scratch) {
   __shared__ int s_warp[8];
   __shared__ int s_base;
-  const int64_t lr = rows_list[blockIdx.x];
-  const int64_t row = row_begin + lr;
+  const int64_t n_list = list_len ? (int64_t)*list_len : n_list_host;
   float* acc = scratch + (int64_t)blockIdx.x * N;
+  for (int64_t li = blockIdx.x; li < n_list; li += gridDim.x) {
+  const int64_t lr = rows_list[li];
+  const int64_t row = row_begin + lr;
+  __syncthreads();
   for (int64_t j = threadIdx.x; j < N; j += blockDim.x) __stcg(&acc[j], 0.f);
   if (threadIdx.x == 0) s_base = 0;
   __syncthreads();
@@ -203,8 +295,66 @@ __global__ void __launch_bounds__(256) jaccard_neighbors_heavy_kernel(
     __syncthreads();
   }
   if (threadIdx.x == 0) nbr_cnt[lr] = s_base;
+  }
 }
 
+}  // namespace reid
+
+namespace reid {
+struct JnArgs {
+  const int64_t* Q_ptr; const int32_t* Q_idx; const float* Q_val;
+  const int64_t* C_ptr; const int32_t* C_idx; const float* C_val;
+  int64_t row_begin; float eps; const int64_t* slot_ptr; int32_t* nbr_idx; float* nbr_val; int32_t* nbr_cnt;
+};
+
+// one launch of the table kernel: `n_max` bounds the grid, the real row count is *queue_len when given
+template <int kWarps>
+static int launch_jn(const JnArgs& a, int slots, int64_t n_max, const int32_t* queue, const int32_t* queue_len,
+                     int32_t* next_queue, int32_t* next_len, cudaStream_t st) {
+  const size_t smem = (size_t)kWarps * slots * 8;
+  REID_CUDA(cudaFuncSetAttribute(jaccard_neighbors_kernel<kWarps>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+  int per_sm = 1;      // persistent grid = exactly the resident CTAs (a later wave would only add a tail)
+  REID_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jaccard_neighbors_kernel<kWarps>, kWarps * 32, smem));
+  if (per_sm < 1) per_sm = 1;
+  int64_t grid = (n_max + kWarps - 1) / kWarps;
+  const int64_t cap = (int64_t)num_sms() * per_sm;
+  if (grid > cap) grid = cap;
+  jaccard_neighbors_kernel<kWarps><<<(unsigned)grid, kWarps * 32, smem, st>>>(
+      a.Q_ptr, a.Q_idx, a.Q_val, a.C_ptr, a.C_idx, a.C_val, a.row_begin, n_max, queue, queue_len, next_queue, next_len,
+      a.eps, a.slot_ptr, a.nbr_idx, a.nbr_val, a.nbr_cnt, slots);
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+
+static int launch_jn_slots(const JnArgs& a, int slots, int64_t n_max, const int32_t* queue, const int32_t* queue_len,
+                           int32_t* next_queue, int32_t* next_len, cudaStream_t st) {
+  if (slots <= 1024) return launch_jn<8>(a, slots, n_max, queue, queue_len, next_queue, next_len, st);
+  if (slots <= 2048) return launch_jn<4>(a, slots, n_max, queue, queue_len, next_queue, next_len, st);
+  if (slots <= 4096) return launch_jn<6>(a, slots, n_max, queue, queue_len, next_queue, next_len, st);
+  if (slots <= 8192) return launch_jn<3>(a, slots, n_max, queue, queue_len, next_queue, next_len, st);
+  return launch_jn<1>(a, slots, n_max, queue, queue_len, next_queue, next_len, st);
+}
+
+struct JWs {
+  int32_t* qlen;     // kJClasses + 1 (+ padding)
+  int32_t* queues;   // (kJClasses + 1) x n_rows
+  float* scratch;    // kJHeavyCtas x N
+};
+static size_t jws_carve(void* base, int64_t N, int64_t n, JWs* w) {
+  unsigned char* p = (unsigned char*)base;
+  size_t off = 0;
+  auto take = [&](size_t bytes) {
+    void* r = p ? (void*)(p + off) : nullptr;
+    off += (bytes + 255) / 256 * 256;
+    return r;
+  };
+  JWs t;
+  t.qlen = (int32_t*)take(sizeof(int32_t) * 16);
+  t.queues = (int32_t*)take(sizeof(int32_t) * (size_t)(kJClasses + 1) * (size_t)(n > 0 ? n : 1));
+  t.scratch = (float*)take(sizeof(float) * (size_t)kJHeavyCtas * (size_t)N);
+  if (w) *w = t;
+  return off;
+}
 }  // namespace reid
 
 extern "C" {
@@ -222,6 +372,7 @@ int reid_jaccard_bounds(const int64_t* Q_ptr, const int32_t* Q_idx, const int64_
   return REID_OK;
 }
 
+
 int reid_jaccard_neighbors(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
                            const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin, int64_t row_end,
                            const int32_t* rows_list, int64_t n_list, float eps, const int64_t* slot_ptr,
@@ -232,14 +383,45 @@ int reid_jaccard_neighbors(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
   REID_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= N, "reid_jaccard_neighbors: bad row range");
   REID_CHECK_ARG(table_slots >= 64 && (table_slots & (table_slots - 1)) == 0,
                  "reid_jaccard_neighbors: table_slots=%d must be a power of two >= 64", table_slots);
-  const size_t smem = (size_t)kJWarps * table_slots * 8;
-  REID_CHECK_ARG(smem <= 224 * 1024, "reid_jaccard_neighbors: table_slots=%d does not fit shared memory", table_slots);
+  REID_CHECK_ARG((size_t)table_slots * 8 <= 224 * 1024, "reid_jaccard_neighbors: table_slots=%d does not fit shared memory",
+                 table_slots);
   const int64_t n = rows_list ? n_list : row_end - row_begin;
   if (n == 0) return REID_OK;
-  REID_CUDA(cudaFuncSetAttribute(jaccard_neighbors_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  jaccard_neighbors_kernel<<<(unsigned)((n + kJWarps - 1) / kJWarps), kJWarps * 32, smem, (cudaStream_t)stream>>>(
-      Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, row_begin, n, rows_list, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt,
-      table_slots);
+  const JnArgs a{Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, row_begin, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt};
+  return launch_jn_slots(a, table_slots, n, rows_list, nullptr, nullptr, nullptr, (cudaStream_t)stream);
+}
+
+size_t reid_jaccard_eps_graph_workspace_bytes(int64_t N, int64_t n_rows) {
+  if (N < 0 || n_rows < 0) return 0;
+  return reid::jws_carve(nullptr, N, n_rows, nullptr);
+}
+
+int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
+                           const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin, int64_t row_end,
+                           float eps, const int32_t* T_cnt, const int64_t* slot_ptr, int32_t* nbr_idx, float* nbr_val,
+                           int32_t* nbr_cnt, void* workspace, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(Q_ptr && Q_idx && Q_val && C_ptr && C_idx && C_val && T_cnt && slot_ptr && nbr_idx && nbr_cnt && workspace,
+                 "reid_jaccard_eps_graph: NULL pointer");
+  REID_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= N, "reid_jaccard_eps_graph: bad row range");
+  const int64_t n = row_end - row_begin;
+  if (n == 0) return REID_OK;
+  cudaStream_t st = (cudaStream_t)stream;
+  JWs w;
+  jws_carve(workspace, N, n, &w);
+  REID_CUDA(cudaMemsetAsync(w.qlen, 0, sizeof(int32_t) * 16, st));
+  jaccard_classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(T_cnt, n, w.queues, w.qlen);
+  REID_LAUNCH_CHECK();
+  const JnArgs a{Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, row_begin, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt};
+  for (int c = 0; c < kJClasses; ++c) {
+    int rc = launch_jn_slots(a, jclass_slots(c), n, w.queues + (int64_t)c * n, w.qlen + c, w.queues + (int64_t)(c + 1) * n,
+                             w.qlen + c + 1, st);
+    if (rc != REID_OK) return rc;
+  }
+  const int64_t hg = n < kJHeavyCtas ? n : kJHeavyCtas;
+  jaccard_neighbors_heavy_kernel<<<(unsigned)hg, 256, 0, st>>>(Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin,
+                                                              w.queues + (int64_t)kJClasses * n, 0, w.qlen + kJClasses, eps,
+                                                              slot_ptr, nbr_idx, nbr_val, nbr_cnt, w.scratch);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
@@ -276,8 +458,8 @@ int reid_jaccard_neighbors_heavy(const int64_t* Q_ptr, const int32_t* Q_idx, con
   REID_CHECK_ARG(N > 0 && n_list >= 0, "reid_jaccard_neighbors_heavy: bad shape");
   if (n_list == 0) return REID_OK;
   jaccard_neighbors_heavy_kernel<<<(unsigned)n_list, 256, 0, (cudaStream_t)stream>>>(
-      Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin, rows_list, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt,
-      scratch);
+      Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin, rows_list, n_list, nullptr, eps, slot_ptr, nbr_idx, nbr_val,
+      nbr_cnt, scratch);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

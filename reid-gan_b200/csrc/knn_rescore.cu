@@ -9,6 +9,8 @@
 // fp32(fp64 dot) and ordered by (key desc, index asc) -- bit-identical to reid_knn_exact.  The
 // measured |a - s| is audited against eps; any violation un-certifies the row.  Uncertified rows are
 // redone by the caller with reid_knn_exact, so the result never depends on eps being right.
+#include <stdlib.h>
+
 #include "common.cuh"
 
 namespace reid {
@@ -262,6 +264,196 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_exact_kernel(
   }
 }
 
+// ---- stage 2, grouped: a small FP64 GEMM per group of locality-ordered rows -------------------------
+// rescore_exact_kernel is bound by the fp32 -> fp64 conversions (two per product: 4.8 G F2F at 16/clk/SM
+// = 1.0 ms at N = 32,621).  Rows that are neighbours in the locality order are cluster mates and share
+// most of their window, so a CTA takes kGq consecutive rows, builds the UNION of their windows in shared
+// memory and computes the whole (kGq x |union|) block of exact dots: every candidate row is fetched and
+// converted once per group instead of once per (row, candidate) pair, the query rows are converted once
+// into shared memory, and the pairs that nobody asked for are simply not read back.
+//   thread (cg, ks): 4 candidates x kGq queries over K-slice ks (float4 of every 64 dims) -> 16 fp64
+//   accumulators; the 16 K-slices of a candidate group sit in one half warp and are folded with a
+//   transpose-reduce (15 shuffles of a double instead of 64).  The summation order of a dot is fixed by
+//   (ks, step) alone, so a key does not depend on which group or slot the pair landed in.
+constexpr int kGq = 4;
+constexpr int kGThreads = 256;
+constexpr int kGChunk = 64;                 // candidates per pass = 16 groups of 4
+constexpr int kGSlots = 1024;               // union hash table (|union| <= kGq * kWinMax = 512)
+
+__global__ void __launch_bounds__(kGThreads, 2) rescore_group_kernel(
+    const float* __restrict__ x, int64_t D, int64_t row_begin, int64_t n_rows, const int32_t* __restrict__ perm,
+    const int32_t* __restrict__ win_cnt, const int32_t* __restrict__ win_idx, const float* __restrict__ win_a, int k,
+    float eps_in, const float* __restrict__ max_sqnorm, int32_t* __restrict__ out_idx, float* __restrict__ out_key,
+    int32_t* __restrict__ uncert, unsigned* __restrict__ max_err_bits) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  double* sQ = reinterpret_cast<double*>(smem_raw);                                    // [kGq][D]
+  uint64_t* s_key = reinterpret_cast<uint64_t*>(sQ + (size_t)kGq * D);                 // [kGq][kWinMax]
+  double* s_dot = reinterpret_cast<double*>(s_key + kGq * kWinMax);                    // [kGq][kGChunk]
+  int32_t* s_tab = reinterpret_cast<int32_t*>(s_dot + kGq * kGChunk);                  // [kGSlots] column ids
+  int32_t* s_ulist = s_tab + kGSlots;                                                  // [kGq * kWinMax]
+  uint16_t* s_tid = reinterpret_cast<uint16_t*>(s_ulist + kGq * kWinMax);              // [kGSlots] union position
+  uint16_t* s_pid = s_tid + kGSlots;                                                   // [kGq][kWinMax]
+  __shared__ int s_U;
+  __shared__ int s_nw[kGq];
+  __shared__ int64_t s_lr[kGq];
+  __shared__ unsigned s_worst[kGq];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float eps = max_sqnorm ? reid_tc_err_bound(*max_sqnorm) : eps_in;
+
+  if (tid < kGq) {
+    const int64_t slot = (int64_t)blockIdx.x * kGq + tid;
+    const int64_t lr = slot < n_rows ? (perm ? perm[slot] : slot) : -1;
+    s_lr[tid] = lr;
+    s_nw[tid] = lr >= 0 ? win_cnt[lr] : 0;
+    s_worst[tid] = 0u;
+  }
+  if (tid == 0) s_U = 0;
+  for (int h = tid; h < kGSlots; h += kGThreads) s_tab[h] = -1;
+  __syncthreads();
+
+  // query rows -> fp64 in shared memory (rows of an incomplete last group are zero)
+#pragma unroll
+  for (int q = 0; q < kGq; ++q) {
+    const int64_t lr = s_lr[q];
+    const float4* xi = reinterpret_cast<const float4*>(x + (row_begin + (lr >= 0 ? lr : 0)) * D);
+    for (int64_t d4 = tid; d4 < (D >> 2); d4 += kGThreads) {
+      float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
+      if (lr >= 0) v = xi[d4];
+      double2* dst = reinterpret_cast<double2*>(sQ + (size_t)q * D + d4 * 4);
+      dst[0] = make_double2((double)v.x, (double)v.y);
+      dst[1] = make_double2((double)v.z, (double)v.w);
+    }
+  }
+  // union of the windows
+  for (int it = tid; it < kGq * kWinMax; it += kGThreads) {
+    const int q = it / kWinMax, t = it % kWinMax;
+    if (t < s_nw[q]) {
+      const int32_t j = win_idx[s_lr[q] * kWinMax + t];
+      uint32_t h = ((uint32_t)j * 0x9e3779b1u) >> 22;          // 10 bits
+      while (true) {
+        const int32_t old = atomicCAS(&s_tab[h], -1, j);
+        if (old == -1) {
+          const int id = atomicAdd(&s_U, 1);
+          s_ulist[id] = j;
+          s_tid[h] = (uint16_t)id;
+          break;
+        }
+        if (old == j) break;
+        h = (h + 1) & (kGSlots - 1);
+      }
+    }
+  }
+  __syncthreads();
+  for (int it = tid; it < kGq * kWinMax; it += kGThreads) {
+    const int q = it / kWinMax, t = it % kWinMax;
+    if (t < s_nw[q]) {
+      const int32_t j = win_idx[s_lr[q] * kWinMax + t];
+      uint32_t h = ((uint32_t)j * 0x9e3779b1u) >> 22;
+      while (s_tab[h] != j) h = (h + 1) & (kGSlots - 1);
+      s_pid[it] = s_tid[h];
+    }
+  }
+  __syncthreads();
+  const int U = s_U;
+
+  const int cg = tid >> 4, ks = tid & 15;
+  const int steps = (int)(D >> 6);
+  for (int c0 = 0; c0 < U; c0 += kGChunk) {
+    const float4* xc[4];
+#pragma unroll
+    for (int i = 0; i < 4; ++i) {
+      const int id = c0 + cg * 4 + i;
+      xc[i] = reinterpret_cast<const float4*>(x + (int64_t)s_ulist[id < U ? id : 0] * D) + ks;
+    }
+    double acc[kGq * 4];
+#pragma unroll
+    for (int v = 0; v < kGq * 4; ++v) acc[v] = 0.0;
+    if (c0 + cg * 4 < U) {                                   // candidate groups past the union have nothing to do
+#pragma unroll 2
+      for (int s = 0; s < steps; ++s) {
+        float4 c[4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) c[i] = xc[i][s * 16];
+        double cd[4][4];
+#pragma unroll
+        for (int i = 0; i < 4; ++i) {
+          cd[i][0] = (double)c[i].x;
+          cd[i][1] = (double)c[i].y;
+          cd[i][2] = (double)c[i].z;
+          cd[i][3] = (double)c[i].w;
+        }
+#pragma unroll
+        for (int q = 0; q < kGq; ++q) {
+          const double2* qp = reinterpret_cast<const double2*>(sQ + (size_t)q * D + s * 64 + ks * 4);
+          const double2 q01 = qp[0], q23 = qp[1];
+#pragma unroll
+          for (int i = 0; i < 4; ++i) {
+            double a = acc[q * 4 + i];
+            a = fma(q01.x, cd[i][0], a);
+            a = fma(q01.y, cd[i][1], a);
+            a = fma(q23.x, cd[i][2], a);
+            a = fma(q23.y, cd[i][3], a);
+            acc[q * 4 + i] = a;
+          }
+        }
+      }
+    }
+    // fold the 16 K-slices: after the rounds lane ks holds the complete dot number ks (= q * 4 + i)
+#pragma unroll
+    for (int off = 8, n = 8; off >= 1; off >>= 1, n >>= 1) {
+      const bool up = (ks & off) != 0;
+#pragma unroll
+      for (int m = 0; m < n; ++m) {
+        const double send = up ? acc[m] : acc[m + n];
+        const double keep = up ? acc[m + n] : acc[m];
+        acc[m] = keep + __shfl_xor_sync(kFull, send, off);
+      }
+    }
+    s_dot[(ks >> 2) * kGChunk + cg * 4 + (ks & 3)] = acc[0];
+    __syncthreads();
+    for (int it = tid; it < kGq * kWinMax; it += kGThreads) {
+      const int q = it / kWinMax, t = it % kWinMax;
+      if (t < s_nw[q]) {
+        const int id = (int)s_pid[it] - c0;
+        if (id >= 0 && id < kGChunk) {
+          const int64_t lr = s_lr[q];
+          const float sc = (float)s_dot[q * kGChunk + id];
+          const float err = fabsf(sc - win_a[lr * kWinMax + t]);
+          atomicMax(&s_worst[q], __float_as_uint(err == err ? err : INFINITY));
+          s_key[it] = sel_key(sc, win_idx[lr * kWinMax + t]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // per row: audit, then order by (key desc, idx asc); the first k go out
+  if (warp < kGq && s_lr[warp] >= 0) {
+    const int64_t lr = s_lr[warp];
+    const int n_w = s_nw[warp];
+    const uint64_t* key = s_key + warp * kWinMax;
+    if (lane == 0) {
+      const float worst = __uint_as_float(s_worst[warp]);
+      atomicMax(max_err_bits, __float_as_uint(worst));
+      if (!(worst <= eps)) uncert[lr] = 1;  // the error model was violated (or NaN): do not trust the window
+    }
+    for (int t = lane; t < n_w; t += 32) {
+      const uint64_t me = key[t];
+      int rank = 0;
+      for (int u = 0; u < n_w; ++u) rank += key[u] > me;
+      if (rank < k) {
+        out_idx[lr * k + rank] = sel_key_idx(me);
+        if (out_key) out_key[lr * k + rank] = sel_key_val(me);
+      }
+    }
+  }
+}
+
+inline size_t rescore_group_smem(int64_t D) {
+  return (size_t)kGq * D * 8 + (size_t)kGq * kWinMax * 8 + (size_t)kGq * kGChunk * 8 + (size_t)kGSlots * 4 +
+         (size_t)kGq * kWinMax * 4 + (size_t)kGSlots * 2 + (size_t)kGq * kWinMax * 2;
+}
+
 struct RescoreWs {
   int64_t* ptr;      // N + 1
   int32_t* hist;     // N
@@ -340,7 +532,14 @@ int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, in
                                                            w.win_cnt, w.win_idx, w.win_a, k, err_bound, max_sqnorm,  \
                                                            out_idx, out_key, uncertified_flag, (unsigned*)max_err_out)
   const bool aligned = (((uintptr_t)x) & 15) == 0;
-  if (aligned && D == 2048) REID_RS_LAUNCH(16);
+  static const bool no_group = getenv("REID_RESCORE_GROUP") && atoi(getenv("REID_RESCORE_GROUP")) == 0;
+  if (aligned && D % 64 == 0 && D <= 2048 && !no_group) {
+    const size_t smem = rescore_group_smem(D);
+    REID_CUDA(cudaFuncSetAttribute(rescore_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    rescore_group_kernel<<<(unsigned)((n + kGq - 1) / kGq), kGThreads, smem, st>>>(
+        x, D, row_begin, n, locality_order ? w.perm : nullptr, w.win_cnt, w.win_idx, w.win_a, k, err_bound, max_sqnorm,
+        out_idx, out_key, uncertified_flag, (unsigned*)max_err_out);
+  } else if (aligned && D == 2048) REID_RS_LAUNCH(16);
   else if (aligned && D == 1024) REID_RS_LAUNCH(8);
   else if (aligned && D == 512) REID_RS_LAUNCH(4);
   else if (aligned && D == 256) REID_RS_LAUNCH(2);

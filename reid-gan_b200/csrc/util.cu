@@ -15,55 +15,71 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-// One CTA scans up to a few hundred thousand counts: every thread owns a contiguous chunk, the 1024
-// chunk totals are scanned with warp shuffles (two levels), then the chunk is re-walked.
+// One CTA scans the counts tile by tile: 1024 threads x 4 consecutive elements per tile (coalesced 16-byte
+// loads when the array is 16-byte aligned), warp-shuffle scans at two levels, running carry in a register.
+// 32k counts = 8 tiles, a few microseconds; the stats (total, max) come out of the same pass.
 __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ cnt, int64_t n,
                                                            int64_t* __restrict__ ptr, int64_t* __restrict__ stats) {
-  __shared__ int64_t warp_tot[32];
+  __shared__ int32_t warp_tot[32];
   __shared__ int32_t warp_max_s[32];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
-  const int64_t chunk = (n + 1023) / 1024;
-  const int64_t a = min(n, (int64_t)t * chunk), b = min(n, a + chunk);
-  int64_t s = 0;
+  const bool vec = (((uintptr_t)cnt) & 15) == 0;
+  int64_t carry = 0;
   int32_t mx = 0;
-  for (int64_t i = a; i < b; ++i) {
-    const int32_t c = cnt[i];
-    s += c;
-    mx = max(mx, c);
-  }
-  int64_t inc = s;  // inclusive scan inside the warp
+  for (int64_t base = 0; base < n; base += 4096) {
+    const int64_t i0 = base + (int64_t)t * 4;
+    int32_t c[4] = {0, 0, 0, 0};
+    if (vec && i0 + 4 <= n) {
+      const int4 v = *reinterpret_cast<const int4*>(cnt + i0);
+      c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+    } else {
 #pragma unroll
-  for (int o = 1; o < 32; o <<= 1) {
-    const int64_t v = __shfl_up_sync(kFull, inc, o);
-    if (lane >= o) inc += v;
+      for (int j = 0; j < 4; ++j) if (i0 + j < n) c[j] = cnt[i0 + j];
+    }
+    mx = max(max(mx, max(c[0], c[1])), max(c[2], c[3]));
+    const int32_t s = c[0] + c[1] + c[2] + c[3];      // a tile holds < 2^31 in total (counts are small)
+    int32_t inc = s;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int32_t v = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += v;
+    }
+    if (lane == 31) warp_tot[w] = inc;
+    __syncthreads();
+    if (w == 0) {
+      const int32_t v = warp_tot[lane];
+      int32_t iv = v;
+#pragma unroll
+      for (int o = 1; o < 32; o <<= 1) {
+        const int32_t u = __shfl_up_sync(kFull, iv, o);
+        if (lane >= o) iv += u;
+      }
+      warp_tot[lane] = iv - v;                          // exclusive offset of each warp inside the tile
+      if (lane == 31) warp_max_s[0] = iv;               // tile total
+    }
+    __syncthreads();
+    int64_t run = carry + warp_tot[w] + (inc - s);
+    const int64_t tile_total = warp_max_s[0];
+#pragma unroll
+    for (int j = 0; j < 4; ++j) {
+      if (i0 + j < n) ptr[i0 + j] = run;
+      run += c[j];
+    }
+    carry += tile_total;
+    __syncthreads();                                    // warp_tot / warp_max_s are rewritten by the next tile
   }
   mx = warp_max(mx);
-  if (lane == 31) warp_tot[w] = inc;
   if (lane == 0) warp_max_s[w] = mx;
   __syncthreads();
   if (w == 0) {
-    int64_t v = warp_tot[lane];
-    int64_t iv = v;
-#pragma unroll
-    for (int o = 1; o < 32; o <<= 1) {
-      const int64_t u = __shfl_up_sync(kFull, iv, o);
-      if (lane >= o) iv += u;
-    }
-    warp_tot[lane] = iv - v;  // exclusive offset of each warp
     const int32_t m = warp_max(warp_max_s[lane]);
-    if (lane == 31) {
-      ptr[n] = iv;
+    if (lane == 0) {
+      ptr[n] = carry;
       if (stats) {
-        stats[0] = iv;
+        stats[0] = carry;
         stats[1] = m;
       }
     }
-  }
-  __syncthreads();
-  int64_t run = warp_tot[w] + inc - s;
-  for (int64_t i = a; i < b; ++i) {
-    ptr[i] = run;
-    run += cnt[i];
   }
 }
 

@@ -218,27 +218,10 @@ def jaccard_neighbors(st, eps, with_values=False):
     nbr_val = torch.empty(max(t_total, 1), dtype=torch.float32, device=dev) if with_values else None
     nbr_cnt = torch.empty(n, dtype=torch.int32, device=dev)
     eps32 = float(np.float32(eps))
-    slots = 1024
-    rows_list, n_list = None, 0
-    while True:
-        call("reid_jaccard_neighbors", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
-                                       ptr(st.C_val), st.N, r0, r1, ptr(rows_list), n_list, eps32, ptr(slot_ptr),
-                                       ptr(nbr_idx), ptr(nbr_val), ptr(nbr_cnt), slots, sp)
-        over = torch.nonzero(nbr_cnt < 0).flatten().to(torch.int32)
-        if over.numel() == 0:
-            break
-        if slots >= 4096:
-            # hub rows: dense accumulator rows in global scratch, in batches of <= 256 MiB
-            per = max(1, (256 << 20) // (4 * st.N))
-            for a in range(0, over.numel(), per):
-                part = over[a:a + per].contiguous()
-                scratch = torch.empty(part.numel() * st.N, dtype=torch.float32, device=dev)
-                call("reid_jaccard_neighbors_heavy", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr),
-                                                     ptr(st.C_idx), ptr(st.C_val), st.N, r0, ptr(part), part.numel(),
-                                                     eps32, ptr(slot_ptr), ptr(nbr_idx), ptr(nbr_val), ptr(nbr_cnt),
-                                                     ptr(scratch), sp)
-            break
-        rows_list, n_list, slots = over.contiguous(), over.numel(), slots * 2
+    ws = torch.empty(L.reid_jaccard_eps_graph_workspace_bytes(st.N, n), dtype=torch.uint8, device=dev)
+    call("reid_jaccard_eps_graph", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
+                                   ptr(st.C_val), st.N, r0, r1, eps32, ptr(t_cnt), ptr(slot_ptr), ptr(nbr_idx),
+                                   ptr(nbr_val), ptr(nbr_cnt), ptr(ws), sp)
     return slot_ptr, nbr_idx, nbr_cnt, nbr_val
 
 

@@ -41,7 +41,7 @@ def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=
             torch.cuda.synchronize()
             st.timings["jaccard"] = ev0.elapsed_time(ev1) * 1e-3
             st.timings["dbscan"] = ev1.elapsed_time(ev2) * 1e-3
-        out = dict(labels=labels, core=core, num_clusters=ncl, state=st)
+        out = dict(labels=labels, core=core, num_clusters=ncl, state=st, nbr_cnt=nbr_cnt)
         if centroids:
             C = int(ncl.item())
             cen = torch.empty((C, x.shape[1]), dtype=torch.float32, device=x.device)

@@ -169,7 +169,7 @@ def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=
             torch.cuda.synchronize()
             for nm, a, b in (("jaccard", 0, 1), ("gather_neighbors", 1, 2), ("dbscan", 2, 3)):
                 st.timings[nm] = ev[a].elapsed_time(ev[b]) * 1e-3
-        out = dict(labels=labels, core=core, num_clusters=ncl, state=st)
+        out = dict(labels=labels, core=core, num_clusters=ncl, state=st, nbr_cnt=nbr_cnt)
         if centroids:
             C = int(ncl.item())
             cen = torch.empty((C, x.shape[1]), dtype=torch.float32, device=x.device)

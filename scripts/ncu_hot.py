@@ -1,7 +1,8 @@
 """Hot SASS lines of an ncu report (needs -lineinfo + --import-source on). Usage: ncu_hot.py rep.ncu-rep [top]"""
 import csv, subprocess, sys, io
 rep = sys.argv[1]; top = int(sys.argv[2]) if len(sys.argv) > 2 else 25
-out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"], capture_output=True, text=True).stdout
+kn = sys.argv[3] if len(sys.argv) > 3 else None
+out = subprocess.run(["ncu", "-i", rep, "--page", "source", "--csv"] + (["-k", "regex:" + kn] if kn else []), capture_output=True, text=True).stdout
 rows = list(csv.reader(io.StringIO(out)))
 hdr = rows[1]
 ci, si, ii = hdr.index("Source"), hdr.index("Warp Stall Sampling (All Samples)"), hdr.index("Instructions Executed")
