@@ -81,6 +81,34 @@ int reid_knn_tc_plan(int64_t N, int64_t n_rows, int cta_group, int* n_splits_out
 int reid_knn_candidates_tc(const void* xh, int64_t N, int64_t D, int scale_log2, int64_t row_begin,
                            int64_t row_end, int keep, int n_splits, int cta_group, uint64_t* cand,
                            int32_t* cand_cnt, uint32_t* row_tau, void* stream);
+/* Same kernel with distinct operands: query rows [row_begin,row_end) of xa (Na x D) against all N rows of xb
+ * (column ids = row index in xb).  Used by the sampling prepass of the symmetric search below: a NEGATIVE keep
+ * selects its mode (|keep| entries kept; every list seeds its threshold with the 5th largest of its first 32
+ * scores instead of taking the first tiles unfiltered -- good for an order statistic, not for a top-k). */
+int reid_knn_candidates_tc_ab(const void* xa, int64_t Na, const void* xb, int64_t N, int64_t D, int scale_log2,
+                              int64_t row_begin, int64_t row_end, int keep, int n_splits, int cta_group,
+                              uint64_t* cand, int32_t* cand_cnt, uint32_t* row_tau, void* stream);
+
+/* Symmetric candidate search (single GPU, all N rows): S = Xh Xh^T is symmetric, so only the 256 x 256 tiles
+ * (I, J), I <= J, go through the tensor cores and each off-diagonal tile feeds the lists of both its row
+ * block and its column block -- half the tcgen05 work and half the operand traffic of reid_knn_candidates_tc.
+ * Selection is against a FIXED per-row threshold tau[i] (reid_knn_sample_tau): every column j with
+ * approximate score > tau[i] is appended to row i's single list
+ *   cand[i * cap + p] = (fp32 score bits << 32) | j,  p < min(cand_cnt[i], cap);
+ * cand_cnt[i] > cap means the list overflowed (reid_knn_rescore un-certifies such rows).
+ * tiles: n_tiles (I, J) int32 pairs in processing order (the host orders them for L2 locality). */
+#define REID_SYM_CAP 1024
+int reid_knn_candidates_sym(const void* xh, int64_t N, int64_t D, int scale_log2, const float* tau,
+                            const int32_t* tiles, int64_t n_tiles, int cap, uint64_t* cand, int32_t* cand_cnt,
+                            void* stream);
+/* xs[m] = xh[(m * stride) mod N], m < n_sample: a low-discrepancy sample of the rows (stride coprime with N). */
+int reid_features_sample(const void* xh, int64_t N, int64_t D, int64_t n_sample, int64_t stride, void* xs,
+                         void* stream);
+/* tau[row] = r-th largest score over the row's prepass lists (reid_knn_candidates_tc_ab against the sample),
+ * tau_ord = its order-preserving integer image (0 / -inf when fewer than r scores are listed). */
+int reid_knn_sample_tau(const uint64_t* cand, const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists,
+                        int64_t n_rows, int r, float* tau, uint32_t* tau_ord, void* stream);
+
 /* fp32 features -> scaled fp16 operand; max_sqnorm_out (optional, 1 float) = max_i ||x_i||^2, which
  * scales the fp16 rounding bound  |approx - exact| <= 2^-10 ||x_i|| ||x_j||. */
 int reid_features_to_half(const float* x, int64_t n_rows, int64_t D, int scale_log2, void* xh,
@@ -100,10 +128,12 @@ int reid_features_to_half(const float* x, int64_t n_rows, int64_t D, int scale_l
  * locality_order != 0: the exact stage gathers ~36 feature rows per query row and is HBM bound; rows of one
  * identity cluster share their candidates, so they are visited back to back (counting sort on the smallest
  * index among a row's strong candidates) and repeats become L2 hits.
+ * list_cap: entries reserved per list (REID_TC_CAP for reid_knn_candidates_tc, the cap given to
+ * reid_knn_candidates_sym); a count above it marks an overflowed list and un-certifies the row.
  * workspace: reid_knn_rescore_workspace_bytes(N, row_end - row_begin). */
 int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, int64_t row_end,
-                     const uint64_t* cand, const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists, int k,
-                     float err_bound, const float* max_sqnorm, int locality_order, int32_t* out_idx, float* out_key,
+                     const uint64_t* cand, const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists,
+                     int list_cap, int k, float err_bound, const float* max_sqnorm, int locality_order, int32_t* out_idx, float* out_key,
                      int32_t* uncertified_flag, float* max_err_out, void* workspace, void* stream);
 size_t reid_knn_rescore_workspace_bytes(int64_t N, int64_t n_rows);
 

@@ -12,7 +12,7 @@ objs=()
 for src in "${HERE}"/*.cu; do
   obj="${HERE}/build/$(basename "${src%.cu}").o"
   objs+=("${obj}")
-  if [[ ! -f "${obj}" || "${src}" -nt "${obj}" || "${HERE}/common.cuh" -nt "${obj}" || "${HERE}/../../include/reid_b200.h" -nt "${obj}" ]]; then
+  if [[ ! -f "${obj}" || "${src}" -nt "${obj}" || "${HERE}/common.cuh" -nt "${obj}" || "${HERE}/tc_ptx.cuh" -nt "${obj}" || "${HERE}/../../include/reid_b200.h" -nt "${obj}" ]]; then
     ( "${NVCC}" "${FLAGS[@]}" -c "${src}" -o "${obj}" > "${obj}.log" 2>&1 || { cat "${obj}.log"; exit 1; } ) &
     pids+=($!)
   fi

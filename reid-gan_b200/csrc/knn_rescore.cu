@@ -33,8 +33,8 @@ __host__ __device__ inline float reid_tc_err_bound(float max_sqnorm) {
 // that is the cluster's smallest index, so cluster mates (who share their candidates) get the same key.
 __global__ void __launch_bounds__(kRsWarps * 32) rescore_select_kernel(
     int64_t row_begin, int64_t n_rows, const unsigned long long* __restrict__ cand,
-    const int32_t* __restrict__ cand_cnt, const uint32_t* __restrict__ row_tau, int n_lists, int k, float eps_in,
-    const float* __restrict__ max_sqnorm, int32_t* __restrict__ win_cnt, int32_t* __restrict__ win_idx, float* __restrict__ win_a,
+    const int32_t* __restrict__ cand_cnt, const uint32_t* __restrict__ row_tau, int n_lists, int list_cap, int k,
+    float eps_in, const float* __restrict__ max_sqnorm, int32_t* __restrict__ win_cnt, int32_t* __restrict__ win_idx, float* __restrict__ win_a,
     int32_t* __restrict__ uncert, int32_t* __restrict__ key_out, int32_t* __restrict__ hist) {
   __shared__ float s_a[kRsWarps][kRsMaxC];
   __shared__ int32_t s_j[kRsWarps][kRsMaxC];
@@ -55,8 +55,8 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_select_kernel(
   auto collect = [&](float thr) {
     int cnt = 0;
     for (int q = 0; q < n_lists; ++q) {
-      const int c = min(cand_cnt[lr * n_lists + q], REID_TC_CAP);
-      const unsigned long long* src = cand + (lr * n_lists + q) * (int64_t)REID_TC_CAP;
+      const int c = min(cand_cnt[lr * n_lists + q], list_cap);
+      const unsigned long long* src = cand + (lr * n_lists + q) * (int64_t)list_cap;
       for (int base = 0; base < c; base += 32) {
         const int t = base + lane;
         unsigned long long e = 0;
@@ -98,6 +98,8 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_select_kernel(
     return m >= k ? ord_float(T) : -INFINITY;
   };
 
+  bool list_overflow = false;                       // an overflowed list lost columns above the threshold
+  for (int q = 0; q < n_lists; ++q) list_overflow |= cand_cnt[lr * n_lists + q] > list_cap;
   float thr = bound - 2.0f * eps;
   int n = collect(thr);
   if (n > kRsMaxC) {
@@ -110,7 +112,7 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_select_kernel(
   if (overflow) n = kRsMaxC;
   const float a_k = kth_largest(n);
   const float lo = a_k - 2.0f * eps;
-  bool certified = !overflow && n >= k && bound < lo;
+  bool certified = !overflow && !list_overflow && n >= k && bound < lo;
 
   // best non-self score -> locality threshold
   float best = -INFINITY;
@@ -319,9 +321,11 @@ __global__ void __launch_bounds__(kGThreads, 2) rescore_group_kernel(
     for (int64_t d4 = tid; d4 < (D >> 2); d4 += kGThreads) {
       float4 v = make_float4(0.f, 0.f, 0.f, 0.f);
       if (lr >= 0) v = xi[d4];
-      double2* dst = reinterpret_cast<double2*>(sQ + (size_t)q * D + d4 * 4);
+      // layout [q][step][half][K-slice] in double2 units: the 16 K-slice lanes of a half warp read 256
+      // contiguous bytes per (step, half) -- no bank conflicts
+      double2* dst = reinterpret_cast<double2*>(sQ + (size_t)q * D) + (d4 >> 4) * 32 + (d4 & 15);
       dst[0] = make_double2((double)v.x, (double)v.y);
-      dst[1] = make_double2((double)v.z, (double)v.w);
+      dst[16] = make_double2((double)v.z, (double)v.w);
     }
   }
   // union of the windows
@@ -384,8 +388,8 @@ __global__ void __launch_bounds__(kGThreads, 2) rescore_group_kernel(
         }
 #pragma unroll
         for (int q = 0; q < kGq; ++q) {
-          const double2* qp = reinterpret_cast<const double2*>(sQ + (size_t)q * D + s * 64 + ks * 4);
-          const double2 q01 = qp[0], q23 = qp[1];
+          const double2* qp = reinterpret_cast<const double2*>(sQ + (size_t)q * D) + s * 32 + ks;
+          const double2 q01 = qp[0], q23 = qp[16];
 #pragma unroll
           for (int i = 0; i < 4; ++i) {
             double a = acc[q * 4 + i];
@@ -498,7 +502,7 @@ size_t reid_knn_rescore_workspace_bytes(int64_t N, int64_t n_rows) {
 }
 
 int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, int64_t row_end, const uint64_t* cand,
-                     const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists, int k, float err_bound,
+                     const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists, int list_cap, int k, float err_bound,
                      const float* max_sqnorm, int locality_order, int32_t* out_idx, float* out_key, int32_t* uncertified_flag,
                      float* max_err_out, void* workspace, void* stream) {
   using namespace reid;
@@ -508,6 +512,7 @@ int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, in
   REID_CHECK_ARG(n_lists >= 1 && n_lists <= 2 * REID_TC_MAX_SPLITS, "reid_knn_rescore: n_lists=%d (max %d)", n_lists,
                  2 * REID_TC_MAX_SPLITS);
   REID_CHECK_ARG(k >= 1 && k <= REID_TC_KEEP_MAX, "reid_knn_rescore: k=%d not in 1..%d", k, REID_TC_KEEP_MAX);
+  REID_CHECK_ARG(list_cap >= 1, "reid_knn_rescore: list_cap=%d", list_cap);
   REID_CHECK_ARG(err_bound >= 0.f, "reid_knn_rescore: negative err_bound");
   const int64_t n = row_end - row_begin;
   if (n == 0) return REID_OK;
@@ -518,7 +523,7 @@ int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, in
   if (locality_order) REID_CUDA(cudaMemsetAsync(w.hist, 0, rs_align(sizeof(int32_t) * (size_t)N) * 2, st));  // hist + cursor
   const unsigned grid = (unsigned)((n + kRsWarps - 1) / kRsWarps);
   rescore_select_kernel<<<grid, kRsWarps * 32, 0, st>>>(row_begin, n, (const unsigned long long*)cand, cand_cnt, row_tau,
-                                                        n_lists, k, err_bound, max_sqnorm, w.win_cnt, w.win_idx, w.win_a,
+                                                        n_lists, list_cap, k, err_bound, max_sqnorm, w.win_cnt, w.win_idx, w.win_a,
                                                         uncertified_flag, locality_order ? w.key : nullptr, w.hist);
   REID_LAUNCH_CHECK();
   if (locality_order) {

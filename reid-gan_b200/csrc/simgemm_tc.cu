@@ -19,105 +19,12 @@
 // A work unit is (128-row query tile) x (one of n_splits column ranges); units are dealt round-robin,
 // column-range major so that concurrently running CTAs stream the same B tiles out of L2.
 // The scores are only candidates: knn_rescore.cu re-scores them exactly and certifies the result.
-#include <cuda.h>
-#include <cuda_fp16.h>
 #include <stdlib.h>
 
-#include "common.cuh"
+#include "tc_ptx.cuh"
 
 namespace reid {
 namespace tc {
-
-constexpr int BM = 128, BN = 256, BK = 64;   // tile; BK * 2 B = 128 B = one swizzle atom row
-constexpr int UMMA_K = 16;
-constexpr int kATileBytes = BM * BK * 2;     // 16 KB
-constexpr int kBTileBytes = BN * BK * 2;     // 32 KB
-constexpr int kThreads = 320;               // TMA warp, MMA warp, 2 x 4 epilogue warps
-constexpr int kCap = REID_TC_CAP;            // per (row, split) candidate list capacity
-
-__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
-
-__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
-  asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
-}
-__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
-  asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
-}
-__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
-  asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
-}
-__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
-  uint32_t ok;
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n"
-      "selp.u32 %0, 1, 0, p;\n"
-      "}\n"
-      : "=r"(ok)
-      : "r"(smem_u32(bar)), "r"(parity)
-      : "memory");
-  return ok != 0;
-}
-__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
-  while (!mbar_try_wait(bar, parity)) {
-  }
-}
-
-__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* tmap, uint64_t* bar, int c0, int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(smem_u32(bar)), "r"(c0), "r"(c1)
-      : "memory");
-}
-
-__device__ __forceinline__ void tcgen05_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
-__device__ __forceinline__ void tcgen05_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
-
-// K-major operand tile, 128-byte swizzle: rows are 128 B apart inside an 8-row / 1024 B atom (SBO = 1024 B)
-__device__ __forceinline__ uint64_t make_smem_desc(uint32_t smem_addr) {
-  uint64_t d = 0;
-  d |= (uint64_t)((smem_addr >> 4) & 0x3fffu);        // start address
-  d |= (uint64_t)1 << 16;                             // leading byte offset (unused with swizzle; canonical 1)
-  d |= (uint64_t)(1024 >> 4) << 32;                   // stride byte offset
-  d |= (uint64_t)1 << 46;                             // descriptor version (sm_100)
-  d |= (uint64_t)2 << 61;                             // SWIZZLE_128B
-  return d;
-}
-
-// kind::f16 instruction descriptor: fp16 A/B (K-major), fp32 accumulate, M x N
-__host__ __device__ constexpr uint32_t make_idesc(int M, int N) {
-  return (1u << 4) | ((uint32_t)(N >> 3) << 17) | ((uint32_t)(M >> 4) << 24);
-}
-
-__device__ __forceinline__ void umma_f16(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                         uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_c),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-__device__ __forceinline__ void umma_commit(uint64_t* bar) {
-  asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
-               : "memory");
-}
-
-__device__ __forceinline__ void tmem_ld_32x32b_x32(uint32_t taddr, uint32_t (&v)[32]) {
-  asm volatile(
-      "tcgen05.ld.sync.aligned.32x32b.x32.b32 "
-      "{%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15, "
-      "%16, %17, %18, %19, %20, %21, %22, %23, %24, %25, %26, %27, %28, %29, %30, %31}, [%32];"
-      : "=r"(v[0]), "=r"(v[1]), "=r"(v[2]), "=r"(v[3]), "=r"(v[4]), "=r"(v[5]), "=r"(v[6]), "=r"(v[7]), "=r"(v[8]),
-        "=r"(v[9]), "=r"(v[10]), "=r"(v[11]), "=r"(v[12]), "=r"(v[13]), "=r"(v[14]), "=r"(v[15]), "=r"(v[16]),
-        "=r"(v[17]), "=r"(v[18]), "=r"(v[19]), "=r"(v[20]), "=r"(v[21]), "=r"(v[22]), "=r"(v[23]), "=r"(v[24]),
-        "=r"(v[25]), "=r"(v[26]), "=r"(v[27]), "=r"(v[28]), "=r"(v[29]), "=r"(v[30]), "=r"(v[31])
-      : "r"(taddr));
-  asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
-}
 
 // Cooperative compaction of one row's candidate list (n entries at `list`, n <= kCap) to (at least) its
 // best `keep` entries.  Entry = (score bits << 32) | column.  The threshold is found by a bitwise binary
@@ -185,55 +92,9 @@ struct Params {
   unsigned long long* cand;   // [(rows) x n_splits x kCap]
   int32_t* cand_cnt;          // [(rows) x n_splits]
   uint32_t* row_tau;          // [rows] shared rejection threshold per query row (order-preserving image), 0 = none
+  int boot;                   // sampling prepass: seed tau from the first 32 scores of a unit (see the epilogue)
   int dbg;                    // developer switch (REID_TC_DEBUG): 1 = epilogue skips TMEM reads, 2 = reads but no selection, 4 = no TMA
 };
-
-// ---- cta_group::2 flavours of the PTX wrappers (CTA pair = one 256-row MMA tile) ---------------------
-__device__ __forceinline__ uint32_t cluster_ctarank() {
-  uint32_t r;
-  asm volatile("mov.u32 %0, %%cluster_ctarank;" : "=r"(r));
-  return r;
-}
-__device__ __forceinline__ void cluster_sync_all() {
-  asm volatile("barrier.cluster.arrive.release.aligned;" ::: "memory");
-  asm volatile("barrier.cluster.wait.acquire.aligned;" ::: "memory");
-}
-// address of this CTA's shared object inside CTA `rank` of the cluster (shared::cluster window)
-__device__ __forceinline__ uint32_t mapa_u32(uint32_t local_addr, uint32_t rank) {
-  uint32_t r;
-  asm volatile("mapa.shared::cluster.u32 %0, %1, %2;" : "=r"(r) : "r"(local_addr), "r"(rank));
-  return r;
-}
-__device__ __forceinline__ void mbar_arrive_cluster(uint32_t cluster_addr) {
-  asm volatile("mbarrier.arrive.shared::cluster.b64 _, [%0];" ::"r"(cluster_addr) : "memory");
-}
-// TMA load whose completion is signalled on the LEADER CTA's barrier (cluster address)
-__device__ __forceinline__ void tma_load_2d_pair(void* smem_dst, const CUtensorMap* tmap, uint32_t leader_bar, int c0,
-                                                 int c1) {
-  asm volatile(
-      "cp.async.bulk.tensor.2d.cta_group::2.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%3, %4}], [%2];"
-      ::"r"(smem_u32(smem_dst)), "l"(tmap), "r"(leader_bar), "r"(c0), "r"(c1)
-      : "memory");
-}
-__device__ __forceinline__ void umma_f16_pair(uint32_t tmem_c, uint64_t desc_a, uint64_t desc_b, uint32_t idesc,
-                                              uint32_t accumulate) {
-  asm volatile(
-      "{\n"
-      ".reg .pred p;\n"
-      "setp.ne.b32 p, %4, 0;\n"
-      "tcgen05.mma.cta_group::2.kind::f16 [%0], %1, %2, %3, p;\n"
-      "}\n" ::"r"(tmem_c),
-      "l"(desc_a), "l"(desc_b), "r"(idesc), "r"(accumulate)
-      : "memory");
-}
-// commit arriving on the barrier at the same offset in BOTH CTAs of the pair
-__device__ __forceinline__ void umma_commit_pair(uint64_t* bar) {
-  asm volatile(
-      "tcgen05.commit.cta_group::2.mbarrier::arrive::one.shared::cluster.multicast::cluster.b64 [%0], %1;" ::"r"(
-          smem_u32(bar)),
-      "h"((uint16_t)3)
-      : "memory");
-}
 
 template <int kCtas>
 struct Cfg {
@@ -251,7 +112,8 @@ struct Cfg {
 //            CTA issues the MMAs, both CTAs run a TMA producer and the top-K epilogue on their own
 //            128 accumulator lanes.
 template <int kCtas>
-__global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_constant__ CUtensorMap tmap, const Params p) {
+__global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_constant__ CUtensorMap tmap, const __grid_constant__ CUtensorMap tmap_b,
+                                                                  const Params p) {
   using C = Cfg<kCtas>;
   constexpr int kNumStages = C::kNumStages;
   extern __shared__ __align__(1024) uint8_t smem_raw[];
@@ -268,6 +130,7 @@ __global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_const
 
   if (warp == 0 && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
+    asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap_b) : "memory");
     for (int s = 0; s < kNumStages; ++s) {
       mbar_init(&full_bar[s], 1);
       mbar_init(&empty_bar[s], 1);
@@ -314,14 +177,14 @@ __global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_const
             } else if (kCtas == 1) {
               mbar_expect_tx(&full_bar[stage], C::kStage);
               tma_load_2d(a_dst, &tmap, &full_bar[stage], kb * BK, m_row);
-              tma_load_2d(b_dst, &tmap, &full_bar[stage], kb * BK, t * BN);
-              tma_load_2d(b_dst + kATileBytes, &tmap, &full_bar[stage], kb * BK, t * BN + 128);
+              tma_load_2d(b_dst, &tmap_b, &full_bar[stage], kb * BK, t * BN);
+              tma_load_2d(b_dst + kATileBytes, &tmap_b, &full_bar[stage], kb * BK, t * BN + 128);
             } else {
               // all bytes of the pair are accounted on the leader's barrier
               if (leader) mbar_expect_tx(&full_bar[stage], 2 * C::kStage);
               const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
               tma_load_2d_pair(a_dst, &tmap, lbar, kb * BK, m_row);
-              tma_load_2d_pair(b_dst, &tmap, lbar, kb * BK, t * BN + (int)cta_rank * 128);
+              tma_load_2d_pair(b_dst, &tmap_b, lbar, kb * BK, t * BN + (int)cta_rank * 128);
             }
             if (++stage == kNumStages) {
               stage = 0;
@@ -412,6 +275,24 @@ __global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_const
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + ch * 32, v);
           const int col0 = t * BN + ch * 32;
+          if (p.boot && cnt == 0 && tau == -INFINITY) {
+            // Sampling prepass (reid_knn_sample_tau wants the r-th best of a few thousand scores, r ~ 16): instead
+            // of appending the first tiles unfiltered -- uncoalesced 8-byte stores that outlast the MMA -- seed the
+            // threshold with the 5th largest of the first 32 scores, a value about 5/32 of all scores beat (the chance
+            // that fewer than r of a list's ~1000 scores beat it is ~1e-5).  A seed
+            // that lands too high only makes the final threshold lower (more candidates), never wrong.
+            float m1 = -INFINITY, m2 = -INFINITY, m3 = -INFINITY, m4 = -INFINITY, m5 = -INFINITY;
+#pragma unroll
+            for (int c = 0; c < 32; ++c) {
+              float s = __uint_as_float(v[c]) * p.descale, lo;
+              lo = fminf(m1, s), m1 = fmaxf(m1, s), s = lo;
+              lo = fminf(m2, s), m2 = fmaxf(m2, s), s = lo;
+              lo = fminf(m3, s), m3 = fmaxf(m3, s), s = lo;
+              lo = fminf(m4, s), m4 = fmaxf(m4, s), s = lo;
+              m5 = fmaxf(m5, s);
+            }
+            tau = m5;
+          }
           if (p.dbg & 2) {
             float m = 0.f;
 #pragma unroll
@@ -500,6 +381,27 @@ static EncodeTiledFn get_encode_fn() {
   return fn;
 }
 
+// fp16 row-major (n_rows x D) matrix -> tensor map with a (64 x 128-row) box, 128-byte swizzle
+int make_tmap_rows128(CUtensorMap* tmap, const void* base, int64_t n_rows, int64_t D) {
+  EncodeTiledFn encode = get_encode_fn();
+  if (!encode) {
+    set_error("cuTensorMapEncodeTiled is not available from the driver");
+    return REID_ERR_CUDA;
+  }
+  const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)n_rows};
+  const cuuint64_t gstride[1] = {(cuuint64_t)D * 2};
+  const cuuint32_t box[2] = {(cuuint32_t)BK, 128u};
+  const cuuint32_t estr[2] = {1u, 1u};
+  CUresult cr = encode(tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(base), gdim, gstride, box, estr,
+                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+  if (cr != CUDA_SUCCESS) {
+    set_error("cuTensorMapEncodeTiled failed (%d)", (int)cr);
+    return REID_ERR_CUDA;
+  }
+  return REID_OK;
+}
+
 }  // namespace tc
 }  // namespace reid
 
@@ -545,35 +447,32 @@ int reid_features_to_half(const float* x, int64_t n_rows, int64_t D, int scale_l
 int reid_knn_candidates_tc(const void* xh, int64_t N, int64_t D, int scale_log2, int64_t row_begin, int64_t row_end,
                            int keep, int n_splits, int cta_group, uint64_t* cand, int32_t* cand_cnt, uint32_t* row_tau,
                            void* stream) {
+  return reid_knn_candidates_tc_ab(xh, N, xh, N, D, scale_log2, row_begin, row_end, keep, n_splits, cta_group, cand,
+                                   cand_cnt, row_tau, stream);
+}
+
+int reid_knn_candidates_tc_ab(const void* xa, int64_t Na, const void* xh, int64_t N, int64_t D, int scale_log2,
+                              int64_t row_begin, int64_t row_end, int keep, int n_splits, int cta_group, uint64_t* cand,
+                              int32_t* cand_cnt, uint32_t* row_tau, void* stream) {
   using namespace reid;
-  REID_CHECK_ARG(xh && cand && cand_cnt && row_tau, "reid_knn_candidates_tc: NULL pointer");
-  REID_CHECK_ARG(N > 0 && N < (1ll << 31) && D > 0 && D % tc::BK == 0, "reid_knn_candidates_tc: need D %% 64 == 0 (D=%lld)",
-                 (long long)D);
-  REID_CHECK_ARG(((uintptr_t)xh & 15) == 0, "reid_knn_candidates_tc: xh must be 16-byte aligned");
-  REID_CHECK_ARG(0 <= row_begin && row_begin < row_end && row_end <= N, "reid_knn_candidates_tc: bad row range");
+  const int boot = keep < 0;          // keep < 0: sampling prepass, |keep| kept, threshold seeded from the first scores
+  if (boot) keep = -keep;
+  REID_CHECK_ARG(xa && xh && cand && cand_cnt && row_tau, "reid_knn_candidates_tc: NULL pointer");
+  REID_CHECK_ARG(N > 0 && N < (1ll << 31) && Na > 0 && Na < (1ll << 31) && D > 0 && D % tc::BK == 0,
+                 "reid_knn_candidates_tc: need D %% 64 == 0 (D=%lld)", (long long)D);
+  REID_CHECK_ARG(((uintptr_t)xh & 15) == 0 && ((uintptr_t)xa & 15) == 0, "reid_knn_candidates_tc: operands must be 16-byte aligned");
+  REID_CHECK_ARG(0 <= row_begin && row_begin < row_end && row_end <= Na, "reid_knn_candidates_tc: bad row range");
   REID_CHECK_ARG(keep >= 1 && keep <= REID_TC_KEEP_MAX, "reid_knn_candidates_tc: keep=%d not in 1..%d", keep,
                  REID_TC_KEEP_MAX);
   REID_CHECK_ARG(cta_group == 1 || cta_group == 2, "reid_knn_candidates_tc: cta_group=%d must be 1 or 2", cta_group);
   const int64_t n_tiles = (N + tc::BN - 1) / tc::BN;
   REID_CHECK_ARG(n_splits >= 1 && n_splits <= REID_TC_MAX_SPLITS && n_splits <= n_tiles,
                  "reid_knn_candidates_tc: n_splits=%d", n_splits);
-  tc::EncodeTiledFn encode = tc::get_encode_fn();
-  if (!encode) {
-    set_error("reid_knn_candidates_tc: cuTensorMapEncodeTiled is not available from the driver");
-    return REID_ERR_CUDA;
-  }
-  CUtensorMap tmap;
-  const cuuint64_t gdim[2] = {(cuuint64_t)D, (cuuint64_t)N};
-  const cuuint64_t gstride[1] = {(cuuint64_t)D * 2};
-  const cuuint32_t box[2] = {(cuuint32_t)tc::BK, 128u};
-  const cuuint32_t estr[2] = {1u, 1u};
-  CUresult cr = encode(&tmap, CU_TENSOR_MAP_DATA_TYPE_FLOAT16, 2, const_cast<void*>(xh), gdim, gstride, box, estr,
-                       CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
-                       CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
-  if (cr != CUDA_SUCCESS) {
-    set_error("reid_knn_candidates_tc: cuTensorMapEncodeTiled failed (%d)", (int)cr);
-    return REID_ERR_CUDA;
-  }
+  CUtensorMap tmap, tmap_b;
+  int rc = tc::make_tmap_rows128(&tmap, xa, Na, D);
+  if (rc != REID_OK) return rc;
+  rc = tc::make_tmap_rows128(&tmap_b, xh, N, D);
+  if (rc != REID_OK) return rc;
   tc::Params p;
   p.N = N;
   p.row_begin = row_begin;
@@ -583,6 +482,7 @@ int reid_knn_candidates_tc(const void* xh, int64_t N, int64_t D, int scale_log2,
   p.n_splits = n_splits;
   p.n_tiles = (int)n_tiles;
   p.keep = keep;
+  p.boot = boot;
   p.descale = ldexpf(1.0f, -2 * scale_log2);
   p.cand = (unsigned long long*)cand;
   p.cand_cnt = cand_cnt;
@@ -609,11 +509,11 @@ int reid_knn_candidates_tc(const void* xh, int64_t N, int64_t D, int scale_log2,
   if (cta_group == 1) {
     cfg.dynamicSmemBytes = tc::Cfg<1>::kSmem;
     REID_CUDA(cudaFuncSetAttribute(tc::simtopk_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<1>::kSmem));
-    REID_CUDA(cudaLaunchKernelEx(&cfg, tc::simtopk_kernel<1>, tmap, p));
+    REID_CUDA(cudaLaunchKernelEx(&cfg, tc::simtopk_kernel<1>, tmap, tmap_b, p));
   } else {
     cfg.dynamicSmemBytes = tc::Cfg<2>::kSmem;
     REID_CUDA(cudaFuncSetAttribute(tc::simtopk_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::Cfg<2>::kSmem));
-    REID_CUDA(cudaLaunchKernelEx(&cfg, tc::simtopk_kernel<2>, tmap, p));
+    REID_CUDA(cudaLaunchKernelEx(&cfg, tc::simtopk_kernel<2>, tmap, tmap_b, p));
   }
   REID_LAUNCH_CHECK();
   return REID_OK;

@@ -26,6 +26,59 @@ def err_bound(max_sqnorm):
     return float(max_sqnorm) * (2.0 ** -10) * 1.02 + 2.0 ** -14
 
 
+SYM = __import__("os").environ.get("REID_TC_SYM", "1") != "0"     # symmetric search when the shard is the whole matrix
+SYM_MIN_N = 8192        # below this the sample cannot give a tight threshold; the one-sided kernel is used
+SYM_CAP = 1024          # list capacity per row in the symmetric search
+SYM_RANK = 16           # tau_i = SYM_RANK-th best sample score ...
+SYM_TARGET = 256        # ... with the sample sized so that about SYM_TARGET columns beat it
+_tile_cache = {}
+
+
+def _tile_order(n_t, dev, sb=8):
+    """Upper-triangle 256 x 256 tiles in super-blocks of sb x sb: the ~74 tiles in flight share 2*sb operand
+    blocks, so they stream out of L2.  Cached per (n_t, device)."""
+    key_ = (n_t, str(dev))
+    if key_ not in _tile_cache:
+        out = []
+        nb = (n_t + sb - 1) // sb
+        for bi in range(nb):
+            for bj in range(bi, nb):
+                for i in range(bi * sb, min(n_t, (bi + 1) * sb)):
+                    for j in range(max(i, bj * sb), min(n_t, (bj + 1) * sb)):
+                        out.append((i, j))
+        _tile_cache[key_] = torch.tensor(out, dtype=torch.int32).to(dev).contiguous()
+    return _tile_cache[key_]
+
+
+def _sample_stride(N):
+    """~N / golden ratio, coprime with N: (m * stride) mod N walks the rows with low discrepancy."""
+    import math
+    a = max(1, int(round(N * 0.6180339887498949)))
+    while math.gcd(a, N) != 1:
+        a += 1
+    return a
+
+
+def _candidates_sym(xh, N, D, sp, dev):
+    """Prepass (sample thresholds) + symmetric main pass.  Returns (cand, cand_cnt, tau_ord, cap, stats)."""
+    m = min(N, max(1024, -(-(SYM_RANK * N // SYM_TARGET) // 256) * 256))
+    xs = torch.empty((m, D), dtype=torch.float16, device=dev)
+    call("reid_features_sample", ptr(xh), N, D, m, _sample_stride(N), ptr(xs), sp)
+    cand = torch.empty(N * max(2 * TC_CAP, SYM_CAP), dtype=torch.int64, device=dev)     # prepass lists, then main lists
+    pre_cnt = torch.zeros(N * 2, dtype=torch.int32, device=dev)
+    pre_tau = torch.empty(N, dtype=torch.int32, device=dev)
+    call("reid_knn_candidates_tc_ab", ptr(xh), N, ptr(xs), m, D, SCALE_LOG2, 0, N, -SYM_RANK, 1, 2, ptr(cand), ptr(pre_cnt),
+         ptr(pre_tau), sp)
+    tau = torch.empty(N, dtype=torch.float32, device=dev)
+    tau_ord = torch.empty(N, dtype=torch.int32, device=dev)
+    call("reid_knn_sample_tau", ptr(cand), ptr(pre_cnt), ptr(pre_tau), 2, N, SYM_RANK, ptr(tau), ptr(tau_ord), sp)
+    tiles = _tile_order((N + 255) // 256, dev)
+    cnt = torch.empty(N, dtype=torch.int32, device=dev)
+    call("reid_knn_candidates_sym", ptr(xh), N, D, SCALE_LOG2, ptr(tau), ptr(tiles), tiles.shape[0], SYM_CAP, ptr(cand),
+         ptr(cnt), sp)
+    return cand, cnt, tau_ord, SYM_CAP, dict(sample=m, tiles=int(tiles.shape[0]))
+
+
 def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None):
     L = _lib.lib()
     from .faiss_rerank import _knn_exact_rows
@@ -40,20 +93,26 @@ def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None):
         max_sqnorm = None
     else:
         msq = None
-    n_splits = ctypes.c_int(1)
-    call("reid_knn_tc_plan", N, n, CTA_GROUP, ctypes.byref(n_splits))
-    s = n_splits.value
+    sym = SYM and r0 == 0 and r1 == N and N >= SYM_MIN_N and k <= 32
     keep = max(k, min(k + SLACK, KEEP_MAX))
-    n_lists = 2 * s                                        # two epilogue groups per column range
-    cand = torch.empty(n * n_lists * TC_CAP, dtype=torch.int64, device=dev)
-    cand_cnt = torch.zeros(n * n_lists, dtype=torch.int32, device=dev)
-    row_tau = torch.empty(n, dtype=torch.int32, device=dev)
-    call("reid_knn_candidates_tc", ptr(xh), N, D, SCALE_LOG2, r0, r1, keep, s, CTA_GROUP, ptr(cand), ptr(cand_cnt), ptr(row_tau), sp)
+    if sym:
+        cand, cand_cnt, row_tau, list_cap, sym_info = _candidates_sym(xh, N, D, sp, dev)
+        n_lists, s = 1, 0
+    else:
+        n_splits = ctypes.c_int(1)
+        call("reid_knn_tc_plan", N, n, CTA_GROUP, ctypes.byref(n_splits))
+        s = n_splits.value
+        n_lists = 2 * s                                        # two epilogue groups per column range
+        list_cap, sym_info = TC_CAP, None
+        cand = torch.empty(n * n_lists * TC_CAP, dtype=torch.int64, device=dev)
+        cand_cnt = torch.zeros(n * n_lists, dtype=torch.int32, device=dev)
+        row_tau = torch.empty(n, dtype=torch.int32, device=dev)
+        call("reid_knn_candidates_tc", ptr(xh), N, D, SCALE_LOG2, r0, r1, keep, s, CTA_GROUP, ptr(cand), ptr(cand_cnt), ptr(row_tau), sp)
     eps = err_bound(max_sqnorm) if max_sqnorm is not None else 0.0   # else derived on device from msq
     flag = torch.empty(n, dtype=torch.int32, device=dev)
     max_err = torch.zeros(1, dtype=torch.float32, device=dev)
     ws = torch.empty(L.reid_knn_rescore_workspace_bytes(N, n), dtype=torch.uint8, device=dev)
-    call("reid_knn_rescore", ptr(x), N, D, r0, r1, ptr(cand), ptr(cand_cnt), ptr(row_tau), n_lists, k, eps,
+    call("reid_knn_rescore", ptr(x), N, D, r0, r1, ptr(cand), ptr(cand_cnt), ptr(row_tau), n_lists, list_cap, k, eps,
          ptr(msq), 1 if ORDER_ROWS else 0, ptr(idx), ptr(key), ptr(flag), ptr(max_err), ptr(ws), sp)
     bad = torch.nonzero(flag).flatten().to(torch.int32)
     n_bad = bad.numel()
@@ -64,6 +123,6 @@ def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None):
         _knn_exact_rows(x, k, rows, 0, n_bad, bi, bk)
         idx[bad.long()] = bi
         key[bad.long()] = bk
-    info.update(mode="tc", cta_group=CTA_GROUP, n_splits=s, keep=keep, err_bound=eps if msq is None else None, max_sqnorm=msq, uncertified_rows=int(n_bad),
+    info.update(mode="tc-sym" if sym else "tc", sym=sym_info, cand_cnt=cand_cnt if sym else None, cta_group=CTA_GROUP, n_splits=s, keep=keep, err_bound=eps if msq is None else None, max_sqnorm=msq, uncertified_rows=int(n_bad),
                 max_abs_err=max_err, xh=xh)
     return idx, key, info

@@ -12,9 +12,13 @@ def run(N, D, n_ids, k, noise=0.8, seed=0):
     t = time.time(); ie, ke, _ = fr.knn_search(xd, k, "exact"); torch.cuda.synchronize(); te = time.time() - t
     t = time.time(); it, kt, info = fr.knn_search(xd, k, "tc"); torch.cuda.synchronize(); tt = time.time() - t
     same = bool(torch.equal(ie, it)); samek = bool(torch.equal(ke, kt))
-    print("N=%d D=%d k=%d: idx equal %s, keys equal %s, uncertified %d/%d, splits %d keep %d, max_err %.3e, exact %.3fs tc %.3fs"
-          % (N, D, k, same, samek, info["uncertified_rows"], N, info["n_splits"], info["keep"],
-             float(info["max_abs_err"]), te, tt), flush=True)
+    extra = ""
+    if info.get("cand_cnt") is not None:
+        c = info["cand_cnt"].float()
+        extra = " | sym %s cand/row mean %.0f min %d max %d" % (info["sym"], c.mean(), int(c.min()), int(c.max()))
+    print("N=%d D=%d k=%d [%s]: idx equal %s, keys equal %s, uncertified %d/%d, splits %d keep %d, max_err %.3e, exact %.3fs tc %.3fs%s"
+          % (N, D, k, info["mode"], same, samek, info["uncertified_rows"], N, info["n_splits"], info["keep"],
+             float(info["max_abs_err"]), te, tt, extra), flush=True)
     if not same:
         bad = torch.nonzero((ie != it).any(dim=1)).flatten()
         print("  first bad rows", bad[:10].tolist())
@@ -22,6 +26,8 @@ def run(N, D, n_ids, k, noise=0.8, seed=0):
     return same
 
 ok = True
-for cfg in [(512, 64, 16, 10), (2048, 256, 64, 30), (5000, 512, 5000, 30), (12936, 2048, 751, 30)]:
+cfgs = [(512, 64, 16, 10), (2048, 256, 64, 30), (5000, 512, 5000, 30), (12936, 2048, 751, 30), (9000, 512, 9000, 30),
+        (20000, 256, 100, 30), (32621, 2048, 1041, 30)]
+for cfg in cfgs:
     ok &= run(*cfg)
 print("ALL OK" if ok else "MISMATCH")
