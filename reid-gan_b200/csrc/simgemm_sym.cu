@@ -31,10 +31,16 @@ namespace tc {
 
 int make_tmap_rows128(CUtensorMap* tmap, const void* base, int64_t n_rows, int64_t D);   // simgemm_tc.cu
 
+// Warps 0..7 are the two epilogue groups, warp 8 the TMA producer, warp 9 the MMA issuer: the warp scheduler
+// favours the highest warp id among the eligible ones, and the single-thread MMA / TMA roles are the ones that
+// must never wait for an issue slot behind an epilogue warp.
+constexpr int kTmaWarp = 8, kMmaWarp = 9;
 constexpr int kSymStages = 6;
 constexpr int kSymStage = kATileBytes + 128 * BK * 2;     // 16 KB of A + this CTA's half (128 rows) of B
 constexpr int kSymTauBytes = 2 * BN * 4;                  // column thresholds, one buffer per epilogue group
-constexpr int kSymSmem = kSymStages * kSymStage + 1024 /*align*/ + 256 /*barriers*/ + kSymTauBytes;
+constexpr int kSymHitSlots = 8;                           // staged survivors per lane and tile
+constexpr int kSymHitBytes = 8 * kSymHitSlots * 32 * 8;   // 8 epilogue warps x slots x lanes x 8 B = 16 KB
+constexpr int kSymSmem = kSymStages * kSymStage + 1024 /*align*/ + 256 /*barriers*/ + kSymTauBytes + kSymHitBytes;
 
 struct SymParams {
   int64_t N;
@@ -47,6 +53,8 @@ struct SymParams {
   int cap;                         // list capacity per row
   unsigned long long* cand;        // [N x cap] (score bits << 32) | column
   int32_t* cand_cnt;               // [N] appended entries (may exceed cap: the list overflowed)
+  int dbg;                         // developer switch (REID_TC_DEBUG): 1 = epilogue skips the TMEM reads, 2 = reads but no
+                                   // selection, 4 = no TMA (MMA issue only)
 };
 
 __device__ __forceinline__ void sym_append(const SymParams& p, int64_t row, int col, float s) {
@@ -63,12 +71,13 @@ __global__ void __launch_bounds__(kThreads, 1) simsym_kernel(const __grid_consta
   uint64_t* tempty_bar = tfull_bar + 2;           // [2] accumulator drained (lives in the leader CTA)
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
   float* s_tauc = (float*)(smem + kSymStages * kSymStage + 256);     // [2][BN]
+  unsigned long long* s_hits = (unsigned long long*)(smem + kSymStages * kSymStage + 256 + kSymTauBytes);  // [8][slots][32]
 
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t cta_rank = cluster_ctarank();
   const bool leader = cta_rank == 0;
 
-  if (warp == 0 && lane == 0) {
+  if (warp == kTmaWarp && lane == 0) {
     asm volatile("prefetch.tensormap [%0];" ::"l"(&tmap) : "memory");
     for (int s = 0; s < kSymStages; ++s) {
       mbar_init(&full_bar[s], 1);
@@ -80,7 +89,7 @@ __global__ void __launch_bounds__(kThreads, 1) simsym_kernel(const __grid_consta
     }
     asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
   }
-  if (warp == 1) {  // TMEM: all 512 columns = two 128 x 256 fp32 accumulators (per CTA)
+  if (warp == kMmaWarp) {  // TMEM: all 512 columns = two 128 x 256 fp32 accumulators (per CTA)
     asm volatile("tcgen05.alloc.cta_group::2.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(tmem_slot)), "r"(512));
     asm volatile("tcgen05.relinquish_alloc_permit.cta_group::2.sync.aligned;");
   }
@@ -91,7 +100,7 @@ __global__ void __launch_bounds__(kThreads, 1) simsym_kernel(const __grid_consta
 
   const int unit0 = blockIdx.x >> 1, unit_step = gridDim.x >> 1;
 
-  if (warp == 0) {
+  if (warp == kTmaWarp) {
     // ------------------------------ TMA producer ------------------------------
     if (lane == 0) {
       int stage = 0;
@@ -104,10 +113,14 @@ __global__ void __launch_bounds__(kThreads, 1) simsym_kernel(const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + stage * kSymStage;
           uint8_t* b_dst = a_dst + kATileBytes;
-          if (leader) mbar_expect_tx(&full_bar[stage], 2 * kSymStage);   // the pair's bytes land on the leader's barrier
-          const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
-          tma_load_2d_pair(a_dst, &tmap, lbar, kb * BK, a_row);
-          tma_load_2d_pair(b_dst, &tmap, lbar, kb * BK, b_row);
+          if (p.dbg & 4) {
+            if (leader) mbar_arrive(&full_bar[stage]);
+          } else {
+            if (leader) mbar_expect_tx(&full_bar[stage], 2 * kSymStage);   // the pair's bytes land on the leader's barrier
+            const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
+            tma_load_2d_pair(a_dst, &tmap, lbar, kb * BK, a_row);
+            tma_load_2d_pair(b_dst, &tmap, lbar, kb * BK, b_row);
+          }
           if (++stage == kSymStages) {
             stage = 0;
             phase ^= 1;
@@ -115,7 +128,7 @@ __global__ void __launch_bounds__(kThreads, 1) simsym_kernel(const __grid_consta
         }
       }
     }
-  } else if (warp == 1) {
+  } else if (warp == kMmaWarp) {
     // ------------------------------ MMA issuer (leader CTA only) ----------------
     if (lane == 0 && leader) {
       constexpr uint32_t idesc = make_idesc(BM * 2, BN);
@@ -153,12 +166,13 @@ __global__ void __launch_bounds__(kThreads, 1) simsym_kernel(const __grid_consta
     }
   } else {
     // ------------------------------ epilogue: fixed-threshold selection, both directions -------------
-    const int wg = (warp - 2) >> 2;                     // group g drains accumulator g = every other tile of the CTA
+    const int wg = warp >> 2;                           // group g drains accumulator g = every other tile of the CTA
     const int quarter = warp & 3;                       // TMEM lanes this warp may read
     const int r_in_tile = (int)cta_rank * BM + quarter * 32 + lane;
-    const int gt = (warp - 2 - wg * 4) * 32 + lane;     // 0..127 inside the group
+    const int gt = (warp - wg * 4) * 32 + lane;         // 0..127 inside the group
     const uint32_t tempty_remote = mapa_u32(smem_u32(&tempty_bar[wg]), 0);
     float* tauc = s_tauc + wg * BN;
+    unsigned long long* hits = s_hits + (size_t)warp * kSymHitSlots * 32;
     uint32_t acc_phase = 0;
     int tile_ctr = 0;
     for (int u = unit0; u < p.n_units; u += unit_step, ++tile_ctr) {
@@ -182,11 +196,20 @@ __global__ void __launch_bounds__(kThreads, 1) simsym_kernel(const __grid_consta
       acc_phase ^= 1;
       tcgen05_fence_after();
       const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wg * BN);
+      int n_hit = 0;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
+        if (p.dbg & 1) break;
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + ch * 32, v);
         const int col0 = tj * BN + ch * 32;
+        if (p.dbg & 2) {
+          float mx = 0.f;
+#pragma unroll
+          for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
+          if (mx == 123.456f) sym_append(p, 0, 0, mx);
+          continue;
+        }
         const float4* tc4 = reinterpret_cast<const float4*>(tauc + ch * 32);
         unsigned hit = 0;
 #pragma unroll
@@ -205,10 +228,24 @@ __global__ void __launch_bounds__(kThreads, 1) simsym_kernel(const __grid_consta
           float a = 0.f;
 #pragma unroll
           for (int e = 0; e < 32; ++e) a = e == c ? __uint_as_float(v[e]) : a;   // v[] stays in registers
-          const int col = col0 + c;
-          const float s = a * p.descale;
-          if (a > tr && col < p.N) sym_append(p, row, col, s);
-          if (row_ok && a > tauc[ch * 32 + c]) sym_append(p, col, (int)row, s);
+          const int cl = ch * 32 + c;                    // column inside the tile
+          const bool d_hit = a > tr && col0 + c < p.N;
+          const bool t_hit = row_ok && a > tauc[cl];
+          // Survivors are parked in shared memory (lane-private slots) and appended to the global lists only
+          // after the accumulator has gone back to the MMA warp: an atomicAdd round trip per survivor inside the
+          // drain would outlast the tile period.  entry = score | column-in-tile | both-directions flags.
+          if (d_hit | t_hit) {
+            const unsigned long long e8 = ((unsigned long long)__float_as_uint(a * p.descale) << 32) |
+                                          ((unsigned long long)cl << 2) | (d_hit ? 1ull : 0ull) | (t_hit ? 2ull : 0ull);
+            if (n_hit < kSymHitSlots) {
+              hits[n_hit * 32 + lane] = e8;
+              ++n_hit;
+            } else {                                     // lane out of slots: append right away
+              const float sc = a * p.descale;
+              if (d_hit) sym_append(p, row, col0 + c, sc);
+              if (t_hit) sym_append(p, col0 + c, (int)row, sc);
+            }
+          }
         }
       }
       // the accumulator is drained: hand it back to the MMA warp
@@ -218,12 +255,23 @@ __global__ void __launch_bounds__(kThreads, 1) simsym_kernel(const __grid_consta
         if (leader) mbar_arrive(&tempty_bar[wg]);
         else mbar_arrive_cluster(tempty_remote);
       }
+      // flush the parked survivors (every lane its own; the atomics of the 32 lanes overlap)
+      const int max_hit = __reduce_max_sync(kFull, n_hit);
+      for (int h = 0; h < max_hit; ++h) {
+        if (h < n_hit) {
+          const unsigned long long e8 = hits[h * 32 + lane];
+          const float sc = __uint_as_float((uint32_t)(e8 >> 32));
+          const int col = tj * BN + (int)((e8 >> 2) & 0xffu);
+          if (e8 & 1ull) sym_append(p, row, col, sc);
+          if (e8 & 2ull) sym_append(p, col, (int)row, sc);
+        }
+      }
     }
   }
 
   tcgen05_fence_before();
   cluster_sync_all();
-  if (warp == 1) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
+  if (warp == kMmaWarp) asm volatile("tcgen05.dealloc.cta_group::2.sync.aligned.b32 %0, %1;" ::"r"(tmem_base), "r"(512));
 }
 
 // xs[m] = xh[(m * stride) mod N]: a low-discrepancy sample of the rows (stride ~ N / golden ratio, coprime
@@ -342,6 +390,10 @@ int reid_knn_candidates_sym(const void* xh, int64_t N, int64_t D, int scale_log2
   p.cap = cap;
   p.cand = (unsigned long long*)cand;
   p.cand_cnt = cand_cnt;
+  {
+    const char* e = getenv("REID_TC_DEBUG");
+    p.dbg = e ? atoi(e) : 0;
+  }
   REID_CUDA(cudaMemsetAsync(cand_cnt, 0, sizeof(int32_t) * (size_t)N, st));
   const int slots = num_sms() / 2;
   const int grid = (int)(n_tiles < slots ? n_tiles : slots) * 2;
