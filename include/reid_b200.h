@@ -130,10 +130,13 @@ int reid_features_to_half(const float* x, int64_t n_rows, int64_t D, int scale_l
  * index among a row's strong candidates) and repeats become L2 hits.
  * list_cap: entries reserved per list (REID_TC_CAP for reid_knn_candidates_tc, the cap given to
  * reid_knn_candidates_sym); a count above it marks an overflowed list and un-certifies the row.
+ * list_pitch_rows: 0 = lists are row-major, list l of local row r at index r * n_lists + l (what the candidate
+ * kernels write); > 0 = list-major, index l * list_pitch_rows + r (what an all-to-all of per-rank partial lists
+ * leaves behind in the tile-sharded multi-GPU search).
  * workspace: reid_knn_rescore_workspace_bytes(N, row_end - row_begin). */
 int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, int64_t row_end,
                      const uint64_t* cand, const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists,
-                     int list_cap, int k, float err_bound, const float* max_sqnorm, int locality_order, int32_t* out_idx, float* out_key,
+                     int list_cap, int64_t list_pitch_rows, int k, float err_bound, const float* max_sqnorm, int locality_order, int32_t* out_idx, float* out_key,
                      int32_t* uncertified_flag, float* max_err_out, void* workspace, void* stream);
 size_t reid_knn_rescore_workspace_bytes(int64_t N, int64_t n_rows);
 

@@ -13,7 +13,7 @@ from .faiss_rerank import compute_jaccard_distance, JaccardDistance, rerank_stat
 from .dbscan import DBSCAN  # noqa: F401
 from .centroids import generate_cluster_features  # noqa: F401
 from .cm import CM, CM_Hard, cm, cm_hard, ClusterMemory  # noqa: F401
-from .synth import synth, synth_cm_batch  # noqa: F401
+from .synth import synth, synth_cm_batch, synth_device  # noqa: F401
 
 __all__ = ["compute_jaccard_distance", "JaccardDistance", "DBSCAN", "generate_cluster_features",
            "CM", "CM_Hard", "cm", "cm_hard", "ClusterMemory", "synth", "synth_cm_batch"]

@@ -33,8 +33,8 @@ __host__ __device__ inline float reid_tc_err_bound(float max_sqnorm) {
 // that is the cluster's smallest index, so cluster mates (who share their candidates) get the same key.
 __global__ void __launch_bounds__(kRsWarps * 32) rescore_select_kernel(
     int64_t row_begin, int64_t n_rows, const unsigned long long* __restrict__ cand,
-    const int32_t* __restrict__ cand_cnt, const uint32_t* __restrict__ row_tau, int n_lists, int list_cap, int k,
-    float eps_in, const float* __restrict__ max_sqnorm, int32_t* __restrict__ win_cnt, int32_t* __restrict__ win_idx, float* __restrict__ win_a,
+    const int32_t* __restrict__ cand_cnt, const uint32_t* __restrict__ row_tau, int n_lists, int list_cap,
+    int64_t list_pitch_rows, int k, float eps_in, const float* __restrict__ max_sqnorm, int32_t* __restrict__ win_cnt, int32_t* __restrict__ win_idx, float* __restrict__ win_a,
     int32_t* __restrict__ uncert, int32_t* __restrict__ key_out, int32_t* __restrict__ hist) {
   __shared__ float s_a[kRsWarps][kRsMaxC];
   __shared__ int32_t s_j[kRsWarps][kRsMaxC];
@@ -55,8 +55,9 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_select_kernel(
   auto collect = [&](float thr) {
     int cnt = 0;
     for (int q = 0; q < n_lists; ++q) {
-      const int c = min(cand_cnt[lr * n_lists + q], list_cap);
-      const unsigned long long* src = cand + (lr * n_lists + q) * (int64_t)list_cap;
+      const int64_t li = list_pitch_rows ? q * list_pitch_rows + lr : lr * n_lists + q;   // list-major / row-major
+      const int c = min(cand_cnt[li], list_cap);
+      const unsigned long long* src = cand + li * (int64_t)list_cap;
       for (int base = 0; base < c; base += 32) {
         const int t = base + lane;
         unsigned long long e = 0;
@@ -99,7 +100,8 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_select_kernel(
   };
 
   bool list_overflow = false;                       // an overflowed list lost columns above the threshold
-  for (int q = 0; q < n_lists; ++q) list_overflow |= cand_cnt[lr * n_lists + q] > list_cap;
+  for (int q = 0; q < n_lists; ++q)
+    list_overflow |= cand_cnt[list_pitch_rows ? q * list_pitch_rows + lr : lr * n_lists + q] > list_cap;
   float thr = bound - 2.0f * eps;
   int n = collect(thr);
   if (n > kRsMaxC) {
@@ -502,15 +504,15 @@ size_t reid_knn_rescore_workspace_bytes(int64_t N, int64_t n_rows) {
 }
 
 int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, int64_t row_end, const uint64_t* cand,
-                     const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists, int list_cap, int k, float err_bound,
-                     const float* max_sqnorm, int locality_order, int32_t* out_idx, float* out_key, int32_t* uncertified_flag,
+                     const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists, int list_cap, int64_t list_pitch_rows,
+                     int k, float err_bound, const float* max_sqnorm, int locality_order, int32_t* out_idx, float* out_key, int32_t* uncertified_flag,
                      float* max_err_out, void* workspace, void* stream) {
   using namespace reid;
   REID_CHECK_ARG(x && cand && cand_cnt && row_tau && out_idx && uncertified_flag && max_err_out && workspace,
                  "reid_knn_rescore: NULL pointer");
   REID_CHECK_ARG(N > 0 && D > 0 && 0 <= row_begin && row_begin <= row_end && row_end <= N, "reid_knn_rescore: bad shape");
-  REID_CHECK_ARG(n_lists >= 1 && n_lists <= 2 * REID_TC_MAX_SPLITS, "reid_knn_rescore: n_lists=%d (max %d)", n_lists,
-                 2 * REID_TC_MAX_SPLITS);
+  REID_CHECK_ARG(n_lists >= 1 && n_lists <= 64, "reid_knn_rescore: n_lists=%d (max 64)", n_lists);
+  REID_CHECK_ARG(list_pitch_rows == 0 || list_pitch_rows >= row_end - row_begin, "reid_knn_rescore: list_pitch_rows too small");
   REID_CHECK_ARG(k >= 1 && k <= REID_TC_KEEP_MAX, "reid_knn_rescore: k=%d not in 1..%d", k, REID_TC_KEEP_MAX);
   REID_CHECK_ARG(list_cap >= 1, "reid_knn_rescore: list_cap=%d", list_cap);
   REID_CHECK_ARG(err_bound >= 0.f, "reid_knn_rescore: negative err_bound");
@@ -523,7 +525,8 @@ int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, in
   if (locality_order) REID_CUDA(cudaMemsetAsync(w.hist, 0, rs_align(sizeof(int32_t) * (size_t)N) * 2, st));  // hist + cursor
   const unsigned grid = (unsigned)((n + kRsWarps - 1) / kRsWarps);
   rescore_select_kernel<<<grid, kRsWarps * 32, 0, st>>>(row_begin, n, (const unsigned long long*)cand, cand_cnt, row_tau,
-                                                        n_lists, list_cap, k, err_bound, max_sqnorm, w.win_cnt, w.win_idx, w.win_a,
+                                                        n_lists, list_cap, list_pitch_rows, k, err_bound, max_sqnorm, w.win_cnt,
+                                                        w.win_idx, w.win_a,
                                                         uncertified_flag, locality_order ? w.key : nullptr, w.hist);
   REID_LAUNCH_CHECK();
   if (locality_order) {

@@ -102,7 +102,7 @@ def _knn_exact_rows(x, k, rows_list, row_begin, n_rows, idx_out, key_out):
                            ptr(scratch), scratch.numel() * 4, stream_ptr())
 
 
-def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None):
+def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_result=None):
     """Run a1-a6 on device.  Single GPU: all rows.  Row-sharded (comm = sharded.RowComm): this rank
     computes rows [comm.r0, comm.r1) of every per-row stage and the stages' outputs are all-gathered
     (neighbour lists, V rows, V_qe rows), so the returned state always holds GLOBAL rank / V / V_qe /
@@ -135,9 +135,16 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None):
 
     mark("start")
     # a1 ------------------------------------------------------------------
-    rank_local, key_local, info = knn_search(x, k1, knn, rows=(r0, r1))
+    if knn_result is not None:                               # searched elsewhere (sharded.knn_search_tiles): rows r0:r1 of it
+        rank_g, key_g, info = knn_result
+        rank_local, key_local = rank_g[r0:r1].contiguous(), key_g[r0:r1].contiguous()
+    else:
+        rank_local, key_local, info = knn_search(x, k1, knn, rows=(r0, r1))
     st.knn_info = info
-    rank = comm.gather_rows(rank_local) if comm is not None else rank_local      # global (N, k1)
+    if knn_result is not None:
+        rank = knn_result[0].contiguous()
+    else:
+        rank = comm.gather_rows(rank_local) if comm is not None else rank_local  # global (N, k1)
     st.rank, st.rank_key = rank, key_local
     mark("knn")
     # a2 ------------------------------------------------------------------

@@ -112,7 +112,7 @@ def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None):
     flag = torch.empty(n, dtype=torch.int32, device=dev)
     max_err = torch.zeros(1, dtype=torch.float32, device=dev)
     ws = torch.empty(L.reid_knn_rescore_workspace_bytes(N, n), dtype=torch.uint8, device=dev)
-    call("reid_knn_rescore", ptr(x), N, D, r0, r1, ptr(cand), ptr(cand_cnt), ptr(row_tau), n_lists, list_cap, k, eps,
+    call("reid_knn_rescore", ptr(x), N, D, r0, r1, ptr(cand), ptr(cand_cnt), ptr(row_tau), n_lists, list_cap, 0, k, eps,
          ptr(msq), 1 if ORDER_ROWS else 0, ptr(idx), ptr(key), ptr(flag), ptr(max_err), ptr(ws), sp)
     bad = torch.nonzero(flag).flatten().to(torch.int32)
     n_bad = bad.numel()

@@ -21,6 +21,10 @@ import torch
 import torch.distributed as dist
 
 
+TRACE_STEPS = __import__("os").environ.get("REID_TRACE_STEPS", "0") != "0"
+ROWS_PLAN_MIN_N = 65536     # from this N on the sparse stages are row-sharded too (see pseudo_labels)
+
+
 def partition(N, world, rank):
     """Contiguous row block of `rank`: [N*rank//world, N*(rank+1)//world)."""
     return (N * rank) // world, (N * (rank + 1)) // world
@@ -133,9 +137,123 @@ class RowComm:
         return g_ptr, g_idx, g_cnt.contiguous()
 
 
+def block_partition(N, world, rank):
+    """Equal blocks of B = ceil(N / world) rows (the last ranks may hold fewer): row -> owner is row // B, which
+    lets an all-to-all address per-rank partial lists without a lookup.  Used by the tile-sharded search."""
+    B = -(-N // world)
+    return min(N, rank * B), min(N, (rank + 1) * B), B
+
+
+@torch.no_grad()
+def knn_search_tiles(x, k, group=None):
+    """a1 on W GPUs, symmetric form: every rank holds all N feature rows; the sampling prepass is split by rows
+    (all-gather of the N thresholds), the upper-triangle tiles of the similarity are dealt round-robin to the
+    ranks, each rank appends the survivors of ITS tiles to per-row partial lists, one all-to-all hands every
+    row's W partial lists to the row's owner, the owner re-scores and certifies its rows, and the final lists
+    are all-gathered.  Returns (rank (N, k) int32, key (N, k) fp32, info) -- identical on every rank and
+    bit-identical to the single-GPU search (the exact key and the (key desc, index asc) order decide, not
+    the candidate sets)."""
+    from . import knn_tc as kt
+    from ._lib import call, lib, ptr, stream_ptr
+    from .faiss_rerank import _knn_exact_rows
+    L = lib()
+    W, me = dist.get_world_size(group), dist.get_rank(group)
+    N, D = x.shape
+    dev = x.device
+    sp = stream_ptr()
+    marks = []
+
+    def mark(name):
+        if TRACE_STEPS:
+            e = torch.cuda.Event(enable_timing=True)
+            e.record()
+            marks.append((name, e))
+
+    mark("start")
+    b0, b1, B = block_partition(N, W, me)
+    nb = b1 - b0
+    xh = torch.empty((N, D), dtype=torch.float16, device=dev)
+    msq = torch.zeros(1, dtype=torch.float32, device=dev)
+    call("reid_features_to_half", ptr(x), N, D, kt.SCALE_LOG2, ptr(xh), ptr(msq), sp)
+    # 1. thresholds of my rows from the sample, all-gathered (tau as float and as order-preserving image)
+    m = min(N, max(1024, -(-(kt.SYM_RANK * N // kt.SYM_TARGET) // 256) * 256))
+    xs = torch.empty((m, D), dtype=torch.float16, device=dev)
+    call("reid_features_sample", ptr(xh), N, D, m, kt._sample_stride(N), ptr(xs), sp)
+    tau2 = torch.zeros((B, 2), dtype=torch.int32, device=dev)          # [:, 0] float bits, [:, 1] ordered image
+    if nb:
+        pre = torch.empty(nb * 2 * kt.TC_CAP, dtype=torch.int64, device=dev)
+        pre_cnt = torch.zeros(nb * 2, dtype=torch.int32, device=dev)
+        pre_tau = torch.empty(nb, dtype=torch.int32, device=dev)
+        call("reid_knn_candidates_tc_ab", ptr(xh), N, ptr(xs), m, D, kt.SCALE_LOG2, b0, b1, -kt.SYM_RANK, 1, 2, ptr(pre),
+             ptr(pre_cnt), ptr(pre_tau), sp)
+        t_f = torch.empty(nb, dtype=torch.float32, device=dev)
+        t_o = torch.empty(nb, dtype=torch.int32, device=dev)
+        call("reid_knn_sample_tau", ptr(pre), ptr(pre_cnt), ptr(pre_tau), 2, nb, kt.SYM_RANK, ptr(t_f), ptr(t_o), sp)
+        tau2[:nb, 0] = t_f.view(torch.int32)
+        tau2[:nb, 1] = t_o
+    mark("prepass")
+    tau_all = torch.empty((W * B, 2), dtype=torch.int32, device=dev)
+    dist.all_gather_into_tensor(tau_all, tau2, group=group)
+    tau = tau_all[:, 0].contiguous().view(torch.float32)              # rows >= N are padding (never read)
+    tau_ord = tau_all[:, 1].contiguous()
+    mark("gather_tau")
+    # 2. my share of the tiles -> partial lists of ALL rows (W * B row slots so that slot == row)
+    # tile (I, J) goes to rank (I + J) mod W: balanced for the rows of block I (J varies) AND for the rows of block J
+    # (I varies), so every row's candidates split evenly over the W partial lists
+    tiles = kt._tile_order((N + 255) // 256, dev)
+    tiles = tiles[((tiles[:, 0] + tiles[:, 1]) % W) == me].contiguous()
+    cap = max(128, kt.SYM_CAP // W)
+    part = torch.empty((W * B, cap), dtype=torch.int64, device=dev)
+    part_cnt = torch.zeros(W * B, dtype=torch.int32, device=dev)
+    if tiles.shape[0]:
+        call("reid_knn_candidates_sym", ptr(xh), N, D, kt.SCALE_LOG2, ptr(tau), ptr(tiles), tiles.shape[0], cap, ptr(part),
+             ptr(part_cnt), sp)
+    mark("tiles")
+    # 3. all-to-all: block w of `part` (rows owned by rank w) goes to rank w; I receive W partial lists per own row
+    recv = torch.empty_like(part)
+    recv_cnt = torch.empty_like(part_cnt)
+    dist.all_to_all_single(recv, part, group=group)
+    dist.all_to_all_single(recv_cnt, part_cnt, group=group)
+    mark("all_to_all")
+    # 4. exact re-score + certificate of my rows (list q of local row r at q * B + r)
+    idx = torch.zeros((B, k), dtype=torch.int32, device=dev)
+    key = torch.zeros((B, k), dtype=torch.float32, device=dev)
+    n_bad = 0
+    max_err = torch.zeros(1, dtype=torch.float32, device=dev)
+    if nb:
+        flag = torch.empty(nb, dtype=torch.int32, device=dev)
+        ws = torch.empty(L.reid_knn_rescore_workspace_bytes(N, nb), dtype=torch.uint8, device=dev)
+        my_tau = tau_ord[b0:b1].contiguous()
+        call("reid_knn_rescore", ptr(x), N, D, b0, b1, ptr(recv), ptr(recv_cnt), ptr(my_tau), W, cap, B, k, 0.0, ptr(msq),
+             1 if kt.ORDER_ROWS else 0, ptr(idx), ptr(key), ptr(flag), ptr(max_err), ptr(ws), sp)
+        bad = torch.nonzero(flag).flatten().to(torch.int32)
+        n_bad = bad.numel()
+        if n_bad:                                          # uncertified rows: exact CUDA-core search
+            rows = (bad + b0).contiguous()
+            bi = torch.empty((n_bad, k), dtype=torch.int32, device=dev)
+            bk = torch.empty((n_bad, k), dtype=torch.float32, device=dev)
+            _knn_exact_rows(x, k, rows, 0, n_bad, bi, bk)
+            idx[bad.long()] = bi
+            key[bad.long()] = bk
+    mark("rescore")
+    # 5. final lists of all rows on every rank
+    g_idx = torch.empty((W * B, k), dtype=torch.int32, device=dev)
+    g_key = torch.empty((W * B, k), dtype=torch.float32, device=dev)
+    dist.all_gather_into_tensor(g_idx, idx, group=group)
+    dist.all_gather_into_tensor(g_key, key, group=group)
+    mark("gather_lists")
+    steps = None
+    if TRACE_STEPS:
+        torch.cuda.synchronize()
+        steps = {b[0]: round(a[1].elapsed_time(b[1]), 3) for a, b in zip(marks[:-1], marks[1:])}
+    info = dict(mode="tc-sym-tiles", steps_ms=steps, world=W, sym=dict(sample=m, tiles=int(tiles.shape[0])), n_splits=0, keep=cap,
+                uncertified_rows=int(n_bad), max_abs_err=max_err, xh=xh, cand_cnt=recv_cnt)
+    return g_idx[:N], g_key[:N], info
+
+
 @torch.no_grad()
 def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=False, group=None, N=None,
-                  timers=False):
+                  timers=False, plan="auto"):
     """Row-sharded pass.  `x`: either all N rows (every rank holds a replica) or this rank's row block
     (then N must be given and the blocks are all-gathered first).  Returns the same dict as
     pipeline.pseudo_labels with GLOBAL labels on every rank."""
@@ -153,7 +271,51 @@ def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=
             if x.shape[0] != comm.r1 - comm.r0:
                 raise ValueError("rank %d holds %d rows, expected %d" % (comm.rank, x.shape[0], comm.r1 - comm.r0))
             x = comm.gather_rows(x.contiguous())                    # collective (1): features
-        st = rerank_state(x.contiguous(), k1, k2, knn=knn, comm=comm, timers=timers)
+        # kNN: tile-sharded symmetric search when the shape allows it, else own rows x all columns.
+        # Sparse stages a2-a8: plan "tiles" REPLICATES them on every rank (they total ~2 ms at N = 32,621 and their
+        # exchange steps cost more than sharding saves at that size); plan "tiles+rows" / "rows" shards every per-row
+        # stage with the all-gathers listed in the module docstring (default from ROWS_PLAN_MIN_N rows on).
+        from . import knn_tc as kt
+        sym_ok = (knn in ("auto", "tc") and kt.SYM and N >= kt.SYM_MIN_N and k1 <= 32 and x.shape[1] % 64 == 0)
+        if plan == "auto":
+            plan = ("tiles" if N < ROWS_PLAN_MIN_N else "tiles+rows") if sym_ok else "rows"
+        if plan in ("tiles", "tiles+rows") and not sym_ok:
+            raise ValueError("plan %r needs the symmetric tensor-core search (N >= %d, k1 <= 32, D %% 64 == 0)" % (plan, kt.SYM_MIN_N))
+        res = None
+        if plan in ("tiles", "tiles+rows"):
+            if timers:
+                ek = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+                ek[0].record()
+            res = knn_search_tiles(x.contiguous(), k1, group)
+            if timers:
+                ek[1].record()
+        if plan == "tiles":
+            st = rerank_state(x.contiguous(), k1, k2, knn_result=res, timers=timers)
+            if timers:
+                st.timings["knn_tiles"] = ek[0].elapsed_time(ek[1]) * 1e-3
+            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timers else None
+            if timers:
+                ev[0].record()
+            slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, eps)
+            if timers:
+                ev[1].record()
+            labels, core, ncl = dbscan_from_neighbors(N, slot_ptr, nbr_idx, nbr_cnt, min_samples)
+            if timers:
+                ev[2].record()
+                torch.cuda.synchronize()
+                st.timings["jaccard"] = ev[0].elapsed_time(ev[1]) * 1e-3
+                st.timings["dbscan"] = ev[1].elapsed_time(ev[2]) * 1e-3
+            out = dict(labels=labels, core=core, num_clusters=ncl, state=st, nbr_cnt=nbr_cnt)
+            if centroids:
+                C = int(ncl.item())
+                cen = torch.empty((C, x.shape[1]), dtype=torch.float32, device=x.device)
+                if C:
+                    call("reid_centroids", ptr(x), N, x.shape[1], ptr(labels), C, 1, ptr(cen), None, stream_ptr())
+                out["centroids"] = cen
+            return out
+        st = rerank_state(x.contiguous(), k1, k2, knn=knn, comm=comm, timers=timers, knn_result=res)
+        if timers and res is not None:
+            st.timings["knn_tiles"] = ek[0].elapsed_time(ek[1]) * 1e-3
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timers else None
         if timers:
             ev[0].record()

@@ -44,3 +44,20 @@ def synth_cm_batch(x, ids, centroid_labels, num_ids=16, num_instances=16, seed=0
     scale = 1.0 + 0.1 * torch.randn(rows.numel(), 1, generator=g)
     inputs = (x[rows] * scale.abs().clamp_min(0.1)).contiguous()
     return inputs, tg
+
+
+def synth_device(N, D=2048, n_ids=None, noise=0.8, seed=0, device="cuda"):
+    """Same construction as `synth`, generated on the device (seeded CUDA generator) -- for the scale sweep
+    (N = 100k / 250k), where the host generator would take longer than the passes being measured.  The bytes
+    differ from `synth`'s (different RNG), but are identical on every rank of one box."""
+    if n_ids is None:
+        n_ids = max(1, N // 31)
+    g = torch.Generator(device=device).manual_seed(int(seed))
+    centres = F.normalize(torch.randn(n_ids, D, generator=g, device=device), dim=1)
+    ids = torch.randint(0, n_ids, (N,), generator=g, device=device)
+    x = torch.empty((N, D), dtype=torch.float32, device=device)
+    step = 1 << 16
+    for a in range(0, N, step):                      # chunked: bounds the temporaries at 250k x 2048
+        b = min(N, a + step)
+        x[a:b] = F.normalize(centres[ids[a:b]] + noise * torch.randn(b - a, D, generator=g, device=device) / (D ** 0.5), dim=1)
+    return x, ids
