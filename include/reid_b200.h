@@ -150,9 +150,11 @@ int reid_reciprocal_masks(const int32_t* rank, int64_t N, int ncols, int k, int6
  * E(row) = sort_unique( R(row) + all R_half(c), c in R(row), 3*|R_half(c) & R(row)| > 2*|R_half(c)| ).
  * One pass into padded rows: E_pad[(row-row_begin)*stride + t], t < E_cnt[row-row_begin].  A row that does
  * not fit reports E_cnt = stride + 1 (stride >= k1 + k1*(k1/2 + 1) always fits).  Rmask is local,
- * Rhalf_mask is global (all N rows). */
-int reid_expand(const int32_t* rank, int64_t N, int ncols, const uint64_t* Rmask, const uint64_t* Rhalf_mask,
-                int64_t row_begin, int64_t row_end, int stride, int32_t* E_pad, int32_t* E_cnt, void* stream);
+ * Rhalf_mask is global (all N rows); half_cols = the `cols` of the reid_reciprocal_masks call that made it
+ * (no R_half mask has a bit at or above it) -- it sizes the per-warp pair buffer. */
+int reid_expand(const int32_t* rank, int64_t N, int ncols, int half_cols, const uint64_t* Rmask,
+                const uint64_t* Rhalf_mask, int64_t row_begin, int64_t row_end, int stride, int32_t* E_pad,
+                int32_t* E_cnt, void* stream);
 
 /* ---- a4: Gaussian weights  (faiss_rerank.py:81-85) ------------------------------
  * V_val[p] = softmax over the row of -(2 - 2 x_row.x_e), e in E(row); fp32.  Reads the padded sets of
@@ -184,7 +186,7 @@ int reid_lists_compact(const int64_t* slot_ptr, const int32_t* idx, const int32_
 int reid_transpose_count(const int32_t* idx, int64_t nnz, int64_t n_cols, int32_t* col_cnt, void* stream);
 int reid_transpose_fill(const int64_t* ptr, const int32_t* idx, const float* val, int64_t n_rows,
                         int64_t n_cols, const int64_t* C_ptr, int32_t* cursor, int32_t* C_idx, float* C_val,
-                        void* stream);
+                        int max_col_len, void* stream);
 
 /* ---- a7: Jaccard min-sum  (faiss_rerank.py:102-119) -----------------------------
  * t_ij = sum over shared columns c (ascending) of min(Vq[i,c], Vq[j,c]) in sequential fp32;

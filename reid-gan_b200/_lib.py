@@ -42,14 +42,14 @@ SIGNATURES = {
     "reid_features_sample": (_I, [_P, _L, _L, _L, _L, _P, _P]),
     "reid_knn_sample_tau": (_I, [_P, _P, _P, _I, _L, _I, _P, _P, _P]),
     "reid_reciprocal_masks": (_I, [_P, _L, _I, _I, _L, _L, _P, _P]),
-    "reid_expand": (_I, [_P, _L, _I, _P, _P, _L, _L, _I, _P, _P, _P]),
+    "reid_expand": (_I, [_P, _L, _I, _I, _P, _P, _L, _L, _I, _P, _P, _P]),
     "reid_v_weights": (_I, [_P, _L, _L, _P, _I, _P, _L, _L, _P, _P, _I, _P, _P, _P]),
     "reid_query_expand_stride": (_I, [_I, _I]),
     "reid_query_expand": (_I, [_P, _L, _I, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P]),
     "reid_csr_compact": (_I, [_P, _P, _L, _P, _P, _L, _P, _P, _P]),
     "reid_lists_compact": (_I, [_P, _P, _P, _P, _L, _P, _P]),
     "reid_transpose_count": (_I, [_P, _L, _L, _P, _P]),
-    "reid_transpose_fill": (_I, [_P, _P, _P, _L, _L, _P, _P, _P, _P, _P]),
+    "reid_transpose_fill": (_I, [_P, _P, _P, _L, _L, _P, _P, _P, _P, _I, _P]),
     "reid_jaccard_bounds": (_I, [_P, _P, _P, _L, _L, _P, _P]),
     "reid_jaccard_neighbors": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _P, _L, _F, _P, _P, _P, _P, _I, _P]),
     "reid_jaccard_neighbors_heavy": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _P, _L, _F, _P, _P, _P, _P, _P, _P]),

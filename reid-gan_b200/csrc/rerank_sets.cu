@@ -26,9 +26,8 @@ __global__ void __launch_bounds__(256) reciprocal_kernel(const int32_t* __restri
   if (lane == 0) mask_out[row - row_begin] = mask;
 }
 
-constexpr int kSetSlots = 2048;   // > 2 * (64 + 64*33) is not needed in practice; overflow is checked
 constexpr int kListCap = 1024;    // max |E| handled (theoretical max for k1=30 is 30 + 30*16 = 510)
-constexpr int kExpandWarps = 4;
+constexpr int kExpandWarps = 8;
 
 __device__ __forceinline__ uint32_t hash32(uint32_t v) {
   v ^= v >> 16;
@@ -60,87 +59,169 @@ __device__ __forceinline__ void warp_bitonic_sort(int32_t* a, int n2) {
   }
 }
 
-struct ExpandSmem {
-  int32_t rlist[64];
-  int32_t set[kSetSlots];
-  int32_t list[kListCap];
+// Per-warp shared memory, carved by the host for the call's (ncols, half_cols):
+//   pairs_cap = ncols * half_cols (rounded up to 32): every (candidate c in R(i), member g of R_half(c)) pair
+//   set_slots = power of two >= 2 * (ncols + pairs_cap): de-duplication table of E(i)
+struct ExpandLayout {
+  int pairs_cap, set_slots, bytes;
 };
+__host__ __device__ inline ExpandLayout expand_layout(int ncols, int half_cols) {
+  ExpandLayout l;
+  l.pairs_cap = (ncols * half_cols + 31) / 32 * 32;
+  int s = 64;
+  while (s < 2 * (ncols + l.pairs_cap)) s <<= 1;
+  l.set_slots = s;
+  // rlist[64] hr[128] off[65 -> 68] m[64] cnt[64] pass[64] hm[64 x u64] | g[pairs_cap] (later: list) | ci[pairs_cap x u8] | set[]
+  const int list_ints = l.pairs_cap + 64;                 // |E| <= ncols + pairs
+  l.bytes = (64 + 128 + 68 + 64 + 64 + 64) * 4 + 64 * 8 + list_ints * 4 + l.pairs_cap + l.set_slots * 4;
+  l.bytes = (l.bytes + 15) / 16 * 16;
+  return l;
+}
 
+// One warp per row.  The 2/3-overlap test of faiss_rerank.py:74-78 is evaluated pair-parallel: the (c, g) pairs
+// -- c a member of R(i), g a member of R_half(c) -- are spread over the lanes (load-balanced over the scanned
+// sizes |R_half(c)|), each lane gathers its g = rank[c, pos] and looks it up in a small hash table of R(i);
+// the hits are counted per c with shared-memory atomics.  Candidates that pass contribute their R_half to the
+// de-duplication table, which is then compacted and sorted (np.unique order).
 __global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(
-    const int32_t* __restrict__ rank, int ncols, const uint64_t* __restrict__ Rmask,
+    const int32_t* __restrict__ rank, int ncols, int half_cols, const uint64_t* __restrict__ Rmask,
     const uint64_t* __restrict__ Rhmask, int64_t row_begin, int64_t row_end, int stride,
     int32_t* __restrict__ E_pad, int32_t* __restrict__ E_cnt) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
-  ExpandSmem& sm = reinterpret_cast<ExpandSmem*>(smem_raw)[threadIdx.x >> 5];
-  const int64_t row = row_begin + (int64_t)blockIdx.x * kExpandWarps + (threadIdx.x >> 5);
+  const ExpandLayout L = expand_layout(ncols, half_cols);
+  unsigned char* base = smem_raw + (size_t)(threadIdx.x >> 5) * L.bytes;
+  uint64_t* s_hm = reinterpret_cast<uint64_t*>(base);                 // [64]
+  int32_t* rlist = reinterpret_cast<int32_t*>(base + 64 * 8);         // [64]
+  int32_t* hr = rlist + 64;                                           // [128]
+  int32_t* s_off = hr + 128;                                          // [68]
+  int32_t* s_m = s_off + 68;                                          // [64]
+  int32_t* s_cnt = s_m + 64;                                          // [64]
+  int32_t* s_pass = s_cnt + 64;                                       // [64]
+  int32_t* s_g = s_pass + 64;                                         // [pairs_cap (+64)]  pairs, later the sorted list
+  const int list_ints = L.pairs_cap + 64;
+  uint8_t* s_ci = reinterpret_cast<uint8_t*>(s_g + list_ints);        // [pairs_cap]
+  int32_t* set = reinterpret_cast<int32_t*>(s_ci + L.pairs_cap);      // [set_slots]
+  const int64_t row = row_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= row_end) return;
   const int lane = lane_id();
+  const unsigned lt = (1u << lane) - 1u;
 
-  for (int s = lane; s < kSetSlots; s += 32) sm.set[s] = -1;
+  for (int s = lane; s < L.set_slots; s += 32) set[s] = -1;
+  for (int s = lane; s < 128; s += 32) hr[s] = -1;
+  for (int s = lane; s < 64; s += 32) s_cnt[s] = 0;
   // R(row) in rank order
   const uint64_t rm = Rmask[row - row_begin];
   int nR = 0;
-  for (int base = 0; base < ncols; base += 32) {
-    const int r = base + lane;
+  for (int b0 = 0; b0 < ncols; b0 += 32) {
+    const int r = b0 + lane;
     const bool in = r < ncols && ((rm >> r) & 1ull);
     const unsigned b = __ballot_sync(kFull, in);
-    if (in) sm.rlist[nR + __popc(b & ((1u << lane) - 1u))] = rank[row * ncols + r];
+    if (in) rlist[nR + __popc(b & lt)] = rank[row * ncols + r];
     nR += __popc(b);
   }
   __syncwarp();
 
-  bool lost = false;  // the hash set filled up: reported through an impossible count
-  auto insert = [&](int32_t g) {
-    uint32_t h = hash32((uint32_t)g) & (kSetSlots - 1);
-    for (int probe = 0; probe < kSetSlots; ++probe) {
-      int32_t old = atomicCAS(&sm.set[h], -1, g);
+  bool lost = false;  // a table filled up / a mask was wider than announced: reported through an impossible count
+  auto insert = [&](int32_t* tab, int slots, int32_t g) {
+    uint32_t h = hash32((uint32_t)g) & (uint32_t)(slots - 1);
+    for (int probe = 0; probe < slots; ++probe) {
+      const int32_t old = atomicCAS(&tab[h], -1, g);
       if (old == -1 || old == g) return;
-      h = (h + 1) & (kSetSlots - 1);
+      h = (h + 1) & (uint32_t)(slots - 1);
     }
     lost = true;
   };
-
-  // lane <-> candidate c = R(row)[lane (+32)]
-  for (int ci = lane; ci < nR; ci += 32) {
-    const int32_t c = sm.rlist[ci];
-    insert(c);
-    const uint64_t hm = Rhmask[c];
-    const int m = __popcll(hm);
-    const int32_t* crow = rank + (int64_t)c * ncols;
-    int cnt = 0;
-    for (uint64_t bits = hm; bits; bits &= bits - 1) {
-      const int32_t g = crow[__ffsll((long long)bits) - 1];
-      bool in = false;
-      for (int u = 0; u < nR; ++u) in |= (sm.rlist[u] == g);
-      cnt += in;
+  // hash table of R(row), sizes |R_half(c)| and their scan
+  int carry = 0;
+  for (int b0 = 0; b0 < nR; b0 += 32) {
+    const int ci = b0 + lane;
+    int m = 0;
+    if (ci < nR) {
+      const int32_t c = rlist[ci];
+      insert(hr, 128, c);
+      const uint64_t hm = Rhmask[c];
+      s_hm[ci] = hm;
+      m = __popcll(hm);
+      s_m[ci] = m;
     }
-    if (3 * cnt > 2 * m) {  // == len(intersect1d) > 2/3*len  (faiss_rerank.py:77)
-      for (uint64_t bits = hm; bits; bits &= bits - 1) insert(crow[__ffsll((long long)bits) - 1]);
+    int inc = m;
+#pragma unroll
+    for (int o = 1; o < 32; o <<= 1) {
+      const int v = __shfl_up_sync(kFull, inc, o);
+      if (lane >= o) inc += v;
     }
+    if (ci < nR) s_off[ci] = carry + inc - m;
+    carry += __shfl_sync(kFull, inc, 31);
+  }
+  const int P = carry;
+  if (lane == 0) s_off[nR] = P;
+  __syncwarp();
+  if (P > L.pairs_cap) {                         // R_half masks wider than half_cols: cannot happen for a consistent call
+    if (lane == 0) E_cnt[row - row_begin] = stride + 1;
+    return;
+  }
+  // pairs: gather g, test membership in R(row)
+  for (int p = lane; p < P; p += 32) {
+    int lo = 0, hi = nR;                         // largest ci with s_off[ci] <= p
+    while (hi - lo > 1) {
+      const int mid = (lo + hi) >> 1;
+      if (s_off[mid] <= p) lo = mid; else hi = mid;
+    }
+    const int ci = lo;
+    const int kth = p - s_off[ci];
+    const uint64_t hm = s_hm[ci];
+    const uint32_t mlo = (uint32_t)hm, mhi = (uint32_t)(hm >> 32);
+    const int nlo = __popc(mlo);
+    const int pos = kth < nlo ? (int)__fns(mlo, 0, kth + 1) : 32 + (int)__fns(mhi, 0, kth - nlo + 1);
+    const int32_t g = rank[(int64_t)rlist[ci] * ncols + pos];
+    s_g[p] = g;
+    s_ci[p] = (uint8_t)ci;
+    uint32_t h = hash32((uint32_t)g) & 127u;
+    bool in = false;
+    for (int probe = 0; probe < 128; ++probe) {
+      const int32_t o = hr[h];
+      if (o == g) {
+        in = true;
+        break;
+      }
+      if (o == -1) break;
+      h = (h + 1) & 127u;
+    }
+    if (in) atomicAdd(&s_cnt[ci], 1);
   }
   __syncwarp();
+  for (int ci = lane; ci < nR; ci += 32) {
+    s_pass[ci] = 3 * s_cnt[ci] > 2 * s_m[ci];    // == len(intersect1d) > 2/3*len  (faiss_rerank.py:77)
+    insert(set, L.set_slots, rlist[ci]);
+  }
+  __syncwarp();
+  for (int p = lane; p < P; p += 32)
+    if (s_pass[s_ci[p]]) insert(set, L.set_slots, s_g[p]);
+  __syncwarp();
 
-  // compact the set into list[], count
+  // compact the set into the list (re-using the pair buffer), count
+  int32_t* list = s_g;
+  const int list_cap = list_ints < kListCap ? list_ints : kListCap;
   int nE = 0;
-  for (int base = 0; base < kSetSlots; base += 32) {
-    const int32_t v = sm.set[base + lane];
+  for (int b0 = 0; b0 < L.set_slots; b0 += 32) {
+    const int32_t v = set[b0 + lane];
     const unsigned b = __ballot_sync(kFull, v >= 0);
     if (v >= 0) {
-      int p = nE + __popc(b & ((1u << lane) - 1u));
-      if (p < kListCap) sm.list[p] = v;
+      const int p = nE + __popc(b & lt);
+      if (p < list_cap) list[p] = v;
     }
     nE += __popc(b);
   }
-  const int cap = stride < kListCap ? stride : kListCap;
+  const int cap = stride < list_cap ? stride : list_cap;
   const bool overflow = __any_sync(kFull, lost) || nE > cap;
   if (nE > cap) nE = cap;
   int n2 = 32;
   while (n2 < nE) n2 <<= 1;
-  for (int t = nE + lane; t < n2; t += 32) sm.list[t] = 0x7fffffff;
+  for (int t = nE + lane; t < n2; t += 32) list[t] = 0x7fffffff;
   __syncwarp();
-  warp_bitonic_sort(sm.list, n2);
+  warp_bitonic_sort(list, n2);
   int32_t* dst = E_pad + (row - row_begin) * (int64_t)stride;
-  for (int t = lane; t < nE; t += 32) dst[t] = sm.list[t];
+  for (int t = lane; t < nE; t += 32) dst[t] = list[t];
   if (lane == 0) E_cnt[row - row_begin] = overflow ? stride + 1 : nE;  // stride + 1 = "did not fit"
 }
 
@@ -164,20 +245,24 @@ int reid_reciprocal_masks(const int32_t* rank, int64_t N, int ncols, int k, int6
   return REID_OK;
 }
 
-int reid_expand(const int32_t* rank, int64_t N, int ncols, const uint64_t* Rmask, const uint64_t* Rhalf_mask,
+int reid_expand(const int32_t* rank, int64_t N, int ncols, int half_cols, const uint64_t* Rmask, const uint64_t* Rhalf_mask,
                 int64_t row_begin, int64_t row_end, int stride, int32_t* E_pad, int32_t* E_cnt, void* stream) {
   using namespace reid;
   REID_CHECK_ARG(rank && Rmask && Rhalf_mask && E_pad && E_cnt, "reid_expand: NULL pointer");
   REID_CHECK_ARG(ncols >= 1 && ncols <= REID_MAX_K1, "reid_expand: ncols=%d not in 1..%d", ncols, REID_MAX_K1);
   REID_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= N, "reid_expand: bad row range");
   REID_CHECK_ARG(stride >= 1, "reid_expand: stride=%d", stride);
+  REID_CHECK_ARG(half_cols >= 1 && half_cols <= ncols, "reid_expand: half_cols=%d not in 1..ncols", half_cols);
   const int64_t n = row_end - row_begin;
   if (n == 0) return REID_OK;
-  const size_t smem = sizeof(ExpandSmem) * kExpandWarps;
-  const unsigned grid = (unsigned)((n + kExpandWarps - 1) / kExpandWarps);
+  int warps = kExpandWarps;                    // as many rows per CTA as fit (k1 = 64 needs ~45 KB per row)
+  while (warps > 1 && (size_t)expand_layout(ncols, half_cols).bytes * warps > 100 * 1024) warps >>= 1;
+  const size_t smem = (size_t)expand_layout(ncols, half_cols).bytes * warps;
+  REID_CHECK_ARG(smem <= 220 * 1024, "reid_expand: ncols=%d half_cols=%d need %zu B of shared memory", ncols, half_cols, smem);
+  const unsigned grid = (unsigned)((n + warps - 1) / warps);
   REID_CUDA(cudaFuncSetAttribute(expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  expand_kernel<<<grid, kExpandWarps * 32, smem, (cudaStream_t)stream>>>(rank, ncols, Rmask, Rhalf_mask, row_begin,
-                                                                         row_end, stride, E_pad, E_cnt);
+  expand_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(rank, ncols, half_cols, Rmask, Rhalf_mask,
+                                                                         row_begin, row_end, stride, E_pad, E_cnt);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

@@ -119,12 +119,13 @@ __global__ void __launch_bounds__(kVWarps * 32) v_weights_kernel(
 }
 
 // ---------------------------------------------------------------------------------------
-// a5: one warp per row.  The k2 neighbour rows of V are concatenated in shared memory with
-// key = col * K2P + r, sorted (warp bitonic network on key/value pairs), and every run of
-// equal columns is summed in r order with sequential fp32 adds, then divided by k2 --
-// the arithmetic of np.mean(V[rank[i,:k2]], axis=0) restricted to the structural non-zeros.
+// a5: one warp per row.  V_qe[i, :] = mean_{r < k2} V[rank[i, r], :]  (np.mean: the k2 rows are added in r
+// order in fp32, then divided by k2).  The k2 neighbour rows are folded one after the other (r ascending) into a
+// per-warp open-addressing table column -> running sum: inside one V row every column is distinct, so the lanes
+// of a step never meet on a slot and each column's additions happen in r order -- the reference's arithmetic
+// restricted to the structural non-zeros.  The distinct columns (a few dozen) are then compacted and sorted.
 // ---------------------------------------------------------------------------------------
-constexpr int kQWarps = 4;
+constexpr int kQWarps = 8;
 
 __device__ __forceinline__ void warp_bitonic_sort_kv(uint32_t* key, float* val, int n2) {
   const int lane = lane_id();
@@ -149,27 +150,60 @@ __device__ __forceinline__ void warp_bitonic_sort_kv(uint32_t* key, float* val, 
   }
 }
 
+// cap = slots of the table = padded output slots per row, a power of two >= k2 * max_row_nnz: the table only has
+// to hold the DISTINCT columns (<= k2 * max_row_nnz, so probing always terminates) and the k2 rows overlap heavily,
+// which keeps the load factor around 1/8 in practice.
 __global__ void __launch_bounds__(kQWarps * 32) query_expand_kernel(
-    const int32_t* __restrict__ rank, int ncols, int k2, int k2p_log2, const int64_t* __restrict__ V_ptr,
+    const int32_t* __restrict__ rank, int ncols, int k2, const int64_t* __restrict__ V_ptr,
     const int32_t* __restrict__ V_idx, const float* __restrict__ V_val, int cap, int64_t row_begin, int64_t row_end,
     int32_t* __restrict__ Q_cnt, int32_t* __restrict__ Q_idx, float* __restrict__ Q_val) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = lane_id();
-  uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)w * cap;
+  uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)w * cap;              // table keys, then sort keys
   float* val = reinterpret_cast<float*>(smem_raw + (size_t)kQWarps * cap * sizeof(uint32_t)) + (size_t)w * cap;
   const int64_t row = row_begin + (int64_t)blockIdx.x * kQWarps + w;
   if (row >= row_end) return;
-
-  int n = 0;
+  const uint32_t smask = (uint32_t)cap - 1u;
+  for (int t = lane; t < cap; t += 32) key[t] = 0xffffffffu;
+  __syncwarp();
   for (int r = 0; r < k2; ++r) {
     const int64_t j = rank[row * ncols + r];
     const int64_t a = V_ptr[j];
     const int m = (int)(V_ptr[j + 1] - a);
     for (int e = lane; e < m; e += 32) {
-      key[n + e] = ((uint32_t)V_idx[a + e] << k2p_log2) | (uint32_t)r;
-      val[n + e] = V_val[a + e];
+      const uint32_t c = (uint32_t)V_idx[a + e];
+      const float v = V_val[a + e];
+      uint32_t h = (c * 0x9e3779b1u) >> 7 & smask;
+      while (true) {
+        const uint32_t old = atomicCAS(&key[h], 0xffffffffu, c);
+        if (old == 0xffffffffu) {
+          val[h] = v;
+          break;
+        }
+        if (old == c) {
+          val[h] = __fadd_rn(val[h], v);
+          break;
+        }
+        h = (h + 1) & smask;
+      }
     }
-    n += m;
+    __syncwarp();                                    // row r is folded before row r + 1 starts
+  }
+  // compact the occupied slots to the front (in place: the write position never passes the read position)
+  int n = 0;
+  for (int base = 0; base < cap; base += 32) {
+    const uint32_t c = key[base + lane];
+    const float v = val[base + lane];
+    const bool occ = c != 0xffffffffu;
+    const unsigned b = __ballot_sync(kFull, occ);
+    __syncwarp();
+    if (occ) {
+      const int p = n + __popc(b & ((1u << lane) - 1u));
+      key[p] = c;
+      val[p] = v;
+    }
+    n += __popc(b);
+    __syncwarp();
   }
   int n2 = 32;
   while (n2 < n) n2 <<= 1;
@@ -179,30 +213,13 @@ __global__ void __launch_bounds__(kQWarps * 32) query_expand_kernel(
   }
   __syncwarp();
   warp_bitonic_sort_kv(key, val, n2);
-
   const float k2f = (float)k2;
-  int64_t out = (row - row_begin) * (int64_t)cap;   // padded output: `cap` slots per row
-  int total = 0;
-  for (int base = 0; base < n; base += 32) {
-    const int t = base + lane;
-    bool head = false;
-    uint32_t col = 0;
-    if (t < n) {
-      col = key[t] >> k2p_log2;
-      head = (t == 0) || ((key[t - 1] >> k2p_log2) != col);
-    }
-    const unsigned b = __ballot_sync(kFull, head);
-    if (head) {
-      float acc = val[t];
-      for (int u = t + 1; u < n && (key[u] >> k2p_log2) == col; ++u) acc = __fadd_rn(acc, val[u]);
-      const int64_t p = out + __popc(b & ((1u << lane) - 1u));
-      Q_idx[p] = (int32_t)col;
-      Q_val[p] = __fdiv_rn(acc, k2f);
-    }
-    out += __popc(b);
-    total += __popc(b);
+  const int64_t out = (row - row_begin) * (int64_t)cap;   // padded output: `cap` slots per row
+  for (int t = lane; t < n; t += 32) {
+    Q_idx[out + t] = (int32_t)key[t];
+    Q_val[out + t] = __fdiv_rn(val[t], k2f);
   }
-  if (lane == 0) Q_cnt[row - row_begin] = total;
+  if (lane == 0) Q_cnt[row - row_begin] = n;
 }
 
 // padded rows (stride slots, cnt valid) -> CSR at ptr
@@ -264,17 +281,17 @@ constexpr int kColSortWarps = 4;
 
 __global__ void __launch_bounds__(kColSortWarps * 32) col_sort_kernel(const int64_t* __restrict__ C_ptr, int64_t n_cols,
                                                                       int32_t* __restrict__ C_idx,
-                                                                      float* __restrict__ C_val) {
+                                                                      float* __restrict__ C_val, int cap) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = lane_id();
-  uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)w * kColSortCap;
-  float* val = reinterpret_cast<float*>(smem_raw + (size_t)kColSortWarps * kColSortCap * 4) + (size_t)w * kColSortCap;
+  uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)w * cap;
+  float* val = reinterpret_cast<float*>(smem_raw + (size_t)kColSortWarps * cap * 4) + (size_t)w * cap;
   const int64_t c = (int64_t)blockIdx.x * kColSortWarps + w;
   if (c >= n_cols) return;
   const int64_t a = C_ptr[c];
   const int64_t n = C_ptr[c + 1] - a;
   if (n <= 1) return;
-  if (n <= kColSortCap) {
+  if (n <= cap) {
     int n2 = 32;
     while (n2 < n) n2 <<= 1;
     for (int t = lane; t < n2; t += 32) {
@@ -348,9 +365,7 @@ int reid_query_expand(const int32_t* rank, int64_t N, int ncols, int k2, const i
   REID_CHECK_ARG(k2 >= 1 && k2 <= ncols && ncols <= REID_MAX_K1, "reid_query_expand: k2=%d ncols=%d", k2, ncols);
   REID_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= N, "reid_query_expand: bad row range");
   REID_CHECK_ARG(max_row_nnz >= 1, "reid_query_expand: max_row_nnz=%d", max_row_nnz);
-  int k2p_log2 = 0;
-  while ((1 << k2p_log2) < k2) ++k2p_log2;
-  REID_CHECK_ARG(((uint64_t)N << k2p_log2) < 0xffffffffull, "reid_query_expand: N * k2 exceeds the 32-bit sort key");
+  REID_CHECK_ARG(N < 0xffffffffll, "reid_query_expand: N exceeds the 32-bit column key");
   const int cap = reid_query_expand_stride(k2, max_row_nnz);
   const size_t smem = (size_t)kQWarps * cap * 8;
   REID_CHECK_ARG(smem <= 200 * 1024, "reid_query_expand: k2 * max_row_nnz = %d needs %zu B of shared memory",
@@ -360,7 +375,7 @@ int reid_query_expand(const int32_t* rank, int64_t N, int ncols, int k2, const i
   const unsigned grid = (unsigned)((n + kQWarps - 1) / kQWarps);
   REID_CUDA(cudaFuncSetAttribute(query_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   query_expand_kernel<<<grid, kQWarps * 32, smem, (cudaStream_t)stream>>>(
-      rank, ncols, k2, k2p_log2, V_ptr, V_idx, V_val, cap, row_begin, row_end, Q_cnt, Q_pad_idx, Q_pad_val);
+      rank, ncols, k2, V_ptr, V_idx, V_val, cap, row_begin, row_end, Q_cnt, Q_pad_idx, Q_pad_val);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
@@ -402,7 +417,8 @@ int reid_transpose_count(const int32_t* idx, int64_t nnz, int64_t n_cols, int32_
 }
 
 int reid_transpose_fill(const int64_t* ptr, const int32_t* idx, const float* val, int64_t n_rows, int64_t n_cols,
-                        const int64_t* C_ptr, int32_t* cursor, int32_t* C_idx, float* C_val, void* stream) {
+                        const int64_t* C_ptr, int32_t* cursor, int32_t* C_idx, float* C_val, int max_col_len,
+                        void* stream) {
   using namespace reid;
   REID_CHECK_ARG(ptr && idx && val && C_ptr && cursor && C_idx && C_val, "reid_transpose_fill: NULL pointer");
   REID_CHECK_ARG(n_rows >= 0 && n_cols > 0, "reid_transpose_fill: bad shape");
@@ -411,10 +427,15 @@ int reid_transpose_fill(const int64_t* ptr, const int32_t* idx, const float* val
   if (n_rows == 0) return REID_OK;
   col_scatter_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(ptr, idx, val, n_rows, C_ptr, cursor, C_idx, C_val);
   REID_LAUNCH_CHECK();
-  const size_t smem = (size_t)kColSortWarps * kColSortCap * 8;
+  // shared-memory sort buffers sized for the longest column (the caller knows it from the scan of the counts);
+  // max_col_len <= 0: unknown, reserve the maximum
+  int cap = 32;
+  while (cap < max_col_len && cap < kColSortCap) cap <<= 1;
+  if (max_col_len <= 0) cap = kColSortCap;
+  const size_t smem = (size_t)kColSortWarps * cap * 8;
   REID_CUDA(cudaFuncSetAttribute(col_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   col_sort_kernel<<<(unsigned)((n_cols + kColSortWarps - 1) / kColSortWarps), kColSortWarps * 32, smem, st>>>(
-      C_ptr, n_cols, C_idx, C_val);
+      C_ptr, n_cols, C_idx, C_val, cap);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

@@ -159,7 +159,7 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_
     e_stride = min(k1 + k1 * (h + 1), 1024)                  # |E| <= |R| + |R| * |R_half|
     e_pad = torch.empty(max(n, 1) * e_stride, dtype=torch.int32, device=dev)
     e_cnt = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-    call("reid_expand", ptr(rank), N, k1, ptr(R), ptr(Rh), r0, r1, e_stride, ptr(e_pad), ptr(e_cnt), sp)
+    call("reid_expand", ptr(rank), N, k1, min(h + 1, k1), ptr(R), ptr(Rh), r0, r1, e_stride, ptr(e_pad), ptr(e_cnt), sp)
     e_ptr, e_total, e_max = _scan(e_cnt, n, dev)
     if e_max > e_stride:
         raise RuntimeError("reid_expand: an expansion set exceeded %d entries" % e_stride)
@@ -199,7 +199,7 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_
     c_idx = torch.empty(max(q_total, 1), dtype=torch.int32, device=dev)
     c_val = torch.empty(max(q_total, 1), dtype=torch.float32, device=dev)
     call("reid_transpose_fill", ptr(q_ptr), ptr(q_idx), ptr(q_val), N, N, ptr(c_ptr), ptr(c_cnt), ptr(c_idx),
-         ptr(c_val), sp)
+         ptr(c_val), int(c_max), sp)
     st.C_ptr, st.C_idx, st.C_val = c_ptr, c_idx, c_val
     st.c_max = c_max
     mark("transpose")
