@@ -46,7 +46,7 @@ uint64_t reid_launch_count(void);
 /* ---- utilities ---------------------------------------------------------- */
 
 /* ptr_out[0..n] = exclusive prefix sum of cnt[0..n-1] (ptr_out[n] = total);
- * stats_out (optional, 2 x int64) = {total, max(cnt)}. */
+ * stats_out (optional, 3 x int64) = {total, max(cnt), sum(cnt^2)}. */
 int reid_scan_counts(const int32_t* cnt, int64_t n, int64_t* ptr_out, int64_t* stats_out, void* stream);
 
 /* ---- a1: kNN search  (utils/faiss_rerank.py:58-62, faiss IndexFlatL2.search) ----
@@ -182,8 +182,10 @@ int reid_lists_compact(const int64_t* slot_ptr, const int32_t* idx, const int32_
 
 /* ---- a6: inverted index  (faiss_rerank.py:98-100) -------------------------------
  * CSC of a CSR with n_rows x n_cols; column lists sorted by row.
- * Step 1 writes col_cnt; caller scans it into C_ptr; step 2 fills.  cursor: n_cols int32 scratch. */
-int reid_transpose_count(const int32_t* idx, int64_t nnz, int64_t n_cols, int32_t* col_cnt, void* stream);
+ * Step 1 writes col_cnt; caller scans it into C_ptr; step 2 fills.  cursor: n_cols int32 scratch.
+ * nnz_dev (optional device scalar): the real nnz when the host only knows the upper bound `nnz` (no read-back). */
+int reid_transpose_count(const int32_t* idx, int64_t nnz, const int64_t* nnz_dev, int64_t n_cols, int32_t* col_cnt,
+                         void* stream);
 int reid_transpose_fill(const int64_t* ptr, const int32_t* idx, const float* val, int64_t n_rows,
                         int64_t n_cols, const int64_t* C_ptr, int32_t* cursor, int32_t* C_idx, float* C_val,
                         int max_col_len, void* stream);

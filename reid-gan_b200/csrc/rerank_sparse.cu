@@ -255,7 +255,9 @@ __global__ void __launch_bounds__(256) lists_compact_kernel(const int64_t* __res
 // a6: CSR -> CSC.  Column histogram, (caller scans), atomic-cursor scatter, then each
 // column list is sorted by row so the result does not depend on scheduling.
 // ---------------------------------------------------------------------------------------
-__global__ void col_count_kernel(const int32_t* __restrict__ idx, int64_t nnz, int32_t* __restrict__ cnt) {
+__global__ void col_count_kernel(const int32_t* __restrict__ idx, int64_t nnz_host, const int64_t* __restrict__ nnz_dev,
+                                 int32_t* __restrict__ cnt) {
+  const int64_t nnz = nnz_dev ? *nnz_dev : nnz_host;
   for (int64_t p = (int64_t)blockIdx.x * blockDim.x + threadIdx.x; p < nnz; p += (int64_t)gridDim.x * blockDim.x)
     atomicAdd(&cnt[idx[p]], 1);
 }
@@ -403,7 +405,8 @@ int reid_lists_compact(const int64_t* slot_ptr, const int32_t* idx, const int32_
   return REID_OK;
 }
 
-int reid_transpose_count(const int32_t* idx, int64_t nnz, int64_t n_cols, int32_t* col_cnt, void* stream) {
+int reid_transpose_count(const int32_t* idx, int64_t nnz, const int64_t* nnz_dev, int64_t n_cols, int32_t* col_cnt,
+                         void* stream) {
   using namespace reid;
   REID_CHECK_ARG(col_cnt && (nnz == 0 || idx) && n_cols > 0, "reid_transpose_count: bad arguments");
   cudaStream_t st = (cudaStream_t)stream;
@@ -411,7 +414,7 @@ int reid_transpose_count(const int32_t* idx, int64_t nnz, int64_t n_cols, int32_
   if (nnz == 0) return REID_OK;
   int64_t blocks = (nnz + 255) / 256;
   if (blocks > 148 * 16) blocks = 148 * 16;
-  col_count_kernel<<<(unsigned)blocks, 256, 0, st>>>(idx, nnz, col_cnt);
+  col_count_kernel<<<(unsigned)blocks, 256, 0, st>>>(idx, nnz, nnz_dev, col_cnt);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

@@ -24,7 +24,7 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __rest
   __shared__ int32_t warp_max_s[32];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const bool vec = (((uintptr_t)cnt) & 15) == 0;
-  int64_t carry = 0;
+  int64_t carry = 0, sq = 0;
   int32_t mx = 0;
   for (int64_t base = 0; base < n; base += 4096) {
     const int64_t i0 = base + (int64_t)t * 4;
@@ -37,6 +37,7 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __rest
       for (int j = 0; j < 4; ++j) if (i0 + j < n) c[j] = cnt[i0 + j];
     }
     mx = max(max(mx, max(c[0], c[1])), max(c[2], c[3]));
+    sq += (int64_t)c[0] * c[0] + (int64_t)c[1] * c[1] + (int64_t)c[2] * c[2] + (int64_t)c[3] * c[3];
     const int32_t s = c[0] + c[1] + c[2] + c[3];      // a tile holds < 2^31 in total (counts are small)
     int32_t inc = s;
 #pragma unroll
@@ -68,16 +69,23 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __rest
     carry += tile_total;
     __syncthreads();                                    // warp_tot / warp_max_s are rewritten by the next tile
   }
+  __shared__ int64_t warp_sq[32];
   mx = warp_max(mx);
-  if (lane == 0) warp_max_s[w] = mx;
+  sq = warp_sum(sq);
+  if (lane == 0) {
+    warp_max_s[w] = mx;
+    warp_sq[w] = sq;
+  }
   __syncthreads();
   if (w == 0) {
     const int32_t m = warp_max(warp_max_s[lane]);
+    const int64_t q = warp_sum(warp_sq[lane]);
     if (lane == 0) {
       ptr[n] = carry;
       if (stats) {
         stats[0] = carry;
         stats[1] = m;
+        stats[2] = q;
       }
     }
   }

@@ -38,13 +38,18 @@ def _device_of(t):
     return torch.device("cuda", torch.cuda.current_device())
 
 
+def _scan_async(cnt, n, dev):
+    """counts (int32, device) -> (ptr int64 (n+1), stats int64 (3) = [total, max, sum of squares]) -- no host sync."""
+    out = torch.empty(n + 1, dtype=torch.int64, device=dev)
+    stats = torch.empty(3, dtype=torch.int64, device=dev)
+    call("reid_scan_counts", ptr(cnt), n, ptr(out), ptr(stats), stream_ptr())
+    return out, stats
+
+
 def _scan(cnt, n, dev):
     """counts (int32, device) -> (ptr int64 (n+1), total, max) -- one small host sync."""
-    L = _lib.lib()
-    out = torch.empty(n + 1, dtype=torch.int64, device=dev)
-    stats = torch.empty(2, dtype=torch.int64, device=dev)
-    call("reid_scan_counts", ptr(cnt), n, ptr(out), ptr(stats), stream_ptr())
-    total, mx = stats.tolist()
+    out, stats = _scan_async(cnt, n, dev)
+    total, mx, _ = stats.tolist()
     return out, int(total), int(mx)
 
 
@@ -63,7 +68,7 @@ class RerankState:
         self.knn_info = {}
 
 
-def knn_search(x, k, mode="auto", rows=None):
+def knn_search(x, k, mode="auto", rows=None, defer=False):
     """a1: exact top-k neighbour lists (faiss_rerank.py:58-62).  Returns (idx int32, key fp32).
     mode "exact": CUDA-core fp64 search for every row; "tc": tensor-core candidates + exact
     re-score + certificate, uncertified rows redone exactly; "auto": "tc" when the shape allows."""
@@ -83,7 +88,7 @@ def knn_search(x, k, mode="auto", rows=None):
         info["mode"] = mode
     if mode == "tc":
         from .knn_tc import knn_search_tc
-        return knn_search_tc(x, k, r0, r1, idx, key, info)
+        return knn_search_tc(x, k, r0, r1, idx, key, info, defer=defer)
     if mode != "exact":
         raise ValueError("unknown kNN mode %r" % (mode,))
     _knn_exact_rows(x, k, None, r0, n, idx, key)
@@ -139,7 +144,9 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_
         rank_g, key_g, info = knn_result
         rank_local, key_local = rank_g[r0:r1].contiguous(), key_g[r0:r1].contiguous()
     else:
-        rank_local, key_local, info = knn_search(x, k1, knn, rows=(r0, r1))
+        # single GPU: the certificate flags are not read back here -- they ride on the next unavoidable read-back
+        # (the size of E, below); the rare uncertified rows are then repaired and a2/a3 redone
+        rank_local, key_local, info = knn_search(x, k1, knn, rows=(r0, r1), defer=comm is None)
     st.knn_info = info
     if knn_result is not None:
         rank = knn_result[0].contiguous()
@@ -147,20 +154,35 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_
         rank = comm.gather_rows(rank_local) if comm is not None else rank_local  # global (N, k1)
     st.rank, st.rank_key = rank, key_local
     mark("knn")
-    # a2 ------------------------------------------------------------------
     h = half_k(k1)
+    e_stride = min(k1 + k1 * (h + 1), 1024)                  # |E| <= |R| + |R| * |R_half|
     R = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
     Rh = torch.empty(N, dtype=torch.int64, device=dev)        # every rank needs R_half of all rows
-    call("reid_reciprocal_masks", ptr(rank), N, k1, k1, r0, r1, ptr(R), sp)
-    call("reid_reciprocal_masks", ptr(rank), N, k1, h, 0, N, ptr(Rh), sp)
-    st.R_mask, st.Rh_mask = R, Rh
-    mark("reciprocal")
-    # a3 ------------------------------------------------------------------
-    e_stride = min(k1 + k1 * (h + 1), 1024)                  # |E| <= |R| + |R| * |R_half|
     e_pad = torch.empty(max(n, 1) * e_stride, dtype=torch.int32, device=dev)
     e_cnt = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
-    call("reid_expand", ptr(rank), N, k1, min(h + 1, k1), ptr(R), ptr(Rh), r0, r1, e_stride, ptr(e_pad), ptr(e_cnt), sp)
-    e_ptr, e_total, e_max = _scan(e_cnt, n, dev)
+
+    def sets():
+        # a2 ------------------------------------------------------------------
+        call("reid_reciprocal_masks", ptr(rank), N, k1, k1, r0, r1, ptr(R), sp)
+        call("reid_reciprocal_masks", ptr(rank), N, k1, h, 0, N, ptr(Rh), sp)
+        # a3 ------------------------------------------------------------------
+        call("reid_expand", ptr(rank), N, k1, min(h + 1, k1), ptr(R), ptr(Rh), r0, r1, e_stride, ptr(e_pad), ptr(e_cnt), sp)
+        return _scan_async(e_cnt, n, dev)
+
+    e_ptr, e_stats = sets()
+    pending = info.pop("pending", None)
+    if pending is not None:
+        vals = torch.cat([e_stats, pending["flag"].sum(dtype=torch.int64).view(1)]).tolist()
+        if vals[3]:                                           # uncertified rows: exact search for them, then redo a2/a3
+            pending["repair"]()
+            e_ptr, e_stats = sets()
+            vals = e_stats.tolist()
+        info["uncertified_rows"] = int(vals[3]) if len(vals) > 3 else info.get("uncertified_rows", 0)
+    else:
+        vals = e_stats.tolist()
+    e_total, e_max = int(vals[0]), int(vals[1])
+    st.R_mask, st.Rh_mask = R, Rh
+    mark("reciprocal")
     if e_max > e_stride:
         raise RuntimeError("reid_expand: an expansion set exceeded %d entries" % e_stride)
     mark("expand")
@@ -181,25 +203,39 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_
         qp_val = torch.empty(max(n, 1) * q_stride, dtype=torch.float32, device=dev)
         call("reid_query_expand", ptr(rank), N, k1, k2, ptr(e_ptr), ptr(e_idx), ptr(v_val), max(e_max, 1), r0, r1,
              ptr(q_cnt), ptr(qp_idx), ptr(qp_val), sp)
-        q_ptr, q_total, _ = _scan(q_cnt, n, dev)
-        q_idx = torch.empty(max(q_total, 1), dtype=torch.int32, device=dev)
-        q_val = torch.empty(max(q_total, 1), dtype=torch.float32, device=dev)
+        if comm is None:
+            # single GPU: no read-back here -- the CSR is compacted into upper-bound storage and nnz stays on the
+            # device until the inverted index needs its own sizes (one read-back for a5 + a6 together)
+            q_ptr, q_stats = _scan_async(q_cnt, n, dev)
+            q_idx = torch.empty(max(n, 1) * q_stride, dtype=torch.int32, device=dev)
+            q_val = torch.empty(max(n, 1) * q_stride, dtype=torch.float32, device=dev)
+            q_total = None
+        else:
+            q_ptr, q_total, _ = _scan(q_cnt, n, dev)
+            q_idx = torch.empty(max(q_total, 1), dtype=torch.int32, device=dev)
+            q_val = torch.empty(max(q_total, 1), dtype=torch.float32, device=dev)
         call("reid_csr_compact", ptr(qp_idx), ptr(qp_val), q_stride, ptr(q_cnt), ptr(q_ptr), n, ptr(q_idx), ptr(q_val), sp)
         if comm is not None:
             q_ptr, q_idx, q_val, q_total, _ = comm.gather_csr(q_cnt[:n], q_idx[:q_total], q_val[:q_total])
     else:                                                    # faiss_rerank.py:89: skipped when k2 == 1
         q_ptr, q_idx, q_val, q_total = e_ptr, e_idx, v_val, e_total
     st.Q_ptr, st.Q_idx, st.Q_val = q_ptr, q_idx, q_val        # global CSR (N + 1)
-    st.q_total = q_total
     mark("query_expand")
     # a6 (replicated on every rank: it needs every row of V_qe and is tiny) ---------------------
     c_cnt = torch.empty(N, dtype=torch.int32, device=dev)
-    call("reid_transpose_count", ptr(q_idx), q_total, N, ptr(c_cnt), sp)
-    c_ptr, _, c_max = _scan(c_cnt, N, dev)
+    if q_total is None:
+        call("reid_transpose_count", ptr(q_idx), q_idx.numel(), ptr(q_ptr[n:]), N, ptr(c_cnt), sp)
+    else:
+        call("reid_transpose_count", ptr(q_idx), q_total, None, N, ptr(c_cnt), sp)
+    c_ptr, c_stats = _scan_async(c_cnt, N, dev)
+    q_total, c_max, c_sq = (int(v) for v in c_stats.tolist())   # total of the column counts == nnz(V_qe)
+    st.q_total = q_total
     c_idx = torch.empty(max(q_total, 1), dtype=torch.int32, device=dev)
     c_val = torch.empty(max(q_total, 1), dtype=torch.float32, device=dev)
     call("reid_transpose_fill", ptr(q_ptr), ptr(q_idx), ptr(q_val), N, N, ptr(c_ptr), ptr(c_cnt), ptr(c_idx),
          ptr(c_val), int(c_max), sp)
+    # sum_i T_i over ALL rows = sum_c |col(c)|^2: the slot total of the eps-graph stage, known without a read-back
+    st.t_total_all = c_sq
     st.C_ptr, st.C_idx, st.C_val = c_ptr, c_idx, c_val
     st.c_max = c_max
     mark("transpose")
@@ -220,7 +256,11 @@ def jaccard_neighbors(st, eps, with_values=False):
     sp = stream_ptr()
     t_cnt = torch.empty(n, dtype=torch.int32, device=dev)
     call("reid_jaccard_bounds", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.C_ptr), r0, r1, ptr(t_cnt), sp)
-    slot_ptr, t_total, t_max = _scan(t_cnt, n, dev)
+    if r0 == 0 and r1 == st.N and getattr(st, "t_total_all", None) is not None:
+        slot_ptr, _ = _scan_async(t_cnt, n, dev)              # the total is already known (rerank_state, a6)
+        t_total = st.t_total_all
+    else:
+        slot_ptr, t_total, _ = _scan(t_cnt, n, dev)
     nbr_idx = torch.empty(max(t_total, 1), dtype=torch.int32, device=dev)
     nbr_val = torch.empty(max(t_total, 1), dtype=torch.float32, device=dev) if with_values else None
     nbr_cnt = torch.empty(n, dtype=torch.int32, device=dev)

@@ -79,7 +79,7 @@ def _candidates_sym(xh, N, D, sp, dev):
     return cand, cnt, tau_ord, SYM_CAP, dict(sample=m, tiles=int(tiles.shape[0]))
 
 
-def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None):
+def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None, defer=False):
     L = _lib.lib()
     from .faiss_rerank import _knn_exact_rows
     N, D = x.shape
@@ -114,15 +114,24 @@ def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None):
     ws = torch.empty(L.reid_knn_rescore_workspace_bytes(N, n), dtype=torch.uint8, device=dev)
     call("reid_knn_rescore", ptr(x), N, D, r0, r1, ptr(cand), ptr(cand_cnt), ptr(row_tau), n_lists, list_cap, 0, k, eps,
          ptr(msq), 1 if ORDER_ROWS else 0, ptr(idx), ptr(key), ptr(flag), ptr(max_err), ptr(ws), sp)
-    bad = torch.nonzero(flag).flatten().to(torch.int32)
-    n_bad = bad.numel()
-    if n_bad:
-        rows = (bad + r0).contiguous()
-        bi = torch.empty((n_bad, k), dtype=torch.int32, device=dev)
-        bk = torch.empty((n_bad, k), dtype=torch.float32, device=dev)
-        _knn_exact_rows(x, k, rows, 0, n_bad, bi, bk)
-        idx[bad.long()] = bi
-        key[bad.long()] = bk
+    def repair():
+        """Exact CUDA-core search for the rows the certificate rejected (none on typical data)."""
+        bad = torch.nonzero(flag).flatten().to(torch.int32)
+        nb = bad.numel()
+        if nb:
+            rows = (bad + r0).contiguous()
+            bi = torch.empty((nb, k), dtype=torch.int32, device=dev)
+            bk = torch.empty((nb, k), dtype=torch.float32, device=dev)
+            _knn_exact_rows(x, k, rows, 0, nb, bi, bk)
+            idx[bad.long()] = bi
+            key[bad.long()] = bk
+        return nb
+
+    if defer:            # the caller folds the flag count into its next read-back and calls repair() if needed
+        n_bad = 0
+        info["pending"] = dict(flag=flag, repair=repair)
+    else:
+        n_bad = repair()
     info.update(mode="tc-sym" if sym else "tc", sym=sym_info, cand_cnt=cand_cnt if sym else None, cta_group=CTA_GROUP, n_splits=s, keep=keep, err_bound=eps if msq is None else None, max_sqnorm=msq, uncertified_rows=int(n_bad),
                 max_abs_err=max_err, xh=xh)
     return idx, key, info
