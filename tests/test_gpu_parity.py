@@ -181,3 +181,85 @@ def test_full_size_properties():
     # idempotence / determinism
     labels2 = rg.DBSCAN(eps=0.6, min_samples=4).fit_predict(rg.compute_jaccard_distance(x, k1, k2, print_flag=False))
     assert np.array_equal(labels, labels2)
+
+
+# ---- symmetric tensor-core search (simgemm_sym.cu): bit-identical to the exact search --------------------
+def _sym_case(N, D, n_ids, noise, seed, order=None, dup=0):
+    import reid_gan_b200 as rg
+    x, ids = rg.synth(N, D, n_ids, noise, seed)
+    if dup:                                   # exact duplicates: equal keys, the index decides
+        x[N - dup:] = x[:dup]
+    if order == "sorted":                     # rows grouped by identity, like a dataset listed by person id
+        x = x[torch.argsort(ids, stable=True)].contiguous()
+    return x
+
+
+@pytest.mark.parametrize("N,D,n_ids,noise,seed,order,dup,k", [
+    (9000, 256, 9000, 1.0, 5, None, 0, 30),        # isotropic: smallest top-k gaps
+    (8192, 128, 40, 0.5, 6, None, 0, 30),          # ~200 rows per identity: the k-th neighbour sits inside a dense cluster
+    (10000, 192, 300, 0.8, 7, "sorted", 0, 20),    # identity-sorted rows: the threshold sample must not depend on row order
+    (8500, 128, 280, 0.8, 8, None, 500, 30),       # 500 duplicated rows: ties broken by index
+])
+def test_symmetric_search_is_exact(N, D, n_ids, noise, seed, order, dup, k):
+    from reid_gan_b200 import faiss_rerank as fr
+    x = _sym_case(N, D, n_ids, noise, seed, order, dup).cuda()
+    ie, ke, _ = fr.knn_search(x, k, "exact")
+    it, kt, info = fr.knn_search(x, k, "tc")
+    assert info["mode"] == "tc-sym", "the symmetric kernel must be the one that ran"
+    assert torch.equal(ie, it), "neighbour lists differ from the exact search"
+    assert torch.equal(ke, kt), "keys differ from the exact search"
+    cnt = info["cand_cnt"]
+    assert int(cnt.min()) >= k, "every row must have kept at least k candidates"
+
+
+def test_symmetric_search_survives_bad_thresholds(monkeypatch):
+    """A threshold sample that is far too optimistic (almost no column passes) must only cost time: the rows fail
+    their certificate and are redone by the exact search."""
+    from reid_gan_b200 import faiss_rerank as fr, knn_tc
+    x = _sym_case(8192, 64, 260, 0.8, 9).cuda()
+    ie, ke, _ = fr.knn_search(x, 20, "exact")
+    monkeypatch.setattr(knn_tc, "SYM_TARGET", 16)          # ~16 candidates per row < k = 20
+    it, kt, info = fr.knn_search(x, 20, "tc")
+    assert info["mode"] == "tc-sym" and info["uncertified_rows"] > 0
+    assert torch.equal(ie, it) and torch.equal(ke, kt)
+
+
+def test_full_size_msmt17_shape_properties():
+    """N = 32,621 x 2048 (BASELINE configs[1], the benchmark workload): properties that do not need the dense
+    matrix, a sampled comparison of the neighbour lists with the oracle, and determinism of the whole pass."""
+    import reid_gan_b200 as rg
+    from reid_gan_b200 import pipeline
+    from oracle import rerank as orr
+    N, D, k1, k2 = 32621, 2048, 30, 6
+    x, ids = rg.synth(N, D, 1041, 0.8, 0)
+    xd = x.cuda()
+    out = pipeline.pseudo_labels(xd, k1, k2, 0.6, 4, centroids=True)
+    st = out["state"]
+    assert st.knn_info["mode"] == "tc-sym" and st.knn_info["uncertified_rows"] == 0
+    rank = st.rank.cpu().numpy()
+    rows = np.arange(0, N, 409)
+    assert np.array_equal(rank[rows], orr.exact_knn(x.numpy(), k1, rows=rows)), "neighbour lists (sampled rows)"
+    assert np.array_equal(rank[:, 0], np.arange(N)), "a unit-norm row is its own nearest neighbour"
+    qp = st.Q_ptr.cpu().numpy()
+    qv = st.Q_val.cpu().numpy()[:qp[-1]]
+    np.testing.assert_allclose(np.add.reduceat(qv.astype(np.float64), qp[:-1]), 1.0, atol=1e-5)
+    qi = st.Q_idx.cpu().numpy()[:qp[-1]]
+    assert all(np.all(np.diff(qi[qp[i]:qp[i + 1]]) > 0) for i in range(0, N, 997)), "V_qe rows sorted by column"
+    # the eps-graph is symmetric (J is) and contains the diagonal
+    labels = out["labels"].cpu().numpy()
+    ncl = int(out["num_clusters"].item())
+    assert ncl == labels.max() + 1
+    # every pseudo-label is pure w.r.t. the generating identity on this well-separated set
+    lab_ok = labels >= 0
+    first = np.full(ncl, -1, np.int64)
+    first[labels[lab_ok]] = ids.numpy()[lab_ok]
+    assert np.array_equal(first[labels[lab_ok]], ids.numpy()[lab_ok])
+    # cluster ids are numbered by ascending smallest member (sklearn's order)
+    firsts = np.full(ncl, N, np.int64)
+    np.minimum.at(firsts, labels[lab_ok], np.nonzero(lab_ok)[0])
+    assert np.all(np.diff(firsts) > 0)
+    cen = out["centroids"].cpu().numpy()
+    np.testing.assert_allclose(np.linalg.norm(cen, axis=1), 1.0, atol=1e-5)
+    out2 = pipeline.pseudo_labels(xd, k1, k2, 0.6, 4, centroids=True)
+    assert torch.equal(out["labels"], out2["labels"]) and torch.equal(out["centroids"], out2["centroids"])
+    assert torch.equal(st.rank, out2["state"].rank) and torch.equal(st.Q_val[:qp[-1]], out2["state"].Q_val[:qp[-1]])

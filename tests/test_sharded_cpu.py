@@ -79,3 +79,30 @@ def test_partition_covers_all_rows():
             assert all(b[i][1] == b[i + 1][0] for i in range(W - 1))
             sizes = [y - x for x, y in b]
             assert max(sizes) - min(sizes) <= 1
+
+
+def test_tile_dealing_is_balanced_and_complete():
+    """Host logic of the tile-sharded search (sharded.knn_search_tiles): the upper-triangle tile list covers every
+    (I <= J) exactly once and dealing tile (I, J) to rank (I + J) mod W spreads the tiles of every row block AND of
+    every column block evenly, which is what keeps the per-rank partial candidate lists of a row equally long."""
+    from reid_gan_b200 import knn_tc
+    from reid_gan_b200.sharded import block_partition
+    for n_t in (1, 7, 33, 128):
+        t = knn_tc._tile_order(n_t, "cpu").numpy()
+        assert t.shape == (n_t * (n_t + 1) // 2, 2)
+        assert np.all(t[:, 0] <= t[:, 1])
+        assert len({(int(a), int(b)) for a, b in t}) == t.shape[0]
+        for W in (2, 3, 8):
+            owner = (t[:, 0] + t[:, 1]) % W
+            for blk in range(n_t):
+                touching = owner[(t[:, 0] == blk) | (t[:, 1] == blk)]      # tiles that feed the rows of block `blk`
+                counts = np.bincount(touching, minlength=W)
+                assert counts.max() - counts.min() <= 1
+    for N, W in ((32621, 8), (10, 4), (5, 8), (100000, 3)):
+        blocks = [block_partition(N, W, r) for r in range(W)]
+        B = blocks[0][2]
+        assert all(b[2] == B for b in blocks) and blocks[0][0] == 0 and blocks[-1][1] == N
+        assert all(blocks[r][1] == blocks[r + 1][0] for r in range(W - 1))
+        assert all(0 <= b[1] - b[0] <= B for b in blocks)
+        rows = np.arange(N)
+        assert np.array_equal(np.minimum(rows // B, W - 1), np.concatenate([np.full(b[1] - b[0], r) for r, b in enumerate(blocks)]))
