@@ -193,15 +193,19 @@ def stage_rooflines(out, W, prof, steps, peaks, world):
     qa, qb = int(st.Q_ptr[st.row_begin]), int(st.Q_ptr[st.row_end])
     T = int(col_cnt[st.Q_idx[qa:qb].long()].sum())
     edges = int(out["nbr_cnt"].sum()) if "nbr_cnt" in out else 0
-    win = out["state"].knn_info.get("window_total")
-    win = int(win) if win is not None else n * k1
+    win = out["state"].knn_info.get("window_counts")
+    win = int(win.sum()) if win is not None else n * k1
     hbm = peaks["hbm_gbs"]
 
     def ms(*names):
         return sum(prof[nm][1] for nm in names if nm in prof) / steps
 
+    sym = st.knn_info.get("sym") or {}
     rows = [
         ("features_to_half", ("reid_features_to_half",), 6.0 * N * D, "4ND read + 2ND write"),
+        ("K1 sample thresholds", ("reid_features_sample", "reid_knn_candidates_tc_ab", "reid_knn_sample_tau"),
+         -2.0 * (n if world == 1 else -(-N // world)) * sym.get("sample", 0) * D,
+         "tensor bound: 2 * rows * sample(%d) * D flops (tcgen05 prepass) + r-th best selection" % sym.get("sample", 0)),
         ("K2 re-score", ("reid_knn_rescore",), 4.0 * D * (win + n) + 4.0 * n * k1,
          "4D*(window members + rows) + 4*rows*k1; window total %d (%.1f/row)" % (win, win / max(n, 1))),
         ("K3 reciprocal+expand", ("reid_reciprocal_masks", "reid_expand"),
@@ -212,8 +216,8 @@ def stage_rooflines(out, W, prof, steps, peaks, world):
         ("K5 query expansion", ("reid_query_expand", "reid_csr_compact"), 8.0 * (sum_qe_in + nnz_q_local),
          "8*(sum_i sum_{r<k2}|E(rank[i,r])| + nnz(V_qe)); L2-resident"),
         ("K6 inverted index", ("reid_transpose_count", "reid_transpose_fill"), 16.0 * nnz_q, "2*8*nnz(V_qe); L2-resident"),
-        ("K7 Jaccard eps-graph", ("reid_jaccard_bounds", "reid_jaccard_neighbors", "reid_jaccard_neighbors_heavy",
-                                  "reid_jaccard_classify"),
+        ("K7 Jaccard eps-graph", ("reid_jaccard_bounds", "reid_jaccard_eps_graph", "reid_jaccard_neighbors",
+                                  "reid_jaccard_neighbors_heavy"),
          8.0 * T + 8.0 * edges, "8*T + 8*edges, T=%d (%.0f/row), edges=%d; L2-resident" % (T, T / max(n, 1), edges)),
         ("K8 DBSCAN", ("reid_dbscan_labels",), 8.0 * edges + 16.0 * N, "8*edges + 16N; L2-resident"),
         ("scans", ("reid_scan_counts",), 0.0, "count->pointer scans between count/fill passes (latency bound)"),
@@ -222,6 +226,12 @@ def stage_rooflines(out, W, prof, steps, peaks, world):
     for name, entries, nbytes, note in rows:
         t = ms(*entries)
         if t <= 0:
+            continue
+        if nbytes < 0:                                       # negative = flops of a tensor-bound stage
+            tf = -nbytes / (t * 1e-3) / 1e12
+            table.append({"stage": name, "ms": round(t, 4), "bound": "tensor", "flops": int(-nbytes),
+                          "achieved_tflops": round(tf, 1), "peak_tflops": peaks["bf16_tflops"],
+                          "frac": round(tf / peaks["bf16_tflops"], 4), "note": note})
             continue
         gbs = nbytes / (t * 1e-3) / 1e9 if nbytes else None
         table.append({"stage": name, "ms": round(t, 4), "bound": "hbm", "bytes": int(nbytes),
@@ -365,7 +375,10 @@ def main():
         ach = exec_flops / (k_ms * 1e-3) / 1e12
         roof = {"kernel": "simsym_kernel (reid_knn_candidates_sym)", "bound": "tensor", "achieved": ach,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
-                "traffic": None, "ms_per_launch": k_ms, "flops_per_launch": exec_flops,
+                # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full` capture of this
+                # workload on one GPU (profiles/r01_v6_summary.txt); the fp16 operand alone is 134 MB
+                "traffic": 978.1e6 if (world == 1 and W["N"] == WORKLOAD["N"]) else None,
+                "ms_per_launch": k_ms, "flops_per_launch": exec_flops,
                 "algorithmic_flops": flops, "algorithmic_tflops": flops / ((k_ms + pre_ms) * 1e-3) / 1e12,
                 "prepass_ms": pre_ms,
                 "peak_source": peaks["source"] + " cuBLAS bf16 burst (kernel lasts a few ms)"}

@@ -139,6 +139,9 @@ int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, in
                      int list_cap, int64_t list_pitch_rows, int k, float err_bound, const float* max_sqnorm, int locality_order, int32_t* out_idx, float* out_key,
                      int32_t* uncertified_flag, float* max_err_out, void* workspace, void* stream);
 size_t reid_knn_rescore_workspace_bytes(int64_t N, int64_t n_rows);
+/* byte offset, inside that workspace, of the int32[n_rows] window sizes of the last call (for reporting the
+ * bytes the exact stage really had to gather) */
+size_t reid_knn_rescore_window_counts_offset(int64_t N, int64_t n_rows);
 
 /* ---- a2: reciprocal sets  (faiss_rerank.py:23-27, 65-69) -----------------------
  * mask_out[row - row_begin] bit r  <=>  row in rank[rank[row,r], :cols], cols = min(k+1, ncols).

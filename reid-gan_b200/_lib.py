@@ -36,6 +36,7 @@ SIGNATURES = {
     "reid_knn_candidates_tc": (_I, [_P, _L, _L, _I, _L, _L, _I, _I, _I, _P, _P, _P, _P]),
     "reid_features_to_half": (_I, [_P, _L, _L, _I, _P, _P, _P]),
     "reid_knn_rescore_workspace_bytes": (_Z, [_L, _L]),
+    "reid_knn_rescore_window_counts_offset": (_Z, [_L, _L]),
     "reid_knn_rescore": (_I, [_P, _L, _L, _L, _L, _P, _P, _P, _I, _I, _L, _I, _F, _P, _I, _P, _P, _P, _P, _P, _P]),
     "reid_knn_candidates_tc_ab": (_I, [_P, _L, _P, _L, _L, _I, _L, _L, _I, _I, _I, _P, _P, _P, _P]),
     "reid_knn_candidates_sym": (_I, [_P, _L, _L, _I, _P, _P, _L, _I, _P, _P, _P]),

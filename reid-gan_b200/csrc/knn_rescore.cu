@@ -498,6 +498,13 @@ inline size_t rescore_carve(void* base, int64_t N, int64_t n, RescoreWs* w) {
 
 extern "C" {
 
+size_t reid_knn_rescore_window_counts_offset(int64_t N, int64_t n_rows) {
+  if (N < 0 || n_rows < 0) return 0;
+  reid::RescoreWs w;
+  reid::rescore_carve((void*)256, N, n_rows, &w);            // any non-null base: only the offset matters
+  return (size_t)((unsigned char*)w.win_cnt - (unsigned char*)256);
+}
+
 size_t reid_knn_rescore_workspace_bytes(int64_t N, int64_t n_rows) {
   if (N < 0 || n_rows < 0) return 0;
   return reid::rescore_carve(nullptr, N, n_rows, nullptr);

@@ -286,7 +286,8 @@ __global__ void __launch_bounds__(256) sample_rows_kernel(const uint4* __restric
 // tau[row] = r-th largest sample score of the row (over all of its prepass lists); -inf when the lists hold
 // fewer than r entries.  One warp per row.  The prepass already published a threshold row_tau with at least
 // keep >= r listed scores at or above it, so only those entries can matter: they are collected into shared
-// memory (<= 512) and the r-th largest is found by a bitwise binary search on the order-preserving image.
+// memory (<= 512) and the r-th largest is found by a bitwise binary search on the order-preserving image
+// (16 bits deep).
 constexpr int kTauMax = 512;
 constexpr int kTauWarps = 8;
 __global__ void __launch_bounds__(kTauWarps * 32) sample_tau_kernel(const unsigned long long* __restrict__ cand,
@@ -322,9 +323,10 @@ __global__ void __launch_bounds__(kTauWarps * 32) sample_tau_kernel(const unsign
     const int t = u * 32 + lane;
     o[u] = t < m ? s_o[w][t] : 0u;
   }
+  // the top 16 bits of the image are plenty: a threshold rounded DOWN only lets a few more columns through
   uint32_t T = 0;
 #pragma unroll 1
-  for (int bit = 31; bit >= 0; --bit) {
+  for (int bit = 31; bit >= 16; --bit) {
     const uint32_t c2 = T | (1u << bit);
     int c = 0;
 #pragma unroll

@@ -15,30 +15,39 @@ void set_error(const char* fmt, ...) {
   va_end(ap);
 }
 
-// One CTA scans the counts tile by tile: 1024 threads x 4 consecutive elements per tile (coalesced 16-byte
-// loads when the array is 16-byte aligned), warp-shuffle scans at two levels, running carry in a register.
-// 32k counts = 8 tiles, a few microseconds; the stats (total, max) come out of the same pass.
+// One CTA scans the counts tile by tile: 1024 threads x 16 consecutive elements per tile (four 16-byte loads per
+// thread when the array is 16-byte aligned), warp-shuffle scans at two levels, running carry in a register.
+// 32k counts = 2 tiles; the stats (total, max, sum of squares) come out of the same pass.
+constexpr int kScanPer = 16;
 __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __restrict__ cnt, int64_t n,
                                                            int64_t* __restrict__ ptr, int64_t* __restrict__ stats) {
   __shared__ int32_t warp_tot[32];
   __shared__ int32_t warp_max_s[32];
+  __shared__ int64_t warp_sq[32];
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   const bool vec = (((uintptr_t)cnt) & 15) == 0;
   int64_t carry = 0, sq = 0;
   int32_t mx = 0;
-  for (int64_t base = 0; base < n; base += 4096) {
-    const int64_t i0 = base + (int64_t)t * 4;
-    int32_t c[4] = {0, 0, 0, 0};
-    if (vec && i0 + 4 <= n) {
-      const int4 v = *reinterpret_cast<const int4*>(cnt + i0);
-      c[0] = v.x; c[1] = v.y; c[2] = v.z; c[3] = v.w;
+  for (int64_t base = 0; base < n; base += 1024 * kScanPer) {
+    const int64_t i0 = base + (int64_t)t * kScanPer;
+    int32_t c[kScanPer];
+    if (vec && i0 + kScanPer <= n) {
+#pragma unroll
+      for (int q = 0; q < kScanPer / 4; ++q) {
+        const int4 v = *reinterpret_cast<const int4*>(cnt + i0 + 4 * q);
+        c[4 * q] = v.x; c[4 * q + 1] = v.y; c[4 * q + 2] = v.z; c[4 * q + 3] = v.w;
+      }
     } else {
 #pragma unroll
-      for (int j = 0; j < 4; ++j) if (i0 + j < n) c[j] = cnt[i0 + j];
+      for (int j = 0; j < kScanPer; ++j) c[j] = i0 + j < n ? cnt[i0 + j] : 0;
     }
-    mx = max(max(mx, max(c[0], c[1])), max(c[2], c[3]));
-    sq += (int64_t)c[0] * c[0] + (int64_t)c[1] * c[1] + (int64_t)c[2] * c[2] + (int64_t)c[3] * c[3];
-    const int32_t s = c[0] + c[1] + c[2] + c[3];      // a tile holds < 2^31 in total (counts are small)
+    int32_t s = 0;                                     // a tile holds < 2^31 in total (counts are small)
+#pragma unroll
+    for (int j = 0; j < kScanPer; ++j) {
+      mx = max(mx, c[j]);
+      sq += (int64_t)c[j] * c[j];
+      s += c[j];
+    }
     int32_t inc = s;
 #pragma unroll
     for (int o = 1; o < 32; o <<= 1) {
@@ -62,14 +71,13 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __rest
     int64_t run = carry + warp_tot[w] + (inc - s);
     const int64_t tile_total = warp_max_s[0];
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
+    for (int j = 0; j < kScanPer; ++j) {
       if (i0 + j < n) ptr[i0 + j] = run;
       run += c[j];
     }
     carry += tile_total;
     __syncthreads();                                    // warp_tot / warp_max_s are rewritten by the next tile
   }
-  __shared__ int64_t warp_sq[32];
   mx = warp_max(mx);
   sq = warp_sum(sq);
   if (lane == 0) {

@@ -132,6 +132,8 @@ def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None, defer=
         info["pending"] = dict(flag=flag, repair=repair)
     else:
         n_bad = repair()
+    off = L.reid_knn_rescore_window_counts_offset(N, n)
+    info["window_counts"] = ws[off:off + 4 * n].view(torch.int32)     # window size per row (reporting only)
     info.update(mode="tc-sym" if sym else "tc", sym=sym_info, cand_cnt=cand_cnt if sym else None, cta_group=CTA_GROUP, n_splits=s, keep=keep, err_bound=eps if msq is None else None, max_sqnorm=msq, uncertified_rows=int(n_bad),
                 max_abs_err=max_err, xh=xh)
     return idx, key, info
