@@ -100,7 +100,13 @@ int reid_knn_candidates_tc_ab(const void* xa, int64_t Na, const void* xb, int64_
 #define REID_SYM_CAP 1024
 int reid_knn_candidates_sym(const void* xh, int64_t N, int64_t D, int scale_log2, const float* tau,
                             const int32_t* tiles, int64_t n_tiles, int cap, uint64_t* cand, int32_t* cand_cnt,
-                            void* stream);
+                            int reset_counts, void* stream);
+/* reset_counts = 0 keeps appending to the lists of earlier launches: the tiles may be issued in several launches
+ * as the feature rows arrive from the host (tiles whose rows are all resident), see knn_tc.knn_search_upload. */
+/* n_rows rows of row_bytes each, src_pitch_bytes apart in (pinned) HOST memory -> packed on the device
+ * (cudaMemcpy2DAsync): the regularly strided threshold sample goes up before the bulk of the features. */
+int reid_upload_rows_strided(void* dst, const void* src_host, size_t row_bytes, size_t src_pitch_bytes,
+                             int64_t n_rows, void* stream);
 /* xs[m] = xh[(m * stride) mod N], m < n_sample: a low-discrepancy sample of the rows (stride coprime with N). */
 int reid_features_sample(const void* xh, int64_t N, int64_t D, int64_t n_sample, int64_t stride, void* xs,
                          void* stream);
@@ -113,6 +119,9 @@ int reid_knn_sample_tau(const uint64_t* cand, const int32_t* cand_cnt, const uin
  * scales the fp16 rounding bound  |approx - exact| <= 2^-10 ||x_i|| ||x_j||. */
 int reid_features_to_half(const float* x, int64_t n_rows, int64_t D, int scale_log2, void* xh,
                           float* max_sqnorm_out, void* stream);
+/* same, but max_sqnorm_inout is NOT reset: a matrix converted in several row blocks accumulates one maximum */
+int reid_features_to_half_acc(const float* x, int64_t n_rows, int64_t D, int scale_log2, void* xh,
+                              float* max_sqnorm_inout, void* stream);
 
 /* Exact re-score of the candidates with the canonical key, certificate, final order.
  * Let a_(k) be the k-th best approximate score of a row.  Every member of the exact top-k has an

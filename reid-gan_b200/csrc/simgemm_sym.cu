@@ -368,8 +368,19 @@ int reid_knn_sample_tau(const uint64_t* cand, const int32_t* cand_cnt, const uin
   return REID_OK;
 }
 
+int reid_upload_rows_strided(void* dst, const void* src_host, size_t row_bytes, size_t src_pitch_bytes, int64_t n_rows,
+                             void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(dst && src_host && row_bytes > 0 && src_pitch_bytes >= row_bytes && n_rows >= 0,
+                 "reid_upload_rows_strided: bad arguments");
+  if (n_rows == 0) return REID_OK;
+  REID_CUDA(cudaMemcpy2DAsync(dst, row_bytes, src_host, src_pitch_bytes, row_bytes, (size_t)n_rows, cudaMemcpyHostToDevice,
+                              (cudaStream_t)stream));
+  return REID_OK;
+}
+
 int reid_knn_candidates_sym(const void* xh, int64_t N, int64_t D, int scale_log2, const float* tau, const int32_t* tiles,
-                            int64_t n_tiles, int cap, uint64_t* cand, int32_t* cand_cnt, void* stream) {
+                            int64_t n_tiles, int cap, uint64_t* cand, int32_t* cand_cnt, int reset_counts, void* stream) {
   using namespace reid;
   REID_CHECK_ARG(xh && tau && tiles && cand && cand_cnt, "reid_knn_candidates_sym: NULL pointer");
   REID_CHECK_ARG(N > 0 && N < (1ll << 31) && D > 0 && D % tc::BK == 0, "reid_knn_candidates_sym: need D %% 64 == 0 (D=%lld)",
@@ -396,7 +407,7 @@ int reid_knn_candidates_sym(const void* xh, int64_t N, int64_t D, int scale_log2
     const char* e = getenv("REID_TC_DEBUG");
     p.dbg = e ? atoi(e) : 0;
   }
-  REID_CUDA(cudaMemsetAsync(cand_cnt, 0, sizeof(int32_t) * (size_t)N, st));
+  if (reset_counts) REID_CUDA(cudaMemsetAsync(cand_cnt, 0, sizeof(int32_t) * (size_t)N, st));
   const int slots = num_sms() / 2;
   const int grid = (int)(n_tiles < slots ? n_tiles : slots) * 2;
   cudaLaunchConfig_t cfg = {};

@@ -430,6 +430,18 @@ int reid_knn_tc_plan(int64_t N, int64_t n_rows, int cta_group, int* n_splits_out
   return REID_OK;
 }
 
+int reid_features_to_half_acc(const float* x, int64_t n_rows, int64_t D, int scale_log2, void* xh, float* max_sqnorm_inout,
+                              void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(x && xh && n_rows >= 0 && D > 0, "reid_features_to_half_acc: bad arguments");
+  REID_CHECK_ARG(scale_log2 >= -8 && scale_log2 <= 12, "reid_features_to_half_acc: scale_log2=%d out of range", scale_log2);
+  if (n_rows == 0) return REID_OK;
+  tc::to_half_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, n_rows, D, ldexpf(1.0f, scale_log2),
+                                                                                     (__half*)xh, max_sqnorm_inout);
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+
 int reid_features_to_half(const float* x, int64_t n_rows, int64_t D, int scale_log2, void* xh, float* max_sqnorm_out,
                           void* stream) {
   using namespace reid;

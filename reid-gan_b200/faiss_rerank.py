@@ -113,7 +113,7 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_
     (neighbour lists, V rows, V_qe rows), so the returned state always holds GLOBAL rank / V / V_qe /
     inverted index while `row_begin:row_end` remembers the rank's own rows."""
     L = _lib.lib()
-    assert x.is_cuda and x.dtype == torch.float32 and x.is_contiguous()
+    assert (x.is_cuda or knn_result == "upload") and x.dtype == torch.float32 and x.is_contiguous()
     N, D = x.shape
     if not (1 <= k1 <= 64):
         raise ValueError("k1=%d outside the supported range 1..64" % k1)
@@ -121,7 +121,7 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_
         raise ValueError("k1=%d exceeds the number of samples N=%d" % (k1, N))
     if not (1 <= k2 <= k1):
         raise ValueError("k2=%d must be in 1..k1" % k2)
-    dev = x.device
+    dev = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
     if comm is not None:
         r0, r1 = comm.r0, comm.r1
     else:
@@ -140,7 +140,11 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_
 
     mark("start")
     # a1 ------------------------------------------------------------------
-    if knn_result is not None:                               # searched elsewhere (sharded.knn_search_tiles): rows r0:r1 of it
+    if knn_result == "upload":                               # x is still on the host: search while it is uploaded
+        from .knn_tc import knn_search_upload
+        x, rank_local, key_local, info = knn_search_upload(x, k1, dev, defer=True)
+        knn_result = None
+    elif knn_result is not None:                             # searched elsewhere (sharded.knn_search_tiles): rows r0:r1 of it
         rank_g, key_g, info = knn_result
         rank_local, key_local = rank_g[r0:r1].contiguous(), key_g[r0:r1].contiguous()
     else:
@@ -370,8 +374,14 @@ def compute_jaccard_distance(target_features, k1=20, k2=6, print_flag=True, sear
         raise ValueError("target_features must be (N, D)")
     dev = _device_of(target_features)
     with torch.cuda.device(dev), torch.no_grad():
-        x = target_features.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
-        st = rerank_state(x, k1, k2, knn=knn)
+        from .knn_tc import sym_eligible
+        N, D = target_features.shape
+        if (not target_features.is_cuda and target_features.dtype == torch.float32 and target_features.is_contiguous()
+                and knn in ("auto", "tc") and sym_eligible(N, D, k1) and 1 <= k2 <= k1 <= N):
+            st = rerank_state(target_features, k1, k2, knn=knn, knn_result="upload")   # search overlaps the upload
+        else:
+            x = target_features.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+            st = rerank_state(x, k1, k2, knn=knn)
         out = JaccardDistance(st)
         torch.cuda.current_stream().synchronize()
     if print_flag:

@@ -75,18 +75,115 @@ def _candidates_sym(xh, N, D, sp, dev):
     tiles = _tile_order((N + 255) // 256, dev)
     cnt = torch.empty(N, dtype=torch.int32, device=dev)
     call("reid_knn_candidates_sym", ptr(xh), N, D, SCALE_LOG2, ptr(tau), ptr(tiles), tiles.shape[0], SYM_CAP, ptr(cand),
-         ptr(cnt), sp)
+         ptr(cnt), 1, sp)
     return cand, cnt, tau_ord, SYM_CAP, dict(sample=m, tiles=int(tiles.shape[0]))
 
 
-def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None, defer=False):
+def sym_eligible(N, D, k):
+    return SYM and N >= SYM_MIN_N and k <= 32 and D % 64 == 0
+
+
+UPLOAD_CHUNKS = int(__import__("os").environ.get("REID_UPLOAD_CHUNKS", "12"))
+
+
+def knn_search_upload(x_host, k, dev, idx=None, key=None, info=None, defer=False, chunks=None):
+    """a1 for features that still live in (pinned) HOST memory: the upload is cut into `chunks` row blocks on a copy
+    stream and the candidate search follows it block by block -- fp16 conversion, sampling prepass and thresholds
+    of the block's rows, then every upper-triangle tile whose rows are all resident -- so that when the last block
+    lands only its own share of the tiles is left.  The threshold sample (rows at two interleaved regular strides,
+    one cudaMemcpy2DAsync each) goes up first.  Returns (x_dev, idx, key, info); same results as knn_search."""
+    L = _lib.lib()
+    chunks = UPLOAD_CHUNKS if chunks is None else chunks
+    N, D = x_host.shape
+    assert x_host.dtype == torch.float32 and x_host.is_contiguous() and not x_host.is_cuda
+    info = {} if info is None else info
+    main = torch.cuda.current_stream()
+    copy = torch.cuda.Stream(device=dev)
+    sp = stream_ptr()
+    x = torch.empty((N, D), dtype=torch.float32, device=dev)
+    xh = torch.empty((N, D), dtype=torch.float16, device=dev)
+    msq = torch.zeros(1, dtype=torch.float32, device=dev)
+    # sample: two interleaved regular strides (odd, different) so that no single period of the row order can bias it
+    m = min(N, max(1024, -(-(SYM_RANK * N // SYM_TARGET) // 256) * 256))
+    s = max(2, N // m)
+    halves = [(0, 2 * s - 1), (s // 2, 2 * s - 3 if s > 2 else 2 * s - 1)]
+    rows_h = [min(m // 2, (N - 1 - o) // st + 1) for o, st in halves]
+    m = sum(rows_h)
+    xs32 = torch.empty((m, D), dtype=torch.float32, device=dev)
+    xs = torch.empty((m, D), dtype=torch.float16, device=dev)
+    n_t = (N + 255) // 256
+    bounds = [min(N, 256 * (n_t * c // chunks)) for c in range(chunks)] + [N]
+    copy.wait_stream(main)                       # the destination buffers were just allocated on `main`
+    events = []
+    with torch.cuda.stream(copy):
+        cp = ctypes.c_void_p(copy.cuda_stream)
+        base = x_host.data_ptr()
+        done = 0
+        for (o, st), nr in zip(halves, rows_h):
+            call("reid_upload_rows_strided", ptr(xs32[done:]), ctypes.c_void_p(base + o * D * 4), D * 4, st * D * 4, nr, cp)
+            done += nr
+        ev_s = torch.cuda.Event()
+        ev_s.record(copy)
+        for c in range(chunks):
+            a, b = bounds[c], bounds[c + 1]
+            if b > a:
+                x[a:b].copy_(x_host[a:b], non_blocking=True)
+            e = torch.cuda.Event()
+            e.record(copy)
+            events.append(e)
+    main.wait_event(ev_s)
+    msq_s = torch.zeros(1, dtype=torch.float32, device=dev)
+    call("reid_features_to_half", ptr(xs32), m, D, SCALE_LOG2, ptr(xs), ptr(msq_s), sp)
+    cand = torch.empty(N * SYM_CAP, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(N, dtype=torch.int32, device=dev)
+    tau = torch.empty(N, dtype=torch.float32, device=dev)
+    tau_ord = torch.empty(N, dtype=torch.int32, device=dev)
+    max_rows = max(bounds[c + 1] - bounds[c] for c in range(chunks))
+    pre = torch.empty(max_rows * 2 * TC_CAP, dtype=torch.int64, device=dev)
+    pre_cnt = torch.empty(max_rows * 2, dtype=torch.int32, device=dev)
+    pre_tau = torch.empty(max_rows, dtype=torch.int32, device=dev)
+    order = _tile_order(n_t, dev)
+    n_tiles = 0
+    for c in range(chunks):
+        a, b = bounds[c], bounds[c + 1]
+        main.wait_event(events[c])
+        if b <= a:
+            continue
+        call("reid_features_to_half_acc", ptr(x[a:]), b - a, D, SCALE_LOG2, ptr(xh[a:]), ptr(msq), sp)
+        pre_cnt.zero_()
+        call("reid_knn_candidates_tc_ab", ptr(xh), N, ptr(xs), m, D, SCALE_LOG2, a, b, -SYM_RANK, 1, 2, ptr(pre), ptr(pre_cnt),
+             ptr(pre_tau), sp)
+        call("reid_knn_sample_tau", ptr(pre), ptr(pre_cnt), ptr(pre_tau), 2, b - a, SYM_RANK, ptr(tau[a:]), ptr(tau_ord[a:]), sp)
+        key_ = ("chunk", n_t, chunks, c, str(dev))
+        if key_ not in _tile_cache:                            # tiles whose larger block index falls into this chunk
+            t0, t1 = a // 256, (b + 255) // 256
+            sel = (order[:, 1] >= t0) & (order[:, 1] < t1)
+            _tile_cache[key_] = order[sel].contiguous()
+        tiles = _tile_cache[key_]
+        n_tiles += int(tiles.shape[0])
+        if tiles.shape[0]:
+            call("reid_knn_candidates_sym", ptr(xh), N, D, SCALE_LOG2, ptr(tau), ptr(tiles), tiles.shape[0], SYM_CAP, ptr(cand),
+                 ptr(cnt), 0, sp)
+    if idx is None:
+        idx = torch.empty((N, k), dtype=torch.int32, device=dev)
+        key = torch.empty((N, k), dtype=torch.float32, device=dev)
+    x.record_stream(copy)
+    idx, key, info = knn_search_tc(x, k, 0, N, idx, key, info, xh=xh, defer=defer,
+                                   cands=(cand, cnt, tau_ord, SYM_CAP, dict(sample=m, tiles=n_tiles, chunks=chunks), msq))
+    return x, idx, key, info
+
+
+def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None, defer=False, cands=None):
     L = _lib.lib()
     from .faiss_rerank import _knn_exact_rows
     N, D = x.shape
     dev = x.device
     n = r1 - r0
     sp = stream_ptr()
-    if xh is None:
+    if cands is not None:
+        msq = cands[5]
+        max_sqnorm = None
+    elif xh is None:
         xh = torch.empty((N, D), dtype=torch.float16, device=dev)
         msq = torch.zeros(1, dtype=torch.float32, device=dev)
         call("reid_features_to_half", ptr(x), N, D, SCALE_LOG2, ptr(xh), ptr(msq), sp)
@@ -95,7 +192,10 @@ def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None, defer=
         msq = None
     sym = SYM and r0 == 0 and r1 == N and N >= SYM_MIN_N and k <= 32
     keep = max(k, min(k + SLACK, KEEP_MAX))
-    if sym:
+    if cands is not None:
+        cand, cand_cnt, row_tau, list_cap, sym_info = cands[:5]
+        n_lists, s, sym = 1, 0, True
+    elif sym:
         cand, cand_cnt, row_tau, list_cap, sym_info = _candidates_sym(xh, N, D, sp, dev)
         n_lists, s = 1, 0
     else:

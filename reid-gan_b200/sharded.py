@@ -207,7 +207,7 @@ def knn_search_tiles(x, k, group=None):
     part_cnt = torch.zeros(W * B, dtype=torch.int32, device=dev)
     if tiles.shape[0]:
         call("reid_knn_candidates_sym", ptr(xh), N, D, kt.SCALE_LOG2, ptr(tau), ptr(tiles), tiles.shape[0], cap, ptr(part),
-             ptr(part_cnt), sp)
+             ptr(part_cnt), 1, sp)
     mark("tiles")
     # 3. all-to-all: block w of `part` (rows owned by rank w) goes to rank w; I receive W partial lists per own row
     recv = torch.empty_like(part)
