@@ -239,6 +239,86 @@ def stage_rooflines(out, W, prof, steps, peaks, world):
                       "frac": None if gbs is None else round(gbs / hbm, 4), "note": note})
     return table
 
+# ------------------------------------------------------------------ ClusterMemory (configs[2]) ----
+def run_cm(args):
+    """BASELINE configs[2]: ClusterMemory CM_Hard forward + backward + momentum update, bs=256 (16 labels x 16),
+    ~700 centroids x 2048-d, temp 0.05, momentum 0.2.  Latency bound (1.5 GFLOP, 16 MB): reported as microseconds
+    per step with the launch count; the CPU arm is the oracle's numpy restatement of cm.py on the host cores."""
+    import numpy as np
+    import torch
+    import reid_gan_b200 as rg
+    from reid_gan_b200 import _lib
+    C, D, B = 700, 2048, 256
+    x, ids = rg.synth(C * 24, D, C, 0.8, 0)
+    labels = ids.clone()
+    cen = torch.nn.functional.normalize(torch.stack([x[ids == c].mean(0) if (ids == c).any() else x[0] for c in range(C)]), dim=1)
+    batches = [rg.synth_cm_batch(x, None, labels, num_ids=16, num_instances=16, seed=s) for s in range(8)]
+    if args.impl == "reference":
+        from oracle import memory as omem
+        f = cen.numpy().copy()
+        ts = []
+        for i in range(args.warmup + args.steps):
+            inp, tgt = batches[i % len(batches)]
+            t0 = time.perf_counter()
+            loss, z, xhat, nrm = omem.cm_forward(inp.numpy(), tgt.numpy(), f, 0.05)
+            g = omem.cm_backward(np.full(B, 1.0 / B, np.float32), z, tgt.numpy(), f, xhat, nrm, 0.05)
+            f, _ = omem.cm_hard_update(f, xhat, tgt.numpy(), 0.2)
+            if i >= args.warmup:
+                ts.append(time.perf_counter() - t0)
+        v = sum(ts) / len(ts)
+        print(json.dumps({"impl": "reference", "metric": "ClusterMemory CM_Hard fwd+bwd+update sec/step", "value": v, "unit": "s",
+                          "n_gpus": args.gpus, "steps": args.steps, "warmup": args.warmup, "ms_per_step": v * 1e3,
+                          "higher_is_better": False, "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                          "config": {"workload": "ClusterMemory CM_Hard bs=256 temp=0.05 momentum=0.2, 700 clusters x 2048-d (numpy oracle)"},
+                          "cpu_baseline": {"value": v, "unit": "s", "cores": os.cpu_count(), "kind": "port", "sample": "every step"},
+                          "e2e": {"value": v, "unit": "s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0}}))
+        return
+    dev = torch.device("cuda", int(os.environ.get("LOCAL_RANK", "0")))
+    torch.cuda.set_device(dev)
+    mem = rg.ClusterMemory(D, C, temp=0.05, momentum=0.2, use_hard=True).to(dev)
+    mem.features = cen.to(dev).clone()
+    dbat = [(a.to(dev), b.to(dev)) for a, b in batches]
+    hbat = [(a.pin_memory(), b.pin_memory()) for a, b in batches]
+
+    def step(inp, tgt):
+        inp = inp.requires_grad_(True)
+        loss = mem(inp, tgt).mean()
+        loss.backward()
+        return loss
+
+    for i in range(max(args.warmup, 3)):
+        step(*dbat[i % 8])
+    torch.cuda.synchronize()
+    l0 = _lib.launch_count()
+    e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+    e0.record()
+    for i in range(args.steps):
+        step(dbat[i % 8][0].detach(), dbat[i % 8][1])
+    e1.record()
+    torch.cuda.synchronize()
+    ms = e0.elapsed_time(e1) / args.steps
+    launches = (_lib.launch_count() - l0) // args.steps
+    t0 = time.perf_counter()
+    for i in range(args.steps):
+        a, b = hbat[i % 8]
+        lv = float(step(a.to(dev, non_blocking=True), b.to(dev, non_blocking=True)).item())
+    e2e_s = (time.perf_counter() - t0) / args.steps
+    peaks = measured_peaks()
+    nbytes = 4.0 * (2 * B * D + 2 * C * D + B * C)
+    print(json.dumps({"metric": "ClusterMemory CM_Hard fwd+bwd+update sec/step", "value": ms * 1e-3, "unit": "s", "n_gpus": 1,
+                      "steps": args.steps, "warmup": max(args.warmup, 3), "ms_per_step": ms, "higher_is_better": False,
+                      "scaling": "weak", "vs_baseline": None, "dtype": "f32", "data": "synthetic",
+                      "config": {"workload": "ClusterMemory CM_Hard fwd/bwd bs=256 temp=0.05 momentum=0.2, 700 clusters x 2048-d",
+                                 "B": B, "C": C, "D": D, "l2": "working set 16 MB: L2 resident by nature (latency-bound stage)"},
+                      "e2e": {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": B * D * 4 + B * 8, "d2h_bytes_per_step": 4},
+                      "gpu_launches": int(launches),
+                      "roofline": {"kernel": "reid_cm_forward/backward/update (6 launches)", "bound": "hbm",
+                                   "achieved": nbytes / (ms * 1e-3) / 1e9, "peak": peaks["hbm_gbs"], "unit": "GB/s",
+                                   "frac": nbytes / (ms * 1e-3) / 1e9 / peaks["hbm_gbs"], "traffic": None,
+                                   "note": "latency bound: 16 MB and 1.5 GFLOP per step; the figure to read is us/step and the launch count"},
+                      "loss": lv}))
+
+
 # ------------------------------------------------------------------ GPU arm ------------------
 def main():
     ap = argparse.ArgumentParser()
@@ -251,8 +331,12 @@ def main():
     ap.add_argument("--ref-sample", type=int, default=4096)
     ap.add_argument("--no-cpu-baseline", action="store_true")
     ap.add_argument("--no-e2e", action="store_true")
+    ap.add_argument("--workload", default="rerank", choices=["rerank", "cm"],
+                    help="rerank = BASELINE configs[1] (the headline); cm = configs[2], ClusterMemory CM_Hard fwd/bwd/update")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 0)
+    if args.workload == "cm":
+        return run_cm(args)
     if args.impl == "reference":
         return run_reference(args)
 

@@ -255,6 +255,15 @@ int reid_dbscan_labels(int64_t N, const int64_t* nbr_ptr, const int32_t* nbr_idx
                        int min_samples, int64_t* labels, uint8_t* core_mask, int64_t* num_clusters_out,
                        void* workspace, void* stream);
 
+/* ---- f1 (next row): edge filter of the Infomap variant  (utils/infomap_cluster.py:129-144) ----
+ * nbrs / dists: (N, k) neighbour lists in ascending distance 1 - sim (reid_knn_* keys give sim).  Row i links to
+ * every non-self entry up to the first one with dist > 1 - min_sim (compared in fp64 like the reference's
+ * float64 arrays); weight = 1 - dist.  Count, scan (reid_scan_counts), fill; rows with count 0 are "single". */
+int reid_links_count(const int32_t* nbrs, const float* dists, int64_t N, int k, double min_sim, int32_t* link_cnt,
+                     void* stream);
+int reid_links_fill(const int32_t* nbrs, const float* dists, int64_t N, int k, double min_sim,
+                    const int64_t* link_ptr, int32_t* link_dst, double* link_weight, void* stream);
+
 /* ---- a9: centroid init  (train_usl.py:169-182, 191) -------------------------------
  * out[k] = mean of x[i] over labels[i] == k, k = 0..C-1 (labels < 0 skipped), members added in
  * ascending i; normalize != 0 fuses the F.normalize of :191.  workspace: reid_centroids_workspace_bytes(N, C). */

@@ -48,10 +48,31 @@ class _IndexFlatL2:
         return (2.0 - 2.0 * key).astype(np.float32), idx
 
 
+class _IndexFlatIP:
+    """Stand-in for faiss.IndexFlatIP (call site infomap_cluster.py:70-73): exact k largest inner products,
+    descending; ties by index."""
+
+    def __init__(self, d):
+        self.d = d
+        self._xb = None
+
+    def add(self, xb):
+        self._xb = np.ascontiguousarray(xb, dtype=np.float32)
+
+    def search(self, xq, k):
+        from oracle.rerank import exact_knn
+        xq = np.ascontiguousarray(xq, dtype=np.float32)
+        if xq.shape != self._xb.shape or not np.array_equal(xq, self._xb):
+            raise NotImplementedError("stub only supports self-search (the reference's use)")
+        idx, key = exact_knn(self._xb, k, return_keys=True)
+        return key.astype(np.float32), idx
+
+
 def _stub_faiss():
     m = types.ModuleType("faiss")
     m.get_num_gpus = lambda: 0
     m.IndexFlatL2 = _IndexFlatL2
+    m.IndexFlatIP = _IndexFlatIP
     m.METRIC_L2 = 1
     return m
 
@@ -82,6 +103,28 @@ def load_faiss_rerank():
     _load("clustercontrast.utils.faiss_utils", os.path.join(REF_ROOT, "clustercontrast/utils/faiss_utils.py"))
     mod = _load("clustercontrast.utils.faiss_rerank", os.path.join(REF_ROOT, "clustercontrast/utils/faiss_rerank.py"))
     _cache["rerank"] = mod
+    return mod
+
+
+def load_infomap_cluster():
+    """The reference module clustercontrast.utils.infomap_cluster, unmodified (the `infomap` package it imports at
+    module level is stubbed: only the kNN front end and get_links are exercised)."""
+    if "infomap" in _cache:
+        return _cache["infomap"]
+    if not available():
+        raise RuntimeError("reference tree not present at " + REF_ROOT)
+    sys.modules.setdefault("faiss", _stub_faiss())
+    if not hasattr(sys.modules["faiss"], "IndexFlatIP"):
+        sys.modules["faiss"].IndexFlatIP = _IndexFlatIP
+    sys.modules.setdefault("infomap", types.ModuleType("infomap"))
+    for pkg, sub in (("clustercontrast", "clustercontrast"), ("clustercontrast.utils", "clustercontrast/utils")):
+        if pkg not in sys.modules:
+            p = types.ModuleType(pkg)
+            p.__path__ = [os.path.join(REF_ROOT, sub)]
+            sys.modules[pkg] = p
+    _load("clustercontrast.utils.infomap_utils", os.path.join(REF_ROOT, "clustercontrast/utils/infomap_utils.py"))
+    mod = _load("clustercontrast.utils.infomap_cluster", os.path.join(REF_ROOT, "clustercontrast/utils/infomap_cluster.py"))
+    _cache["infomap"] = mod
     return mod
 
 

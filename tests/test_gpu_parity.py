@@ -263,3 +263,20 @@ def test_full_size_msmt17_shape_properties():
     out2 = pipeline.pseudo_labels(xd, k1, k2, 0.6, 4, centroids=True)
     assert torch.equal(out["labels"], out2["labels"]) and torch.equal(out["centroids"], out2["centroids"])
     assert torch.equal(st.rank, out2["state"].rank) and torch.equal(st.Q_val[:qp[-1]], out2["state"].Q_val[:qp[-1]])
+
+
+@pytest.mark.parametrize("N,D,n_ids,k", [(3000, 128, 100, 15), (9000, 256, 300, 15), (1200, 64, 40, 80)])
+def test_infomap_front_end(N, D, n_ids, k):
+    """f1: get_dist_nbr / get_links (utils/infomap_cluster.py:230-234, 129-144) against the oracle: bit-exact."""
+    import reid_gan_b200 as rg
+    from reid_gan_b200 import infomap_cluster as ic
+    from oracle import infomap as oi
+    x, _ = rg.synth(N, D, n_ids, 0.8, 21)
+    d, n = ic.get_dist_nbr(features=x.numpy(), k=k, knn_method='faiss-gpu')
+    d_ref, n_ref = oi.get_dist_nbr(x.numpy(), k)
+    assert d.dtype == np.float64 and n.dtype == np.int32
+    assert np.array_equal(n, n_ref) and np.array_equal(d, d_ref)
+    for min_sim in (0.3, 0.5):
+        s, l = ic.get_links(single=[], links={}, nbrs=n, dists=d, min_sim=min_sim)
+        s_ref, l_ref = oi.get_links(n_ref, d_ref, min_sim)
+        assert s == s_ref and l == l_ref

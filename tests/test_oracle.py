@@ -124,3 +124,21 @@ def test_cluster_memory_oracle_matches_reference(path):
                                rtol=1e-4, atol=1e-6)
     f_hard, _ = omem.cm_hard_update(g["features"], xhat, g["targets"], mom)
     np.testing.assert_allclose(f_hard, g["features_after_hard"], rtol=1e-4, atol=1e-6)
+
+
+def test_infomap_front_end_oracle_matches_reference():
+    """f1: oracle/infomap.py against the unmodified reference functions (infomap_cluster.py get_dist_nbr, get_links)."""
+    from oracle import ref_shim, infomap as oi
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    from reid_gan_b200.synth import synth
+    m = ref_shim.load_infomap_cluster()
+    x, _ = synth(500, 64, 20, 0.8, 3)
+    d_ref, n_ref = m.get_dist_nbr(features=x.numpy(), k=15, knn_method='faiss-cpu')
+    d, n = oi.get_dist_nbr(x.numpy(), 15)
+    assert d.dtype == d_ref.dtype and n.dtype == n_ref.dtype
+    assert np.array_equal(n_ref, n) and np.array_equal(d_ref, d)
+    for min_sim in (0.3, 0.5, 0.9):
+        s_ref, l_ref = m.get_links(single=[], links={}, nbrs=n_ref, dists=d_ref, min_sim=min_sim)
+        s, l = oi.get_links(n, d, min_sim)
+        assert s_ref == s and l_ref == l
