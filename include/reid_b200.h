@@ -192,6 +192,20 @@ int reid_csr_compact(const int32_t* pad_idx, const float* pad_val, int64_t strid
 int reid_lists_compact(const int64_t* slot_ptr, const int32_t* idx, const int32_t* cnt, const int64_t* ptr,
                        int64_t n_rows, int32_t* out, void* stream);
 
+/* ---- multi-GPU exchange format of the row-sharded plan -------------------------------------
+ * One fixed-stride record per row: rec[row] = { count, idx[stride], (val bits[stride]) } in int32 words, so that a
+ * single all-gather moves a ragged stage output (V rows, V_qe rows, eps-neighbour lists).
+ *   pack   : local rows (cnt, starts `ptr` into idx / val; val may be NULL) -> n_rows_padded records (padding: count 0)
+ *   unpack : gathered records of `world` ranks (max_rows records each; rank r owns rows [bounds[r], bounds[r+1]))
+ *            -> global counts; after the caller's scan -> global CSR.  A count above `stride` means the row did
+ *            not fit: the caller must fall back to a variable-length exchange. */
+int reid_rows_pack(const int32_t* cnt, const int64_t* ptr, const int32_t* idx, const float* val, int64_t n_rows,
+                   int64_t n_rows_padded, int stride, int32_t* rec, void* stream);
+int reid_rows_unpack_counts(const int32_t* rec, int stride, int has_val, int world, int64_t max_rows,
+                            const int64_t* bounds, int64_t N, int32_t* g_cnt, void* stream);
+int reid_rows_unpack_fill(const int32_t* rec, int stride, int world, int64_t max_rows, const int64_t* bounds,
+                          int64_t N, const int64_t* g_ptr, int32_t* out_idx, float* out_val, void* stream);
+
 /* ---- a6: inverted index  (faiss_rerank.py:98-100) -------------------------------
  * CSC of a CSR with n_rows x n_cols; column lists sorted by row.
  * Step 1 writes col_cnt; caller scans it into C_ptr; step 2 fills.  cursor: n_cols int32 scratch.

@@ -51,6 +51,9 @@ SIGNATURES = {
     "reid_query_expand": (_I, [_P, _L, _I, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P]),
     "reid_csr_compact": (_I, [_P, _P, _L, _P, _P, _L, _P, _P, _P]),
     "reid_lists_compact": (_I, [_P, _P, _P, _P, _L, _P, _P]),
+    "reid_rows_pack": (_I, [_P, _P, _P, _P, _L, _L, _I, _P, _P]),
+    "reid_rows_unpack_counts": (_I, [_P, _I, _I, _I, _L, _P, _L, _P, _P]),
+    "reid_rows_unpack_fill": (_I, [_P, _I, _I, _L, _P, _L, _P, _P, _P, _P]),
     "reid_transpose_count": (_I, [_P, _L, _P, _L, _P, _P]),
     "reid_transpose_fill": (_I, [_P, _P, _P, _L, _L, _P, _P, _P, _P, _I, _P]),
     "reid_jaccard_bounds": (_I, [_P, _P, _P, _L, _L, _P, _P]),

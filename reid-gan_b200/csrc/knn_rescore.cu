@@ -288,7 +288,7 @@ __global__ void __launch_bounds__(kGThreads, 2) rescore_group_kernel(
     const float* __restrict__ x, int64_t D, int64_t row_begin, int64_t n_rows, const int32_t* __restrict__ perm,
     const int32_t* __restrict__ win_cnt, const int32_t* __restrict__ win_idx, const float* __restrict__ win_a, int k,
     float eps_in, const float* __restrict__ max_sqnorm, int32_t* __restrict__ out_idx, float* __restrict__ out_key,
-    int32_t* __restrict__ uncert, unsigned* __restrict__ max_err_bits) {
+    int32_t* __restrict__ uncert, unsigned* __restrict__ max_err_bits, int dbg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sQ = reinterpret_cast<double*>(smem_raw);                                    // [kGq][D]
   uint64_t* s_key = reinterpret_cast<uint64_t*>(sQ + (size_t)kGq * D);                 // [kGq][kWinMax]
@@ -363,8 +363,8 @@ __global__ void __launch_bounds__(kGThreads, 2) rescore_group_kernel(
   const int U = s_U;
 
   const int cg = tid >> 4, ks = tid & 15;
-  const int steps = (int)(D >> 6);
-  for (int c0 = 0; c0 < U; c0 += kGChunk) {
+  const int steps = (dbg & 1) ? 0 : (int)(D >> 6);
+  for (int c0 = 0; c0 < ((dbg & 2) ? 0 : U); c0 += kGChunk) {
     const float4* xc[4];
 #pragma unroll
     for (int i = 0; i < 4; ++i) {
@@ -553,7 +553,7 @@ int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, in
     REID_CUDA(cudaFuncSetAttribute(rescore_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rescore_group_kernel<<<(unsigned)((n + kGq - 1) / kGq), kGThreads, smem, st>>>(
         x, D, row_begin, n, locality_order ? w.perm : nullptr, w.win_cnt, w.win_idx, w.win_a, k, err_bound, max_sqnorm,
-        out_idx, out_key, uncertified_flag, (unsigned*)max_err_out);
+        out_idx, out_key, uncertified_flag, (unsigned*)max_err_out, getenv("REID_RG_DEBUG") ? atoi(getenv("REID_RG_DEBUG")) : 0);
   } else if (aligned && D == 2048) REID_RS_LAUNCH(16);
   else if (aligned && D == 1024) REID_RS_LAUNCH(8);
   else if (aligned && D == 512) REID_RS_LAUNCH(4);

@@ -252,6 +252,68 @@ __global__ void __launch_bounds__(256) lists_compact_kernel(const int64_t* __res
 }
 
 // ---------------------------------------------------------------------------------------
+// Exchange format of the row-sharded multi-GPU plan: one fixed-stride record per row,
+//   rec[row] = { count, idx[0 .. stride), (val bits[0 .. stride)) }   (int32 words),
+// so that ONE all-gather moves a ragged stage output (V rows, V_qe rows, eps-neighbour lists) and every rank
+// rebuilds the global CSR from the gathered records itself -- no per-rank length exchange, no padding copies.
+// A row longer than `stride` keeps its true count in the record (the receivers see the overflow and the caller
+// falls back to the variable-length gather).
+// ---------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) rows_pack_kernel(const int32_t* __restrict__ cnt, const int64_t* __restrict__ ptr,
+                                                        const int32_t* __restrict__ idx, const float* __restrict__ val,
+                                                        int64_t n_rows, int64_t n_rows_padded, int stride, int words,
+                                                        int32_t* __restrict__ rec) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= n_rows_padded) return;
+  int32_t* r = rec + row * words;
+  const int lane = lane_id();
+  if (row >= n_rows) {                     // padding rows of the last block
+    if (lane == 0) r[0] = 0;
+    return;
+  }
+  const int c = cnt[row];
+  if (lane == 0) r[0] = c;
+  const int m = c < stride ? c : stride;
+  const int64_t a = ptr[row];
+  for (int t = lane; t < m; t += 32) {
+    r[1 + t] = idx[a + t];
+    if (val) r[1 + stride + t] = __float_as_int(val[a + t]);
+  }
+}
+
+// rank that owns global row i under the partition `bounds` (W + 1 ascending entries)
+__device__ __forceinline__ int rows_owner(const int64_t* __restrict__ bounds, int W, int64_t i) {
+  int r = 0;
+  while (r + 1 < W && i >= bounds[r + 1]) ++r;
+  return r;
+}
+
+__global__ void __launch_bounds__(256) rows_unpack_counts_kernel(const int32_t* __restrict__ rec, int words, int W,
+                                                                 int64_t max_rows, const int64_t* __restrict__ bounds,
+                                                                 int64_t N, int32_t* __restrict__ g_cnt) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  const int r = rows_owner(bounds, W, i);
+  g_cnt[i] = rec[((int64_t)r * max_rows + (i - bounds[r])) * words];
+}
+
+__global__ void __launch_bounds__(256) rows_unpack_fill_kernel(const int32_t* __restrict__ rec, int words, int stride,
+                                                               int W, int64_t max_rows, const int64_t* __restrict__ bounds,
+                                                               int64_t N, const int64_t* __restrict__ g_ptr,
+                                                               int32_t* __restrict__ out_idx, float* __restrict__ out_val) {
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= N) return;
+  const int r = rows_owner(bounds, W, i);
+  const int32_t* src = rec + ((int64_t)r * max_rows + (i - bounds[r])) * words;
+  const int c = min(src[0], stride);
+  const int64_t o = g_ptr[i];
+  for (int t = lane_id(); t < c; t += 32) {
+    out_idx[o + t] = src[1 + t];
+    if (out_val) out_val[o + t] = __int_as_float(src[1 + stride + t]);
+  }
+}
+
+// ---------------------------------------------------------------------------------------
 // a6: CSR -> CSC.  Column histogram, (caller scans), atomic-cursor scatter, then each
 // column list is sorted by row so the result does not depend on scheduling.
 // ---------------------------------------------------------------------------------------
@@ -401,6 +463,44 @@ int reid_lists_compact(const int64_t* slot_ptr, const int32_t* idx, const int32_
   if (n_rows == 0) return REID_OK;
   lists_compact_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(slot_ptr, idx, cnt, ptr, n_rows,
                                                                                       out);
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+
+int reid_rows_pack(const int32_t* cnt, const int64_t* ptr, const int32_t* idx, const float* val, int64_t n_rows,
+                   int64_t n_rows_padded, int stride, int32_t* rec, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(rec && stride >= 1 && n_rows >= 0 && n_rows_padded >= n_rows, "reid_rows_pack: bad arguments");
+  REID_CHECK_ARG(n_rows == 0 || (cnt && ptr && idx), "reid_rows_pack: NULL pointer");
+  if (n_rows_padded == 0) return REID_OK;
+  const int words = 1 + stride * (val ? 2 : 1);
+  rows_pack_kernel<<<(unsigned)((n_rows_padded + 7) / 8), 256, 0, (cudaStream_t)stream>>>(cnt, ptr, idx, val, n_rows,
+                                                                                       n_rows_padded, stride, words, rec);
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+
+int reid_rows_unpack_counts(const int32_t* rec, int stride, int has_val, int world, int64_t max_rows, const int64_t* bounds,
+                            int64_t N, int32_t* g_cnt, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(rec && bounds && g_cnt && stride >= 1 && world >= 1 && max_rows >= 0 && N >= 0, "reid_rows_unpack_counts: bad arguments");
+  if (N == 0) return REID_OK;
+  const int words = 1 + stride * (has_val ? 2 : 1);
+  rows_unpack_counts_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rec, words, world, max_rows, bounds,
+                                                                                         N, g_cnt);
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+
+int reid_rows_unpack_fill(const int32_t* rec, int stride, int world, int64_t max_rows, const int64_t* bounds, int64_t N,
+                          const int64_t* g_ptr, int32_t* out_idx, float* out_val, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(rec && bounds && g_ptr && out_idx && stride >= 1 && world >= 1 && max_rows >= 0 && N >= 0,
+                 "reid_rows_unpack_fill: bad arguments");
+  if (N == 0) return REID_OK;
+  const int words = 1 + stride * (out_val ? 2 : 1);
+  rows_unpack_fill_kernel<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(rec, words, stride, world, max_rows,
+                                                                                   bounds, N, g_ptr, out_idx, out_val);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

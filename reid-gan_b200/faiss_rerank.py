@@ -197,7 +197,7 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_
          k1, ptr(e_idx), ptr(v_val), sp)
     mark("v_weights")
     if comm is not None:                                     # V rows of other shards are read by a5
-        e_ptr, e_idx, v_val, e_total, e_max = comm.gather_csr(e_cnt[:n], e_idx[:e_total], v_val[:e_total])
+        e_ptr, e_idx, v_val, e_total, e_max = comm.gather_csr(e_cnt[:n], e_idx[:e_total], v_val[:e_total], row_ptr=e_ptr)
     st.E_ptr, st.E_idx, st.V_val = e_ptr, e_idx, v_val       # global CSR when sharded
     # a5 ------------------------------------------------------------------
     if k2 != 1:
@@ -220,7 +220,7 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_
             q_val = torch.empty(max(q_total, 1), dtype=torch.float32, device=dev)
         call("reid_csr_compact", ptr(qp_idx), ptr(qp_val), q_stride, ptr(q_cnt), ptr(q_ptr), n, ptr(q_idx), ptr(q_val), sp)
         if comm is not None:
-            q_ptr, q_idx, q_val, q_total, _ = comm.gather_csr(q_cnt[:n], q_idx[:q_total], q_val[:q_total])
+            q_ptr, q_idx, q_val, q_total, _ = comm.gather_csr(q_cnt[:n], q_idx[:q_total], q_val[:q_total], row_ptr=q_ptr)
     else:                                                    # faiss_rerank.py:89: skipped when k2 == 1
         q_ptr, q_idx, q_val, q_total = e_ptr, e_idx, v_val, e_total
     st.Q_ptr, st.Q_idx, st.Q_val = q_ptr, q_idx, q_val        # global CSR (N + 1)

@@ -22,6 +22,7 @@ import torch.distributed as dist
 
 
 TRACE_STEPS = __import__("os").environ.get("REID_TRACE_STEPS", "0") != "0"
+RECORD_GATHER = __import__("os").environ.get("REID_RECORD_GATHER", "1") != "0"   # one-collective ragged gathers
 ROWS_PLAN_MIN_N = 65536     # from this N on the sparse stages are row-sharded too (see pseudo_labels)
 
 
@@ -82,9 +83,42 @@ class RowComm:
         out = self._all_gather_padded(t, length, max(max(lens), 1))
         return torch.cat([out[r, :l] for r, l in enumerate(lens)], dim=0), lens
 
-    def gather_csr(self, cnt, idx, val):
+    def gather_records(self, cnt, row_ptr, idx, val, stride):
+        """CUDA only: ragged rows (cnt, row starts `row_ptr` into idx / val) -> global CSR through ONE all-gather of
+        fixed-stride records (csrc/rerank_sparse.cu rows_pack / rows_unpack).  Returns (g_ptr, g_idx, g_val, total,
+        max, g_cnt), or None when some row is longer than `stride` (every rank sees the same gathered counts, so
+        all ranks take the fallback together)."""
+        from ._lib import call, ptr as p_, stream_ptr
+        from .faiss_rerank import _scan_async
+        dev = idx.device
+        n = self.r1 - self.r0
+        words = 1 + stride * (2 if val is not None else 1)
+        rec = torch.empty((self.max_rows, words), dtype=torch.int32, device=dev)
+        call("reid_rows_pack", p_(cnt), p_(row_ptr), p_(idx), p_(val), n, self.max_rows, stride, p_(rec), stream_ptr())
+        out = torch.empty((self.world, self.max_rows, words), dtype=torch.int32, device=dev)
+        dist.all_gather_into_tensor(out, rec, group=self.group)
+        if getattr(self, "_bounds_dev", None) is None or self._bounds_dev.device != dev:
+            self._bounds_dev = torch.tensor([a for a, _ in self.bounds] + [self.N], dtype=torch.int64, device=dev)
+        g_cnt = torch.empty(self.N, dtype=torch.int32, device=dev)
+        call("reid_rows_unpack_counts", p_(out), stride, 1 if val is not None else 0, self.world, self.max_rows,
+             p_(self._bounds_dev), self.N, p_(g_cnt), stream_ptr())
+        g_ptr, stats = _scan_async(g_cnt, self.N, dev)
+        total, mx, _ = (int(v) for v in stats.tolist())
+        if mx > stride:
+            return None
+        g_idx = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+        g_val = torch.empty(max(total, 1), dtype=torch.float32, device=dev) if val is not None else None
+        call("reid_rows_unpack_fill", p_(out), stride, self.world, self.max_rows, p_(self._bounds_dev), self.N, p_(g_ptr),
+             p_(g_idx), p_(g_val), stream_ptr())
+        return g_ptr, g_idx, g_val, total, mx, g_cnt
+
+    def gather_csr(self, cnt, idx, val, row_ptr=None, stride=128):
         """Local CSR pieces (row counts, column indices, values) -> global (ptr, idx, val, nnz, max_row_nnz)."""
         from .faiss_rerank import _scan
+        if idx.is_cuda and row_ptr is not None and RECORD_GATHER:
+            got = self.gather_records(cnt, row_ptr, idx, val, stride)
+            if got is not None:
+                return got[:5]
         g_cnt = self.gather_rows(cnt)
         if g_cnt.is_cuda:
             g_ptr, total, mx = _scan(g_cnt, self.N, g_cnt.device)
@@ -106,6 +140,11 @@ class RowComm:
         """Per-row neighbour lists stored at slot_ptr (upper-bound slots) -> compact global lists:
         (ptr int64 (N+1), idx, cnt int32 (N))."""
         n = self.r1 - self.r0
+        if nbr_idx.is_cuda and RECORD_GATHER:
+            got = self.gather_records(nbr_cnt, slot_ptr, nbr_idx, None, 128)
+            if got is not None:
+                g_idx = got[1] if got[3] else torch.zeros(1, dtype=torch.int32, device=nbr_idx.device)
+                return got[0], g_idx, got[5]
         g_cnt = self.gather_rows(nbr_cnt[:n])
         dev = nbr_idx.device
         if g_cnt.is_cuda:
