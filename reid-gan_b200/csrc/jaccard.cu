@@ -36,11 +36,10 @@ __device__ __forceinline__ float jaccard_from_t(float t) {
 // eps-neighbourhoods, one warp per row, per-warp open-addressing table (j -> running t) in shared memory.
 //
 // The reference's inner loop is "for each non-zero column c of row i (ascending): temp_min[rows of c] += min(..)"
-// (:109-110).  Here the (column, row-of-column) pairs of a row form ONE flat sequence in that same order and the
-// warp consumes it 32 entries at a time (load-balanced search over the scanned column lengths), so short columns
-// no longer cost a dependent round trip each.  Two entries of a batch that hit the same j come from different
-// columns; __match_any_sync finds them and their adds are replayed in lane (= column) order, which keeps every
-// t_ij the exact sequential fp32 sum of the reference, bit-symmetric and independent of sharding.
+// (:109-110).  The warp loads the metadata of 32 columns at once (lane-parallel: column id, V_ic, start, length),
+// then walks the columns in order, 32 entries of one column per step, with the next step's loads in flight --
+// a column no longer costs three dependent round trips.  Every t_ij is the exact sequential fp32 sum of the
+// reference, bit-symmetric and independent of sharding.
 //
 // Rows are dealt to table-size classes on the device (jaccard_classify_kernel); a row that overflows its table
 // is pushed to the next class's queue, the last resort being the dense-accumulator kernel further down.  Each
@@ -84,81 +83,70 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
       const float vic = has ? Q_val[p] : 0.f;
       const int64_t ca = has ? C_ptr[c] : 0;
       const int len = has ? (int)(C_ptr[c + 1] - ca) : 0;
-      int inc = len;                                            // inclusive scan of the column lengths
-#pragma unroll
-      for (int o = 1; o < 32; o <<= 1) {
-        const int v = __shfl_up_sync(kFull, inc, o);
-        if (lane >= o) inc += v;
+      const int ncol = (int)min((int64_t)32, qb - pc);
+      // Walk the columns in ascending order, 32 entries of ONE column per step: inside a column every j is
+      // distinct, so a step needs no ordering between its lanes, and the step sequence is the reference's
+      // accumulation order.  The loads of the next step are issued before the current one goes through the table.
+      int k = 0, base = 0;
+      int64_t cak = __shfl_sync(kFull, ca, 0);
+      int lenk = __shfl_sync(kFull, len, 0);
+      float vk = __shfl_sync(kFull, vic, 0);
+      int32_t j = -1;
+      float m = 0.f;
+      if (lane < lenk) {
+        j = C_idx[cak + lane];
+        m = fminf(vk, C_val[cak + lane]);
       }
-      const int total = __shfl_sync(kFull, inc, 31);
-      const int excl = inc - len;
-      // entry f of the chunk's flat sequence -> (j, min(V_ic, V_jc), column slot); loads only, so the next
-      // batch's loads are in flight while the current one goes through the table
-      auto fetch = [&](int base, int32_t& j, float& m, int& col) {
-        const int f = base + lane;
-        const bool act = f < total;
-        col = 0;                                                // number of columns that end at or before f
-#pragma unroll
-        for (int step = 16; step >= 1; step >>= 1) {
-          const int iv = __shfl_sync(kFull, inc, col + step - 1);
-          if (iv <= f) col += step;
+      while (k < ncol) {
+        int nk = k, nbase = base + 32;
+        int64_t ncak = cak;
+        int nlen = lenk;
+        float nv = vk;
+        if (nbase >= lenk) {                                   // warp-uniform: next column
+          nk = k + 1;
+          nbase = 0;
+          if (nk < ncol) {
+            ncak = __shfl_sync(kFull, ca, nk);
+            nlen = __shfl_sync(kFull, len, nk);
+            nv = __shfl_sync(kFull, vic, nk);
+          }
         }
-        col = act ? col : 32;
-        const int src = col & 31;
-        const int e0 = __shfl_sync(kFull, excl, src);
-        const int64_t cb = __shfl_sync(kFull, ca, src);
-        const float vv = __shfl_sync(kFull, vic, src);
-        j = -1;
-        m = 0.f;
-        if (act) {
-          const int64_t q = cb + (f - e0);
-          j = C_idx[q];
-          m = fminf(vv, C_val[q]);
-        }
-      };
-      int32_t j;
-      float m;
-      int col;
-      fetch(0, j, m, col);
-      for (int base = 0; base < total; base += 32) {
         int32_t jn = -1;
         float mn = 0.f;
-        int coln = 32;
-        if (base + 32 < total) fetch(base + 32, jn, mn, coln);
-        // a batch spans a few columns; inside one column every j is distinct, so the columns of the batch are
-        // replayed one after the other (ascending) and lanes never meet on a slot
-        const int c_lo = __shfl_sync(kFull, col, 0);
-        const int c_hi = __reduce_max_sync(kFull, col < 32 ? col : 0);
-        int fresh_n = 0;
-        for (int cc = c_lo; cc <= c_hi; ++cc) {
-          bool fresh = false;
-          if (col == cc) {
-            uint32_t h = jhash((uint32_t)j) & smask;
-            while (true) {
-              const int32_t old = atomicCAS(&tkey[h], -1, j);
-              if (old == -1) {
-                tval[h] = m;                                    // 0 + m
-                fresh = true;
-                break;
-              }
-              if (old == j) {
-                tval[h] = __fadd_rn(tval[h], m);
-                break;
-              }
-              h = (h + 1) & smask;
-            }
-          }
-          fresh_n += __popc(__ballot_sync(kFull, fresh));
-          __syncwarp();                                         // this column's adds land before the next column's
+        if (nk < ncol && nbase + lane < nlen) {
+          jn = C_idx[ncak + nbase + lane];
+          mn = fminf(nv, C_val[ncak + nbase + lane]);
         }
-        used += fresh_n;
-        j = jn;
-        m = mn;
-        col = coln;
+        bool fresh = false;
+        if (j >= 0) {
+          uint32_t h = jhash((uint32_t)j) & smask;
+          while (true) {
+            const int32_t old = atomicCAS(&tkey[h], -1, j);
+            if (old == -1) {
+              tval[h] = m;                                     // 0 + m
+              fresh = true;
+              break;
+            }
+            if (old == j) {
+              tval[h] = __fadd_rn(tval[h], m);
+              break;
+            }
+            h = (h + 1) & smask;
+          }
+        }
+        used += __popc(__ballot_sync(kFull, fresh));
+        __syncwarp();                                          // this step's adds land before the next step's
         if (used > limit) {
           overflow = true;
           break;
         }
+        k = nk;
+        base = nbase;
+        cak = ncak;
+        lenk = nlen;
+        vk = nv;
+        j = jn;
+        m = mn;
       }
     }
     if (overflow) {
