@@ -278,6 +278,22 @@ int reid_links_count(const int32_t* nbrs, const float* dists, int64_t N, int k, 
 int reid_links_fill(const int32_t* nbrs, const float* dists, int64_t N, int k, double min_sim,
                     const int64_t* link_ptr, int32_t* link_dst, double* link_weight, void* stream);
 
+/* ---- f2 (next row): evaluation-time re-ranking  (utils/rerank.py re_ranking :31-97) ----------
+ * dense front end: dist (M x M, M = Q + G) = transpose( block^2 / column max ) of [[q_q, q_g], [q_g^T, g_g]]
+ * (:36-41); scratch_mm: M*M floats, colmax: M floats.  The neighbour lists are reid_select_rows(dist, ascending)
+ * (:43 argsort, first k1+1 columns; ties by index), the sets / V_qe / inverted index / Jaccard rows are the entries
+ * above, the weights are exp(-dist) normalised per row (:66-67), the result is (1-lambda) J + lambda dist (:95-96). */
+int reid_rr_normalised_distance(const float* q_g, const float* q_q, const float* g_g, int64_t Q, int64_t G,
+                                float* scratch_mm, float* colmax, float* dist, void* stream);
+int reid_rr_weights(const float* dist, int64_t M, const int32_t* E_pad, int stride, const int64_t* E_ptr,
+                    int64_t n_rows, int32_t* E_idx, float* V_val, void* stream);
+int reid_rr_final(const float* J, int64_t ldJ, const float* dist, int64_t Q, int64_t G, float one_minus_lambda,
+                  float lambda, float* out, void* stream);
+/* exact top-k of every row of a dense (n_rows x N) key matrix: descending (ties by smaller index), or the k
+ * smallest in ascending order when `ascending` != 0. */
+int reid_select_rows(const float* keys, int64_t N, int64_t n_rows, int k, int ascending, int32_t* out_idx,
+                     float* out_key, void* stream);
+
 /* ---- a9: centroid init  (train_usl.py:169-182, 191) -------------------------------
  * out[k] = mean of x[i] over labels[i] == k, k = 0..C-1 (labels < 0 skipped), members added in
  * ascending i; normalize != 0 fuses the F.normalize of :191.  workspace: reid_centroids_workspace_bytes(N, C). */

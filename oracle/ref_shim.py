@@ -128,6 +128,15 @@ def load_infomap_cluster():
     return mod
 
 
+def load_eval_rerank():
+    """The reference module clustercontrast/utils/rerank.py (numpy only), unmodified."""
+    if "eval_rerank" not in _cache:
+        if not available():
+            raise RuntimeError("reference tree not present at " + REF_ROOT)
+        _cache["eval_rerank"] = _load("_ref_eval_rerank", os.path.join(REF_ROOT, "clustercontrast/utils/rerank.py"))
+    return _cache["eval_rerank"]
+
+
 def load_cm():
     """The reference module clustercontrast/models/cm.py (torch + numpy only)."""
     if "cm" not in _cache:

@@ -74,6 +74,8 @@ __global__ void __launch_bounds__(256) dot64_tile_kernel(const float* __restrict
 constexpr int kSelThreads = 256;
 constexpr int kMaxK = 128;
 
+// negate = true selects the k SMALLEST keys (ascending, ties by index) -- the order of np.argsort on distances.
+template <bool kNegate>
 __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* __restrict__ keys, int64_t N, int k,
                                                                   int32_t* __restrict__ out_idx,
                                                                   float* __restrict__ out_key) {
@@ -96,7 +98,7 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* _
     if (s_done) break;
     const uint64_t pfx = s_prefix;
     for (int64_t j = t; j < N; j += kSelThreads) {
-      uint64_t key = sel_key(kr[j], (int)j);
+      uint64_t key = sel_key(kNegate ? -kr[j] : kr[j], (int)j);
       if (pass == 0 || (key >> (shift + 8)) == pfx) atomicAdd(&hist[(unsigned)(key >> shift) & 255u], 1u);
     }
     __syncthreads();
@@ -118,7 +120,7 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* _
   const int low = shift + 8;
   const uint64_t pfx = s_prefix;
   for (int64_t j = t; j < N; j += kSelThreads) {
-    uint64_t key = sel_key(kr[j], (int)j);
+    uint64_t key = sel_key(kNegate ? -kr[j] : kr[j], (int)j);
     if ((low >= 64 ? 0 : (key >> low)) >= pfx) {
       int p = atomicAdd(&s_count, 1);
       if (p < kMaxK) sel[p] = key;
@@ -131,7 +133,7 @@ __global__ void __launch_bounds__(kSelThreads) select_topk_kernel(const float* _
     int rank = 0;
     for (int u = 0; u < n; ++u) rank += sel[u] > me;
     out_idx[(int64_t)blockIdx.x * k + rank] = sel_key_idx(me);
-    if (out_key) out_key[(int64_t)blockIdx.x * k + rank] = sel_key_val(me);
+    if (out_key) out_key[(int64_t)blockIdx.x * k + rank] = kNegate ? -sel_key_val(me) : sel_key_val(me);
   }
 }
 
@@ -162,10 +164,22 @@ int reid_knn_exact(const float* x, int64_t N, int64_t D, const int32_t* rows_lis
     dim3 grid((unsigned)((N + TN - 1) / TN), (unsigned)((m + TM - 1) / TM));
     dot64_tile_kernel<<<grid, 256, 0, st>>>(x, N, D, rows_list ? rows_list + s : nullptr, row_begin + s, m, keys);
     REID_LAUNCH_CHECK();
-    select_topk_kernel<<<(unsigned)m, kSelThreads, 0, st>>>(keys, N, k, out_idx + s * k,
+    select_topk_kernel<false><<<(unsigned)m, kSelThreads, 0, st>>>(keys, N, k, out_idx + s * k,
                                                            out_key ? out_key + s * k : nullptr);
     REID_LAUNCH_CHECK();
   }
+  return REID_OK;
+}
+
+int reid_select_rows(const float* keys, int64_t N, int64_t n_rows, int k, int ascending, int32_t* out_idx, float* out_key,
+                     void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(keys && out_idx && N > 0 && n_rows >= 0, "reid_select_rows: bad arguments");
+  REID_CHECK_ARG(k >= 1 && k <= kMaxK && k <= N && N < (1ll << 31), "reid_select_rows: k=%d out of range", k);
+  if (n_rows == 0) return REID_OK;
+  if (ascending) select_topk_kernel<true><<<(unsigned)n_rows, kSelThreads, 0, (cudaStream_t)stream>>>(keys, N, k, out_idx, out_key);
+  else select_topk_kernel<false><<<(unsigned)n_rows, kSelThreads, 0, (cudaStream_t)stream>>>(keys, N, k, out_idx, out_key);
+  REID_LAUNCH_CHECK();
   return REID_OK;
 }
 }

@@ -280,3 +280,23 @@ def test_infomap_front_end(N, D, n_ids, k):
         s, l = ic.get_links(single=[], links={}, nbrs=n, dists=d, min_sim=min_sim)
         s_ref, l_ref = oi.get_links(n_ref, d_ref, min_sim)
         assert s == s_ref and l == l_ref
+
+
+@pytest.mark.parametrize("N,Q,D,n_ids,k1,k2,lam", [(900, 250, 64, 40, 20, 6, 0.3), (500, 120, 32, 30, 7, 1, 0.5),
+                                                    (3000, 700, 128, 150, 20, 6, 0.3)])
+def test_eval_rerank(N, Q, D, n_ids, k1, k2, lam):
+    """f2: re_ranking (utils/rerank.py:31-97) against the oracle: neighbour lists and sets bit-exact, result within 1e-5."""
+    import reid_gan_b200 as rg
+    from oracle import eval_rerank as oe
+    qg, qq, gg = oe.synthetic_distances(N, Q, D, n_ids, 31)
+    ref, parts = oe.re_ranking(qg, qq, gg, k1, k2, lam, return_parts=True)
+    # the comparison of the lists is only meaningful on tie-free fixtures (np.argsort is unstable at rerank.py:43)
+    d = parts["dist"]
+    srt = np.sort(d, axis=1)[:, :k1 + 2]
+    assert (np.diff(srt, axis=1) > 0).all(), "fixture has ties inside the first k1+2 columns"
+    got = rg.re_ranking(qg, qq, gg, k1=k1, k2=k2, lambda_value=lam)
+    assert got.dtype == np.float32 and got.shape == (Q, N - Q)
+    assert np.abs(got - ref).max() <= 1e-5
+    # and through torch tensors, like evaluators.py would pass them without the .numpy()
+    got2 = rg.re_ranking(torch.from_numpy(qg), torch.from_numpy(qq), torch.from_numpy(gg), k1=k1, k2=k2, lambda_value=lam)
+    assert np.array_equal(got, got2)

@@ -142,3 +142,17 @@ def test_infomap_front_end_oracle_matches_reference():
         s_ref, l_ref = m.get_links(single=[], links={}, nbrs=n_ref, dists=d_ref, min_sim=min_sim)
         s, l = oi.get_links(n, d, min_sim)
         assert s_ref == s and l_ref == l
+
+
+def test_eval_rerank_oracle_matches_reference():
+    """f2: oracle/eval_rerank.py against the unmodified utils/rerank.py re_ranking."""
+    from oracle import ref_shim, eval_rerank as oe
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    m = ref_shim.load_eval_rerank()
+    qg, qq, gg = oe.synthetic_distances(360, 100, 64, 24, 4)
+    for k1, k2, lam in ((20, 6, 0.3), (7, 1, 0.5), (12, 3, 0.0)):
+        ref = m.re_ranking(qg, qq, gg, k1=k1, k2=k2, lambda_value=lam)
+        got = oe.re_ranking(qg, qq, gg, k1, k2, lam)
+        assert got.dtype == ref.dtype and got.shape == ref.shape
+        assert np.abs(ref - got).max() <= 1e-6
