@@ -294,6 +294,23 @@ int reid_rr_final(const float* J, int64_t ldJ, const float* dist, int64_t Q, int
 int reid_select_rows(const float* keys, int64_t N, int64_t n_rows, int k, int ascending, int32_t* out_idx,
                      float* out_key, void* stream);
 
+/* ---- f3 (next row): evaluation metrics  (evaluators.py pairwise_distance :71-88; ----------------
+ *      evaluation_metrics/ranking.py mean_ap :82-115, cmc :18-79)
+ * out[i][j] = (||x_i||^2 + ||y_j||^2) - 2 x_i.y_j in fp32; scratch_norms: m + n floats. */
+int reid_pairwise_distance(const float* x, const float* y, int64_t m, int64_t n, int64_t D, float* scratch_norms,
+                           float* out, void* stream);
+/* Per query i: valid gallery items = different id or different camera (and, with separate_camera_set, different
+ * camera); positives = valid items of the same id.  ap_out[i] = uninterpolated average precision (sklearn's
+ * average_precision_score: ties share a threshold), has_pos[i] = 1 / 0 (no positive: the query is skipped by the
+ * reference) / -1 (more positives than the kernel handles).  With cmc buffers: cmc_contrib (m x topk doubles) gets
+ * the query's additions to the CMC histogram (first_match_break or 1/P per match) and cmc_ret (topk) their sum over
+ * the queries in order; ties in distance are ranked by gallery index (the reference's argsort leaves them unordered). */
+size_t reid_rank_metrics_smem_bytes(int64_t n);
+int reid_rank_metrics(const float* dist, int64_t m, int64_t n, int64_t ld, const int64_t* q_ids, const int64_t* g_ids,
+                      const int64_t* q_cams, const int64_t* g_cams, int separate_camera_set, int topk,
+                      int first_match_break, double* ap_out, int32_t* has_pos, double* cmc_contrib, double* cmc_ret,
+                      void* stream);
+
 /* ---- a9: centroid init  (train_usl.py:169-182, 191) -------------------------------
  * out[k] = mean of x[i] over labels[i] == k, k = 0..C-1 (labels < 0 skipped), members added in
  * ascending i; normalize != 0 fuses the F.normalize of :191.  workspace: reid_centroids_workspace_bytes(N, C). */

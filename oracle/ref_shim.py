@@ -137,6 +137,28 @@ def load_eval_rerank():
     return _cache["eval_rerank"]
 
 
+def load_ranking():
+    """The reference module clustercontrast/evaluation_metrics/ranking.py, unmodified (its relative import
+    `from ..utils import to_numpy` is served by the real clustercontrast/utils/__init__.py)."""
+    if "ranking" in _cache:
+        return _cache["ranking"]
+    if not available():
+        raise RuntimeError("reference tree not present at " + REF_ROOT)
+    for pkg, sub in (("clustercontrast", "clustercontrast"), ("clustercontrast.utils", "clustercontrast/utils"),
+                     ("clustercontrast.evaluation_metrics", "clustercontrast/evaluation_metrics")):
+        if pkg not in sys.modules:
+            p = types.ModuleType(pkg)
+            p.__path__ = [os.path.join(REF_ROOT, sub)]
+            sys.modules[pkg] = p
+    if not hasattr(sys.modules["clustercontrast.utils"], "to_numpy"):
+        real = _load("_ref_utils_init", os.path.join(REF_ROOT, "clustercontrast/utils/__init__.py"))
+        sys.modules["clustercontrast.utils"].to_numpy = real.to_numpy
+        sys.modules["clustercontrast.utils"].to_torch = real.to_torch
+    mod = _load("clustercontrast.evaluation_metrics.ranking", os.path.join(REF_ROOT, "clustercontrast/evaluation_metrics/ranking.py"))
+    _cache["ranking"] = mod
+    return mod
+
+
 def load_cm():
     """The reference module clustercontrast/models/cm.py (torch + numpy only)."""
     if "cm" not in _cache:

@@ -65,6 +65,9 @@ SIGNATURES = {
     "reid_rr_weights": (_I, [_P, _L, _P, _I, _P, _L, _P, _P, _P]),
     "reid_rr_final": (_I, [_P, _L, _P, _L, _L, _F, _F, _P, _P]),
     "reid_select_rows": (_I, [_P, _L, _L, _I, _I, _P, _P, _P]),
+    "reid_pairwise_distance": (_I, [_P, _P, _L, _L, _L, _P, _P, _P]),
+    "reid_rank_metrics_smem_bytes": (_Z, [_L]),
+    "reid_rank_metrics": (_I, [_P, _L, _L, _L, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "reid_links_count": (_I, [_P, _P, _L, _I, ctypes.c_double, _P, _P]),
     "reid_links_fill": (_I, [_P, _P, _L, _I, ctypes.c_double, _P, _P, _P, _P]),
     "reid_jaccard_dense": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _P, _L, _P]),

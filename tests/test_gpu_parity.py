@@ -300,3 +300,51 @@ def test_eval_rerank(N, Q, D, n_ids, k1, k2, lam):
     # and through torch tensors, like evaluators.py would pass them without the .numpy()
     got2 = rg.re_ranking(torch.from_numpy(qg), torch.from_numpy(qq), torch.from_numpy(gg), k1=k1, k2=k2, lambda_value=lam)
     assert np.array_equal(got, got2)
+
+
+@pytest.mark.parametrize("N,D,n_ids,k1", [(8192, 128, 260, 20), (10001, 192, 330, 30), (8200, 64, 8200, 12)])
+def test_streamed_upload_matches_device_path(N, D, n_ids, k1):
+    """Host-resident features (the reference's case, evaluators.py:19 `.cpu()`): the search that follows the chunked
+    upload (knn_tc.knn_search_upload) must give the neighbour lists, V_qe and labels of the device-resident pass."""
+    import reid_gan_b200 as rg
+    from reid_gan_b200 import pipeline
+    x, _ = rg.synth(N, D, n_ids, 0.8, 17)
+    ref = pipeline.pseudo_labels(x.cuda(), k1, 6, 0.6, 4)
+    for host in (x, x.pin_memory()):
+        d = rg.compute_jaccard_distance(host, k1=k1, k2=6, print_flag=False)
+        st = d.state
+        assert st.knn_info["mode"] == "tc-sym" and st.knn_info["sym"].get("chunks")
+        assert torch.equal(st.rank, ref["state"].rank)
+        nq = ref["state"].q_total
+        assert st.q_total == nq and torch.equal(st.Q_val[:nq], ref["state"].Q_val[:nq])
+        labels = rg.DBSCAN(eps=0.6, min_samples=4).fit_predict(d)
+        assert np.array_equal(labels, ref["labels"].cpu().numpy())
+
+
+@pytest.mark.parametrize("N,Q,D,n_ids", [(2500, 600, 128, 80), (700, 150, 32, 30), (5000, 40, 64, 400)])
+def test_evaluation_metrics(N, Q, D, n_ids):
+    """f3: pairwise_distance / mean_ap / cmc against the oracle (metrics on the same matrix: 1e-12; distances 1e-4)."""
+    import reid_gan_b200 as rg
+    from reid_gan_b200 import evaluation as ev
+    from oracle import ranking as orank
+    x, ids = rg.synth(N, D, n_ids, 1.2, 5)
+    cams = np.random.default_rng(5).integers(0, 4, N)
+    q, g = x[:Q], x[Q:]
+    qi, gi, qc, gc = ids[:Q].numpy(), ids[Q:].numpy(), cams[:Q], cams[Q:]
+    feats = {"f%d" % i: x[i] for i in range(N)}
+    query = [("f%d" % i, int(ids[i]), int(cams[i])) for i in range(Q)]
+    gallery = [("f%d" % i, int(ids[i]), int(cams[i])) for i in range(Q, N)]
+    dm, xq, yg = ev.pairwise_distance(feats, query, gallery)
+    assert isinstance(dm, torch.Tensor) and dm.shape == (Q, N - Q) and np.array_equal(xq, q.numpy()) and np.array_equal(yg, g.numpy())
+    d_ref = orank.pairwise_distance(q.numpy(), g.numpy())
+    assert np.abs(dm.numpy() - d_ref).max() <= 1e-4
+    d = dm.numpy().copy()
+    d[:, 5] = d[:, 7]                                # force exact ties: same threshold for AP, index order for CMC
+    assert abs(ev.mean_ap(d, qi, gi, qc, gc) - orank.mean_ap(d, qi, gi, qc, gc)) <= 1e-12
+    for kw in (dict(first_match_break=True), dict(), dict(separate_camera_set=True, first_match_break=True)):
+        a = ev.cmc(d, qi, gi, qc, gc, topk=50, **kw)
+        b = orank.cmc(d, qi, gi, qc, gc, topk=50, **kw)
+        assert np.abs(a - b).max() <= 1e-12
+    assert abs(ev.mean_ap(d[:, :Q]) - orank.mean_ap(d[:, :Q])) <= 1e-12          # default ids / cameras
+    with pytest.raises(NotImplementedError):
+        ev.cmc(d, qi, gi, qc, gc, single_gallery_shot=True)

@@ -156,3 +156,32 @@ def test_eval_rerank_oracle_matches_reference():
         got = oe.re_ranking(qg, qq, gg, k1, k2, lam)
         assert got.dtype == ref.dtype and got.shape == ref.shape
         assert np.abs(ref - got).max() <= 1e-6
+
+
+def _eval_set(N, Q, D, n_ids, seed, n_cams=4):
+    from reid_gan_b200.synth import synth
+    x, ids = synth(N, D, n_ids, 1.2, seed)
+    cams = np.random.default_rng(seed).integers(0, n_cams, N)
+    return (x[:Q].numpy(), x[Q:].numpy(), ids[:Q].numpy(), ids[Q:].numpy(), cams[:Q], cams[Q:])
+
+
+def test_ranking_oracle_matches_reference():
+    """f3: oracle/ranking.py against the unmodified evaluation_metrics/ranking.py and evaluators.pairwise_distance."""
+    import torch
+    from oracle import ref_shim, ranking as orank
+    if not ref_shim.available():
+        pytest.skip("reference tree not present")
+    m = ref_shim.load_ranking()
+    q, g, qi, gi, qc, gc = _eval_set(600, 130, 32, 28, 5)
+    xx, yy = torch.from_numpy(q), torch.from_numpy(g)
+    dm = torch.pow(xx, 2).sum(1, keepdim=True).expand(len(q), len(g)) + torch.pow(yy, 2).sum(1, keepdim=True).expand(len(g), len(q)).t()
+    dm = dm.clone()
+    dm.addmm_(xx, yy.t(), beta=1, alpha=-2)                    # evaluators.py:84-86
+    assert np.abs(orank.pairwise_distance(q, g) - dm.numpy()).max() <= 2e-6
+    assert abs(m.mean_ap(dm, qi, gi, qc, gc) - orank.mean_ap(dm.numpy(), qi, gi, qc, gc)) <= 1e-12
+    for kw in (dict(first_match_break=True), dict(), dict(separate_camera_set=True, first_match_break=True)):
+        a = m.cmc(dm, qi, gi, qc, gc, topk=30, single_gallery_shot=False, **kw)
+        b = orank.cmc(dm.numpy(), qi, gi, qc, gc, topk=30, **kw)
+        assert np.abs(a - b).max() <= 1e-12
+    # defaults (ids = arange, cameras 0 / 1)
+    assert abs(m.mean_ap(dm[:, :130]) - orank.mean_ap(dm.numpy()[:, :130])) <= 1e-12
