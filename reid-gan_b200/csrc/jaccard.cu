@@ -46,6 +46,7 @@ __device__ __forceinline__ float jaccard_from_t(float t) {
 // class is one persistent launch that reads its queue length from device memory: no host round trip.
 constexpr int kJWarps = 4;
 constexpr int kJClasses = 5;                 // 512, 1024, 2048, 4096, 8192 slots
+constexpr int kJE = 1;                       // entries of a column per lane and step, table kernel (registers = occupancy)
 constexpr int kJHeavyCtas = 64;              // dense-accumulator rows processed at a time by the last resort
 
 __host__ __device__ constexpr int jclass_slots(int c) { return 512 << c; }
@@ -87,18 +88,26 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
       // Walk the columns in ascending order, 32 entries of ONE column per step: inside a column every j is
       // distinct, so a step needs no ordering between its lanes, and the step sequence is the reference's
       // accumulation order.  The loads of the next step are issued before the current one goes through the table.
+      // kJE entries per lane and step (128 entries of ONE column per step): most columns are a single step, and
+      // with the next step's loads issued ahead a lane keeps 2 * kJE independent loads in flight
       int k = 0, base = 0;
       int64_t cak = __shfl_sync(kFull, ca, 0);
       int lenk = __shfl_sync(kFull, len, 0);
       float vk = __shfl_sync(kFull, vic, 0);
-      int32_t j = -1;
-      float m = 0.f;
-      if (lane < lenk) {
-        j = C_idx[cak + lane];
-        m = fminf(vk, C_val[cak + lane]);
+      int32_t j[kJE];
+      float m[kJE];
+#pragma unroll
+      for (int u = 0; u < kJE; ++u) {
+        const int e = u * 32 + lane;
+        j[u] = -1;
+        m[u] = 0.f;
+        if (e < lenk) {
+          j[u] = C_idx[cak + e];
+          m[u] = fminf(vk, C_val[cak + e]);
+        }
       }
       while (k < ncol) {
-        int nk = k, nbase = base + 32;
+        int nk = k, nbase = base + 32 * kJE;
         int64_t ncak = cak;
         int nlen = lenk;
         float nv = vk;
@@ -111,30 +120,41 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
             nv = __shfl_sync(kFull, vic, nk);
           }
         }
-        int32_t jn = -1;
-        float mn = 0.f;
-        if (nk < ncol && nbase + lane < nlen) {
-          jn = C_idx[ncak + nbase + lane];
-          mn = fminf(nv, C_val[ncak + nbase + lane]);
-        }
-        bool fresh = false;
-        if (j >= 0) {
-          uint32_t h = jhash((uint32_t)j) & smask;
-          while (true) {
-            const int32_t old = atomicCAS(&tkey[h], -1, j);
-            if (old == -1) {
-              tval[h] = m;                                     // 0 + m
-              fresh = true;
-              break;
-            }
-            if (old == j) {
-              tval[h] = __fadd_rn(tval[h], m);
-              break;
-            }
-            h = (h + 1) & smask;
+        int32_t jn[kJE];
+        float mn[kJE];
+#pragma unroll
+        for (int u = 0; u < kJE; ++u) {
+          const int e = nbase + u * 32 + lane;
+          jn[u] = -1;
+          mn[u] = 0.f;
+          if (nk < ncol && e < nlen) {
+            jn[u] = C_idx[ncak + e];
+            mn[u] = fminf(nv, C_val[ncak + e]);
           }
         }
-        used += __popc(__ballot_sync(kFull, fresh));
+        int fresh_n = 0;
+#pragma unroll
+        for (int u = 0; u < kJE; ++u) {
+          bool fresh = false;
+          if (j[u] >= 0) {
+            uint32_t h = jhash((uint32_t)j[u]) & smask;
+            while (true) {
+              const int32_t old = atomicCAS(&tkey[h], -1, j[u]);
+              if (old == -1) {
+                tval[h] = m[u];                                // 0 + m
+                fresh = true;
+                break;
+              }
+              if (old == j[u]) {
+                tval[h] = __fadd_rn(tval[h], m[u]);
+                break;
+              }
+              h = (h + 1) & smask;
+            }
+          }
+          fresh_n += __popc(__ballot_sync(kFull, fresh));
+        }
+        used += fresh_n;
         __syncwarp();                                          // this step's adds land before the next step's
         if (used > limit) {
           overflow = true;
@@ -145,8 +165,11 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
         cak = ncak;
         lenk = nlen;
         vk = nv;
-        j = jn;
-        m = mn;
+#pragma unroll
+        for (int u = 0; u < kJE; ++u) {
+          j[u] = jn[u];
+          m[u] = mn[u];
+        }
       }
     }
     if (overflow) {
@@ -177,18 +200,120 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
   }
 }
 
+// Rows with thousands of partners (k1 larger than the identity clusters: every row overlaps a sizeable part of the
+// set) make the hash tables big and their probing long.  When N floats fit a few times into shared memory the
+// accumulator is simply the dense row t[0..N) itself, owned by a whole CTA: the columns are still consumed one after
+// the other (the reference's accumulation order), the entries of a column by all threads at once (a column holds
+// every j once, so no two threads meet), with the next column's loads in flight.  An update is one load-add-store,
+// nothing can overflow, and the ordered emit pass clears the row on the way.
+constexpr int kJDThreads = 128;
+
+__global__ void __launch_bounds__(kJDThreads) jaccard_direct_kernel(
+    const int64_t* __restrict__ Q_ptr, const int32_t* __restrict__ Q_idx, const float* __restrict__ Q_val,
+    const int64_t* __restrict__ C_ptr, const int32_t* __restrict__ C_idx, const float* __restrict__ C_val, int64_t N,
+    int64_t row_begin, const int32_t* __restrict__ queue, const int32_t* __restrict__ queue_len, float eps,
+    const int64_t* __restrict__ slot_ptr, int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_val,
+    int32_t* __restrict__ nbr_cnt) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  float* acc = reinterpret_cast<float*>(smem_raw);
+  __shared__ int64_t s_ca[32];
+  __shared__ int s_len[32];
+  __shared__ float s_v[32];
+  __shared__ int s_warp[kJDThreads / 32];
+  __shared__ int s_base;
+  const int t = threadIdx.x, lane = t & 31, w = t >> 5;
+  const int64_t n_pad = (N + kJDThreads - 1) / kJDThreads * kJDThreads;
+  const int64_t n_rows = *queue_len;
+  for (int64_t s0 = t; s0 < n_pad; s0 += kJDThreads) acc[s0] = 0.f;
+  __syncthreads();
+  for (int64_t li = blockIdx.x; li < n_rows; li += gridDim.x) {
+    const int64_t lr = queue[li];
+    const int64_t row = row_begin + lr;
+    const int64_t qa = Q_ptr[row], qb = Q_ptr[row + 1];
+    for (int64_t pc = qa; pc < qb; pc += 32) {
+      const int ncol = (int)min((int64_t)32, qb - pc);
+      if (t < ncol) {
+        const int32_t c = Q_idx[pc + t];
+        const int64_t ca = C_ptr[c];
+        s_ca[t] = ca;
+        s_len[t] = (int)(C_ptr[c + 1] - ca);
+        s_v[t] = Q_val[pc + t];
+      }
+      __syncthreads();
+      int32_t j = -1;
+      float m = 0.f;
+      if (t < s_len[0]) {
+        j = C_idx[s_ca[0] + t];
+        m = fminf(s_v[0], C_val[s_ca[0] + t]);
+      }
+      for (int k = 0; k < ncol; ++k) {
+        int32_t jn = -1;
+        float mn = 0.f;
+        if (k + 1 < ncol && t < s_len[k + 1]) {               // first entry of the next column, ahead of time
+          jn = C_idx[s_ca[k + 1] + t];
+          mn = fminf(s_v[k + 1], C_val[s_ca[k + 1] + t]);
+        }
+        if (j >= 0) acc[j] = __fadd_rn(acc[j], m);
+        const int len = s_len[k];
+        for (int e = t + kJDThreads; e < len; e += kJDThreads) {   // columns longer than the CTA (rare)
+          const int32_t j2 = C_idx[s_ca[k] + e];
+          acc[j2] = __fadd_rn(acc[j2], fminf(s_v[k], C_val[s_ca[k] + e]));
+        }
+        __syncthreads();                                       // column k is in before column k + 1 starts
+        j = jn;
+        m = mn;
+      }
+    }
+    // ordered emit of { j : J <= eps }; the accumulator is cleared on the way
+    const int64_t o = slot_ptr[lr];
+    if (t == 0) s_base = 0;
+    __syncthreads();
+    for (int64_t b0 = 0; b0 < n_pad; b0 += kJDThreads) {
+      const float tv = acc[b0 + t];
+      acc[b0 + t] = 0.f;
+      float jd = 2.f;
+      if (tv > 0.f) jd = jaccard_from_t(tv);
+      const bool keep = tv > 0.f && jd <= eps;
+      const unsigned b = __ballot_sync(kFull, keep);
+      if (__syncthreads_or(b != 0)) {                          // most 128-wide windows hold no neighbour at all
+        if (lane == 0) s_warp[w] = __popc(b);
+        __syncthreads();
+        int before = s_base;
+        for (int ww = 0; ww < w; ++ww) before += s_warp[ww];
+        if (keep) {
+          const int64_t dst = o + before + __popc(b & ((1u << lane) - 1u));
+          nbr_idx[dst] = (int32_t)(b0 + t);
+          if (nbr_val) nbr_val[dst] = jd;
+        }
+        __syncthreads();
+        if (t == 0) {
+          int tot = 0;
+          for (int ww = 0; ww < kJDThreads / 32; ++ww) tot += s_warp[ww];
+          s_base += tot;
+        }
+      }
+    }
+    __syncthreads();
+    if (t == 0) nbr_cnt[lr] = s_base;
+  }
+}
+
 // T_cnt (upper bound of the partner count) -> table class.  T counts every (column, row) pair; the number of
 // DISTINCT partners is a small fraction of it (a partner shares many columns with the row), and the latency-bound
 // table kernel lives on occupancy, so the first guess is optimistic -- the class that holds T/4 -- and rows that
 // do overflow move up one class at a time.
+// direct_from: rows that would need class >= direct_from go to the direct-indexed kernel instead (queue kJClasses + 1);
+// kJClasses + 1 when that kernel is not available for this N.
 __global__ void __launch_bounds__(256) jaccard_classify_kernel(const int32_t* __restrict__ T_cnt, int64_t n_rows,
-                                                               int32_t* __restrict__ queues, int32_t* __restrict__ qlen) {
+                                                               int direct_from, int32_t* __restrict__ queues,
+                                                               int32_t* __restrict__ qlen) {
   const int64_t lr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (lr >= n_rows) return;
   const int t = T_cnt[lr];
   const int need = t < 2048 ? t >> 2 : t >> 1;           // a retry of a long row is expensive: less optimism there
   int c = 0;
   while (c < kJClasses && need > ((jclass_slots(c) >> 1) + (jclass_slots(c) >> 2))) ++c;   // c == kJClasses: heavy
+  if (c >= direct_from) c = kJClasses + 1;
   queues[(int64_t)c * n_rows + atomicAdd(&qlen[c], 1)] = (int32_t)lr;
 }
 
@@ -325,7 +450,7 @@ static int launch_jn_slots(const JnArgs& a, int slots, int64_t n_max, const int3
 
 struct JWs {
   int32_t* qlen;     // kJClasses + 1 (+ padding)
-  int32_t* queues;   // (kJClasses + 1) x n_rows
+  int32_t* queues;   // (kJClasses + 2) x n_rows: table classes, heavy, direct
   float* scratch;    // kJHeavyCtas x N
 };
 static size_t jws_carve(void* base, int64_t N, int64_t n, JWs* w) {
@@ -338,7 +463,7 @@ static size_t jws_carve(void* base, int64_t N, int64_t n, JWs* w) {
   };
   JWs t;
   t.qlen = (int32_t*)take(sizeof(int32_t) * 16);
-  t.queues = (int32_t*)take(sizeof(int32_t) * (size_t)(kJClasses + 1) * (size_t)(n > 0 ? n : 1));
+  t.queues = (int32_t*)take(sizeof(int32_t) * (size_t)(kJClasses + 2) * (size_t)(n > 0 ? n : 1));
   t.scratch = (float*)take(sizeof(float) * (size_t)kJHeavyCtas * (size_t)N);
   if (w) *w = t;
   return off;
@@ -398,13 +523,33 @@ int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
   JWs w;
   jws_carve(workspace, N, n, &w);
   REID_CUDA(cudaMemsetAsync(w.qlen, 0, sizeof(int32_t) * 16, st));
-  jaccard_classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(T_cnt, n, w.queues, w.qlen);
+  // direct-indexed accumulator rows (N floats each) when at least two fit into shared memory: they take over from
+  // the 4096-slot class up, and the overflow of the last hash class below
+  const size_t row_bytes = (size_t)((N + kJDThreads - 1) / kJDThreads * kJDThreads) * sizeof(float);
+  const int direct_from = row_bytes * 2 <= 220u * 1024u ? 3 : kJClasses + 1;
+  int32_t* direct_q = w.queues + (int64_t)(kJClasses + 1) * n;
+  int32_t* direct_len = w.qlen + kJClasses + 1;
+  jaccard_classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(T_cnt, n, direct_from, w.queues, w.qlen);
   REID_LAUNCH_CHECK();
   const JnArgs a{Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, row_begin, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt};
-  for (int c = 0; c < kJClasses; ++c) {
-    int rc = launch_jn_slots(a, jclass_slots(c), n, w.queues + (int64_t)c * n, w.qlen + c, w.queues + (int64_t)(c + 1) * n,
-                             w.qlen + c + 1, st);
+  const int n_hash = direct_from < kJClasses ? direct_from : kJClasses;
+  for (int c = 0; c < n_hash; ++c) {
+    const bool last = c + 1 == n_hash && direct_from <= kJClasses;
+    int rc = launch_jn_slots(a, jclass_slots(c), n, w.queues + (int64_t)c * n, w.qlen + c,
+                             last ? direct_q : w.queues + (int64_t)(c + 1) * n, last ? direct_len : w.qlen + c + 1, st);
     if (rc != REID_OK) return rc;
+  }
+  if (direct_from <= kJClasses) {
+    REID_CUDA(cudaFuncSetAttribute(jaccard_direct_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)row_bytes));
+    int per_sm = 1;
+    REID_CUDA(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, jaccard_direct_kernel, kJDThreads, row_bytes));
+    if (per_sm < 1) per_sm = 1;
+    int64_t grid = (int64_t)num_sms() * per_sm;
+    if (grid > n) grid = n;
+    jaccard_direct_kernel<<<(unsigned)grid, kJDThreads, row_bytes, st>>>(Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin,
+                                                                        direct_q, direct_len, eps, slot_ptr, nbr_idx, nbr_val,
+                                                                        nbr_cnt);
+    REID_LAUNCH_CHECK();
   }
   const int64_t hg = n < kJHeavyCtas ? n : kJHeavyCtas;
   jaccard_neighbors_heavy_kernel<<<(unsigned)hg, 256, 0, st>>>(Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin,
