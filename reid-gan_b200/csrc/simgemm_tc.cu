@@ -4,21 +4,25 @@
 //
 //   S = Xh . Xh^T,  Xh = fp16(2^s X)  (N x D, K-major for both operands)
 //
-// One persistent CTA per SM, warp-specialised:
-//   warp 0      TMA producer : cp.async.bulk.tensor 128B-swizzled 64-wide K slices of a 128-row query
-//                              tile (A) and a 256-row column tile (B) into a 4-stage shared-memory ring
-//   warp 1      MMA issuer   : one elected lane issues tcgen05.mma (M=128, N=256, K=16, fp16 -> fp32)
-//                              into one of two 256-column TMEM accumulators; tcgen05.commit frees the
-//                              ring slot / publishes the accumulator
-//   warps 2..5  epilogue     : tcgen05.ld 32 columns at a time; thread <-> query row; every score is
-//                              compared with the row's running threshold tau and survivors are appended
-//                              to the row's candidate list (global scratch, L2 resident).  When a list
-//                              nears capacity the warp compacts it cooperatively to the best K
-//                              (bitwise binary search for the K-th value, ballot prefix sums) and raises
-//                              tau, so after warm-up almost every score dies on a single compare.
-// A work unit is (128-row query tile) x (one of n_splits column ranges); units are dealt round-robin,
+// One persistent CTA per SM (kCtas = 2: CTA pairs, tcgen05 cta_group::2), warp-specialised:
+//   warp 0      TMA producer : cp.async.bulk.tensor 128B-swizzled 64-wide K slices of the CTA's 128 query rows
+//                              (A) and of its share of the 256-row column tile (B) into a 4 / 6-stage
+//                              shared-memory ring
+//   warp 1      MMA issuer   : one elected lane (leader CTA) issues tcgen05.mma (M = 128 * kCtas, N = 256, K = 16,
+//                              fp16 -> fp32) into one of two 256-column TMEM accumulators; tcgen05.commit frees
+//                              the ring slot / publishes the accumulator
+//   warps 2..9  epilogue     : two groups of four warps, group g drains accumulator g (every other column tile):
+//                              tcgen05.ld 32 columns at a time; thread <-> query row; every score is compared
+//                              with the row's running threshold tau and survivors are appended to the row's
+//                              candidate list (global scratch).  The accumulator is handed back first; lists
+//                              that could overflow during the next tile are then compacted warp-cooperatively
+//                              to the best K (bitwise binary search, ballot prefix sums) and tau is raised and
+//                              published per row, so after warm-up almost every score dies on a single compare.
+// A work unit is (128 * kCtas-row query tile) x (one of n_splits column ranges); units are dealt round-robin,
 // column-range major so that concurrently running CTAs stream the same B tiles out of L2.
 // The scores are only candidates: knn_rescore.cu re-scores them exactly and certifies the result.
+// Since the symmetric search (simgemm_sym.cu) this kernel serves N < 8192, k > 32, the row shards of the "rows"
+// multi-GPU plan, and -- with a negative `keep` -- the sampling prepass that finds the symmetric search's thresholds.
 #include <stdlib.h>
 
 #include "tc_ptx.cuh"
