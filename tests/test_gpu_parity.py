@@ -348,3 +348,25 @@ def test_evaluation_metrics(N, Q, D, n_ids):
     assert abs(ev.mean_ap(d[:, :Q]) - orank.mean_ap(d[:, :Q])) <= 1e-12          # default ids / cameras
     with pytest.raises(NotImplementedError):
         ev.cmc(d, qi, gi, qc, gc, single_gallery_shot=True)
+
+
+@pytest.mark.parametrize("ci,N,D,n_ids,noise", [
+    (0, 8193, 64, 264, 0.8), (1, 8447, 192, 8447, 1.0), (2, 9000, 192, 8, 0.3), (3, 12345, 64, 398, 0.8),
+    (4, 16384, 64, 8, 0.3), (5, 20001, 192, 20001, 1.0), (6, 8192, 192, 8, 0.3), (7, 20001, 64, 645, 0.8)])
+def test_symmetric_search_random_shapes(ci, N, D, n_ids, noise):
+    """Shapes that are not multiples of the 128 / 256-row tiles, huge near-duplicate clusters (windows that overflow
+    and fall back to the exact search), duplicated rows, rows that are not unit norm, k from 1 to 32."""
+    import reid_gan_b200 as rg
+    from reid_gan_b200 import faiss_rerank as fr
+    k = (1, 5, 30, 32)[ci % 4]
+    x, _ = rg.synth(N, D, n_ids, noise, ci)
+    if ci % 3 == 0:
+        x[N // 2: N // 2 + 300] = x[:300]
+    if ci % 5 == 0:
+        g = torch.Generator().manual_seed(ci)
+        x = x * (0.5 + torch.rand(N, 1, generator=g))
+    xd = x.cuda()
+    ie, ke, _ = fr.knn_search(xd, k, "exact")
+    it, kt, info = fr.knn_search(xd, k, "tc")
+    assert info["mode"] == "tc-sym"
+    assert torch.equal(ie, it) and torch.equal(ke, kt)
