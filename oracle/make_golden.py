@@ -9,6 +9,9 @@ need /root/reference.  Reference entry points exercised:
   sklearn.cluster.DBSCAN(...).fit_predict    (examples/cluster_contrast_train_usl.py:160,163)
   examples/cluster_contrast_train_usl.py:169-182,191  (closure twin in ref_shim)
   clustercontrast/models/cm.py:36,75,125-135 cm / cm_hard + ClusterMemory.forward body (CPU)
+  clustercontrast/utils/infomap_cluster.py:230-234, 129-144   get_dist_nbr / get_links            (next row f1)
+  clustercontrast/utils/rerank.py:31-97                       re_ranking                          (next row f2)
+  clustercontrast/evaluation_metrics/ranking.py:18-115 + evaluators.py:78-87   cmc / mean_ap / pairwise distance (f3)
 """
 import importlib.util
 import os
@@ -103,8 +106,66 @@ def make_cm(sm):
         print("cm", name, "loss mean", float(out["loss_cm"].mean()))
 
 
+def _pdist(a, b):
+    """evaluators.py:78-87 pairwise_distance (the reference function takes feature dicts; this is its arithmetic)."""
+    m, n = a.size(0), b.size(0)
+    d = torch.pow(a, 2).sum(dim=1, keepdim=True).expand(m, n) + torch.pow(b, 2).sum(dim=1, keepdim=True).expand(n, m).t()
+    d = d.clone()
+    d.addmm_(a, b.t(), beta=1, alpha=-2)
+    return d
+
+
+def make_next_rows(sm):
+    """f1 / f2 / f3: outputs of the unmodified reference functions on small seeded inputs."""
+    torch.set_num_threads(1)
+    # f1 -- infomap front end
+    im = ref_shim.load_infomap_cluster()
+    x, _ = sm.synth(400, 64, 16, 0.8, 11)
+    dists, nbrs = im.get_dist_nbr(features=x.numpy(), k=15, knn_method='faiss-cpu')
+    out = dict(x=x.numpy(), k=15, dists=dists, nbrs=nbrs)
+    for min_sim in (0.3, 0.5):
+        single, links = im.get_links(single=[], links={}, nbrs=nbrs, dists=dists, min_sim=min_sim)
+        tag = "ms%02d" % round(min_sim * 100)
+        keys = np.array(sorted(links.keys()), dtype=np.int64).reshape(-1, 2)
+        out["links_ij_" + tag] = keys
+        out["links_w_" + tag] = np.array([links[(int(a), int(b))] for a, b in keys], dtype=np.float64)
+        out["single_" + tag] = np.array(single, dtype=np.int64)
+    np.savez_compressed(os.path.join(GOLD, "infomap_n400_k15.npz"), **out)
+    print("infomap", len(out["links_w_ms50"]), "links at 0.5")
+    # f2 -- evaluation re-ranking
+    rr = ref_shim.load_eval_rerank()
+    x, _ = sm.synth(360, 64, 24, 0.8, 12)
+    q, g = x[:100], x[100:]
+    qg, qq, gg = _pdist(q, g).numpy(), _pdist(q, q).numpy(), _pdist(g, g).numpy()
+    out = dict(q_g=qg, q_q=qq, g_g=gg)
+    for k1, k2, lam in ((20, 6, 0.3), (7, 1, 0.5)):
+        out["final_k%d_%d" % (k1, k2)] = rr.re_ranking(qg, qq, gg, k1=k1, k2=k2, lambda_value=lam)
+        out["lambda_k%d_%d" % (k1, k2)] = lam
+    np.savez_compressed(os.path.join(GOLD, "evalrerank_q100_g260.npz"), **out)
+    print("eval rerank", out["final_k20_6"].shape)
+    # f3 -- ranking metrics
+    rk = ref_shim.load_ranking()
+    x, ids = sm.synth(500, 32, 25, 1.2, 13)
+    cams = np.random.default_rng(13).integers(0, 4, 500)
+    q, g = x[:120], x[120:]
+    dm = _pdist(q, g)
+    qi, gi, qc, gc = ids[:120].numpy(), ids[120:].numpy(), cams[:120], cams[120:]
+    out = dict(q=q.numpy(), g=g.numpy(), distmat=dm.numpy(), q_ids=qi, g_ids=gi, q_cams=qc, g_cams=gc,
+               mAP=np.float64(rk.mean_ap(dm, qi, gi, qc, gc)),
+               cmc_market=rk.cmc(dm, qi, gi, qc, gc, topk=50, separate_camera_set=False, single_gallery_shot=False,
+                                 first_match_break=True),
+               cmc_allshots=rk.cmc(dm, qi, gi, qc, gc, topk=50, separate_camera_set=False, single_gallery_shot=False,
+                                   first_match_break=False),
+               cmc_sepcam=rk.cmc(dm, qi, gi, qc, gc, topk=50, separate_camera_set=True, single_gallery_shot=False,
+                                 first_match_break=True))
+    np.savez_compressed(os.path.join(GOLD, "ranking_q120_g380.npz"), **out)
+    print("ranking mAP", float(out["mAP"]))
+
+
 if __name__ == "__main__":
     os.makedirs(GOLD, exist_ok=True)
     sm = _synth_mod()
-    make_rerank(sm)
-    make_cm(sm)
+    if "--next-only" not in sys.argv:
+        make_rerank(sm)
+        make_cm(sm)
+    make_next_rows(sm)

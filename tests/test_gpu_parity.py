@@ -370,3 +370,37 @@ def test_symmetric_search_random_shapes(ci, N, D, n_ids, noise):
     it, kt, info = fr.knn_search(xd, k, "tc")
     assert info["mode"] == "tc-sym"
     assert torch.equal(ie, it) and torch.equal(ke, kt)
+
+
+# ---- CUDA path against the golden vectors of the "next" rows (outputs of the unmodified reference) -----------
+def test_golden_infomap_front_end_cuda():
+    from reid_gan_b200 import infomap_cluster as ic
+    g = np.load(os.path.join(GOLD, "infomap_n400_k15.npz"))
+    d, n = ic.get_dist_nbr(features=g["x"], k=int(g["k"]), knn_method='faiss-gpu')
+    assert d.dtype == g["dists"].dtype and n.dtype == g["nbrs"].dtype
+    assert np.array_equal(n, g["nbrs"]) and np.array_equal(d, g["dists"])
+    for min_sim, tag in ((0.3, "ms30"), (0.5, "ms50")):
+        single, links = ic.get_links(single=[], links={}, nbrs=n, dists=d, min_sim=min_sim)
+        ref = {(int(a), int(b)): float(w) for (a, b), w in zip(g["links_ij_" + tag], g["links_w_" + tag])}
+        assert links == ref and single == [int(v) for v in g["single_" + tag]]
+
+
+def test_golden_eval_rerank_cuda():
+    import reid_gan_b200 as rg
+    g = np.load(os.path.join(GOLD, "evalrerank_q100_g260.npz"))
+    for k1, k2 in ((20, 6), (7, 1)):
+        ref = g["final_k%d_%d" % (k1, k2)]
+        got = rg.re_ranking(g["q_g"], g["q_q"], g["g_g"], k1=k1, k2=k2, lambda_value=float(g["lambda_k%d_%d" % (k1, k2)]))
+        assert got.dtype == ref.dtype and got.shape == ref.shape and np.abs(got - ref).max() <= 1e-5
+
+
+def test_golden_ranking_metrics_cuda():
+    from reid_gan_b200 import evaluation as ev
+    g = np.load(os.path.join(GOLD, "ranking_q120_g380.npz"))
+    d = ev.pairwise_distance_device(torch.from_numpy(g["q"]).cuda(), torch.from_numpy(g["g"]).cuda()).cpu().numpy()
+    assert np.abs(d - g["distmat"]).max() <= 1e-4
+    args = (g["distmat"], g["q_ids"], g["g_ids"], g["q_cams"], g["g_cams"])
+    assert abs(ev.mean_ap(*args) - float(g["mAP"])) <= 1e-12
+    assert np.abs(ev.cmc(*args, topk=50, first_match_break=True) - g["cmc_market"]).max() <= 1e-12
+    assert np.abs(ev.cmc(*args, topk=50) - g["cmc_allshots"]).max() <= 1e-12
+    assert np.abs(ev.cmc(*args, topk=50, separate_camera_set=True, first_match_break=True) - g["cmc_sepcam"]).max() <= 1e-12

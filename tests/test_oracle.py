@@ -185,3 +185,45 @@ def test_ranking_oracle_matches_reference():
         assert np.abs(a - b).max() <= 1e-12
     # defaults (ids = arange, cameras 0 / 1)
     assert abs(m.mean_ap(dm[:, :130]) - orank.mean_ap(dm.numpy()[:, :130])) <= 1e-12
+
+
+# ---- golden vectors of the "next" rows (generated by oracle/make_golden.py from the unmodified reference) ----
+def _gold(name):
+    return np.load(os.path.join(GOLD, name))
+
+
+def _links_from_gold(g, tag):
+    return ({(int(a), int(b)): float(w) for (a, b), w in zip(g["links_ij_" + tag], g["links_w_" + tag])},
+            [int(v) for v in g["single_" + tag]])
+
+
+def test_golden_infomap_front_end():
+    from oracle import infomap as oi
+    g = _gold("infomap_n400_k15.npz")
+    d, n = oi.get_dist_nbr(g["x"], int(g["k"]))
+    assert d.dtype == g["dists"].dtype and n.dtype == g["nbrs"].dtype
+    assert np.array_equal(n, g["nbrs"]) and np.array_equal(d, g["dists"])
+    for min_sim, tag in ((0.3, "ms30"), (0.5, "ms50")):
+        links_ref, single_ref = _links_from_gold(g, tag)
+        single, links = oi.get_links(n, d, min_sim)
+        assert links == links_ref and single == single_ref
+
+
+def test_golden_eval_rerank():
+    from oracle import eval_rerank as oe
+    g = _gold("evalrerank_q100_g260.npz")
+    for k1, k2 in ((20, 6), (7, 1)):
+        ref = g["final_k%d_%d" % (k1, k2)]
+        got = oe.re_ranking(g["q_g"], g["q_q"], g["g_g"], k1, k2, float(g["lambda_k%d_%d" % (k1, k2)]))
+        assert got.dtype == ref.dtype and np.abs(got - ref).max() <= 1e-6
+
+
+def test_golden_ranking_metrics():
+    from oracle import ranking as orank
+    g = _gold("ranking_q120_g380.npz")
+    assert np.abs(orank.pairwise_distance(g["q"], g["g"]) - g["distmat"]).max() <= 2e-6
+    args = (g["distmat"], g["q_ids"], g["g_ids"], g["q_cams"], g["g_cams"])
+    assert abs(orank.mean_ap(*args) - float(g["mAP"])) <= 1e-12
+    assert np.abs(orank.cmc(*args, topk=50, first_match_break=True) - g["cmc_market"]).max() <= 1e-12
+    assert np.abs(orank.cmc(*args, topk=50) - g["cmc_allshots"]).max() <= 1e-12
+    assert np.abs(orank.cmc(*args, topk=50, separate_camera_set=True, first_match_break=True) - g["cmc_sepcam"]).max() <= 1e-12
