@@ -1,7 +1,7 @@
 #!/usr/bin/env python
 """Benchmark of the pseudo-label hot path (BASELINE.json: "k-reciprocal Jaccard+DBSCAN sec at N=32,621").
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--workload rerank|cm]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N ...
 
 A step = one full pass: kNN (tcgen05 GEMM + fused top-K + exact re-score) -> k-reciprocal sets ->
@@ -10,7 +10,8 @@ DBSCAN labels, on synthetic L2-normalised 2048-d features (BASELINE configs[1]: 
 k2=6, eps=0.6, min_samples=4).  `value` = seconds per pass with the features resident in HBM;
 `e2e` = the same pass through the drop-in API (compute_jaccard_distance + DBSCAN.fit_predict)
 from pinned HOST features to HOST labels.  With --gpus N the rows are partitioned across N ranks
-(strong scaling: the job is one N=32,621 pass).  `--impl reference` times the CPU restatement of the
+(strong scaling: the job is one N=32,621 pass).  `--workload cm` times BASELINE configs[2] instead (ClusterMemory
+CM_Hard forward + backward + momentum update, latency bound: reported as seconds per step with the launch count).  `--impl reference` times the CPU restatement of the
 reference (oracle/, numpy) on the host cores instead -- the reference itself is pure Python with a
 faiss dependency that is not in this image and cannot travel to the GPU box.
 """
