@@ -151,6 +151,9 @@ size_t reid_knn_rescore_workspace_bytes(int64_t N, int64_t n_rows);
 /* byte offset, inside that workspace, of the int32[n_rows] window sizes of the last call (for reporting the
  * bytes the exact stage really had to gather) */
 size_t reid_knn_rescore_window_counts_offset(int64_t N, int64_t n_rows);
+/* byte offset of the int32[n_rows] cluster-locality visiting order (a permutation of the local rows; valid when the
+ * call had locality_order != 0): reid_v_weights can walk the rows in the same order */
+size_t reid_knn_rescore_order_offset(int64_t N, int64_t n_rows);
 
 /* ---- a2: reciprocal sets  (faiss_rerank.py:23-27, 65-69) -----------------------
  * mask_out[row - row_begin] bit r  <=>  row in rank[rank[row,r], :cols], cols = min(k+1, ncols).
@@ -172,10 +175,12 @@ int reid_expand(const int32_t* rank, int64_t N, int ncols, int half_cols, const 
  * V_val[p] = softmax over the row of -(2 - 2 x_row.x_e), e in E(row); fp32.  Reads the padded sets of
  * reid_expand and writes the CSR (E_idx, V_val) at E_ptr (local, from a scan of E_cnt) in the same pass.
  * rank/rank_key (optional, the shard's rows of the search result) let the kernel reuse the search keys
- * for members that are among the row's k1 neighbours instead of gathering 4*D bytes. */
+ * for members that are among the row's k1 neighbours instead of gathering 4*D bytes.
+ * visit_order (optional): a permutation of the local rows to walk them in (reid_knn_rescore's cluster-locality
+ * order): cluster mates gather the same feature rows and find them in L2.  The output does not depend on it. */
 int reid_v_weights(const float* x, int64_t N, int64_t D, const int32_t* E_pad, int stride, const int64_t* E_ptr,
                    int64_t row_begin, int64_t row_end, const int32_t* rank_local, const float* rank_key_local,
-                   int ncols, int32_t* E_idx, float* V_val, void* stream);
+                   int ncols, const int32_t* visit_order, int32_t* E_idx, float* V_val, void* stream);
 
 /* ---- a5: k2 query expansion  (faiss_rerank.py:89-94) ----------------------------
  * Vq[row] = (V[rank[row,0]] + ... + V[rank[row,k2-1]]) / k2, adds in that order, fp32.

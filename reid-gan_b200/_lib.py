@@ -46,7 +46,8 @@ SIGNATURES = {
     "reid_knn_sample_tau": (_I, [_P, _P, _P, _I, _L, _I, _P, _P, _P]),
     "reid_reciprocal_masks": (_I, [_P, _L, _I, _I, _L, _L, _P, _P]),
     "reid_expand": (_I, [_P, _L, _I, _I, _P, _P, _L, _L, _I, _P, _P, _P]),
-    "reid_v_weights": (_I, [_P, _L, _L, _P, _I, _P, _L, _L, _P, _P, _I, _P, _P, _P]),
+    "reid_v_weights": (_I, [_P, _L, _L, _P, _I, _P, _L, _L, _P, _P, _I, _P, _P, _P, _P]),
+    "reid_knn_rescore_order_offset": (_Z, [_L, _L]),
     "reid_query_expand_stride": (_I, [_I, _I]),
     "reid_query_expand": (_I, [_P, _L, _I, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P]),
     "reid_csr_compact": (_I, [_P, _P, _L, _P, _P, _L, _P, _P, _P]),

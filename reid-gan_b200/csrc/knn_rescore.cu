@@ -505,6 +505,13 @@ size_t reid_knn_rescore_window_counts_offset(int64_t N, int64_t n_rows) {
   return (size_t)((unsigned char*)w.win_cnt - (unsigned char*)256);
 }
 
+size_t reid_knn_rescore_order_offset(int64_t N, int64_t n_rows) {
+  if (N < 0 || n_rows < 0) return 0;
+  reid::RescoreWs w;
+  reid::rescore_carve((void*)256, N, n_rows, &w);
+  return (size_t)((unsigned char*)w.perm - (unsigned char*)256);
+}
+
 size_t reid_knn_rescore_workspace_bytes(int64_t N, int64_t n_rows) {
   if (N < 0 || n_rows < 0) return 0;
   return reid::rescore_carve(nullptr, N, n_rows, nullptr);

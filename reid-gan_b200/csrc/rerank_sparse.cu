@@ -18,12 +18,16 @@ template <int kChunks>
 __global__ void __launch_bounds__(kVWarps * 32) v_weights_kernel(
     const float* __restrict__ x, int64_t D, const int32_t* __restrict__ E_pad, int stride,
     const int64_t* __restrict__ E_ptr, int64_t row_begin, int64_t row_end, const int32_t* __restrict__ rank_local,
-    const float* __restrict__ key_local, int ncols, int32_t* __restrict__ E_idx, float* __restrict__ V_val) {
+    const float* __restrict__ key_local, int ncols, const int32_t* __restrict__ perm, int32_t* __restrict__ E_idx,
+    float* __restrict__ V_val) {
   __shared__ float s_val[kVWarps][kVMaxRow];
   const int w = threadIdx.x >> 5, lane = lane_id();
-  const int64_t row = row_begin + (int64_t)blockIdx.x * kVWarps + w;
-  if (row >= row_end) return;
-  const int64_t lr = row - row_begin;
+  const int64_t slot = (int64_t)blockIdx.x * kVWarps + w;
+  if (slot >= row_end - row_begin) return;
+  // optional visiting order (the cluster-locality order of the re-score stage): cluster mates gather the same few
+  // feature rows, so run back to back they find them in L2
+  const int64_t lr = perm ? (int64_t)perm[slot] : slot;
+  const int64_t row = row_begin + lr;
   const int64_t p0 = E_ptr[lr];
   const int n = (int)(E_ptr[lr + 1] - p0);
   if (n == 0) return;
@@ -392,7 +396,7 @@ extern "C" {
 
 int reid_v_weights(const float* x, int64_t N, int64_t D, const int32_t* E_pad, int stride, const int64_t* E_ptr,
                    int64_t row_begin, int64_t row_end, const int32_t* rank_local, const float* rank_key_local,
-                   int ncols, int32_t* E_idx, float* V_val, void* stream) {
+                   int ncols, const int32_t* visit_order, int32_t* E_idx, float* V_val, void* stream) {
   using namespace reid;
   REID_CHECK_ARG(x && E_pad && E_ptr && E_idx && V_val, "reid_v_weights: NULL pointer");
   REID_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= N && D > 0 && stride >= 1,
@@ -403,7 +407,7 @@ int reid_v_weights(const float* x, int64_t N, int64_t D, const int32_t* E_pad, i
   if (n == 0) return REID_OK;
 #define REID_V_LAUNCH(CH)                                                                                          \
   v_weights_kernel<CH><<<(unsigned)((n + kVWarps - 1) / kVWarps), kVWarps * 32, 0, (cudaStream_t)stream>>>(          \
-      x, D, E_pad, stride, E_ptr, row_begin, row_end, rank_local, rank_key_local, ncols, E_idx, V_val)
+      x, D, E_pad, stride, E_ptr, row_begin, row_end, rank_local, rank_key_local, ncols, visit_order, E_idx, V_val)
   const bool aligned = (((uintptr_t)x) & 15) == 0;
   if (aligned && D == 2048) REID_V_LAUNCH(16);
   else if (aligned && D == 1024) REID_V_LAUNCH(8);

@@ -174,6 +174,7 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_
         return _scan_async(e_cnt, n, dev)
 
     e_ptr, e_stats = sets()
+    pending_repaired = False
     pending = info.pop("pending", None)
     if pending is not None:
         vals = torch.cat([e_stats, pending["flag"].sum(dtype=torch.int64).view(1)]).tolist()
@@ -193,8 +194,11 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_
     # a4 ------------------------------------------------------------------
     e_idx = torch.empty(max(e_total, 1), dtype=torch.int32, device=dev)
     v_val = torch.empty(max(e_total, 1), dtype=torch.float32, device=dev)
+    order = info.get("visit_order") if knn_result is None else None
+    if order is not None and (order.numel() != n or pending_repaired):
+        order = None                                          # only valid for exactly these rows
     call("reid_v_weights", ptr(x), N, D, ptr(e_pad), e_stride, ptr(e_ptr), r0, r1, ptr(rank_local), ptr(key_local),
-         k1, ptr(e_idx), ptr(v_val), sp)
+         k1, ptr(order), ptr(e_idx), ptr(v_val), sp)
     mark("v_weights")
     if comm is not None:                                     # V rows of other shards are read by a5
         e_ptr, e_idx, v_val, e_total, e_max = comm.gather_csr(e_cnt[:n], e_idx[:e_total], v_val[:e_total], row_ptr=e_ptr)

@@ -34,8 +34,8 @@ SYM_TARGET = 256        # ... with the sample sized so that about SYM_TARGET col
 _tile_cache = {}
 
 
-def _tile_order(n_t, dev, sb=8):
-    """Upper-triangle 256 x 256 tiles in super-blocks of sb x sb: the ~74 tiles in flight share 2*sb operand
+def _tile_order(n_t, dev, sb=16):
+    """Upper-triangle 256 x 256 tiles in super-blocks of sb x sb: the ~74 tiles in flight share a few dozen operand
     blocks, so they stream out of L2.  Cached per (n_t, device)."""
     key_ = (n_t, str(dev))
     if key_ not in _tile_cache:
@@ -234,6 +234,9 @@ def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None, defer=
         n_bad = repair()
     off = L.reid_knn_rescore_window_counts_offset(N, n)
     info["window_counts"] = ws[off:off + 4 * n].view(torch.int32)     # window size per row (reporting only)
+    if ORDER_ROWS:                                                    # cluster-locality order of the rows (for a4)
+        off = L.reid_knn_rescore_order_offset(N, n)
+        info["visit_order"] = ws[off:off + 4 * n].view(torch.int32)
     info.update(mode="tc-sym" if sym else "tc", sym=sym_info, cand_cnt=cand_cnt if sym else None, cta_group=CTA_GROUP, n_splits=s, keep=keep, err_bound=eps if msq is None else None, max_sqnorm=msq, uncertified_rows=int(n_bad),
                 max_abs_err=max_err, xh=xh)
     return idx, key, info
