@@ -122,14 +122,17 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(
   __syncwarp();
 
   bool lost = false;  // a table filled up / a mask was wider than announced: reported through an impossible count
+  // returns true when g was not in the table yet
   auto insert = [&](int32_t* tab, int slots, int32_t g) {
     uint32_t h = hash32((uint32_t)g) & (uint32_t)(slots - 1);
     for (int probe = 0; probe < slots; ++probe) {
       const int32_t old = atomicCAS(&tab[h], -1, g);
-      if (old == -1 || old == g) return;
+      if (old == -1) return true;
+      if (old == g) return false;
       h = (h + 1) & (uint32_t)(slots - 1);
     }
     lost = true;
+    return false;
   };
   // hash table of R(row), sizes |R_half(c)| and their scan
   int carry = 0;
@@ -161,13 +164,9 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(
     return;
   }
   // pairs: gather g, test membership in R(row)
+  int ci = 0;                                    // the lane's pairs come in ascending order: the owner only moves forward
   for (int p = lane; p < P; p += 32) {
-    int lo = 0, hi = nR;                         // largest ci with s_off[ci] <= p
-    while (hi - lo > 1) {
-      const int mid = (lo + hi) >> 1;
-      if (s_off[mid] <= p) lo = mid; else hi = mid;
-    }
-    const int ci = lo;
+    while (s_off[ci + 1] <= p) ++ci;             // largest ci with s_off[ci] <= p  (s_off[nR] == P > p)
     const int kth = p - s_off[ci];
     const uint64_t hm = s_hm[ci];
     const uint32_t mlo = (uint32_t)hm, mhi = (uint32_t)(hm >> 32);
