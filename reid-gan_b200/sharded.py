@@ -311,13 +311,15 @@ def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=
                 raise ValueError("rank %d holds %d rows, expected %d" % (comm.rank, x.shape[0], comm.r1 - comm.r0))
             x = comm.gather_rows(x.contiguous())                    # collective (1): features
         # kNN: tile-sharded symmetric search when the shape allows it, else own rows x all columns.
-        # Sparse stages a2-a8: plan "tiles" REPLICATES them on every rank (they total ~2 ms at N = 32,621 and their
-        # exchange steps cost more than sharding saves at that size); plan "tiles+rows" / "rows" shards every per-row
-        # stage with the all-gathers listed in the module docstring (default from ROWS_PLAN_MIN_N rows on).
+        # Sparse stages a2-a8: plan "tiles" REPLICATES them on every rank (they total ~1.5 ms at N = 32,621 and on two
+        # GPUs their exchange steps cost more than sharding saves); plan "tiles+rows" / "rows" shards every per-row
+        # stage with the all-gathers listed in the module docstring (default from 4 GPUs or ROWS_PLAN_MIN_N rows on).
         from . import knn_tc as kt
         sym_ok = (knn in ("auto", "tc") and kt.SYM and N >= kt.SYM_MIN_N and k1 <= 32 and x.shape[1] % 64 == 0)
         if plan == "auto":
-            plan = ("tiles" if N < ROWS_PLAN_MIN_N else "tiles+rows") if sym_ok else "rows"
+            # measured at N = 32,621: 2 GPUs 3.6 (tiles) vs 4.1 ms (tiles+rows); 8 GPUs 2.9 vs 2.6 ms
+            replicate = N < ROWS_PLAN_MIN_N and comm.world <= 2
+            plan = ("tiles" if replicate else "tiles+rows") if sym_ok else "rows"
         if plan in ("tiles", "tiles+rows") and not sym_ok:
             raise ValueError("plan %r needs the symmetric tensor-core search (N >= %d, k1 <= 32, D %% 64 == 0)" % (plan, kt.SYM_MIN_N))
         res = None
