@@ -103,7 +103,7 @@ __global__ void __launch_bounds__(1024) scan_counts_kernel(const int32_t* __rest
 
 extern "C" {
 
-int reid_abi_version(void) { return 1; }
+int reid_abi_version(void) { return 2; }
 const char* reid_last_error(void) { return reid::g_err; }
 uint64_t reid_launch_count(void) { return reid::g_launches; }
 
