@@ -32,7 +32,7 @@ extern "C" {
 #define REID_OK 0
 #define REID_ERR_INVALID_ARG (-1)
 #define REID_ERR_CUDA (-2)
-#define REID_ERR_NCCL (-3)
+#define REID_ERR_NCCL (-3)          /* reserved: collectives live in the host layer (torch.distributed), no entry returns it */
 #define REID_ERR_CERTIFICATE (-4)
 #define REID_ERR_UNSUPPORTED (-5)
 
@@ -46,7 +46,9 @@ uint64_t reid_launch_count(void);
 /* ---- utilities ---------------------------------------------------------- */
 
 /* ptr_out[0..n] = exclusive prefix sum of cnt[0..n-1] (ptr_out[n] = total);
- * stats_out (optional, 3 x int64) = {total, max(cnt), sum(cnt^2)}. */
+ * stats_out (optional, 3 x int64) = {total, max(cnt), sum(cnt^2)}.  One multi-CTA pass (decoupled look-back), 64-bit
+ * sums throughout.  The tile state lives in a small library-owned buffer per (device, stream), created at the first
+ * call on that stream -- so the first call must not happen inside a stream capture. */
 int reid_scan_counts(const int32_t* cnt, int64_t n, int64_t* ptr_out, int64_t* stats_out, void* stream);
 
 /* ---- a1: kNN search  (utils/faiss_rerank.py:58-62, faiss IndexFlatL2.search) ----
@@ -146,7 +148,10 @@ int reid_features_to_half_acc(const float* x, int64_t n_rows, int64_t D, int sca
 int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, int64_t row_end,
                      const uint64_t* cand, const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists,
                      int list_cap, int64_t list_pitch_rows, int k, float err_bound, const float* max_sqnorm, int locality_order, int32_t* out_idx, float* out_key,
-                     int32_t* uncertified_flag, float* max_err_out, void* workspace, void* stream);
+                     int32_t* uncertified_flag, float* max_err_out, void* workspace, uint64_t* uncertified_count,
+                     void* stream);
+/* uncertified_count (optional device scalar): += number of rows whose flag is set -- lets a caller that does not
+ * want a host round trip here read the count later together with its other sizes. */
 size_t reid_knn_rescore_workspace_bytes(int64_t N, int64_t n_rows);
 /* byte offset, inside that workspace, of the int32[n_rows] window sizes of the last call (for reporting the
  * bytes the exact stage really had to gather) */
@@ -185,11 +190,15 @@ int reid_v_weights(const float* x, int64_t N, int64_t D, const int32_t* E_pad, i
 /* ---- a5: k2 query expansion  (faiss_rerank.py:89-94) ----------------------------
  * Vq[row] = (V[rank[row,0]] + ... + V[rank[row,k2-1]]) / k2, adds in that order, fp32.
  * V is the GLOBAL CSR (all N rows); max_row_nnz = max |E|.  One pass into padded rows of
- * reid_query_expand_stride(k2, max_row_nnz) slots; reid_csr_compact packs them into a CSR. */
+ * reid_query_expand_stride(k2, max_row_nnz) slots; reid_csr_compact packs them into a CSR.
+ * A caller that has not read max |E| back may pass a guess: a row whose distinct columns do not fit the table
+ * sized from it reports Q_cnt = 0 and is counted in *overflow_rows (optional device scalar, accumulates); with the
+ * true maximum no row can overflow. */
 int reid_query_expand_stride(int k2, int max_row_nnz);
 int reid_query_expand(const int32_t* rank, int64_t N, int ncols, int k2, const int64_t* V_ptr,
                       const int32_t* V_idx, const float* V_val, int max_row_nnz, int64_t row_begin,
-                      int64_t row_end, int32_t* Q_cnt, int32_t* Q_pad_idx, float* Q_pad_val, void* stream);
+                      int64_t row_end, int32_t* Q_cnt, int32_t* Q_pad_idx, float* Q_pad_val, uint64_t* overflow_rows,
+                      void* stream);
 int reid_csr_compact(const int32_t* pad_idx, const float* pad_val, int64_t stride, const int32_t* cnt,
                      const int64_t* ptr, int64_t n_rows, int32_t* out_idx, float* out_val, void* stream);
 
@@ -214,7 +223,9 @@ int reid_rows_unpack_fill(const int32_t* rec, int stride, int world, int64_t max
 /* ---- a6: inverted index  (faiss_rerank.py:98-100) -------------------------------
  * CSC of a CSR with n_rows x n_cols; column lists sorted by row.
  * Step 1 writes col_cnt; caller scans it into C_ptr; step 2 fills.  cursor: n_cols int32 scratch.
- * nnz_dev (optional device scalar): the real nnz when the host only knows the upper bound `nnz` (no read-back). */
+ * nnz_dev (optional device scalar): the real nnz when the host only knows the upper bound `nnz` (no read-back).
+ * max_col_len: the longest column (sizes the shared-memory sort), or <= 0 when the caller has not read it back:
+ * columns of up to 256 entries are then sorted by warps and a second launch gives every longer one a whole CTA. */
 int reid_transpose_count(const int32_t* idx, int64_t nnz, const int64_t* nnz_dev, int64_t n_cols, int32_t* col_cnt,
                          void* stream);
 int reid_transpose_fill(const int64_t* ptr, const int32_t* idx, const float* val, int64_t n_rows,
@@ -225,9 +236,12 @@ int reid_transpose_fill(const int64_t* ptr, const int32_t* idx, const float* val
  * t_ij = sum over shared columns c (ascending) of min(Vq[i,c], Vq[j,c]) in sequential fp32;
  * J = max(0, 1 - t/(2-t)); pairs without a shared column have J == 1 exactly.
  * Q (CSR) and C (CSC) are global. */
-/* upper bound of the number of distinct j per row: T_cnt[row-row_begin] = sum_c |col(c)| */
-int reid_jaccard_bounds(const int64_t* Q_ptr, const int32_t* Q_idx, const int64_t* C_ptr, int64_t row_begin,
-                        int64_t row_end, int32_t* T_cnt, void* stream);
+/* T_cnt[row-row_begin] = sum_c |col(c)|: the work of the row and an upper bound of its number of distinct partners.
+ * S_cnt (optional, needs Q_val): a much tighter bound of the number of eps-NEIGHBOURS, min(T, B / t_min + 2) with
+ * B = sum_c Vq[row,c] |col(c)| >= sum_j t_ij and t_min the smallest t with J(t) <= eps (Markov); scanning S_cnt
+ * instead of T_cnt gives slots of about twice the edge count instead of sum_c |col(c)|^2. */
+int reid_jaccard_bounds(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
+                        int64_t row_begin, int64_t row_end, float eps, int32_t* T_cnt, int32_t* S_cnt, void* stream);
 /* eps-neighbourhoods { j : J_ij <= eps } (what DBSCAN consumes), written at slot_ptr (local, from a
  * scan of T_cnt); nbr_cnt[row-row_begin] = size, or -1 when the row overflowed the shared-memory
  * table (redo those rows with a larger table_slots).  J values optional (nbr_val may be NULL).
@@ -247,12 +261,17 @@ int reid_jaccard_neighbors_heavy(const int64_t* Q_ptr, const int32_t* Q_idx, con
 /* The whole eps-graph of the shard in one call, no host round trip: rows are dealt to shared-memory table
  * classes (512 .. 8192 slots) on the device from T_cnt (reid_jaccard_bounds), overflowing rows move up a
  * class, the last resort is the dense-accumulator kernel.  nbr_cnt is never -1 on return.
+ * slot_ptr: n + 1 entries (a scan of T_cnt or S_cnt); row r owns [slot_ptr[r], slot_ptr[r+1]).  No kernel writes
+ * outside a row's slots or at / beyond nbr_capacity (<= 0: unlimited): a row with more neighbours than slots keeps its
+ * true nbr_cnt, loses the surplus entries and is counted in *slot_overflow (optional device scalar) -- with slots
+ * from T_cnt that cannot happen.
  * workspace: reid_jaccard_eps_graph_workspace_bytes(N, row_end - row_begin). */
 size_t reid_jaccard_eps_graph_workspace_bytes(int64_t N, int64_t n_rows);
 int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
                            const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin,
                            int64_t row_end, float eps, const int32_t* T_cnt, const int64_t* slot_ptr,
-                           int32_t* nbr_idx, float* nbr_val, int32_t* nbr_cnt, void* workspace, void* stream);
+                           int32_t* nbr_idx, float* nbr_val, int32_t* nbr_cnt, int64_t nbr_capacity,
+                           uint64_t* slot_overflow, void* workspace, void* stream);
 /* dense rows: out[(row-row_begin)*ld + j] for all j < N  (the reference's return value). */
 int reid_jaccard_dense(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
                        const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin,
@@ -322,6 +341,11 @@ int reid_rank_metrics(const float* dist, int64_t m, int64_t n, int64_t ld, const
 size_t reid_centroids_workspace_bytes(int64_t N, int64_t C);
 int reid_centroids(const float* x, int64_t N, int64_t D, const int64_t* labels, int64_t C, int normalize,
                    float* out, void* workspace, void* stream);
+/* The same with the cluster count still on the device (reid_dbscan_labels' num_clusters_out): the grid covers
+ * `capacity` clusters (<= N: every cluster holds a core point), rows >= *num_clusters_dev of `out` are not written.
+ * Lets the whole pseudo-label pass run without a host round trip (train_usl.py:163-191 back to back). */
+int reid_centroids_dev(const float* x, int64_t N, int64_t D, const int64_t* labels, const int64_t* num_clusters_dev,
+                       int64_t capacity, int normalize, float* out, void* stream);
 
 /* ---- a10-a12: ClusterMemory  (models/cm.py:9-76, 110-137) --------------------------
  * forward: xhat = normalize(inputs); z = xhat . F^T / temp; loss_b = logsumexp(z_b) - z_b[y_b].

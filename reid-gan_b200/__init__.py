@@ -16,7 +16,8 @@ from .cm import CM, CM_Hard, cm, cm_hard, ClusterMemory  # noqa: F401
 from .rerank import re_ranking  # noqa: F401
 from .evaluation import pairwise_distance, mean_ap, cmc  # noqa: F401
 from .infomap_cluster import get_dist_nbr, get_links  # noqa: F401
-from .synth import synth, synth_cm_batch, synth_device  # noqa: F401
+from .synth import synth, synth_cm_batch, synth_device, synth_hard  # noqa: F401
+from . import pipeline  # noqa: F401
 
 __all__ = ["pairwise_distance", "mean_ap", "cmc", "re_ranking", "get_dist_nbr", "get_links", "compute_jaccard_distance", "JaccardDistance", "DBSCAN", "generate_cluster_features",
            "CM", "CM_Hard", "cm", "cm_hard", "ClusterMemory", "synth", "synth_cm_batch"]

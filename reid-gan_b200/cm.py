@@ -48,6 +48,8 @@ class _CMBase(autograd.Function):
     def _fwd(ctx, inputs, targets, features, momentum):
         _need_cuda(inputs, targets, features)
         L = _lib.lib()
+        if features.dtype != torch.float32 or not features.is_contiguous():
+            raise ValueError("the centroid buffer must be a contiguous float32 tensor (it is read and updated in place)")
         ctx.features = features                      # alias, not a copy (cm.py:13)
         ctx.momentum = _momentum_value(momentum)
         x = inputs.detach().to(torch.float32).contiguous()
@@ -114,6 +116,8 @@ class _FusedClusterLoss(autograd.Function):
     def forward(ctx, inputs, targets, features, momentum, temp, hard):
         _need_cuda(inputs, targets, features)
         L = _lib.lib()
+        if features.dtype != torch.float32 or not features.is_contiguous():
+            raise ValueError("the centroid buffer must be a contiguous float32 tensor (it is read and updated in place)")
         x = inputs.detach().to(torch.float32).contiguous()
         t = targets.to(torch.int64).contiguous()
         B, D = x.shape

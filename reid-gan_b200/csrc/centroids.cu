@@ -12,10 +12,12 @@ constexpr int kCenMaxPerThread = 16;  // D <= 4096
 
 __global__ void __launch_bounds__(kCenThreads) centroids_kernel(const float* __restrict__ x, int64_t N, int64_t D,
                                                                 const int64_t* __restrict__ labels, int normalize,
-                                                                float* __restrict__ out) {
+                                                                float* __restrict__ out,
+                                                                const int64_t* __restrict__ n_clusters_dev) {
   __shared__ unsigned s_mask[kCenThreads / 32];
   __shared__ float s_red[kCenThreads / 32];
   const int64_t k = blockIdx.x;
+  if (n_clusters_dev && k >= *n_clusters_dev) return;      // the grid was sized for the capacity, not the count
   const int t = threadIdx.x, lane = t & 31, w = t >> 5;
   float acc[kCenMaxPerThread];
 #pragma unroll
@@ -87,7 +89,20 @@ int reid_centroids(const float* x, int64_t N, int64_t D, const int64_t* labels, 
                  "reid_centroids: bad shape N=%lld C=%lld D=%lld (D <= %d)", (long long)N, (long long)C, (long long)D,
                  kCenThreads * kCenMaxPerThread);
   if (C == 0) return REID_OK;
-  centroids_kernel<<<(unsigned)C, kCenThreads, 0, (cudaStream_t)stream>>>(x, N, D, labels, normalize, out);
+  centroids_kernel<<<(unsigned)C, kCenThreads, 0, (cudaStream_t)stream>>>(x, N, D, labels, normalize, out, nullptr);
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+
+int reid_centroids_dev(const float* x, int64_t N, int64_t D, const int64_t* labels, const int64_t* num_clusters_dev,
+                       int64_t capacity, int normalize, float* out, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(x && labels && num_clusters_dev && out, "reid_centroids_dev: NULL pointer");
+  REID_CHECK_ARG(N >= 0 && capacity >= 1 && capacity < (1ll << 31) && D > 0 && D <= (int64_t)kCenThreads * kCenMaxPerThread,
+                 "reid_centroids_dev: bad shape N=%lld capacity=%lld D=%lld (D <= %d)", (long long)N, (long long)capacity,
+                 (long long)D, kCenThreads * kCenMaxPerThread);
+  centroids_kernel<<<(unsigned)capacity, kCenThreads, 0, (cudaStream_t)stream>>>(x, N, D, labels, normalize, out,
+                                                                                num_clusters_dev);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

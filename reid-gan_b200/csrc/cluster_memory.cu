@@ -124,7 +124,12 @@ __global__ void __launch_bounds__(256) cm_loss_kernel(const float* __restrict__ 
   float se = 0.f;
   for (int64_t c = threadIdx.x; c < C; c += blockDim.x) se += expf(z[b * C + c] - mx);
   se = block_sum(se, red);
-  if (threadIdx.x == 0) loss[b] = (mx + logf(se)) - z[b * C + targets[b]];  // cross_entropy(reduction='none'), :135
+  if (threadIdx.x == 0) {
+    // cross_entropy(reduction='none'), :135.  A target outside [0, C) (e.g. a DBSCAN outlier label -1 that was not
+    // filtered out) is a device assert in PyTorch; here the sample's loss is NaN and no memory outside z is read.
+    const int64_t y = targets[b];
+    loss[b] = (y >= 0 && y < C) ? (mx + logf(se)) - z[b * C + y] : __int_as_float(0x7fc00000);
+  }
 }
 
 // gz[b][c] = (softmax(z_b)[c] - [c == y_b]) * grad_loss[b] / temp
@@ -167,12 +172,13 @@ constexpr int kUpdMaxPerThread = 16;  // D <= 4096 with 256 threads
 
 __global__ void __launch_bounds__(256) cm_update_kernel(const float* __restrict__ xhat,
                                                         const int64_t* __restrict__ targets,
-                                                        float* __restrict__ centroids, int64_t B, int64_t D,
+                                                        float* __restrict__ centroids, int64_t B, int64_t C, int64_t D,
                                                         float momentum, int hard) {
   __shared__ float red[8];
   __shared__ int s_skip, s_best;
   const int64_t b0 = blockIdx.x;
   const int64_t y = targets[b0];
+  if (y < 0 || y >= C) return;                         // invalid label: no centroid row to update (loss was NaN)
   if (threadIdx.x == 0) {
     int skip = 0;
     for (int64_t u = 0; u < b0; ++u) skip |= (targets[u] == y);
@@ -330,10 +336,9 @@ int reid_cm_update(const float* xhat, const int64_t* targets, float* centroids, 
                    float momentum, int hard, void* workspace, void* stream) {
   using namespace reid;
   (void)workspace;
-  (void)C;
-  REID_CHECK_ARG(xhat && targets && centroids && B > 0 && D > 0, "reid_cm_update: bad arguments");
+  REID_CHECK_ARG(xhat && targets && centroids && B > 0 && C > 0 && D > 0, "reid_cm_update: bad arguments");
   REID_CHECK_ARG(D <= 256 * kUpdMaxPerThread, "reid_cm_update: D=%lld exceeds %d", (long long)D, 256 * kUpdMaxPerThread);
-  cm_update_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(xhat, targets, centroids, B, D, momentum, hard);
+  cm_update_kernel<<<(unsigned)B, 256, 0, (cudaStream_t)stream>>>(xhat, targets, centroids, B, C, D, momentum, hard);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

@@ -3,6 +3,7 @@
 #include <cuda_runtime.h>
 #include <stdint.h>
 #include <stdio.h>
+#include <stdlib.h>
 #include <string.h>
 
 #include "../../include/reid_b200.h"
@@ -27,6 +28,19 @@ void set_error(const char* fmt, ...);
       return REID_ERR_CUDA;                                                          \
     }                                                                                \
   } while (0)
+
+// Developer switches (skip parts of a kernel to time the rest) exist only in builds with -DREID_DEV; a release
+// library has no environment variable that changes what a kernel computes.
+#ifdef REID_DEV
+#define REID_DBG(p) ((p).dbg)
+inline int dev_env(const char* name, int dflt) {
+  const char* e = getenv(name);
+  return e ? atoi(e) : dflt;
+}
+#else
+#define REID_DBG(p) 0
+inline int dev_env(const char*, int dflt) { return dflt; }
+#endif
 
 extern unsigned long long g_launches;  // kernels launched by this library in this process
 

@@ -8,19 +8,38 @@
 
 namespace reid {
 
+// T_i = sum_{c in nz(i)} |col(c)|: every (column, partner) pair of the row -- the work of the row and an upper bound of
+// its partner count.  S_i (optional) = a much tighter bound of the eps-NEIGHBOUR count: sum_j t_ij <= B_i = sum_c
+// V_ic |col(c)| (every min() is at most V_ic), so at most B_i / t_min partners reach t >= t_min (Markov), t_min the
+// smallest t with J(t) <= eps.  For a row inside an identity cluster B_i is about the cluster size.  The emitting
+// kernels never write past a row's slots (a violated bound is reported, not trusted).
 __global__ void __launch_bounds__(256) jaccard_bounds_kernel(const int64_t* __restrict__ Q_ptr,
                                                              const int32_t* __restrict__ Q_idx,
+                                                             const float* __restrict__ Q_val,
                                                              const int64_t* __restrict__ C_ptr, int64_t row_begin,
-                                                             int64_t row_end, int32_t* __restrict__ T_cnt) {
+                                                             int64_t row_end, float t_min, int32_t* __restrict__ T_cnt,
+                                                             int32_t* __restrict__ S_cnt) {
   const int64_t row = row_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= row_end) return;
   int64_t s = 0;
+  double b = 0.0;
   for (int64_t p = Q_ptr[row] + lane_id(); p < Q_ptr[row + 1]; p += 32) {
     const int32_t c = Q_idx[p];
-    s += C_ptr[c + 1] - C_ptr[c];
+    const int64_t len = C_ptr[c + 1] - C_ptr[c];
+    s += len;
+    if (S_cnt) b += (double)Q_val[p] * (double)len;
   }
   s = warp_sum(s);
-  if (lane_id() == 0) T_cnt[row - row_begin] = (int32_t)(s > 0x7fffffff ? 0x7fffffff : s);
+  b = warp_sum(b);
+  if (lane_id() == 0) {
+    const int32_t t = (int32_t)(s > 0x7fffffff ? 0x7fffffff : s);
+    T_cnt[row - row_begin] = t;
+    if (S_cnt) {
+      double need = t_min > 0.f ? b / (double)t_min + 2.0 : (double)t;
+      if (need > (double)t) need = (double)t;
+      S_cnt[row - row_begin] = (int32_t)need;
+    }
+  }
 }
 
 __device__ __forceinline__ uint32_t jhash(uint32_t v) {
@@ -58,7 +77,7 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
     int64_t row_begin, int64_t n_rows_host, const int32_t* __restrict__ queue, const int32_t* __restrict__ queue_len,
     int32_t* __restrict__ next_queue, int32_t* __restrict__ next_len, float eps,
     const int64_t* __restrict__ slot_ptr, int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_val,
-    int32_t* __restrict__ nbr_cnt, int slots) {
+    int32_t* __restrict__ nbr_cnt, int slots, int64_t nbr_capacity, unsigned long long* __restrict__ slot_overflow) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = lane_id();
   int32_t* tkey = reinterpret_cast<int32_t*>(smem_raw) + (size_t)w * slots;
@@ -181,6 +200,7 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
       continue;
     }
     const int64_t o = slot_ptr[lr];
+    const int64_t o_end = min(slot_ptr[lr + 1], nbr_capacity);   // the row's slots (speculative sizes are never trusted)
     int cnt = 0;
     for (int base = 0; base < slots; base += 32) {
       const int32_t j = tkey[base + lane];
@@ -190,12 +210,17 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
       const unsigned b = __ballot_sync(kFull, keep);
       if (keep) {
         const int64_t dst = o + cnt + __popc(b & lt);
-        nbr_idx[dst] = j;
-        if (nbr_val) nbr_val[dst] = jd;
+        if (dst < o_end) {
+          nbr_idx[dst] = j;
+          if (nbr_val) nbr_val[dst] = jd;
+        }
       }
       cnt += __popc(b);
     }
-    if (lane == 0) nbr_cnt[lr] = cnt;
+    if (lane == 0) {
+      nbr_cnt[lr] = cnt;
+      if (o + cnt > o_end && slot_overflow) atomicAdd(slot_overflow, 1ull);
+    }
     __syncwarp();
   }
 }
@@ -213,7 +238,7 @@ __global__ void __launch_bounds__(kJDThreads) jaccard_direct_kernel(
     const int64_t* __restrict__ C_ptr, const int32_t* __restrict__ C_idx, const float* __restrict__ C_val, int64_t N,
     int64_t row_begin, const int32_t* __restrict__ queue, const int32_t* __restrict__ queue_len, float eps,
     const int64_t* __restrict__ slot_ptr, int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_val,
-    int32_t* __restrict__ nbr_cnt) {
+    int32_t* __restrict__ nbr_cnt, int64_t nbr_capacity, unsigned long long* __restrict__ slot_overflow) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* acc = reinterpret_cast<float*>(smem_raw);
   __shared__ int64_t s_ca[32];
@@ -266,6 +291,7 @@ __global__ void __launch_bounds__(kJDThreads) jaccard_direct_kernel(
     }
     // ordered emit of { j : J <= eps }; the accumulator is cleared on the way
     const int64_t o = slot_ptr[lr];
+    const int64_t o_end = min(slot_ptr[lr + 1], nbr_capacity);
     if (t == 0) s_base = 0;
     __syncthreads();
     for (int64_t b0 = 0; b0 < n_pad; b0 += kJDThreads) {
@@ -282,8 +308,10 @@ __global__ void __launch_bounds__(kJDThreads) jaccard_direct_kernel(
         for (int ww = 0; ww < w; ++ww) before += s_warp[ww];
         if (keep) {
           const int64_t dst = o + before + __popc(b & ((1u << lane) - 1u));
-          nbr_idx[dst] = (int32_t)(b0 + t);
-          if (nbr_val) nbr_val[dst] = jd;
+          if (dst < o_end) {
+            nbr_idx[dst] = (int32_t)(b0 + t);
+            if (nbr_val) nbr_val[dst] = jd;
+          }
         }
         __syncthreads();
         if (t == 0) {
@@ -294,7 +322,10 @@ __global__ void __launch_bounds__(kJDThreads) jaccard_direct_kernel(
       }
     }
     __syncthreads();
-    if (t == 0) nbr_cnt[lr] = s_base;
+    if (t == 0) {
+      nbr_cnt[lr] = s_base;
+      if (o + s_base > o_end && slot_overflow) atomicAdd(slot_overflow, 1ull);
+    }
   }
 }
 
@@ -308,13 +339,24 @@ __global__ void __launch_bounds__(256) jaccard_classify_kernel(const int32_t* __
                                                                int direct_from, int32_t* __restrict__ queues,
                                                                int32_t* __restrict__ qlen) {
   const int64_t lr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-  if (lr >= n_rows) return;
-  const int t = T_cnt[lr];
-  const int need = t < 2048 ? t >> 2 : t >> 1;           // a retry of a long row is expensive: less optimism there
-  int c = 0;
-  while (c < kJClasses && need > ((jclass_slots(c) >> 1) + (jclass_slots(c) >> 2))) ++c;   // c == kJClasses: heavy
-  if (c >= direct_from) c = kJClasses + 1;
-  queues[(int64_t)c * n_rows + atomicAdd(&qlen[c], 1)] = (int32_t)lr;
+  int c = -1;
+  if (lr < n_rows) {
+    const int t = T_cnt[lr];
+    const int need = t < 2048 ? t >> 2 : t >> 1;         // a retry of a long row is expensive: less optimism there
+    c = 0;
+    while (c < kJClasses && need > ((jclass_slots(c) >> 1) + (jclass_slots(c) >> 2))) ++c;   // c == kJClasses: heavy
+    if (c >= direct_from) c = kJClasses + 1;
+  }
+  // one atomic per (warp, class) instead of one per row
+  const int lane = lane_id();
+  for (int q = 0; q <= kJClasses + 1; ++q) {
+    const unsigned m = __ballot_sync(kFull, c == q);
+    if (!m) continue;
+    int base = 0;
+    if (lane == __ffs(m) - 1) base = atomicAdd(&qlen[q], __popc(m));
+    base = __shfl_sync(kFull, base, __ffs(m) - 1);
+    if (c == q) queues[(int64_t)q * n_rows + base + __popc(m & ((1u << lane) - 1u))] = (int32_t)lr;
+  }
 }
 
 // Dense rows for the drop-in return value.  One CTA per row; the accumulator row lives in
@@ -361,7 +403,7 @@ __global__ void __launch_bounds__(256) jaccard_neighbors_heavy_kernel(
     int64_t row_begin, const int32_t* __restrict__ rows_list, int64_t n_list_host,
     const int32_t* __restrict__ list_len, float eps, const int64_t* __restrict__ slot_ptr,
     int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_val, int32_t* __restrict__ nbr_cnt,
-    float* __restrict__ scratch) {
+    float* __restrict__ scratch, int64_t nbr_capacity, unsigned long long* __restrict__ slot_overflow) {
   __shared__ int s_warp[8];
   __shared__ int s_base;
   const int64_t n_list = list_len ? (int64_t)*list_len : n_list_host;
@@ -383,6 +425,7 @@ __global__ void __launch_bounds__(256) jaccard_neighbors_heavy_kernel(
     __syncthreads();
   }
   const int64_t o = slot_ptr[lr];
+  const int64_t o_end = min(slot_ptr[lr + 1], nbr_capacity);
   const int lane = lane_id(), w = threadIdx.x >> 5;
   for (int64_t base = 0; base < N; base += blockDim.x) {
     const int64_t j = base + threadIdx.x;
@@ -396,8 +439,10 @@ __global__ void __launch_bounds__(256) jaccard_neighbors_heavy_kernel(
     for (int ww = 0; ww < w; ++ww) before += s_warp[ww];
     if (keep) {
       const int64_t dst = o + before + __popc(b & ((1u << lane) - 1u));
-      nbr_idx[dst] = (int32_t)j;
-      if (nbr_val) nbr_val[dst] = jd;
+      if (dst < o_end) {
+        nbr_idx[dst] = (int32_t)j;
+        if (nbr_val) nbr_val[dst] = jd;
+      }
     }
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -407,7 +452,10 @@ __global__ void __launch_bounds__(256) jaccard_neighbors_heavy_kernel(
     }
     __syncthreads();
   }
-  if (threadIdx.x == 0) nbr_cnt[lr] = s_base;
+  if (threadIdx.x == 0) {
+    nbr_cnt[lr] = s_base;
+    if (o + s_base > o_end && slot_overflow) atomicAdd(slot_overflow, 1ull);
+  }
   }
 }
 
@@ -418,6 +466,7 @@ struct JnArgs {
   const int64_t* Q_ptr; const int32_t* Q_idx; const float* Q_val;
   const int64_t* C_ptr; const int32_t* C_idx; const float* C_val;
   int64_t row_begin; float eps; const int64_t* slot_ptr; int32_t* nbr_idx; float* nbr_val; int32_t* nbr_cnt;
+  int64_t nbr_capacity; unsigned long long* slot_overflow;
 };
 
 // one launch of the table kernel: `n_max` bounds the grid, the real row count is *queue_len when given
@@ -434,7 +483,7 @@ static int launch_jn(const JnArgs& a, int slots, int64_t n_max, const int32_t* q
   if (grid > cap) grid = cap;
   jaccard_neighbors_kernel<kWarps><<<(unsigned)grid, kWarps * 32, smem, st>>>(
       a.Q_ptr, a.Q_idx, a.Q_val, a.C_ptr, a.C_idx, a.C_val, a.row_begin, n_max, queue, queue_len, next_queue, next_len,
-      a.eps, a.slot_ptr, a.nbr_idx, a.nbr_val, a.nbr_cnt, slots);
+      a.eps, a.slot_ptr, a.nbr_idx, a.nbr_val, a.nbr_cnt, slots, a.nbr_capacity, a.slot_overflow);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
@@ -472,15 +521,19 @@ static size_t jws_carve(void* base, int64_t N, int64_t n, JWs* w) {
 
 extern "C" {
 
-int reid_jaccard_bounds(const int64_t* Q_ptr, const int32_t* Q_idx, const int64_t* C_ptr, int64_t row_begin,
-                        int64_t row_end, int32_t* T_cnt, void* stream) {
+int reid_jaccard_bounds(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
+                        int64_t row_begin, int64_t row_end, float eps, int32_t* T_cnt, int32_t* S_cnt, void* stream) {
   using namespace reid;
   REID_CHECK_ARG(Q_ptr && Q_idx && C_ptr && T_cnt, "reid_jaccard_bounds: NULL pointer");
+  REID_CHECK_ARG(!S_cnt || Q_val, "reid_jaccard_bounds: S_cnt needs Q_val");
   REID_CHECK_ARG(0 <= row_begin && row_begin <= row_end, "reid_jaccard_bounds: bad row range");
   const int64_t n = row_end - row_begin;
   if (n == 0) return REID_OK;
-  jaccard_bounds_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(Q_ptr, Q_idx, C_ptr, row_begin,
-                                                                                  row_end, T_cnt);
+  // J(t) = 1 - t / (2 - t) <= eps  <=>  t >= 2 (1 - eps) / (2 - eps); 0.1 % head-room for the fp32 roundings of J
+  float t_min = 0.f;
+  if (eps < 1.f) t_min = (float)(2.0 * (1.0 - (double)eps) / (2.0 - (double)eps) * 0.999);
+  jaccard_bounds_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(Q_ptr, Q_idx, Q_val, C_ptr, row_begin,
+                                                                                  row_end, t_min, T_cnt, S_cnt);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
@@ -500,7 +553,8 @@ int reid_jaccard_neighbors(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
                  table_slots);
   const int64_t n = rows_list ? n_list : row_end - row_begin;
   if (n == 0) return REID_OK;
-  const JnArgs a{Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, row_begin, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt};
+  const JnArgs a{Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, row_begin, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt,
+                 INT64_MAX, nullptr};
   return launch_jn_slots(a, table_slots, n, rows_list, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
@@ -512,7 +566,7 @@ size_t reid_jaccard_eps_graph_workspace_bytes(int64_t N, int64_t n_rows) {
 int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
                            const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin, int64_t row_end,
                            float eps, const int32_t* T_cnt, const int64_t* slot_ptr, int32_t* nbr_idx, float* nbr_val,
-                           int32_t* nbr_cnt, void* workspace, void* stream) {
+                           int32_t* nbr_cnt, int64_t nbr_capacity, uint64_t* slot_overflow, void* workspace, void* stream) {
   using namespace reid;
   REID_CHECK_ARG(Q_ptr && Q_idx && Q_val && C_ptr && C_idx && C_val && T_cnt && slot_ptr && nbr_idx && nbr_cnt && workspace,
                  "reid_jaccard_eps_graph: NULL pointer");
@@ -531,7 +585,10 @@ int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
   int32_t* direct_len = w.qlen + kJClasses + 1;
   jaccard_classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(T_cnt, n, direct_from, w.queues, w.qlen);
   REID_LAUNCH_CHECK();
-  const JnArgs a{Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, row_begin, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt};
+  if (nbr_capacity <= 0) nbr_capacity = INT64_MAX;           // slots sized by the caller from T_cnt: nothing to guard
+  unsigned long long* ovf = (unsigned long long*)slot_overflow;
+  const JnArgs a{Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, row_begin, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt,
+                 nbr_capacity, ovf};
   const int n_hash = direct_from < kJClasses ? direct_from : kJClasses;
   for (int c = 0; c < n_hash; ++c) {
     const bool last = c + 1 == n_hash && direct_from <= kJClasses;
@@ -548,13 +605,13 @@ int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
     if (grid > n) grid = n;
     jaccard_direct_kernel<<<(unsigned)grid, kJDThreads, row_bytes, st>>>(Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin,
                                                                         direct_q, direct_len, eps, slot_ptr, nbr_idx, nbr_val,
-                                                                        nbr_cnt);
+                                                                        nbr_cnt, nbr_capacity, ovf);
     REID_LAUNCH_CHECK();
   }
   const int64_t hg = n < kJHeavyCtas ? n : kJHeavyCtas;
   jaccard_neighbors_heavy_kernel<<<(unsigned)hg, 256, 0, st>>>(Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin,
                                                               w.queues + (int64_t)kJClasses * n, 0, w.qlen + kJClasses, eps,
-                                                              slot_ptr, nbr_idx, nbr_val, nbr_cnt, w.scratch);
+                                                              slot_ptr, nbr_idx, nbr_val, nbr_cnt, w.scratch, nbr_capacity, ovf);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
@@ -592,7 +649,7 @@ int reid_jaccard_neighbors_heavy(const int64_t* Q_ptr, const int32_t* Q_idx, con
   if (n_list == 0) return REID_OK;
   jaccard_neighbors_heavy_kernel<<<(unsigned)n_list, 256, 0, (cudaStream_t)stream>>>(
       Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin, rows_list, n_list, nullptr, eps, slot_ptr, nbr_idx, nbr_val,
-      nbr_cnt, scratch);
+      nbr_cnt, scratch, INT64_MAX, nullptr);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

@@ -170,7 +170,7 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_exact_kernel(
     const float* __restrict__ x, int64_t D, int64_t row_begin, int64_t n_rows, const int32_t* __restrict__ perm,
     const int32_t* __restrict__ win_cnt, const int32_t* __restrict__ win_idx, const float* __restrict__ win_a, int k,
     float eps_in, const float* __restrict__ max_sqnorm, int32_t* __restrict__ out_idx, float* __restrict__ out_key,
-    int32_t* __restrict__ uncert, unsigned* __restrict__ max_err_bits) {
+    int32_t* __restrict__ uncert, unsigned* __restrict__ max_err_bits, unsigned long long* __restrict__ uncert_count) {
   constexpr int kQ = kChunks > 0 ? kChunks : 1;
   constexpr int kH = kChunks > 1 ? kChunks / 2 : 1;
   __shared__ uint64_t s_key[kRsWarps][kWinMax];
@@ -255,6 +255,7 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_exact_kernel(
   if (lane == 0) {
     atomicMax(max_err_bits, __float_as_uint(worst));
     if (!(worst <= eps)) uncert[lr] = 1;  // the error model was violated (or NaN): do not trust the window
+    if (uncert_count && uncert[lr]) atomicAdd(uncert_count, 1ull);
   }
   // order by (key desc, idx asc); the first k go out
   for (int t = lane; t < n_w; t += 32) {
@@ -288,7 +289,7 @@ __global__ void __launch_bounds__(kGThreads, 2) rescore_group_kernel(
     const float* __restrict__ x, int64_t D, int64_t row_begin, int64_t n_rows, const int32_t* __restrict__ perm,
     const int32_t* __restrict__ win_cnt, const int32_t* __restrict__ win_idx, const float* __restrict__ win_a, int k,
     float eps_in, const float* __restrict__ max_sqnorm, int32_t* __restrict__ out_idx, float* __restrict__ out_key,
-    int32_t* __restrict__ uncert, unsigned* __restrict__ max_err_bits, int dbg) {
+    int32_t* __restrict__ uncert, unsigned* __restrict__ max_err_bits, unsigned long long* __restrict__ uncert_count, int dbg) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   double* sQ = reinterpret_cast<double*>(smem_raw);                                    // [kGq][D]
   uint64_t* s_key = reinterpret_cast<uint64_t*>(sQ + (size_t)kGq * D);                 // [kGq][kWinMax]
@@ -442,6 +443,7 @@ __global__ void __launch_bounds__(kGThreads, 2) rescore_group_kernel(
       const float worst = __uint_as_float(s_worst[warp]);
       atomicMax(max_err_bits, __float_as_uint(worst));
       if (!(worst <= eps)) uncert[lr] = 1;  // the error model was violated (or NaN): do not trust the window
+      if (uncert_count && uncert[lr]) atomicAdd(uncert_count, 1ull);
     }
     for (int t = lane; t < n_w; t += 32) {
       const uint64_t me = key[t];
@@ -520,7 +522,7 @@ size_t reid_knn_rescore_workspace_bytes(int64_t N, int64_t n_rows) {
 int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, int64_t row_end, const uint64_t* cand,
                      const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists, int list_cap, int64_t list_pitch_rows,
                      int k, float err_bound, const float* max_sqnorm, int locality_order, int32_t* out_idx, float* out_key, int32_t* uncertified_flag,
-                     float* max_err_out, void* workspace, void* stream) {
+                     float* max_err_out, void* workspace, uint64_t* uncertified_count, void* stream) {
   using namespace reid;
   REID_CHECK_ARG(x && cand && cand_cnt && row_tau && out_idx && uncertified_flag && max_err_out && workspace,
                  "reid_knn_rescore: NULL pointer");
@@ -552,15 +554,17 @@ int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, in
 #define REID_RS_LAUNCH(CH)                                                                                          \
   rescore_exact_kernel<CH><<<grid, kRsWarps * 32, 0, st>>>(x, D, row_begin, n, locality_order ? w.perm : nullptr,     \
                                                            w.win_cnt, w.win_idx, w.win_a, k, err_bound, max_sqnorm,  \
-                                                           out_idx, out_key, uncertified_flag, (unsigned*)max_err_out)
+                                                           out_idx, out_key, uncertified_flag, (unsigned*)max_err_out,       \
+                                                           (unsigned long long*)uncertified_count)
   const bool aligned = (((uintptr_t)x) & 15) == 0;
-  static const bool no_group = getenv("REID_RESCORE_GROUP") && atoi(getenv("REID_RESCORE_GROUP")) == 0;
+  static const bool no_group = dev_env("REID_RESCORE_GROUP", 1) == 0;
   if (aligned && D % 64 == 0 && D <= 2048 && !no_group) {
     const size_t smem = rescore_group_smem(D);
     REID_CUDA(cudaFuncSetAttribute(rescore_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rescore_group_kernel<<<(unsigned)((n + kGq - 1) / kGq), kGThreads, smem, st>>>(
         x, D, row_begin, n, locality_order ? w.perm : nullptr, w.win_cnt, w.win_idx, w.win_a, k, err_bound, max_sqnorm,
-        out_idx, out_key, uncertified_flag, (unsigned*)max_err_out, getenv("REID_RG_DEBUG") ? atoi(getenv("REID_RG_DEBUG")) : 0);
+        out_idx, out_key, uncertified_flag, (unsigned*)max_err_out, (unsigned long long*)uncertified_count,
+        dev_env("REID_RG_DEBUG", 0));
   } else if (aligned && D == 2048) REID_RS_LAUNCH(16);
   else if (aligned && D == 1024) REID_RS_LAUNCH(8);
   else if (aligned && D == 512) REID_RS_LAUNCH(4);

@@ -160,28 +160,38 @@ __device__ __forceinline__ void warp_bitonic_sort_kv(uint32_t* key, float* val, 
 __global__ void __launch_bounds__(kQWarps * 32) query_expand_kernel(
     const int32_t* __restrict__ rank, int ncols, int k2, const int64_t* __restrict__ V_ptr,
     const int32_t* __restrict__ V_idx, const float* __restrict__ V_val, int cap, int64_t row_begin, int64_t row_end,
-    int32_t* __restrict__ Q_cnt, int32_t* __restrict__ Q_idx, float* __restrict__ Q_val) {
+    int32_t* __restrict__ Q_cnt, int32_t* __restrict__ Q_idx, float* __restrict__ Q_val,
+    unsigned long long* __restrict__ overflow_rows) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = lane_id();
   uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)w * cap;              // table keys, then sort keys
-  float* val = reinterpret_cast<float*>(smem_raw + (size_t)kQWarps * cap * sizeof(uint32_t)) + (size_t)w * cap;
-  const int64_t row = row_begin + (int64_t)blockIdx.x * kQWarps + w;
+  const int n_warps = blockDim.x >> 5;                  // rows per CTA (fewer than kQWarps when the tables are big)
+  float* val = reinterpret_cast<float*>(smem_raw + (size_t)n_warps * cap * sizeof(uint32_t)) + (size_t)w * cap;
+  const int64_t row = row_begin + (int64_t)blockIdx.x * n_warps + w;
   if (row >= row_end) return;
   const uint32_t smask = (uint32_t)cap - 1u;
   for (int t = lane; t < cap; t += 32) key[t] = 0xffffffffu;
   __syncwarp();
-  for (int r = 0; r < k2; ++r) {
+  // A speculatively sized table (the caller did not know the longest V row) can fill up: probing is bounded, the
+  // row then reports Q_cnt = 0 and is counted in *overflow_rows (the caller redoes the stage with the exact size).
+  bool lost = false;
+  int used = 0;
+  const int limit = cap - (cap >> 2);
+  for (int r = 0; r < k2 && !lost; ++r) {
     const int64_t j = rank[row * ncols + r];
     const int64_t a = V_ptr[j];
     const int m = (int)(V_ptr[j + 1] - a);
+    int fresh = 0;
     for (int e = lane; e < m; e += 32) {
       const uint32_t c = (uint32_t)V_idx[a + e];
       const float v = V_val[a + e];
       uint32_t h = (c * 0x9e3779b1u) >> 7 & smask;
-      while (true) {
+      int probe = 0;
+      for (; probe < cap; ++probe) {
         const uint32_t old = atomicCAS(&key[h], 0xffffffffu, c);
         if (old == 0xffffffffu) {
           val[h] = v;
+          ++fresh;
           break;
         }
         if (old == c) {
@@ -190,8 +200,17 @@ __global__ void __launch_bounds__(kQWarps * 32) query_expand_kernel(
         }
         h = (h + 1) & smask;
       }
+      if (probe == cap) lost = true;
     }
-    __syncwarp();                                    // row r is folded before row r + 1 starts
+    used += __reduce_add_sync(kFull, fresh);
+    lost = __any_sync(kFull, lost) || used > limit;   // also: row r is folded before row r + 1 starts
+  }
+  if (lost) {
+    if (lane == 0) {
+      Q_cnt[row - row_begin] = 0;
+      if (overflow_rows) atomicAdd(overflow_rows, 1ull);
+    }
+    return;
   }
   // compact the occupied slots to the front (in place: the write position never passes the read position)
   int n = 0;
@@ -349,7 +368,7 @@ constexpr int kColSortWarps = 4;
 
 __global__ void __launch_bounds__(kColSortWarps * 32) col_sort_kernel(const int64_t* __restrict__ C_ptr, int64_t n_cols,
                                                                       int32_t* __restrict__ C_idx,
-                                                                      float* __restrict__ C_val, int cap) {
+                                                                      float* __restrict__ C_val, int cap, int skip_long) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = lane_id();
   uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)w * cap;
@@ -372,7 +391,7 @@ __global__ void __launch_bounds__(kColSortWarps * 32) col_sort_kernel(const int6
       C_idx[a + t] = (int32_t)key[t];
       C_val[a + t] = val[t];
     }
-  } else {
+  } else if (!skip_long) {
     // very long column: odd-even transposition sort in place (rare; correctness path)
     for (int64_t round = 0; round < n; ++round) {
       for (int64_t t = (round & 1) + 2 * (int64_t)lane; t + 1 < n; t += 64) {
@@ -387,6 +406,86 @@ __global__ void __launch_bounds__(kColSortWarps * 32) col_sort_kernel(const int6
       }
       __syncwarp();
     }
+  }
+}
+
+// Columns longer than col_sort_kernel's shared-memory capacity (hub columns; only met when the caller could not
+// size the buffers for the longest column): one CTA per such column, bitonic sort of up to kColLongCap entries in
+// shared memory, odd-even transposition in place beyond that.  Every CTA walks the columns with a stride and skips
+// the short ones, so no queue and no host knowledge of the lengths is needed.
+constexpr int kColLongCap = 8192;
+constexpr int kColLongThreads = 512;
+__global__ void __launch_bounds__(kColLongThreads) col_sort_long_kernel(const int64_t* __restrict__ C_ptr, int64_t n_cols,
+                                                                        int32_t* __restrict__ C_idx, float* __restrict__ C_val,
+                                                                        int short_cap) {
+  extern __shared__ __align__(16) unsigned char smem_raw[];
+  uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw);
+  float* val = reinterpret_cast<float*>(smem_raw + (size_t)kColLongCap * 4);
+  const int t = threadIdx.x;
+  for (int64_t c0 = (int64_t)blockIdx.x * kColLongThreads; c0 < n_cols; c0 += (int64_t)gridDim.x * kColLongThreads) {
+    // which of my 512 columns are long?  (warp-uniform handling: the CTA serves them one after the other)
+    const int64_t c = c0 + t;
+    const int64_t len = c < n_cols ? C_ptr[c + 1] - C_ptr[c] : 0;
+    __shared__ int s_long[kColLongThreads];
+    __shared__ int s_n;
+    if (t == 0) s_n = 0;
+    __syncthreads();
+    if (len > short_cap) s_long[atomicAdd(&s_n, 1)] = t;
+    __syncthreads();
+    const int n_long = s_n;
+    for (int q = 0; q < n_long; ++q) {
+      const int64_t col = c0 + s_long[q];
+      const int64_t a = C_ptr[col];
+      const int64_t n = C_ptr[col + 1] - a;
+      if (n <= kColLongCap) {
+        int n2 = 64;
+        while (n2 < n) n2 <<= 1;
+        for (int u = t; u < n2; u += kColLongThreads) {
+          key[u] = u < n ? (uint32_t)C_idx[a + u] : 0xffffffffu;
+          val[u] = u < n ? C_val[a + u] : 0.f;
+        }
+        __syncthreads();
+        for (int k = 2; k <= n2; k <<= 1) {
+          for (int j = k >> 1; j > 0; j >>= 1) {
+            for (int u = t; u < n2; u += kColLongThreads) {
+              const int p = u ^ j;
+              if (p > u) {
+                const uint32_t x0 = key[u], x1 = key[p];
+                const bool up = ((u & k) == 0);
+                if ((x0 > x1) == up) {
+                  key[u] = x1;
+                  key[p] = x0;
+                  const float v = val[u];
+                  val[u] = val[p];
+                  val[p] = v;
+                }
+              }
+            }
+            __syncthreads();
+          }
+        }
+        for (int u = t; u < n; u += kColLongThreads) {
+          C_idx[a + u] = (int32_t)key[u];
+          C_val[a + u] = val[u];
+        }
+        __syncthreads();
+      } else {
+        for (int64_t round = 0; round < n; ++round) {
+          for (int64_t u = (round & 1) + 2 * (int64_t)t; u + 1 < n; u += 2 * kColLongThreads) {
+            const int32_t x0 = C_idx[a + u], x1 = C_idx[a + u + 1];
+            if (x0 > x1) {
+              C_idx[a + u] = x1;
+              C_idx[a + u + 1] = x0;
+              const float v = C_val[a + u];
+              C_val[a + u] = C_val[a + u + 1];
+              C_val[a + u + 1] = v;
+            }
+          }
+          __syncthreads();
+        }
+      }
+    }
+    __syncthreads();
   }
 }
 
@@ -427,7 +526,7 @@ int reid_query_expand_stride(int k2, int max_row_nnz) {
 
 int reid_query_expand(const int32_t* rank, int64_t N, int ncols, int k2, const int64_t* V_ptr, const int32_t* V_idx,
                       const float* V_val, int max_row_nnz, int64_t row_begin, int64_t row_end, int32_t* Q_cnt,
-                      int32_t* Q_pad_idx, float* Q_pad_val, void* stream) {
+                      int32_t* Q_pad_idx, float* Q_pad_val, uint64_t* overflow_rows, void* stream) {
   using namespace reid;
   REID_CHECK_ARG(rank && V_ptr && V_idx && V_val && Q_cnt && Q_pad_idx && Q_pad_val, "reid_query_expand: NULL pointer");
   REID_CHECK_ARG(k2 >= 1 && k2 <= ncols && ncols <= REID_MAX_K1, "reid_query_expand: k2=%d ncols=%d", k2, ncols);
@@ -435,15 +534,19 @@ int reid_query_expand(const int32_t* rank, int64_t N, int ncols, int k2, const i
   REID_CHECK_ARG(max_row_nnz >= 1, "reid_query_expand: max_row_nnz=%d", max_row_nnz);
   REID_CHECK_ARG(N < 0xffffffffll, "reid_query_expand: N exceeds the 32-bit column key");
   const int cap = reid_query_expand_stride(k2, max_row_nnz);
-  const size_t smem = (size_t)kQWarps * cap * 8;
-  REID_CHECK_ARG(smem <= 200 * 1024, "reid_query_expand: k2 * max_row_nnz = %d needs %zu B of shared memory",
+  // rows per CTA: as many warps as fit into shared memory (a large k1 makes the tables big)
+  int warps = kQWarps;
+  while (warps > 1 && (size_t)warps * cap * 8 > 96 * 1024) warps >>= 1;
+  const size_t smem = (size_t)warps * cap * 8;
+  REID_CHECK_ARG(smem <= 220 * 1024, "reid_query_expand: k2 * max_row_nnz = %d needs %zu B of shared memory per row",
                  k2 * max_row_nnz, smem);
   const int64_t n = row_end - row_begin;
   if (n == 0) return REID_OK;
-  const unsigned grid = (unsigned)((n + kQWarps - 1) / kQWarps);
+  const unsigned grid = (unsigned)((n + warps - 1) / warps);
   REID_CUDA(cudaFuncSetAttribute(query_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
-  query_expand_kernel<<<grid, kQWarps * 32, smem, (cudaStream_t)stream>>>(
-      rank, ncols, k2, V_ptr, V_idx, V_val, cap, row_begin, row_end, Q_cnt, Q_pad_idx, Q_pad_val);
+  query_expand_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(
+      rank, ncols, k2, V_ptr, V_idx, V_val, cap, row_begin, row_end, Q_cnt, Q_pad_idx, Q_pad_val,
+      (unsigned long long*)overflow_rows);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
@@ -534,16 +637,25 @@ int reid_transpose_fill(const int64_t* ptr, const int32_t* idx, const float* val
   if (n_rows == 0) return REID_OK;
   col_scatter_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(ptr, idx, val, n_rows, C_ptr, cursor, C_idx, C_val);
   REID_LAUNCH_CHECK();
-  // shared-memory sort buffers sized for the longest column (the caller knows it from the scan of the counts);
-  // max_col_len <= 0: unknown, reserve the maximum
+  // shared-memory sort buffers sized for the longest column when the caller knows it (from the scan of the counts).
+  // max_col_len <= 0: unknown (the caller does not read sizes back): warps sort the columns of up to 256 entries,
+  // a second launch finds the longer ones itself and gives each a whole CTA.
+  const bool unknown = max_col_len <= 0;
   int cap = 32;
-  while (cap < max_col_len && cap < kColSortCap) cap <<= 1;
-  if (max_col_len <= 0) cap = kColSortCap;
+  while (cap < (unknown ? 256 : max_col_len) && cap < kColSortCap) cap <<= 1;
   const size_t smem = (size_t)kColSortWarps * cap * 8;
   REID_CUDA(cudaFuncSetAttribute(col_sort_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   col_sort_kernel<<<(unsigned)((n_cols + kColSortWarps - 1) / kColSortWarps), kColSortWarps * 32, smem, st>>>(
-      C_ptr, n_cols, C_idx, C_val, cap);
+      C_ptr, n_cols, C_idx, C_val, cap, unknown ? 1 : 0);
   REID_LAUNCH_CHECK();
+  if (unknown) {
+    const size_t smem_long = (size_t)kColLongCap * 8;
+    REID_CUDA(cudaFuncSetAttribute(col_sort_long_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem_long));
+    int64_t g = (n_cols + kColLongThreads - 1) / kColLongThreads;
+    if (g > 2 * num_sms()) g = 2 * num_sms();
+    col_sort_long_kernel<<<(unsigned)g, kColLongThreads, smem_long, st>>>(C_ptr, n_cols, C_idx, C_val, cap);
+    REID_LAUNCH_CHECK();
+  }
   return REID_OK;
 }
 }

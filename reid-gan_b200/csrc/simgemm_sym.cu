@@ -113,7 +113,7 @@ __global__ void __launch_bounds__(kThreads, 1) simsym_kernel(const __grid_consta
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + stage * kSymStage;
           uint8_t* b_dst = a_dst + kATileBytes;
-          if (p.dbg & 4) {
+          if (REID_DBG(p) & 4) {
             if (leader) mbar_arrive(&full_bar[stage]);
           } else {
             if (leader) mbar_expect_tx(&full_bar[stage], 2 * kSymStage);   // the pair's bytes land on the leader's barrier
@@ -199,11 +199,11 @@ __global__ void __launch_bounds__(kThreads, 1) simsym_kernel(const __grid_consta
       int n_hit = 0;
 #pragma unroll 1
       for (int ch = 0; ch < BN / 32; ++ch) {
-        if (p.dbg & 1) break;
+        if (REID_DBG(p) & 1) break;
         uint32_t v[32];
         tmem_ld_32x32b_x32(taddr + ch * 32, v);
         const int col0 = tj * BN + ch * 32;
-        if (p.dbg & 2) {
+        if (REID_DBG(p) & 2) {
           float mx = 0.f;
 #pragma unroll
           for (int c = 0; c < 32; ++c) mx = fmaxf(mx, __uint_as_float(v[c]));
@@ -403,10 +403,7 @@ int reid_knn_candidates_sym(const void* xh, int64_t N, int64_t D, int scale_log2
   p.cap = cap;
   p.cand = (unsigned long long*)cand;
   p.cand_cnt = cand_cnt;
-  {
-    const char* e = getenv("REID_TC_DEBUG");
-    p.dbg = e ? atoi(e) : 0;
-  }
+  p.dbg = dev_env("REID_TC_DEBUG", 0);
   if (reset_counts) REID_CUDA(cudaMemsetAsync(cand_cnt, 0, sizeof(int32_t) * (size_t)N, st));
   const int slots = num_sms() / 2;
   const int grid = (int)(n_tiles < slots ? n_tiles : slots) * 2;

@@ -176,7 +176,7 @@ __global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_const
             mbar_wait(&empty_bar[stage], phase ^ 1);
             uint8_t* a_dst = smem + stage * C::kStage;
             uint8_t* b_dst = a_dst + kATileBytes;
-            if (p.dbg & 4) {
+            if (REID_DBG(p) & 4) {
               if (kCtas == 1 || leader) mbar_arrive(&full_bar[stage]);
             } else if (kCtas == 1) {
               mbar_expect_tx(&full_bar[stage], C::kStage);
@@ -275,7 +275,7 @@ __global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_const
         const uint32_t taddr = tmem_base + ((uint32_t)(quarter * 32) << 16) + (uint32_t)(wg * BN);
 #pragma unroll 1
         for (int ch = 0; ch < BN / 32; ++ch) {
-          if (p.dbg & 1) break;
+          if (REID_DBG(p) & 1) break;
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + ch * 32, v);
           const int col0 = t * BN + ch * 32;
@@ -297,7 +297,7 @@ __global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_const
             }
             tau = m5;
           }
-          if (p.dbg & 2) {
+          if (REID_DBG(p) & 2) {
             float m = 0.f;
 #pragma unroll
             for (int c = 0; c < 32; ++c) m = fmaxf(m, __uint_as_float(v[c]));
@@ -504,10 +504,7 @@ int reid_knn_candidates_tc_ab(const void* xa, int64_t Na, const void* xh, int64_
   p.cand_cnt = cand_cnt;
   p.row_tau = row_tau;
   REID_CUDA(cudaMemsetAsync(row_tau, 0, sizeof(uint32_t) * (size_t)(row_end - row_begin), (cudaStream_t)stream));
-  {
-    const char* e = getenv("REID_TC_DEBUG");
-    p.dbg = e ? atoi(e) : 0;
-  }
+  p.dbg = dev_env("REID_TC_DEBUG", 0);
   const int units = p.n_mblk * n_splits;
   const int slots = num_sms() / cta_group;
   const int grid = (units < slots ? units : slots) * cta_group;

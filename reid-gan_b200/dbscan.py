@@ -16,7 +16,7 @@ import torch
 
 from . import _lib
 from ._lib import call, check, ptr, stream_ptr
-from .faiss_rerank import JaccardDistance, _device_of, _scan, jaccard_neighbors
+from .faiss_rerank import JaccardDistance, R_NBR_OVF, R_S, _device_of, _nbr_cap_hint, _scan, jaccard_neighbors
 
 
 def dbscan_from_neighbors(N, nbr_ptr, nbr_idx, nbr_cnt, min_samples):
@@ -77,8 +77,21 @@ class DBSCAN:
             if float(np.float32(self.eps)) >= 1.0:
                 # pairs without a shared column have J == 1 and are not in the sparse form
                 return self._fit_dense(dist.dense_device())
-            slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, self.eps)
+            # speculative slot sizes first (no host round trip before the labels); the overflow count comes back
+            # with the same synchronisation that fetches the labels, and a pass that did not fit is redone exactly
+            report = torch.zeros(16, dtype=torch.int64, device=st.Q_ptr.device)
+            st.report = report
+            try:
+                slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, self.eps, speculative=True)
+            finally:
+                st.report = None
             labels, core, _ = dbscan_from_neighbors(st.N, slot_ptr, nbr_idx, nbr_cnt, self.min_samples)
+            vals = report.tolist()
+            if vals[R_NBR_OVF]:
+                slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, self.eps, speculative=False)
+                labels, core, _ = dbscan_from_neighbors(st.N, slot_ptr, nbr_idx, nbr_cnt, self.min_samples)
+            elif vals[R_S]:
+                _nbr_cap_hint[st.N] = int(vals[R_S])
         return labels, core
 
     def _fit_dense(self, X):
@@ -91,15 +104,21 @@ class DBSCAN:
             raise ValueError("precomputed distance matrix must be square, got %s" % (tuple(X.shape),))
         N = X.shape[0]
         dev = _device_of(X)
-        # sklearn compares in the matrix dtype: fp32 input -> d <= float32(eps)
-        eps32 = float(np.float32(self.eps)) if X.dtype != torch.float64 else float(self.eps)
+        # sklearn compares in the matrix dtype: fp32 (or narrower) input -> d <= float32(eps) on the fp32 values; a
+        # float64 matrix is compared in float64 (the block is reduced to {0, 2} with that comparison before the fp32
+        # kernels see it, so no distance is rounded across eps)
+        wide = X.dtype == torch.float64
+        eps32 = 1.0 if wide else float(np.float32(self.eps))
         with torch.cuda.device(dev), torch.no_grad():
             sp = stream_ptr()
             block = N if X.is_cuda else max(1, min(N, (512 << 20) // (4 * N)))
             cnts, idxs = [], []
             for a in range(0, N, block):
                 b = min(N, a + block)
-                blk = X[a:b].to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
+                if wide:
+                    blk = torch.where(X[a:b].to(device=dev, non_blocking=True) <= float(self.eps), 0.0, 2.0).to(torch.float32).contiguous()
+                else:
+                    blk = X[a:b].to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
                 cnt = torch.empty(b - a, dtype=torch.int32, device=dev)
                 call("reid_dbscan_dense_count", ptr(blk), N, blk.stride(0), eps32, 0, b - a, ptr(cnt), sp)
                 p_loc, total, _ = _scan(cnt, b - a, dev)

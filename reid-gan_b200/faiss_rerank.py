@@ -38,10 +38,12 @@ def _device_of(t):
     return torch.device("cuda", torch.cuda.current_device())
 
 
-def _scan_async(cnt, n, dev):
-    """counts (int32, device) -> (ptr int64 (n+1), stats int64 (3) = [total, max, sum of squares]) -- no host sync."""
+def _scan_async(cnt, n, dev, stats=None):
+    """counts (int32, device) -> (ptr int64 (n+1), stats int64 (3) = [total, max, sum of squares]) -- no host sync.
+    `stats`: an existing 3-element int64 device view to write into (a slice of a pass report)."""
     out = torch.empty(n + 1, dtype=torch.int64, device=dev)
-    stats = torch.empty(3, dtype=torch.int64, device=dev)
+    if stats is None:
+        stats = torch.empty(3, dtype=torch.int64, device=dev)
     call("reid_scan_counts", ptr(cnt), n, ptr(out), ptr(stats), stream_ptr())
     return out, stats
 
@@ -51,6 +53,21 @@ def _scan(cnt, n, dev):
     out, stats = _scan_async(cnt, n, dev)
     total, mx, _ = stats.tolist()
     return out, int(total), int(mx)
+
+
+# ---- speculative sizes of the sync-free single-GPU pass ---------------------------------------------------------
+# A pass that reads sizes back between stages leaves the GPU idle for every round trip.  The single-GPU pass instead
+# allocates upper bounds where a cheap one exists (|E| <= k1 + k1 (h + 1), nnz(V_qe) <= rows x table slots), guesses
+# the two sizes that have no useful bound (the query-expansion table and the eps-neighbour slots), lets every kernel
+# REPORT what did not fit instead of trusting the guess, and reads one small report at the END of the pass
+# (RerankState.finish): a pass whose guesses held never synchronised in between, any other is redone with exact sizes.
+QE_SPEC_SLOTS = 512          # query-expansion table / padded V_qe row (distinct columns <= 3/4 of it)
+NBR_SPEC_PER_ROW = 128       # eps-neighbour slots per row on average (slots are dealt by the Markov bound S_i)
+_nbr_cap_hint = {}           # N -> slot total of the last finished pass (the next pass allocates 1.25 x that)
+# report (int64 x 16): [0:3] |E| total/max/sumsq  [3:6] nnz(V_qe) rows  [6:9] column counts: nnz, longest, sum len^2
+#                      [9] uncertified kNN rows  [10] V_qe rows that overflowed the table  [11] rows that overflowed
+#                      their eps-neighbour slots  [12:15] slot total/max/sumsq
+R_E, R_Q, R_C, R_UNCERT, R_QE_OVF, R_NBR_OVF, R_S = 0, 3, 6, 9, 10, 11, 12
 
 
 class RerankState:
@@ -66,12 +83,40 @@ class RerankState:
         self.C_ptr = self.C_idx = self.C_val = None      # CSC of V_qe         :98-100
         self.timings = {}
         self.knn_info = {}
+        self.report = None                        # device report of a speculative pass, until finish()
+        self.report_vals = None
+        self._redo = None
+
+    def finish(self, check_nbr=False):
+        """End of a speculative pass: ONE read-back of the report.  Returns the state to use: `self` when every guess
+        held, else a new state recomputed with exact sizes (uncertified kNN rows are searched exactly first).
+        check_nbr: also require that no row overflowed its eps-neighbour slots (-> (state, nbr_ok))."""
+        if self.report is None:
+            return (self, True) if check_nbr else self
+        vals = [int(v) for v in self.report.tolist()]
+        self.report, self.report_vals = None, vals
+        self.knn_info["uncertified_rows"] = vals[R_UNCERT]
+        if vals[R_E + 1] > self.e_stride:
+            raise RuntimeError("reid_expand: an expansion set exceeded %d entries" % self.e_stride)
+        ok = vals[R_UNCERT] == 0 and vals[R_QE_OVF] == 0
+        if ok:
+            self.e_total, self.e_max = vals[R_E], vals[R_E + 1]
+            self.q_total, self.c_max, self.t_total_all = vals[R_C], vals[R_C + 1], vals[R_C + 2]
+            if vals[R_S]:
+                _nbr_cap_hint[self.N] = vals[R_S]
+            nbr_ok = vals[R_NBR_OVF] == 0
+            return (self, nbr_ok) if check_nbr else self
+        st = self._redo(vals)
+        self._redo = None
+        return (st, False) if check_nbr else st
 
 
-def knn_search(x, k, mode="auto", rows=None, defer=False):
-    """a1: exact top-k neighbour lists (faiss_rerank.py:58-62).  Returns (idx int32, key fp32).
+def knn_search(x, k, mode="auto", rows=None, defer=False, uncert_count=None):
+    """a1: exact top-k neighbour lists (faiss_rerank.py:58-62).  Returns (idx int32, key fp32, info).
     mode "exact": CUDA-core fp64 search for every row; "tc": tensor-core candidates + exact
-    re-score + certificate, uncertified rows redone exactly; "auto": "tc" when the shape allows."""
+    re-score + certificate, uncertified rows redone exactly; "auto": "tc" when the shape allows.
+    defer: do not read the certificate flags back (info["pending"] holds them and the repair closure);
+    uncert_count: device scalar that receives the number of uncertified rows."""
     L = _lib.lib()
     N, D = x.shape
     dev = x.device
@@ -88,7 +133,7 @@ def knn_search(x, k, mode="auto", rows=None, defer=False):
         info["mode"] = mode
     if mode == "tc":
         from .knn_tc import knn_search_tc
-        return knn_search_tc(x, k, r0, r1, idx, key, info, defer=defer)
+        return knn_search_tc(x, k, r0, r1, idx, key, info, defer=defer, uncert_count=uncert_count)
     if mode != "exact":
         raise ValueError("unknown kNN mode %r" % (mode,))
     _knn_exact_rows(x, k, None, r0, n, idx, key)
@@ -107,13 +152,7 @@ def _knn_exact_rows(x, k, rows_list, row_begin, n_rows, idx_out, key_out):
                            ptr(scratch), scratch.numel() * 4, stream_ptr())
 
 
-def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_result=None):
-    """Run a1-a6 on device.  Single GPU: all rows.  Row-sharded (comm = sharded.RowComm): this rank
-    computes rows [comm.r0, comm.r1) of every per-row stage and the stages' outputs are all-gathered
-    (neighbour lists, V rows, V_qe rows), so the returned state always holds GLOBAL rank / V / V_qe /
-    inverted index while `row_begin:row_end` remembers the rank's own rows."""
-    L = _lib.lib()
-    assert (x.is_cuda or knn_result == "upload") and x.dtype == torch.float32 and x.is_contiguous()
+def _check_shape(x, k1, k2):
     N, D = x.shape
     if not (1 <= k1 <= 64):
         raise ValueError("k1=%d outside the supported range 1..64" % k1)
@@ -121,12 +160,32 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_
         raise ValueError("k1=%d exceeds the number of samples N=%d" % (k1, N))
     if not (1 <= k2 <= k1):
         raise ValueError("k2=%d must be in 1..k1" % k2)
+
+
+def rerank_state_async(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_result=None, speculative=None):
+    """Run a1-a6 on device.  Single GPU: all rows.  Row-sharded (comm = sharded.RowComm): this rank
+    computes rows [comm.r0, comm.r1) of every per-row stage and the stages' outputs are all-gathered
+    (neighbour lists, V rows, V_qe rows), so the returned state always holds GLOBAL rank / V / V_qe /
+    inverted index while `row_begin:row_end` remembers the rank's own rows.
+
+    speculative (default: on for the unsharded pass): no host read-back between the stages -- sizes are upper
+    bounds or guesses checked on the device, and the caller ends the pass with `st = st.finish()` (one read-back;
+    see RerankState.finish).  speculative=False reads the sizes back where they are needed (two round trips)."""
+    L = _lib.lib()
+    assert (x.is_cuda or knn_result == "upload") and x.dtype == torch.float32 and x.is_contiguous()
+    N, D = x.shape
+    _check_shape(x, k1, k2)
     dev = x.device if x.is_cuda else torch.device("cuda", torch.cuda.current_device())
     if comm is not None:
         r0, r1 = comm.r0, comm.r1
     else:
         r0, r1 = (0, N) if rows is None else rows
     n = r1 - r0
+    full = comm is None and r0 == 0 and r1 == N
+    if speculative is None:
+        speculative = full
+    if speculative and not full:
+        raise ValueError("the speculative pass covers all rows of one GPU")
     st = RerankState()
     st.N, st.D, st.k1, st.k2, st.row_begin, st.row_end = N, D, k1, k2, r0, r1
     sp = stream_ptr()
@@ -138,28 +197,34 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_
             e.record()
             ev.append((name, e))
 
+    report = torch.zeros(16, dtype=torch.int64, device=dev)
     mark("start")
     # a1 ------------------------------------------------------------------
     if knn_result == "upload":                               # x is still on the host: search while it is uploaded
         from .knn_tc import knn_search_upload
-        x, rank_local, key_local, info = knn_search_upload(x, k1, dev, defer=True)
+        x, rank_local, key_local, info = knn_search_upload(x, k1, dev, defer=True, uncert_count=report[R_UNCERT:])
         knn_result = None
     elif knn_result is not None:                             # searched elsewhere (sharded.knn_search_tiles): rows r0:r1 of it
         rank_g, key_g, info = knn_result
         rank_local, key_local = rank_g[r0:r1].contiguous(), key_g[r0:r1].contiguous()
     else:
-        # single GPU: the certificate flags are not read back here -- they ride on the next unavoidable read-back
-        # (the size of E, below); the rare uncertified rows are then repaired and a2/a3 redone
-        rank_local, key_local, info = knn_search(x, k1, knn, rows=(r0, r1), defer=comm is None)
+        # unsharded: the certificate flags are not read back here -- their count rides on the pass report (or, in
+        # the exact-size flavour, on the first unavoidable read-back); the rare uncertified rows are then repaired
+        rank_local, key_local, info = knn_search(x, k1, knn, rows=(r0, r1), defer=comm is None,
+                                                 uncert_count=report[R_UNCERT:])
     st.knn_info = info
+    st.x = x
     if knn_result is not None:
         rank = knn_result[0].contiguous()
     else:
         rank = comm.gather_rows(rank_local) if comm is not None else rank_local  # global (N, k1)
+    if rank.shape[0] != N:
+        raise ValueError("a row shard needs the global neighbour lists (knn_result or comm)")
     st.rank, st.rank_key = rank, key_local
     mark("knn")
     h = half_k(k1)
     e_stride = min(k1 + k1 * (h + 1), 1024)                  # |E| <= |R| + |R| * |R_half|
+    st.e_stride = e_stride
     R = torch.empty(max(n, 1), dtype=torch.int64, device=dev)
     Rh = torch.empty(N, dtype=torch.int64, device=dev)        # every rank needs R_half of all rows
     e_pad = torch.empty(max(n, 1) * e_stride, dtype=torch.int32, device=dev)
@@ -171,50 +236,62 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_
         call("reid_reciprocal_masks", ptr(rank), N, k1, h, 0, N, ptr(Rh), sp)
         # a3 ------------------------------------------------------------------
         call("reid_expand", ptr(rank), N, k1, min(h + 1, k1), ptr(R), ptr(Rh), r0, r1, e_stride, ptr(e_pad), ptr(e_cnt), sp)
-        return _scan_async(e_cnt, n, dev)
+        return _scan_async(e_cnt, n, dev, stats=report[R_E:R_E + 3])
 
     e_ptr, e_stats = sets()
-    pending_repaired = False
     pending = info.pop("pending", None)
-    if pending is not None:
-        vals = torch.cat([e_stats, pending["flag"].sum(dtype=torch.int64).view(1)]).tolist()
-        if vals[3]:                                           # uncertified rows: exact search for them, then redo a2/a3
-            pending["repair"]()
-            e_ptr, e_stats = sets()
-            vals = e_stats.tolist()
-        info["uncertified_rows"] = int(vals[3]) if len(vals) > 3 else info.get("uncertified_rows", 0)
-    else:
-        vals = e_stats.tolist()
-    e_total, e_max = int(vals[0]), int(vals[1])
     st.R_mask, st.Rh_mask = R, Rh
     mark("reciprocal")
-    if e_max > e_stride:
-        raise RuntimeError("reid_expand: an expansion set exceeded %d entries" % e_stride)
+    if speculative:
+        e_total = e_max = None
+        e_cap = max(n, 1) * e_stride                          # upper bound: no size needed on the host
+    else:
+        vals = report.tolist()                                # read-back 1 of 2: |E| sizes + certificate count
+        if pending is not None and vals[R_UNCERT]:            # uncertified rows: exact search for them, then redo a2/a3
+            pending["repair"]()
+            info["visit_order"] = None                        # only valid for the lists it was built from
+            e_ptr, e_stats = sets()
+            n_bad = vals[R_UNCERT]
+            vals = report.tolist()
+            info["uncertified_rows"] = int(n_bad)
+        e_total, e_max = int(vals[R_E]), int(vals[R_E + 1])
+        if e_max > e_stride:
+            raise RuntimeError("reid_expand: an expansion set exceeded %d entries" % e_stride)
+        e_cap = max(e_total, 1)
     mark("expand")
     # a4 ------------------------------------------------------------------
-    e_idx = torch.empty(max(e_total, 1), dtype=torch.int32, device=dev)
-    v_val = torch.empty(max(e_total, 1), dtype=torch.float32, device=dev)
+    e_idx = torch.empty(e_cap, dtype=torch.int32, device=dev)
+    v_val = torch.empty(e_cap, dtype=torch.float32, device=dev)
     order = info.get("visit_order") if knn_result is None else None
-    if order is not None and (order.numel() != n or pending_repaired):
+    if order is not None and order.numel() != n:
         order = None                                          # only valid for exactly these rows
     call("reid_v_weights", ptr(x), N, D, ptr(e_pad), e_stride, ptr(e_ptr), r0, r1, ptr(rank_local), ptr(key_local),
          k1, ptr(order), ptr(e_idx), ptr(v_val), sp)
     mark("v_weights")
     if comm is not None:                                     # V rows of other shards are read by a5
         e_ptr, e_idx, v_val, e_total, e_max = comm.gather_csr(e_cnt[:n], e_idx[:e_total], v_val[:e_total], row_ptr=e_ptr)
+    elif not full:                                           # a row shard without a communicator (tests): a5 cannot run
+        st.E_ptr, st.E_idx, st.V_val, st.e_total, st.e_max = e_ptr, e_idx, v_val, e_total, e_max
+        return st
     st.E_ptr, st.E_idx, st.V_val = e_ptr, e_idx, v_val       # global CSR when sharded
+    st.e_total, st.e_max = e_total, e_max
     # a5 ------------------------------------------------------------------
     if k2 != 1:
-        q_stride = L.reid_query_expand_stride(k2, max(e_max, 1))
+        if speculative:
+            q_stride = QE_SPEC_SLOTS
+            nnz_guess = max(1, QE_SPEC_SLOTS // k2)
+        else:
+            q_stride = L.reid_query_expand_stride(k2, max(e_max, 1))
+            nnz_guess = max(e_max, 1)
         q_cnt = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
         qp_idx = torch.empty(max(n, 1) * q_stride, dtype=torch.int32, device=dev)
         qp_val = torch.empty(max(n, 1) * q_stride, dtype=torch.float32, device=dev)
-        call("reid_query_expand", ptr(rank), N, k1, k2, ptr(e_ptr), ptr(e_idx), ptr(v_val), max(e_max, 1), r0, r1,
-             ptr(q_cnt), ptr(qp_idx), ptr(qp_val), sp)
+        call("reid_query_expand", ptr(rank), N, k1, k2, ptr(e_ptr), ptr(e_idx), ptr(v_val), nnz_guess, r0, r1,
+             ptr(q_cnt), ptr(qp_idx), ptr(qp_val), ptr(report[R_QE_OVF:]), sp)
         if comm is None:
-            # single GPU: no read-back here -- the CSR is compacted into upper-bound storage and nnz stays on the
-            # device until the inverted index needs its own sizes (one read-back for a5 + a6 together)
-            q_ptr, q_stats = _scan_async(q_cnt, n, dev)
+            # unsharded: no read-back here -- the CSR is compacted into upper-bound storage and nnz stays on the
+            # device (the exact-size flavour reads it with the inverted index's sizes: one read-back for a5 + a6)
+            q_ptr, q_stats = _scan_async(q_cnt, n, dev, stats=report[R_Q:R_Q + 3])
             q_idx = torch.empty(max(n, 1) * q_stride, dtype=torch.int32, device=dev)
             q_val = torch.empty(max(n, 1) * q_stride, dtype=torch.float32, device=dev)
             q_total = None
@@ -235,18 +312,33 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_
         call("reid_transpose_count", ptr(q_idx), q_idx.numel(), ptr(q_ptr[n:]), N, ptr(c_cnt), sp)
     else:
         call("reid_transpose_count", ptr(q_idx), q_total, None, N, ptr(c_cnt), sp)
-    c_ptr, c_stats = _scan_async(c_cnt, N, dev)
-    q_total, c_max, c_sq = (int(v) for v in c_stats.tolist())   # total of the column counts == nnz(V_qe)
-    st.q_total = q_total
-    c_idx = torch.empty(max(q_total, 1), dtype=torch.int32, device=dev)
-    c_val = torch.empty(max(q_total, 1), dtype=torch.float32, device=dev)
+    c_ptr, c_stats = _scan_async(c_cnt, N, dev, stats=report[R_C:R_C + 3])
+    if speculative:
+        c_cap, c_max = q_idx.numel(), 0                       # nnz(V_qe) <= its storage; longest column unknown
+    else:
+        q_total, c_max, c_sq = (int(v) for v in c_stats.tolist())   # read-back 2 of 2; total of the counts == nnz(V_qe)
+        c_cap = max(q_total, 1)
+        st.q_total, st.c_max, st.t_total_all = q_total, c_max, c_sq   # sum_c |col(c)|^2 = sum_i T_i over ALL rows
+    c_idx = torch.empty(c_cap, dtype=torch.int32, device=dev)
+    c_val = torch.empty(c_cap, dtype=torch.float32, device=dev)
     call("reid_transpose_fill", ptr(q_ptr), ptr(q_idx), ptr(q_val), N, N, ptr(c_ptr), ptr(c_cnt), ptr(c_idx),
          ptr(c_val), int(c_max), sp)
-    # sum_i T_i over ALL rows = sum_c |col(c)|^2: the slot total of the eps-graph stage, known without a read-back
-    st.t_total_all = c_sq
     st.C_ptr, st.C_idx, st.C_val = c_ptr, c_idx, c_val
-    st.c_max = c_max
     mark("transpose")
+    if speculative:
+        st.report = report
+
+        def redo(vals):
+            # a guess did not hold (or rows were uncertified): exact sizes, read back where they are needed
+            if vals[R_UNCERT] and pending is not None:
+                pending["repair"]()
+                info["visit_order"] = None
+            info["uncertified_rows"] = int(vals[R_UNCERT])
+            info["speculation_failed"] = dict(uncertified=int(vals[R_UNCERT]), qe_overflow_rows=int(vals[R_QE_OVF]))
+            return rerank_state_async(x, k1, k2, knn=knn, timers=timers, knn_result=(rank_local, key_local, info),
+                                      speculative=False)
+
+        st._redo = redo
     if timers:
         torch.cuda.synchronize()
         for (_, a), (nm, b) in zip(ev[:-1], ev[1:]):
@@ -254,16 +346,72 @@ def rerank_state(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_
     return st
 
 
-def jaccard_neighbors(st, eps, with_values=False):
+def rerank_state(x, k1, k2, **kw):
+    """a1-a6 on device, finished: `rerank_state_async(...).finish()` (the pass itself does not synchronise; finish()
+    reads its report once and redoes the pass with exact sizes in the rare case a guessed size did not hold)."""
+    return rerank_state_async(x, k1, k2, **kw).finish()
+
+
+def rank_digest(st):
+    """sha256 of the (N, k1) int32 neighbour lists -- what bench.py prints as config.rank_sha256."""
+    import hashlib
+    return hashlib.sha256(np.ascontiguousarray(st.rank.cpu().numpy().astype(np.int32)).tobytes()).hexdigest()
+
+
+def query_expand_rows(st, row_begin, row_end):
+    """a5 for rows [row_begin, row_end) against the state's GLOBAL V (what a rank of the row-sharded plan computes
+    after the all-gather of the V rows).  Returns (q_cnt int32, q_idx int32, q_val fp32) compact in row order."""
+    L = _lib.lib()
+    dev = st.rank.device
+    n = row_end - row_begin
+    sp = stream_ptr()
+    e_max = int((st.E_ptr[1:] - st.E_ptr[:-1]).max().item())
+    q_stride = L.reid_query_expand_stride(st.k2, max(e_max, 1))
+    q_cnt = torch.empty(max(n, 1), dtype=torch.int32, device=dev)
+    qp_idx = torch.empty(max(n, 1) * q_stride, dtype=torch.int32, device=dev)
+    qp_val = torch.empty(max(n, 1) * q_stride, dtype=torch.float32, device=dev)
+    call("reid_query_expand", ptr(st.rank), st.N, st.k1, st.k2, ptr(st.E_ptr), ptr(st.E_idx), ptr(st.V_val), max(e_max, 1),
+         row_begin, row_end, ptr(q_cnt), ptr(qp_idx), ptr(qp_val), None, sp)
+    q_ptr, q_total, _ = _scan(q_cnt, n, dev)
+    q_idx = torch.empty(max(q_total, 1), dtype=torch.int32, device=dev)
+    q_val = torch.empty(max(q_total, 1), dtype=torch.float32, device=dev)
+    call("reid_csr_compact", ptr(qp_idx), ptr(qp_val), q_stride, ptr(q_cnt), ptr(q_ptr), n, ptr(q_idx), ptr(q_val), sp)
+    return q_cnt[:n], q_idx, q_val
+
+
+def jaccard_neighbors(st, eps, with_values=False, speculative=None):
     """a7 (sparse form): eps-neighbourhoods of the shard's rows.  Returns (slot_ptr int64 (n+1),
-    nbr_idx int32, nbr_cnt int32 (n), nbr_val or None): row r's list is nbr_idx[slot_ptr[r] : +nbr_cnt[r]]."""
+    nbr_idx int32, nbr_cnt int32 (n), nbr_val or None): row r's list is nbr_idx[slot_ptr[r] : +nbr_cnt[r]].
+
+    Exact-size flavour: slots from T_i = sum_c |col(c)| (an upper bound of the partner count), total read back.
+    Speculative flavour (default while the state's report is pending, i.e. inside a sync-free pass): slots from the
+    Markov bound S_i (reid_jaccard_bounds), storage guessed, every kernel guarded; rows that did not fit are counted
+    in the report (finish(check_nbr=True) tells)."""
     L = _lib.lib()
     dev = st.Q_ptr.device
     r0, r1 = st.row_begin, st.row_end
     n = r1 - r0
     sp = stream_ptr()
+    if speculative is None:
+        speculative = st.report is not None
+    eps32 = float(np.float32(eps))
     t_cnt = torch.empty(n, dtype=torch.int32, device=dev)
-    call("reid_jaccard_bounds", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.C_ptr), r0, r1, ptr(t_cnt), sp)
+    ws = torch.empty(L.reid_jaccard_eps_graph_workspace_bytes(st.N, n), dtype=torch.uint8, device=dev)
+    if speculative:
+        report = st.report
+        s_cnt = torch.empty(n, dtype=torch.int32, device=dev)
+        call("reid_jaccard_bounds", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), r0, r1, eps32, ptr(t_cnt),
+             ptr(s_cnt), sp)
+        slot_ptr, _ = _scan_async(s_cnt, n, dev, stats=report[R_S:R_S + 3])
+        cap = max(n * NBR_SPEC_PER_ROW, int(_nbr_cap_hint.get(st.N, 0) * 1.25), 1)
+        nbr_idx = torch.empty(cap, dtype=torch.int32, device=dev)
+        nbr_val = torch.empty(cap, dtype=torch.float32, device=dev) if with_values else None
+        nbr_cnt = torch.empty(n, dtype=torch.int32, device=dev)
+        call("reid_jaccard_eps_graph", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
+             ptr(st.C_val), st.N, r0, r1, eps32, ptr(t_cnt), ptr(slot_ptr), ptr(nbr_idx), ptr(nbr_val), ptr(nbr_cnt),
+             cap, ptr(report[R_NBR_OVF:]), ptr(ws), sp)
+        return slot_ptr, nbr_idx, nbr_cnt, nbr_val
+    call("reid_jaccard_bounds", ptr(st.Q_ptr), ptr(st.Q_idx), None, ptr(st.C_ptr), r0, r1, eps32, ptr(t_cnt), None, sp)
     if r0 == 0 and r1 == st.N and getattr(st, "t_total_all", None) is not None:
         slot_ptr, _ = _scan_async(t_cnt, n, dev)              # the total is already known (rerank_state, a6)
         t_total = st.t_total_all
@@ -272,11 +420,9 @@ def jaccard_neighbors(st, eps, with_values=False):
     nbr_idx = torch.empty(max(t_total, 1), dtype=torch.int32, device=dev)
     nbr_val = torch.empty(max(t_total, 1), dtype=torch.float32, device=dev) if with_values else None
     nbr_cnt = torch.empty(n, dtype=torch.int32, device=dev)
-    eps32 = float(np.float32(eps))
-    ws = torch.empty(L.reid_jaccard_eps_graph_workspace_bytes(st.N, n), dtype=torch.uint8, device=dev)
     call("reid_jaccard_eps_graph", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
                                    ptr(st.C_val), st.N, r0, r1, eps32, ptr(t_cnt), ptr(slot_ptr), ptr(nbr_idx),
-                                   ptr(nbr_val), ptr(nbr_cnt), ptr(ws), sp)
+                                   ptr(nbr_val), ptr(nbr_cnt), 0, None, ptr(ws), sp)
     return slot_ptr, nbr_idx, nbr_cnt, nbr_val
 
 
@@ -385,9 +531,8 @@ def compute_jaccard_distance(target_features, k1=20, k2=6, print_flag=True, sear
             st = rerank_state(target_features, k1, k2, knn=knn, knn_result="upload")   # search overlaps the upload
         else:
             x = target_features.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
-            st = rerank_state(x, k1, k2, knn=knn)
+            st = rerank_state(x, k1, k2, knn=knn)               # finish(): the one host synchronisation of the call
         out = JaccardDistance(st)
-        torch.cuda.current_stream().synchronize()
     if print_flag:
         print("Jaccard distance computing time cost: {}".format(time.time() - end))
     return out

@@ -86,7 +86,7 @@ def sym_eligible(N, D, k):
 UPLOAD_CHUNKS = int(__import__("os").environ.get("REID_UPLOAD_CHUNKS", "12"))
 
 
-def knn_search_upload(x_host, k, dev, idx=None, key=None, info=None, defer=False, chunks=None):
+def knn_search_upload(x_host, k, dev, idx=None, key=None, info=None, defer=False, chunks=None, uncert_count=None):
     """a1 for features that still live in (pinned) HOST memory: the upload is cut into `chunks` row blocks on a copy
     stream and the candidate search follows it block by block -- fp16 conversion, sampling prepass and thresholds
     of the block's rows, then every upper-triangle tile whose rows are all resident -- so that when the last block
@@ -168,12 +168,12 @@ def knn_search_upload(x_host, k, dev, idx=None, key=None, info=None, defer=False
         idx = torch.empty((N, k), dtype=torch.int32, device=dev)
         key = torch.empty((N, k), dtype=torch.float32, device=dev)
     x.record_stream(copy)
-    idx, key, info = knn_search_tc(x, k, 0, N, idx, key, info, xh=xh, defer=defer,
+    idx, key, info = knn_search_tc(x, k, 0, N, idx, key, info, xh=xh, defer=defer, uncert_count=uncert_count,
                                    cands=(cand, cnt, tau_ord, SYM_CAP, dict(sample=m, tiles=n_tiles, chunks=chunks), msq))
     return x, idx, key, info
 
 
-def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None, defer=False, cands=None):
+def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None, defer=False, cands=None, uncert_count=None):
     L = _lib.lib()
     from .faiss_rerank import _knn_exact_rows
     N, D = x.shape
@@ -213,7 +213,8 @@ def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None, defer=
     max_err = torch.zeros(1, dtype=torch.float32, device=dev)
     ws = torch.empty(L.reid_knn_rescore_workspace_bytes(N, n), dtype=torch.uint8, device=dev)
     call("reid_knn_rescore", ptr(x), N, D, r0, r1, ptr(cand), ptr(cand_cnt), ptr(row_tau), n_lists, list_cap, 0, k, eps,
-         ptr(msq), 1 if ORDER_ROWS else 0, ptr(idx), ptr(key), ptr(flag), ptr(max_err), ptr(ws), sp)
+         ptr(msq), 1 if ORDER_ROWS else 0, ptr(idx), ptr(key), ptr(flag), ptr(max_err), ptr(ws), ptr(uncert_count), sp)
+
     def repair():
         """Exact CUDA-core search for the rows the certificate rejected (none on typical data)."""
         bad = torch.nonzero(flag).flatten().to(torch.int32)

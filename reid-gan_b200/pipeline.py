@@ -15,37 +15,56 @@ import torch
 from . import _lib
 from ._lib import call, ptr, stream_ptr
 from .dbscan import dbscan_from_neighbors
-from .faiss_rerank import jaccard_neighbors, rerank_state
+from .faiss_rerank import jaccard_neighbors, rerank_state_async
+
+
+def _labels_from_state(st, eps, min_samples, timers=False):
+    """a7 + a8 on a state (speculative sizes while its report is pending)."""
+    ev0 = ev1 = ev2 = None
+    if timers:
+        ev0 = torch.cuda.Event(enable_timing=True)
+        ev0.record()
+    slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, eps)
+    if timers:
+        ev1 = torch.cuda.Event(enable_timing=True)
+        ev1.record()
+    labels, core, ncl = dbscan_from_neighbors(st.N, slot_ptr, nbr_idx, nbr_cnt, min_samples)
+    if timers:
+        ev2 = torch.cuda.Event(enable_timing=True)
+        ev2.record()
+        torch.cuda.synchronize()
+        st.timings["jaccard"] = ev0.elapsed_time(ev1) * 1e-3
+        st.timings["dbscan"] = ev1.elapsed_time(ev2) * 1e-3
+    return labels, core, ncl, nbr_cnt
 
 
 @torch.no_grad()
 def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=False, timers=False):
     """x: (N, D) fp32 CUDA tensor, rows L2-normalised.  Returns dict(labels int64 cuda (N,), core uint8 cuda,
-    num_clusters 1-elem int64 cuda, [centroids (C, D) cuda], state)."""
+    num_clusters 1-elem int64 cuda, [centroids (C, D) cuda], state).
+
+    The pass is enqueued without a single host synchronisation (speculative sizes, faiss_rerank.py) and ends with ONE
+    read-back: the pass report and, for the centroids, the number of clusters."""
     if not x.is_cuda:
         raise RuntimeError("pseudo_labels needs a CUDA tensor; there is no CPU fallback")
     with torch.cuda.device(x.device):
-        st = rerank_state(x.contiguous(), k1, k2, knn=knn, timers=timers)
-        ev0 = ev1 = ev2 = None
-        if timers:
-            ev0 = torch.cuda.Event(enable_timing=True)
-            ev0.record()
-        slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, eps)
-        if timers:
-            ev1 = torch.cuda.Event(enable_timing=True)
-            ev1.record()
-        labels, core, ncl = dbscan_from_neighbors(st.N, slot_ptr, nbr_idx, nbr_cnt, min_samples)
-        if timers:
-            ev2 = torch.cuda.Event(enable_timing=True)
-            ev2.record()
-            torch.cuda.synchronize()
-            st.timings["jaccard"] = ev0.elapsed_time(ev1) * 1e-3
-            st.timings["dbscan"] = ev1.elapsed_time(ev2) * 1e-3
+        x = x.contiguous()
+        st = rerank_state_async(x, k1, k2, knn=knn, timers=timers)
+        labels, core, ncl, nbr_cnt = _labels_from_state(st, eps, min_samples, timers)
+        cen = None
+        if centroids:
+            # C is not known on the host yet (at most N: every cluster holds a core point): the kernel takes the
+            # capacity and the device-side count, rows beyond the count are never written (nor their memory touched)
+            cap = max(1, x.shape[0])
+            cen = torch.empty((cap, x.shape[1]), dtype=torch.float32, device=x.device)
+            call("reid_centroids_dev", ptr(x), x.shape[0], x.shape[1], ptr(labels), ptr(ncl), cap, 1, ptr(cen), stream_ptr())
+        st2, nbr_ok = st.finish(check_nbr=True)
+        if st2 is not st or not nbr_ok:                       # a guess did not hold: exact sizes (rare)
+            st = st2
+            labels, core, ncl, nbr_cnt = _labels_from_state(st, eps, min_samples, timers)
+            if centroids:
+                call("reid_centroids_dev", ptr(x), x.shape[0], x.shape[1], ptr(labels), ptr(ncl), cap, 1, ptr(cen), stream_ptr())
         out = dict(labels=labels, core=core, num_clusters=ncl, state=st, nbr_cnt=nbr_cnt)
         if centroids:
-            C = int(ncl.item())
-            cen = torch.empty((C, x.shape[1]), dtype=torch.float32, device=x.device)
-            if C:
-                call("reid_centroids", ptr(x), x.shape[0], x.shape[1], ptr(labels), C, 1, ptr(cen), None, stream_ptr())
-            out["centroids"] = cen
+            out["centroids"] = cen[: int(ncl.item())]
         return out

@@ -264,7 +264,7 @@ def knn_search_tiles(x, k, group=None):
         ws = torch.empty(L.reid_knn_rescore_workspace_bytes(N, nb), dtype=torch.uint8, device=dev)
         my_tau = tau_ord[b0:b1].contiguous()
         call("reid_knn_rescore", ptr(x), N, D, b0, b1, ptr(recv), ptr(recv_cnt), ptr(my_tau), W, cap, B, k, 0.0, ptr(msq),
-             1 if kt.ORDER_ROWS else 0, ptr(idx), ptr(key), ptr(flag), ptr(max_err), ptr(ws), sp)
+             1 if kt.ORDER_ROWS else 0, ptr(idx), ptr(key), ptr(flag), ptr(max_err), ptr(ws), None, sp)
         bad = torch.nonzero(flag).flatten().to(torch.int32)
         n_bad = bad.numel()
         if n_bad:                                          # uncertified rows: exact CUDA-core search
@@ -298,7 +298,7 @@ def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=
     pipeline.pseudo_labels with GLOBAL labels on every rank."""
     from ._lib import call, ptr, stream_ptr
     from .dbscan import dbscan_from_neighbors
-    from .faiss_rerank import jaccard_neighbors, rerank_state
+    from .faiss_rerank import jaccard_neighbors, rerank_state_async
     if not x.is_cuda:
         raise RuntimeError("sharded.pseudo_labels needs CUDA tensors; there is no CPU fallback")
     with torch.cuda.device(x.device):
@@ -331,21 +331,16 @@ def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=
             if timers:
                 ek[1].record()
         if plan == "tiles":
-            st = rerank_state(x.contiguous(), k1, k2, knn_result=res, timers=timers)
+            # every rank runs the (replicated) sparse stages as the sync-free speculative pass of pipeline.py
+            from .pipeline import _labels_from_state
+            st = rerank_state_async(x.contiguous(), k1, k2, knn_result=res, timers=timers)
             if timers:
                 st.timings["knn_tiles"] = ek[0].elapsed_time(ek[1]) * 1e-3
-            ev = [torch.cuda.Event(enable_timing=True) for _ in range(3)] if timers else None
-            if timers:
-                ev[0].record()
-            slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, eps)
-            if timers:
-                ev[1].record()
-            labels, core, ncl = dbscan_from_neighbors(N, slot_ptr, nbr_idx, nbr_cnt, min_samples)
-            if timers:
-                ev[2].record()
-                torch.cuda.synchronize()
-                st.timings["jaccard"] = ev[0].elapsed_time(ev[1]) * 1e-3
-                st.timings["dbscan"] = ev[1].elapsed_time(ev[2]) * 1e-3
+            labels, core, ncl, nbr_cnt = _labels_from_state(st, eps, min_samples, timers)
+            st2, nbr_ok = st.finish(check_nbr=True)
+            if st2 is not st or not nbr_ok:
+                st = st2
+                labels, core, ncl, nbr_cnt = _labels_from_state(st, eps, min_samples, timers)
             out = dict(labels=labels, core=core, num_clusters=ncl, state=st, nbr_cnt=nbr_cnt)
             if centroids:
                 C = int(ncl.item())
@@ -354,7 +349,7 @@ def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=
                     call("reid_centroids", ptr(x), N, x.shape[1], ptr(labels), C, 1, ptr(cen), None, stream_ptr())
                 out["centroids"] = cen
             return out
-        st = rerank_state(x.contiguous(), k1, k2, knn=knn, comm=comm, timers=timers, knn_result=res)
+        st = rerank_state_async(x.contiguous(), k1, k2, knn=knn, comm=comm, timers=timers, knn_result=res)
         if timers and res is not None:
             st.timings["knn_tiles"] = ek[0].elapsed_time(ek[1]) * 1e-3
         ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timers else None
