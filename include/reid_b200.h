@@ -262,8 +262,8 @@ int reid_jaccard_neighbors_heavy(const int64_t* Q_ptr, const int32_t* Q_idx, con
  * classes (512 .. 8192 slots) on the device from T_cnt (reid_jaccard_bounds), overflowing rows move up a
  * class, the last resort is the dense-accumulator kernel.  nbr_cnt is never -1 on return.
  * slot_ptr: n + 1 entries (a scan of T_cnt or S_cnt); row r owns [slot_ptr[r], slot_ptr[r+1]).  No kernel writes
- * outside a row's slots or at / beyond nbr_capacity (<= 0: unlimited): a row with more neighbours than slots keeps its
- * true nbr_cnt, loses the surplus entries and is counted in *slot_overflow (optional device scalar) -- with slots
+ * outside a row's slots or at / beyond nbr_capacity (<= 0: unlimited): a row with more neighbours than slots stores
+ * (and counts in nbr_cnt) only what fits and is counted in *slot_overflow (optional device scalar) -- with slots
  * from T_cnt that cannot happen.
  * workspace: reid_jaccard_eps_graph_workspace_bytes(N, row_end - row_begin). */
 size_t reid_jaccard_eps_graph_workspace_bytes(int64_t N, int64_t n_rows);

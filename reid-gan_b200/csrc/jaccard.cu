@@ -218,8 +218,10 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
       cnt += __popc(b);
     }
     if (lane == 0) {
-      nbr_cnt[lr] = cnt;
-      if (o + cnt > o_end && slot_overflow) atomicAdd(slot_overflow, 1ull);
+      // a row that did not fit keeps only what was stored (consumers never read past the slots) and is reported
+      const int64_t room = o_end > o ? o_end - o : 0;
+      nbr_cnt[lr] = cnt <= room ? cnt : (int)room;
+      if (cnt > room && slot_overflow) atomicAdd(slot_overflow, 1ull);
     }
     __syncwarp();
   }
@@ -323,8 +325,9 @@ __global__ void __launch_bounds__(kJDThreads) jaccard_direct_kernel(
     }
     __syncthreads();
     if (t == 0) {
-      nbr_cnt[lr] = s_base;
-      if (o + s_base > o_end && slot_overflow) atomicAdd(slot_overflow, 1ull);
+      const int64_t room = o_end > o ? o_end - o : 0;
+      nbr_cnt[lr] = s_base <= room ? s_base : (int)room;
+      if (s_base > room && slot_overflow) atomicAdd(slot_overflow, 1ull);
     }
   }
 }
@@ -453,8 +456,9 @@ __global__ void __launch_bounds__(256) jaccard_neighbors_heavy_kernel(
     __syncthreads();
   }
   if (threadIdx.x == 0) {
-    nbr_cnt[lr] = s_base;
-    if (o + s_base > o_end && slot_overflow) atomicAdd(slot_overflow, 1ull);
+    const int64_t room = o_end > o ? o_end - o : 0;
+    nbr_cnt[lr] = s_base <= room ? s_base : (int)room;
+    if (s_base > room && slot_overflow) atomicAdd(slot_overflow, 1ull);
   }
   }
 }

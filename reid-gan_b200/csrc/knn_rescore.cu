@@ -267,6 +267,12 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_exact_kernel(
       if (out_key) out_key[lr * k + rank] = sel_key_val(me);
     }
   }
+  // a window with fewer than k members (the row is uncertified and will be redone): the unfilled positions still
+  // get a VALID index, because a caller that defers the certificate check runs the next stages on these lists
+  for (int t = n_w + lane; t < k; t += 32) {
+    out_idx[lr * k + t] = (int32_t)row;
+    if (out_key) out_key[lr * k + t] = -INFINITY;
+  }
 }
 
 // ---- stage 2, grouped: a small FP64 GEMM per group of locality-ordered rows -------------------------
@@ -454,6 +460,189 @@ __global__ void __launch_bounds__(kGThreads, 2) rescore_group_kernel(
         if (out_key) out_key[lr * k + rank] = sel_key_val(me);
       }
     }
+    for (int t = n_w + lane; t < k; t += 32) {       // see rescore_exact_kernel: unfilled positions stay valid indices
+      out_idx[lr * k + t] = (int32_t)(row_begin + lr);
+      if (out_key) out_key[lr * k + t] = -INFINITY;
+    }
+  }
+}
+
+// ---- stage 2, FP64 tensor-core form: DMMA.8x8x4 over groups of 8 locality-ordered rows ------------------
+// The grouped kernel above is bound by two things that have nothing to do with the FP64 pipe (ncu: XU pipe -- the
+// fp32 -> fp64 conversions -- saturated, LSU data pipe 63 % from the shared-memory reads of the fp64 query copies,
+// FP64 pipe 18-23 % busy).  A group's block of dots (8 queries x |union| candidates x D) is a small GEMM, so it
+// is given to the FP64 tensor-core path (mma.sync m8n8k4 f64 = SASS DMMA.8x8x4, full FP64 rate on B200):
+//   * M = 8 = the queries of a group, N = 8 candidates per tile, K = 4;
+//   * both operands come straight from the fp32 feature rows in global memory (L2-resident thanks to the
+//     locality order): lane (g = lane / 4, t = lane % 4) loads ONE float4 of query g and one float4 of candidate g
+//     of every tile per 16-wide K block and feeds its four values to four consecutive MMAs (MMA m of the block
+//     uses k = 4 t + m on both sides: a permutation of K, which a dot product does not notice).  No shared-memory
+//     operand staging at all, 64-byte coalesced segments per (row, block), one conversion per loaded value;
+//   * a query value is converted once per 8 candidates x tiles and a candidate value once per 8 queries (the
+//     grouped kernel: once per 4), so the XU work per FMA is halved and the shared-memory traffic is gone;
+//   * the four warps of a CTA split K into quarters (no imbalance whatever |union| is) and their partial sums are
+//     added in warp order: the summation order of a dot is fixed by the kernel alone, not by the group or the slot
+//     the pair landed in -- keys are identical for every sharding;
+//   * accumulators: 2 doubles per tile and lane -- 16 registers for 64 candidates per pass.
+constexpr int kMq = 8;                      // queries per group (= MMA M)
+constexpr int kMThreads = 128;              // 4 warps = 4 quarters of K
+constexpr int kMTiles = 8;                  // candidate tiles (8 candidates each) per pass
+constexpr int kMChunk = kMTiles * 8;        // 64 candidates per pass
+constexpr int kMSlots = 2048;               // union hash table (|union| <= kMq * kWinMax = 1024)
+
+__device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
+  asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
+               : "+d"(c0), "+d"(c1)
+               : "d"(a), "d"(b));
+}
+
+__global__ void __launch_bounds__(kMThreads) rescore_mma_kernel(
+    const float* __restrict__ x, int64_t D, int64_t row_begin, int64_t n_rows, const int32_t* __restrict__ perm,
+    const int32_t* __restrict__ win_cnt, const int32_t* __restrict__ win_idx, const float* __restrict__ win_a, int k,
+    float eps_in, const float* __restrict__ max_sqnorm, int32_t* __restrict__ out_idx, float* __restrict__ out_key,
+    int32_t* __restrict__ uncert, unsigned* __restrict__ max_err_bits, unsigned long long* __restrict__ uncert_count) {
+  __shared__ int32_t s_tab[kMSlots];                   // union hash table: column ids
+  __shared__ uint16_t s_tid[kMSlots];                  // slot -> position in the union
+  __shared__ int32_t s_ulist[kMq * kWinMax];           // the union
+  __shared__ uint16_t s_pid[kMq * kWinMax];            // window entry -> position in the union
+  __shared__ uint64_t s_key[kMq * kWinMax];            // window entry -> final sort key
+  __shared__ double s_dot[4][kMq][kMChunk];            // per K-quarter partial dots of one pass
+  __shared__ int s_U;
+  __shared__ int s_nw[kMq];
+  __shared__ int64_t s_lr[kMq];
+  __shared__ unsigned s_worst[kMq];
+  const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+  const float eps = max_sqnorm ? reid_tc_err_bound(*max_sqnorm) : eps_in;
+
+  if (tid < kMq) {
+    const int64_t slot = (int64_t)blockIdx.x * kMq + tid;
+    const int64_t lr = slot < n_rows ? (perm ? perm[slot] : slot) : -1;
+    s_lr[tid] = lr;
+    s_nw[tid] = lr >= 0 ? win_cnt[lr] : 0;
+    s_worst[tid] = 0u;
+  }
+  if (tid == 0) s_U = 0;
+  for (int h = tid; h < kMSlots; h += kMThreads) s_tab[h] = -1;
+  __syncthreads();
+  // union of the windows
+  for (int it = tid; it < kMq * kWinMax; it += kMThreads) {
+    const int q = it / kWinMax, t = it % kWinMax;
+    if (t < s_nw[q]) {
+      const int32_t j = win_idx[s_lr[q] * kWinMax + t];
+      uint32_t h = ((uint32_t)j * 0x9e3779b1u) >> 21;          // 11 bits
+      while (true) {
+        const int32_t old = atomicCAS(&s_tab[h], -1, j);
+        if (old == -1) {
+          const int id = atomicAdd(&s_U, 1);
+          s_ulist[id] = j;
+          s_tid[h] = (uint16_t)id;
+          break;
+        }
+        if (old == j) break;
+        h = (h + 1) & (kMSlots - 1);
+      }
+    }
+  }
+  __syncthreads();
+  for (int it = tid; it < kMq * kWinMax; it += kMThreads) {
+    const int q = it / kWinMax, t = it % kWinMax;
+    if (t < s_nw[q]) {
+      const int32_t j = win_idx[s_lr[q] * kWinMax + t];
+      uint32_t h = ((uint32_t)j * 0x9e3779b1u) >> 21;
+      while (s_tab[h] != j) h = (h + 1) & (kMSlots - 1);
+      s_pid[it] = s_tid[h];
+    }
+  }
+  __syncthreads();
+  const int U = s_U;
+
+  const int g = lane >> 2, tg = lane & 3;
+  const int64_t quarter = D >> 2;                               // D % 64 == 0: 16-wide K blocks, four quarters
+  const int64_t lr_g = s_lr[g];
+  // a group that is not full multiplies by row 0's values for the missing queries; those dots are never read
+  const float4* qp = reinterpret_cast<const float4*>(x + (row_begin + (lr_g >= 0 ? lr_g : 0)) * D + warp * quarter) + tg;
+  const int n_blocks = (int)(quarter >> 4);
+
+  for (int c0 = 0; c0 < U; c0 += kMChunk) {
+    const int nt = min(kMTiles, (U - c0 + 7) >> 3);
+    const float4* cp[kMTiles];
+#pragma unroll
+    for (int t = 0; t < kMTiles; ++t) {
+      const int id = c0 + t * 8 + g;
+      cp[t] = reinterpret_cast<const float4*>(x + (int64_t)s_ulist[id < U ? id : U - 1] * D + warp * quarter) + tg;
+    }
+    double acc[kMTiles][2];
+#pragma unroll
+    for (int t = 0; t < kMTiles; ++t) acc[t][0] = acc[t][1] = 0.0;
+#pragma unroll 2
+    for (int kb = 0; kb < n_blocks; ++kb) {
+      const float4 a = qp[kb * 4];
+      float4 b[kMTiles];
+#pragma unroll
+      for (int t = 0; t < kMTiles; ++t)
+        if (t < nt) b[t] = cp[t][kb * 4];
+      const double a0 = (double)a.x, a1 = (double)a.y, a2 = (double)a.z, a3 = (double)a.w;
+#pragma unroll
+      for (int t = 0; t < kMTiles; ++t) {
+        if (t < nt) {
+          dmma_8x8x4(acc[t][0], acc[t][1], a0, (double)b[t].x);
+          dmma_8x8x4(acc[t][0], acc[t][1], a1, (double)b[t].y);
+          dmma_8x8x4(acc[t][0], acc[t][1], a2, (double)b[t].z);
+          dmma_8x8x4(acc[t][0], acc[t][1], a3, (double)b[t].w);
+        }
+      }
+    }
+    // C fragment: row = g (query), columns 2 tg, 2 tg + 1 of the tile
+#pragma unroll
+    for (int t = 0; t < kMTiles; ++t) {
+      if (t < nt) {
+        s_dot[warp][g][t * 8 + 2 * tg] = acc[t][0];
+        s_dot[warp][g][t * 8 + 2 * tg + 1] = acc[t][1];
+      }
+    }
+    __syncthreads();
+    for (int it = tid; it < kMq * kWinMax; it += kMThreads) {
+      const int q = it / kWinMax, t = it % kWinMax;
+      if (t < s_nw[q]) {
+        const int id = (int)s_pid[it] - c0;
+        if (id >= 0 && id < kMChunk) {
+          const int64_t lr = s_lr[q];
+          const double d = ((s_dot[0][q][id] + s_dot[1][q][id]) + s_dot[2][q][id]) + s_dot[3][q][id];   // fixed order
+          const float sc = (float)d;
+          const float err = fabsf(sc - win_a[lr * kWinMax + t]);
+          atomicMax(&s_worst[q], __float_as_uint(err == err ? err : INFINITY));
+          s_key[it] = sel_key(sc, win_idx[lr * kWinMax + t]);
+        }
+      }
+    }
+    __syncthreads();
+  }
+
+  // per row: audit, then order by (key desc, idx asc); the first k go out
+  for (int q = warp; q < kMq; q += kMThreads / 32) {
+    const int64_t lr = s_lr[q];
+    if (lr < 0) continue;
+    const int n_w = s_nw[q];
+    const uint64_t* key = s_key + q * kWinMax;
+    if (lane == 0) {
+      const float worst = __uint_as_float(s_worst[q]);
+      atomicMax(max_err_bits, __float_as_uint(worst));
+      if (!(worst <= eps)) uncert[lr] = 1;  // the error model was violated (or NaN): do not trust the window
+      if (uncert_count && uncert[lr]) atomicAdd(uncert_count, 1ull);
+    }
+    for (int t = lane; t < n_w; t += 32) {
+      const uint64_t me = key[t];
+      int rank = 0;
+      for (int u = 0; u < n_w; ++u) rank += key[u] > me;
+      if (rank < k) {
+        out_idx[lr * k + rank] = sel_key_idx(me);
+        if (out_key) out_key[lr * k + rank] = sel_key_val(me);
+      }
+    }
+    for (int t = n_w + lane; t < k; t += 32) {       // see rescore_exact_kernel: unfilled positions stay valid indices
+      out_idx[lr * k + t] = (int32_t)(row_begin + lr);
+      if (out_key) out_key[lr * k + t] = -INFINITY;
+    }
   }
 }
 
@@ -558,7 +747,12 @@ int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, in
                                                            (unsigned long long*)uncertified_count)
   const bool aligned = (((uintptr_t)x) & 15) == 0;
   static const bool no_group = dev_env("REID_RESCORE_GROUP", 1) == 0;
-  if (aligned && D % 64 == 0 && D <= 2048 && !no_group) {
+  static const int rescore_variant = dev_env("REID_RESCORE_VARIANT", 2);   // developer builds: 1 = CUDA-core grouped kernel
+  if (aligned && D % 64 == 0 && !no_group && rescore_variant == 2) {
+    rescore_mma_kernel<<<(unsigned)((n + kMq - 1) / kMq), kMThreads, 0, st>>>(
+        x, D, row_begin, n, locality_order ? w.perm : nullptr, w.win_cnt, w.win_idx, w.win_a, k, err_bound, max_sqnorm,
+        out_idx, out_key, uncertified_flag, (unsigned*)max_err_out, (unsigned long long*)uncertified_count);
+  } else if (aligned && D % 64 == 0 && D <= 2048 && !no_group) {
     const size_t smem = rescore_group_smem(D);
     REID_CUDA(cudaFuncSetAttribute(rescore_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     rescore_group_kernel<<<(unsigned)((n + kGq - 1) / kGq), kGThreads, smem, st>>>(

@@ -62,7 +62,7 @@ def _scan(cnt, n, dev):
 # REPORT what did not fit instead of trusting the guess, and reads one small report at the END of the pass
 # (RerankState.finish): a pass whose guesses held never synchronised in between, any other is redone with exact sizes.
 QE_SPEC_SLOTS = 512          # query-expansion table / padded V_qe row (distinct columns <= 3/4 of it)
-NBR_SPEC_PER_ROW = 128       # eps-neighbour slots per row on average (slots are dealt by the Markov bound S_i)
+NBR_SPEC_PER_ROW = 256       # eps-neighbour slots per row on average (slots are dealt by the Markov bound S_i)
 _nbr_cap_hint = {}           # N -> slot total of the last finished pass (the next pass allocates 1.25 x that)
 # report (int64 x 16): [0:3] |E| total/max/sumsq  [3:6] nnz(V_qe) rows  [6:9] column counts: nnz, longest, sum len^2
 #                      [9] uncertified kNN rows  [10] V_qe rows that overflowed the table  [11] rows that overflowed
