@@ -62,6 +62,15 @@ size_t reid_knn_exact_scratch_bytes(int64_t N, int64_t n_rows);
 int reid_knn_exact(const float* x, int64_t N, int64_t D, const int32_t* rows_list, int64_t row_begin,
                    int64_t n_rows, int k, int32_t* out_idx, float* out_key, void* scratch,
                    size_t scratch_bytes, void* stream);
+/* The same search for rows that do NOT all have one norm (faiss IndexFlatL2 ranks by squared L2, which is the
+ * inner-product order only then):  key(i,j) = fp32( x_i.x_j - ||x_j||^2 / 2 in fp64 ), descending, j ascending --
+ * squared L2 ascending with the per-query constant ||x_i||^2 dropped.  out_key receives that key (not the dot).
+ * scratch: 256-byte-rounded N doubles (the half norms) + at least N floats. */
+/* sqnorm_range[0..1] = { max_i ||x_i||^2, min_i ||x_i||^2 } (fp32): decides between the two keys */
+int reid_sqnorm_range(const float* x, int64_t N, int64_t D, float* sqnorm_range, void* stream);
+int reid_knn_exact_l2(const float* x, int64_t N, int64_t D, const int32_t* rows_list, int64_t row_begin,
+                      int64_t n_rows, int k, int32_t* out_idx, float* out_key, void* scratch,
+                      size_t scratch_bytes, void* stream);
 
 /* Tensor-core candidate search: fp16 tcgen05 GEMM (TMA-fed, TMEM accumulators) of query rows
  * [row_begin,row_end) against all N rows with a fused per-row running top-`keep` selection in the
@@ -117,11 +126,15 @@ int reid_features_sample(const void* xh, int64_t N, int64_t D, int64_t n_sample,
 int reid_knn_sample_tau(const uint64_t* cand, const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists,
                         int64_t n_rows, int r, float* tau, uint32_t* tau_ord, void* stream);
 
-/* fp32 features -> scaled fp16 operand; max_sqnorm_out (optional, 1 float) = max_i ||x_i||^2, which
- * scales the fp16 rounding bound  |approx - exact| <= 2^-10 ||x_i|| ||x_j||. */
+/* fp32 features -> scaled fp16 operand; max_sqnorm_out (optional, TWO floats) = { max_i ||x_i||^2, min_i ||x_i||^2 }:
+ * the maximum scales the fp16 rounding bound  |approx - exact| <= 2^-10 ||x_i|| ||x_j||, the pair tells the caller
+ * whether all rows have one norm (inner-product order == the reference's L2 order) or reid_knn_exact_l2 is needed. */
 int reid_features_to_half(const float* x, int64_t n_rows, int64_t D, int scale_log2, void* xh,
                           float* max_sqnorm_out, void* stream);
-/* same, but max_sqnorm_inout is NOT reset: a matrix converted in several row blocks accumulates one maximum */
+/* { 0, 3.4e38 }: the identities of the { max, min } pair, for reid_features_to_half_acc */
+int reid_sqnorm_range_reset(float* sqnorm_range, void* stream);
+/* same, but max_sqnorm_inout (two floats, initialised by the caller to { 0, a huge value }) is NOT reset: a matrix
+ * converted in several row blocks accumulates one maximum and one minimum */
 int reid_features_to_half_acc(const float* x, int64_t n_rows, int64_t D, int scale_log2, void* xh,
                               float* max_sqnorm_inout, void* stream);
 
@@ -185,7 +198,12 @@ int reid_expand(const int32_t* rank, int64_t N, int ncols, int half_cols, const 
  * order): cluster mates gather the same feature rows and find them in L2.  The output does not depend on it. */
 int reid_v_weights(const float* x, int64_t N, int64_t D, const int32_t* E_pad, int stride, const int64_t* E_ptr,
                    int64_t row_begin, int64_t row_end, const int32_t* rank_local, const float* rank_key_local,
-                   int ncols, const int32_t* visit_order, int32_t* E_idx, float* V_val, void* stream);
+                   int ncols, const int32_t* visit_order, int32_t* E_idx, float* V_val, int half_precision, void* stream);
+/* half_precision (here, in reid_query_expand, reid_jaccard_eps_graph and reid_jaccard_dense) = the reference's
+ * use_float16=True (faiss_rerank.py:37): V, V_qe, the running Jaccard sums and the distances are float16 ARRAYS there,
+ * and numpy evaluates every float16 operation in float32 and rounds the result to float16.  The kernels keep fp32
+ * storage and apply exactly those roundings (V after the fp32 softmax; V_qe after sum / k2, entries that round to zero
+ * leave the structure; the min-sum after every column; each of the three operations of 1 - t / (2 - t)). */
 
 /* ---- a5: k2 query expansion  (faiss_rerank.py:89-94) ----------------------------
  * Vq[row] = (V[rank[row,0]] + ... + V[rank[row,k2-1]]) / k2, adds in that order, fp32.
@@ -198,7 +216,7 @@ int reid_query_expand_stride(int k2, int max_row_nnz);
 int reid_query_expand(const int32_t* rank, int64_t N, int ncols, int k2, const int64_t* V_ptr,
                       const int32_t* V_idx, const float* V_val, int max_row_nnz, int64_t row_begin,
                       int64_t row_end, int32_t* Q_cnt, int32_t* Q_pad_idx, float* Q_pad_val, uint64_t* overflow_rows,
-                      void* stream);
+                      int half_precision, void* stream);
 int reid_csr_compact(const int32_t* pad_idx, const float* pad_val, int64_t stride, const int32_t* cnt,
                      const int64_t* ptr, int64_t n_rows, int32_t* out_idx, float* out_val, void* stream);
 
@@ -216,7 +234,9 @@ int reid_lists_compact(const int64_t* slot_ptr, const int32_t* idx, const int32_
 int reid_rows_pack(const int32_t* cnt, const int64_t* ptr, const int32_t* idx, const float* val, int64_t n_rows,
                    int64_t n_rows_padded, int stride, int32_t* rec, void* stream);
 int reid_rows_unpack_counts(const int32_t* rec, int stride, int has_val, int world, int64_t max_rows,
-                            const int64_t* bounds, int64_t N, int32_t* g_cnt, void* stream);
+                            const int64_t* bounds, int64_t N, int32_t* g_cnt, uint64_t* overflow_rows, void* stream);
+/* overflow_rows (optional device scalar, accumulates): with it a row whose count exceeds `stride` is counted there and
+ * its count clamped to what travelled -- for a pass that does not read sizes back and is redone if the scalar is set. */
 int reid_rows_unpack_fill(const int32_t* rec, int stride, int world, int64_t max_rows, const int64_t* bounds,
                           int64_t N, const int64_t* g_ptr, int32_t* out_idx, float* out_val, void* stream);
 
@@ -271,11 +291,11 @@ int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
                            const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin,
                            int64_t row_end, float eps, const int32_t* T_cnt, const int64_t* slot_ptr,
                            int32_t* nbr_idx, float* nbr_val, int32_t* nbr_cnt, int64_t nbr_capacity,
-                           uint64_t* slot_overflow, void* workspace, void* stream);
+                           uint64_t* slot_overflow, int half_precision, void* workspace, void* stream);
 /* dense rows: out[(row-row_begin)*ld + j] for all j < N  (the reference's return value). */
 int reid_jaccard_dense(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
                        const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin,
-                       int64_t row_end, float* out, int64_t ld, void* stream);
+                       int64_t row_end, float* out, int64_t ld, int half_precision, void* stream);
 
 /* ---- a8: DBSCAN on precomputed distances -----------------------------------------
  * (examples/cluster_contrast_train_usl.py:160,163; sklearn/cluster/_dbscan.py:397-475)
@@ -346,6 +366,12 @@ int reid_centroids(const float* x, int64_t N, int64_t D, const int64_t* labels, 
  * Lets the whole pseudo-label pass run without a host round trip (train_usl.py:163-191 back to back). */
 int reid_centroids_dev(const float* x, int64_t N, int64_t D, const int64_t* labels, const int64_t* num_clusters_dev,
                        int64_t capacity, int normalize, float* out, void* stream);
+
+/* ---- f4: feature hand-off  (clustercontrast/evaluators.py:16-68, train_usl.py:152-153) ----------------
+ * dst[r] = src[idx[r]] for r < n (rows of D floats, D % 4 == 0): re-orders a device-resident feature store into the
+ * sorted-file-name order the pseudo-label pass expects, replacing the per-row `.cpu()` (evaluators.py:19) and the
+ * N-way torch.cat on the host (train_usl.py:153). */
+int reid_gather_rows(const float* src, int64_t n_src, const int64_t* idx, int64_t n, int64_t D, float* dst, void* stream);
 
 /* ---- a10-a12: ClusterMemory  (models/cm.py:9-76, 110-137) --------------------------
  * forward: xhat = normalize(inputs); z = xhat . F^T / temp; loss_b = logsumexp(z_b) - z_b[y_b].

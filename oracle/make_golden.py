@@ -73,6 +73,21 @@ def make_rerank(sm):
         print("rerank", name, "pairs<1:", rows.size, {k: v for k, v in out.items() if k.startswith("admissible")})
 
 
+def make_rerank_half(sm):
+    """use_float16=True (faiss_rerank.py:37): float16 V / V_qe / sums / distances."""
+    for name, N, D, n_ids, noise, seed, k1, k2 in [("n400_k20", 400, 64, 14, 0.8, 7, 20, 6),
+                                                   ("n300_k15_k2_1", 300, 64, 10, 0.8, 8, 15, 1)]:
+        x, _ = sm.synth(N, D, n_ids, noise, seed)
+        torch.set_num_threads(1)
+        mod = ref_shim.load_faiss_rerank()
+        J = mod.compute_jaccard_distance(x, k1=k1, k2=k2, print_flag=False, search_option=3, use_float16=True)
+        assert J.dtype == np.float16 and J.shape == (N, N)
+        rows, cols = np.nonzero(J != 1.0)
+        np.savez_compressed(os.path.join(GOLD, "halfrerank_%s.npz" % name), x=x.numpy(), k1=k1, k2=k2, use_float16=True,
+                            J_rows=rows.astype(np.int32), J_cols=cols.astype(np.int32), J_vals=J[rows, cols])
+        print("rerank", name, "pairs<1:", rows.size, J.dtype)
+
+
 def make_cm(sm):
     cm_mod = ref_shim.load_cm()
     torch.set_num_threads(1)
@@ -160,6 +175,12 @@ def make_next_rows(sm):
                                  first_match_break=True))
     np.savez_compressed(os.path.join(GOLD, "ranking_q120_g380.npz"), **out)
     print("ranking mAP", float(out["mAP"]))
+    # single_gallery_shot=True draws from the process-wide np.random state (ranking.py:10-16): golden per seed
+    sgs = {}
+    for name, kw in (("sgs", dict()), ("sgs_fmb", dict(first_match_break=True)), ("sgs_sep", dict(separate_camera_set=True))):
+        np.random.seed(1234)
+        sgs["cmc_" + name + "_seed1234"] = rk.cmc(dm, qi, gi, qc, gc, topk=50, single_gallery_shot=True, **kw)
+    np.savez_compressed(os.path.join(GOLD, "ranking_sgs_q120_g380.npz"), **sgs)
 
 
 if __name__ == "__main__":
@@ -167,5 +188,6 @@ if __name__ == "__main__":
     sm = _synth_mod()
     if "--next-only" not in sys.argv:
         make_rerank(sm)
+        make_rerank_half(sm)
         make_cm(sm)
     make_next_rows(sm)

@@ -29,10 +29,10 @@ Two flavours of every stage are kept:
 import numpy as np
 
 __all__ = [
-    "half_k", "exact_knn", "k_reciprocal_masks", "reciprocal_lists",
+    "half_k", "exact_knn", "rows_have_one_norm", "k_reciprocal_masks", "reciprocal_lists",
     "expand", "expand_loops", "v_weights", "query_expand", "transpose_csr",
     "jaccard_sparse", "jaccard_dense_from_sparse", "jaccard_dense_loops",
-    "compute_jaccard_distance_oracle", "sparse_pipeline",
+    "compute_jaccard_distance_oracle", "compute_jaccard_distance_half", "sparse_pipeline",
 ]
 
 
@@ -44,18 +44,37 @@ def half_k(k1):
 # --------------------------------------------------------------------------
 # a1  kNN search  (faiss_rerank.py:58-62; faiss IndexFlatL2 contract)
 # --------------------------------------------------------------------------
-def exact_knn(x, k, chunk=2048, return_keys=False, rows=None):
+UNIT_NORM_TOL = 1e-4      # max ||x||^2 / min ||x||^2 - 1 below which rows count as "all the same norm"
+
+
+def rows_have_one_norm(x):
+    """faiss IndexFlatL2 ranks by squared L2; that is the inner-product order iff every row has the same norm.  Rows
+    that a backbone L2-normalised in fp32 differ by ~1e-7 in squared norm -- below what the reference's own fp32 search
+    resolves -- so they are searched with the inner-product key; anything beyond UNIT_NORM_TOL gets the L2 key."""
+    n = np.einsum("ij,ij->i", x, x, dtype=np.float64)
+    return float(n.max()) <= float(n.min()) * (1.0 + UNIT_NORM_TOL)
+
+
+def exact_knn(x, k, chunk=2048, return_keys=False, rows=None, metric="auto"):
     """Exact top-k by the canonical key.  x: (N, D) float32.  Returns int64 (n, k)
-    (and the fp32 keys).  `rows` restricts the query rows (all N columns searched)."""
+    (and the fp32 keys).  `rows` restricts the query rows (all N columns searched).
+    metric "ip": key = fp32(x_i.x_j in fp64);  "l2": key = fp32(x_i.x_j - ||x_j||^2 / 2 in fp64), i.e. squared L2
+    ascending with the per-query constant ||x_i||^2 dropped;  "auto": "ip" when rows_have_one_norm(x) else "l2"."""
     x = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
     N = x.shape[0]
     x64 = x.astype(np.float64)
+    if metric == "auto":
+        metric = "ip" if rows_have_one_norm(x) else "l2"
+    half_n = 0.5 * np.einsum("ij,ij->i", x64, x64) if metric == "l2" else None
     q = np.arange(N) if rows is None else np.asarray(rows)
     out = np.empty((q.size, k), dtype=np.int64)
     keys = np.empty((q.size, k), dtype=np.float32)
     for s in range(0, q.size, chunk):
         qq = q[s:s + chunk]
-        key = (x64[qq] @ x64.T).astype(np.float32)          # fp64 accumulate, round once
+        key = x64[qq] @ x64.T                               # fp64 accumulate, round once
+        if half_n is not None:
+            key -= half_n[None, :]
+        key = key.astype(np.float32)
         # top-k by (key desc, idx asc).  argpartition is arbitrary inside ties,
         # so rows with a tie across the k-th boundary take the slow exact path.
         part = np.argpartition(-key, k - 1, axis=1)[:, :k]
@@ -308,8 +327,31 @@ def sparse_pipeline(x, k1, k2, rank=None):
                 Vq_ptr=qp, Vq_idx=qi, Vq_val=qv, N=N)
 
 
-def compute_jaccard_distance_oracle(x, k1=20, k2=6, rank=None):
-    """Dense float32 (N, N) Jaccard distance -- same contract as faiss_rerank.py:30,123."""
+def compute_jaccard_distance_half(x, k1=20, k2=6, rank=None):
+    """use_float16=True (faiss_rerank.py:37): dense restatement for small N.  V, V_qe, temp_min and jaccard_dist are
+    float16 arrays; every numpy operation below is the reference's own expression, so numpy applies the same
+    float16 roundings (each op evaluated in float32, result rounded to float16)."""
+    x = np.ascontiguousarray(np.asarray(x, dtype=np.float32))
+    N = x.shape[0]
+    if rank is None:
+        rank = exact_knn(x, k1)
+    ep, ei = expand(rank, k1)
+    ev = v_weights(x, ep, ei)                                          # fp32 softmax (:81, F.softmax of fp32)
+    V = np.zeros((N, N), dtype=np.float16)                             # :71
+    rows = np.repeat(np.arange(N), np.diff(ep))
+    V[rows, ei] = ev.astype(np.float16)                                # :83
+    if k2 != 1:                                                        # :89-94
+        V_qe = np.zeros_like(V, dtype=np.float16)
+        for i in range(N):
+            V_qe[i, :] = np.mean(V[rank[i, :k2], :], axis=0)
+        V = V_qe
+    return jaccard_dense_loops(V)                                      # :98-119 line by line, dtype follows V
+
+
+def compute_jaccard_distance_oracle(x, k1=20, k2=6, rank=None, use_float16=False):
+    """Dense (N, N) Jaccard distance -- same contract as faiss_rerank.py:30,123 (float32, or float16 with use_float16)."""
+    if use_float16:
+        return compute_jaccard_distance_half(x, k1, k2, rank=rank)
     st = sparse_pipeline(x, k1, k2, rank=rank)
     N = st["N"]
     jp, jj, jv = jaccard_sparse(st["Vq_ptr"], st["Vq_idx"], st["Vq_val"], N)

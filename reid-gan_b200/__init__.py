@@ -18,6 +18,7 @@ from .evaluation import pairwise_distance, mean_ap, cmc  # noqa: F401
 from .infomap_cluster import get_dist_nbr, get_links  # noqa: F401
 from .synth import synth, synth_cm_batch, synth_device, synth_hard  # noqa: F401
 from . import pipeline  # noqa: F401
+from .evaluators import DeviceFeatures, extract_features, shard_items  # noqa: F401
 
 __all__ = ["pairwise_distance", "mean_ap", "cmc", "re_ranking", "get_dist_nbr", "get_links", "compute_jaccard_distance", "JaccardDistance", "DBSCAN", "generate_cluster_features",
            "CM", "CM_Hard", "cm", "cm_hard", "ClusterMemory", "synth", "synth_cm_batch"]

@@ -32,9 +32,12 @@ SIGNATURES = {
     "reid_scan_counts": (_I, [_P, _L, _P, _P, _P]),
     "reid_knn_exact_scratch_bytes": (_Z, [_L, _L]),
     "reid_knn_exact": (_I, [_P, _L, _L, _P, _L, _L, _I, _P, _P, _P, _Z, _P]),
+    "reid_sqnorm_range": (_I, [_P, _L, _L, _P, _P]),
+    "reid_knn_exact_l2": (_I, [_P, _L, _L, _P, _L, _L, _I, _P, _P, _P, _Z, _P]),
     "reid_knn_tc_plan": (_I, [_L, _L, _I, _P]),
     "reid_knn_candidates_tc": (_I, [_P, _L, _L, _I, _L, _L, _I, _I, _I, _P, _P, _P, _P]),
     "reid_features_to_half": (_I, [_P, _L, _L, _I, _P, _P, _P]),
+    "reid_sqnorm_range_reset": (_I, [_P, _P]),
     "reid_knn_rescore_workspace_bytes": (_Z, [_L, _L]),
     "reid_knn_rescore_window_counts_offset": (_Z, [_L, _L]),
     "reid_knn_rescore": (_I, [_P, _L, _L, _L, _L, _P, _P, _P, _I, _I, _L, _I, _F, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
@@ -46,14 +49,14 @@ SIGNATURES = {
     "reid_knn_sample_tau": (_I, [_P, _P, _P, _I, _L, _I, _P, _P, _P]),
     "reid_reciprocal_masks": (_I, [_P, _L, _I, _I, _L, _L, _P, _P]),
     "reid_expand": (_I, [_P, _L, _I, _I, _P, _P, _L, _L, _I, _P, _P, _P]),
-    "reid_v_weights": (_I, [_P, _L, _L, _P, _I, _P, _L, _L, _P, _P, _I, _P, _P, _P, _P]),
+    "reid_v_weights": (_I, [_P, _L, _L, _P, _I, _P, _L, _L, _P, _P, _I, _P, _P, _P, _I, _P]),
     "reid_knn_rescore_order_offset": (_Z, [_L, _L]),
     "reid_query_expand_stride": (_I, [_I, _I]),
-    "reid_query_expand": (_I, [_P, _L, _I, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _P]),
+    "reid_query_expand": (_I, [_P, _L, _I, _I, _P, _P, _P, _I, _L, _L, _P, _P, _P, _P, _I, _P]),
     "reid_csr_compact": (_I, [_P, _P, _L, _P, _P, _L, _P, _P, _P]),
     "reid_lists_compact": (_I, [_P, _P, _P, _P, _L, _P, _P]),
     "reid_rows_pack": (_I, [_P, _P, _P, _P, _L, _L, _I, _P, _P]),
-    "reid_rows_unpack_counts": (_I, [_P, _I, _I, _I, _L, _P, _L, _P, _P]),
+    "reid_rows_unpack_counts": (_I, [_P, _I, _I, _I, _L, _P, _L, _P, _P, _P]),
     "reid_rows_unpack_fill": (_I, [_P, _I, _I, _L, _P, _L, _P, _P, _P, _P]),
     "reid_transpose_count": (_I, [_P, _L, _P, _L, _P, _P]),
     "reid_transpose_fill": (_I, [_P, _P, _P, _L, _L, _P, _P, _P, _P, _I, _P]),
@@ -61,7 +64,7 @@ SIGNATURES = {
     "reid_jaccard_neighbors": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _P, _L, _F, _P, _P, _P, _P, _I, _P]),
     "reid_jaccard_neighbors_heavy": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _P, _L, _F, _P, _P, _P, _P, _P, _P]),
     "reid_jaccard_eps_graph_workspace_bytes": (ctypes.c_size_t, [_L, _L]),
-    "reid_jaccard_eps_graph": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _F, _P, _P, _P, _P, _P, _L, _P, _P, _P]),
+    "reid_jaccard_eps_graph": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _F, _P, _P, _P, _P, _P, _L, _P, _I, _P, _P]),
     "reid_rr_normalised_distance": (_I, [_P, _P, _P, _L, _L, _P, _P, _P, _P]),
     "reid_rr_weights": (_I, [_P, _L, _P, _I, _P, _L, _P, _P, _P]),
     "reid_rr_final": (_I, [_P, _L, _P, _L, _L, _F, _F, _P, _P]),
@@ -71,13 +74,14 @@ SIGNATURES = {
     "reid_rank_metrics": (_I, [_P, _L, _L, _L, _P, _P, _P, _P, _I, _I, _I, _P, _P, _P, _P, _P]),
     "reid_links_count": (_I, [_P, _P, _L, _I, ctypes.c_double, _P, _P]),
     "reid_links_fill": (_I, [_P, _P, _L, _I, ctypes.c_double, _P, _P, _P, _P]),
-    "reid_jaccard_dense": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _P, _L, _P]),
+    "reid_jaccard_dense": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _P, _L, _I, _P]),
     "reid_dbscan_dense_count": (_I, [_P, _L, _L, _F, _L, _L, _P, _P]),
     "reid_dbscan_dense_fill": (_I, [_P, _L, _L, _F, _L, _L, _P, _P, _P]),
     "reid_dbscan_workspace_bytes": (_Z, [_L]),
     "reid_dbscan_labels": (_I, [_L, _P, _P, _P, _I, _P, _P, _P, _P, _P]),
     "reid_centroids_workspace_bytes": (_Z, [_L, _L]),
     "reid_centroids": (_I, [_P, _L, _L, _P, _L, _I, _P, _P, _P]),
+    "reid_gather_rows": (_I, [_P, _L, _P, _L, _L, _P, _P]),
     "reid_centroids_dev": (_I, [_P, _L, _L, _P, _P, _L, _I, _P, _P]),
     "reid_cm_forward_scratch_bytes": (_Z, [_L, _L, _L]),
     "reid_cm_forward": (_I, [_P, _P, _P, _L, _L, _L, _F, _P, _P, _P, _P, _P, _P]),

@@ -3,17 +3,24 @@
 set -euo pipefail
 HERE="$(cd "$(dirname "${BASH_SOURCE[0]}")" && pwd)"
 OUT="${HERE}/../libreid_b200.so"
+BUILD="${HERE}/build"
+EXTRA=()
+if [[ "${REID_DEV:-0}" != "0" ]]; then        # developer build: -DREID_DEV enables the timing switches (common.cuh)
+  OUT="${HERE}/../libreid_b200_dev.so"
+  BUILD="${HERE}/build_dev"
+  EXTRA=(-DREID_DEV)
+fi
 NVCC="${NVCC:-/usr/local/cuda/bin/nvcc}"
 FLAGS=(-gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -std=c++17 -Xcompiler -fPIC
        --expt-relaxed-constexpr -Xptxas -v)
-mkdir -p "${HERE}/build"
+mkdir -p "${BUILD}"
 pids=()
 objs=()
 for src in "${HERE}"/*.cu; do
-  obj="${HERE}/build/$(basename "${src%.cu}").o"
+  obj="${BUILD}/$(basename "${src%.cu}").o"
   objs+=("${obj}")
   if [[ ! -f "${obj}" || "${src}" -nt "${obj}" || "${HERE}/common.cuh" -nt "${obj}" || "${HERE}/tc_ptx.cuh" -nt "${obj}" || "${HERE}/../../include/reid_b200.h" -nt "${obj}" ]]; then
-    ( "${NVCC}" "${FLAGS[@]}" -c "${src}" -o "${obj}" > "${obj}.log" 2>&1 || { cat "${obj}.log"; exit 1; } ) &
+    ( "${NVCC}" "${FLAGS[@]}" "${EXTRA[@]}" -c "${src}" -o "${obj}" > "${obj}.log" 2>&1 || { cat "${obj}.log"; exit 1; } ) &
     pids+=($!)
   fi
 done

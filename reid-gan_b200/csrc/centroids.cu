@@ -70,6 +70,17 @@ __global__ void __launch_bounds__(kCenThreads) centroids_kernel(const float* __r
   }
 }
 
+// dst[r] = src[idx[r]]: the device-side form of `torch.cat([features[f].unsqueeze(0) for f, _, _ in sorted(train)], 0)`
+// (examples/cluster_contrast_train_usl.py:153) over a feature store that never left the GPU.
+__global__ void __launch_bounds__(256) gather_rows_kernel(const float4* __restrict__ src, const int64_t* __restrict__ idx,
+                                                          int64_t n, int64_t row_f4, float4* __restrict__ dst) {
+  const int64_t r = blockIdx.x;
+  if (r >= n) return;
+  const float4* s = src + idx[r] * row_f4;
+  float4* d = dst + r * row_f4;
+  for (int64_t t = threadIdx.x; t < row_f4; t += blockDim.x) d[t] = s[t];
+}
+
 }  // namespace reid
 
 extern "C" {
@@ -103,6 +114,16 @@ int reid_centroids_dev(const float* x, int64_t N, int64_t D, const int64_t* labe
                  (long long)D, kCenThreads * kCenMaxPerThread);
   centroids_kernel<<<(unsigned)capacity, kCenThreads, 0, (cudaStream_t)stream>>>(x, N, D, labels, normalize, out,
                                                                                 num_clusters_dev);
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+
+int reid_gather_rows(const float* src, int64_t n_src, const int64_t* idx, int64_t n, int64_t D, float* dst, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(src && idx && dst && n >= 0 && n_src >= 0 && D > 0 && D % 4 == 0, "reid_gather_rows: bad arguments (D %% 4 == 0)");
+  REID_CHECK_ARG((((uintptr_t)src | (uintptr_t)dst) & 15) == 0, "reid_gather_rows: buffers must be 16-byte aligned");
+  if (n == 0) return REID_OK;
+  gather_rows_kernel<<<(unsigned)n, 256, 0, (cudaStream_t)stream>>>((const float4*)src, idx, n, D / 4, (float4*)dst);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

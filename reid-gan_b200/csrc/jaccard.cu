@@ -4,6 +4,8 @@
 // The reference walks the non-zero columns of row i in ascending order and, for each, adds
 // into temp_min[rows of that column] (:109-110); both kernels below keep exactly that order,
 // which is what makes J bit-symmetric and independent of how rows are sharded.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace reid {
@@ -47,8 +49,18 @@ __device__ __forceinline__ uint32_t jhash(uint32_t v) {
   return v ^ (v >> 15);
 }
 
-__device__ __forceinline__ float jaccard_from_t(float t) {
-  float j = __fsub_rn(1.0f, __fdiv_rn(t, __fsub_rn(2.0f, t)));
+// use_float16=True (faiss_rerank.py:37): V, V_qe, temp_min and jaccard_dist are float16 arrays, and numpy evaluates
+// every float16 operation in float32 and rounds the result to float16.  `half` switches those roundings on: the sum
+// is rounded after every column (:110) and each of the three operations of  1 - t / (2 - t)  (:113) separately.
+__device__ __forceinline__ float round_h(float v) { return __half2float(__float2half_rn(v)); }
+__device__ __forceinline__ float acc_add(float a, float b, int half) {
+  const float s = __fadd_rn(a, b);
+  return half ? round_h(s) : s;
+}
+__device__ __forceinline__ float jaccard_from_t(float t, int half = 0) {
+  float j;
+  if (half) j = round_h(__fsub_rn(1.0f, round_h(__fdiv_rn(t, round_h(__fsub_rn(2.0f, t))))));
+  else j = __fsub_rn(1.0f, __fdiv_rn(t, __fsub_rn(2.0f, t)));
   return j < 0.f ? 0.f : j;
 }
 
@@ -77,7 +89,8 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
     int64_t row_begin, int64_t n_rows_host, const int32_t* __restrict__ queue, const int32_t* __restrict__ queue_len,
     int32_t* __restrict__ next_queue, int32_t* __restrict__ next_len, float eps,
     const int64_t* __restrict__ slot_ptr, int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_val,
-    int32_t* __restrict__ nbr_cnt, int slots, int64_t nbr_capacity, unsigned long long* __restrict__ slot_overflow) {
+    int32_t* __restrict__ nbr_cnt, int slots, int64_t nbr_capacity, unsigned long long* __restrict__ slot_overflow,
+    int half) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = lane_id();
   int32_t* tkey = reinterpret_cast<int32_t*>(smem_raw) + (size_t)w * slots;
@@ -165,7 +178,7 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
                 break;
               }
               if (old == j[u]) {
-                tval[h] = __fadd_rn(tval[h], m[u]);
+                tval[h] = acc_add(tval[h], m[u], half);
                 break;
               }
               h = (h + 1) & smask;
@@ -205,7 +218,7 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
     for (int base = 0; base < slots; base += 32) {
       const int32_t j = tkey[base + lane];
       float jd = 2.f;
-      if (j >= 0) jd = jaccard_from_t(tval[base + lane]);
+      if (j >= 0) jd = jaccard_from_t(tval[base + lane], half);
       const bool keep = j >= 0 && jd <= eps;
       const unsigned b = __ballot_sync(kFull, keep);
       if (keep) {
@@ -240,7 +253,7 @@ __global__ void __launch_bounds__(kJDThreads) jaccard_direct_kernel(
     const int64_t* __restrict__ C_ptr, const int32_t* __restrict__ C_idx, const float* __restrict__ C_val, int64_t N,
     int64_t row_begin, const int32_t* __restrict__ queue, const int32_t* __restrict__ queue_len, float eps,
     const int64_t* __restrict__ slot_ptr, int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_val,
-    int32_t* __restrict__ nbr_cnt, int64_t nbr_capacity, unsigned long long* __restrict__ slot_overflow) {
+    int32_t* __restrict__ nbr_cnt, int64_t nbr_capacity, unsigned long long* __restrict__ slot_overflow, int half) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* acc = reinterpret_cast<float*>(smem_raw);
   __shared__ int64_t s_ca[32];
@@ -280,11 +293,11 @@ __global__ void __launch_bounds__(kJDThreads) jaccard_direct_kernel(
           jn = C_idx[s_ca[k + 1] + t];
           mn = fminf(s_v[k + 1], C_val[s_ca[k + 1] + t]);
         }
-        if (j >= 0) acc[j] = __fadd_rn(acc[j], m);
+        if (j >= 0) acc[j] = acc_add(acc[j], m, half);
         const int len = s_len[k];
         for (int e = t + kJDThreads; e < len; e += kJDThreads) {   // columns longer than the CTA (rare)
           const int32_t j2 = C_idx[s_ca[k] + e];
-          acc[j2] = __fadd_rn(acc[j2], fminf(s_v[k], C_val[s_ca[k] + e]));
+          acc[j2] = acc_add(acc[j2], fminf(s_v[k], C_val[s_ca[k] + e]), half);
         }
         __syncthreads();                                       // column k is in before column k + 1 starts
         j = jn;
@@ -300,7 +313,7 @@ __global__ void __launch_bounds__(kJDThreads) jaccard_direct_kernel(
       const float tv = acc[b0 + t];
       acc[b0 + t] = 0.f;
       float jd = 2.f;
-      if (tv > 0.f) jd = jaccard_from_t(tv);
+      if (tv > 0.f) jd = jaccard_from_t(tv, half);
       const bool keep = tv > 0.f && jd <= eps;
       const unsigned b = __ballot_sync(kFull, keep);
       if (__syncthreads_or(b != 0)) {                          // most 128-wide windows hold no neighbour at all
@@ -368,7 +381,7 @@ template <bool kSmemAcc>
 __global__ void __launch_bounds__(256) jaccard_dense_kernel(
     const int64_t* __restrict__ Q_ptr, const int32_t* __restrict__ Q_idx, const float* __restrict__ Q_val,
     const int64_t* __restrict__ C_ptr, const int32_t* __restrict__ C_idx, const float* __restrict__ C_val, int64_t N,
-    int64_t row_begin, float* __restrict__ out, int64_t ld) {
+    int64_t row_begin, float* __restrict__ out, int64_t ld, int half) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int64_t lr = blockIdx.x;
   const int64_t row = row_begin + lr;
@@ -384,16 +397,16 @@ __global__ void __launch_bounds__(256) jaccard_dense_kernel(
       const int32_t j = C_idx[q];
       const float m = fminf(vic, C_val[q]);
       if (kSmemAcc) {
-        acc[j] = __fadd_rn(acc[j], m);
+        acc[j] = acc_add(acc[j], m, half);
       } else {
-        __stcg(&acc[j], __fadd_rn(__ldcg(&acc[j]), m));
+        __stcg(&acc[j], acc_add(__ldcg(&acc[j]), m, half));
       }
     }
     __syncthreads();
   }
   for (int64_t j = threadIdx.x; j < N; j += blockDim.x) {
     const float t = kSmemAcc ? acc[j] : __ldcg(&acc[j]);
-    orow[j] = jaccard_from_t(t);
+    orow[j] = jaccard_from_t(t, half);
   }
 }
 
@@ -406,7 +419,7 @@ __global__ void __launch_bounds__(256) jaccard_neighbors_heavy_kernel(
     int64_t row_begin, const int32_t* __restrict__ rows_list, int64_t n_list_host,
     const int32_t* __restrict__ list_len, float eps, const int64_t* __restrict__ slot_ptr,
     int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_val, int32_t* __restrict__ nbr_cnt,
-    float* __restrict__ scratch, int64_t nbr_capacity, unsigned long long* __restrict__ slot_overflow) {
+    float* __restrict__ scratch, int64_t nbr_capacity, unsigned long long* __restrict__ slot_overflow, int half) {
   __shared__ int s_warp[8];
   __shared__ int s_base;
   const int64_t n_list = list_len ? (int64_t)*list_len : n_list_host;
@@ -423,7 +436,7 @@ __global__ void __launch_bounds__(256) jaccard_neighbors_heavy_kernel(
     const float vic = Q_val[p];
     for (int64_t q = C_ptr[c] + threadIdx.x; q < C_ptr[c + 1]; q += blockDim.x) {
       const int32_t j = C_idx[q];
-      __stcg(&acc[j], __fadd_rn(__ldcg(&acc[j]), fminf(vic, C_val[q])));
+      __stcg(&acc[j], acc_add(__ldcg(&acc[j]), fminf(vic, C_val[q]), half));
     }
     __syncthreads();
   }
@@ -433,7 +446,7 @@ __global__ void __launch_bounds__(256) jaccard_neighbors_heavy_kernel(
   for (int64_t base = 0; base < N; base += blockDim.x) {
     const int64_t j = base + threadIdx.x;
     float jd = 2.f;
-    if (j < N) jd = jaccard_from_t(__ldcg(&acc[j]));
+    if (j < N) jd = jaccard_from_t(__ldcg(&acc[j]), half);
     const bool keep = j < N && jd <= eps;
     const unsigned b = __ballot_sync(kFull, keep);
     if (lane == 0) s_warp[w] = __popc(b);
@@ -470,7 +483,7 @@ struct JnArgs {
   const int64_t* Q_ptr; const int32_t* Q_idx; const float* Q_val;
   const int64_t* C_ptr; const int32_t* C_idx; const float* C_val;
   int64_t row_begin; float eps; const int64_t* slot_ptr; int32_t* nbr_idx; float* nbr_val; int32_t* nbr_cnt;
-  int64_t nbr_capacity; unsigned long long* slot_overflow;
+  int64_t nbr_capacity; unsigned long long* slot_overflow; int half;
 };
 
 // one launch of the table kernel: `n_max` bounds the grid, the real row count is *queue_len when given
@@ -487,7 +500,7 @@ static int launch_jn(const JnArgs& a, int slots, int64_t n_max, const int32_t* q
   if (grid > cap) grid = cap;
   jaccard_neighbors_kernel<kWarps><<<(unsigned)grid, kWarps * 32, smem, st>>>(
       a.Q_ptr, a.Q_idx, a.Q_val, a.C_ptr, a.C_idx, a.C_val, a.row_begin, n_max, queue, queue_len, next_queue, next_len,
-      a.eps, a.slot_ptr, a.nbr_idx, a.nbr_val, a.nbr_cnt, slots, a.nbr_capacity, a.slot_overflow);
+      a.eps, a.slot_ptr, a.nbr_idx, a.nbr_val, a.nbr_cnt, slots, a.nbr_capacity, a.slot_overflow, a.half);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
@@ -558,7 +571,7 @@ int reid_jaccard_neighbors(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
   const int64_t n = rows_list ? n_list : row_end - row_begin;
   if (n == 0) return REID_OK;
   const JnArgs a{Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, row_begin, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt,
-                 INT64_MAX, nullptr};
+                 INT64_MAX, nullptr, 0};
   return launch_jn_slots(a, table_slots, n, rows_list, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
@@ -570,7 +583,8 @@ size_t reid_jaccard_eps_graph_workspace_bytes(int64_t N, int64_t n_rows) {
 int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
                            const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin, int64_t row_end,
                            float eps, const int32_t* T_cnt, const int64_t* slot_ptr, int32_t* nbr_idx, float* nbr_val,
-                           int32_t* nbr_cnt, int64_t nbr_capacity, uint64_t* slot_overflow, void* workspace, void* stream) {
+                           int32_t* nbr_cnt, int64_t nbr_capacity, uint64_t* slot_overflow, int half_precision,
+                           void* workspace, void* stream) {
   using namespace reid;
   REID_CHECK_ARG(Q_ptr && Q_idx && Q_val && C_ptr && C_idx && C_val && T_cnt && slot_ptr && nbr_idx && nbr_cnt && workspace,
                  "reid_jaccard_eps_graph: NULL pointer");
@@ -592,7 +606,7 @@ int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
   if (nbr_capacity <= 0) nbr_capacity = INT64_MAX;           // slots sized by the caller from T_cnt: nothing to guard
   unsigned long long* ovf = (unsigned long long*)slot_overflow;
   const JnArgs a{Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, row_begin, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt,
-                 nbr_capacity, ovf};
+                 nbr_capacity, ovf, half_precision};
   const int n_hash = direct_from < kJClasses ? direct_from : kJClasses;
   for (int c = 0; c < n_hash; ++c) {
     const bool last = c + 1 == n_hash && direct_from <= kJClasses;
@@ -609,20 +623,20 @@ int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
     if (grid > n) grid = n;
     jaccard_direct_kernel<<<(unsigned)grid, kJDThreads, row_bytes, st>>>(Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin,
                                                                         direct_q, direct_len, eps, slot_ptr, nbr_idx, nbr_val,
-                                                                        nbr_cnt, nbr_capacity, ovf);
+                                                                        nbr_cnt, nbr_capacity, ovf, half_precision);
     REID_LAUNCH_CHECK();
   }
   const int64_t hg = n < kJHeavyCtas ? n : kJHeavyCtas;
   jaccard_neighbors_heavy_kernel<<<(unsigned)hg, 256, 0, st>>>(Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin,
                                                               w.queues + (int64_t)kJClasses * n, 0, w.qlen + kJClasses, eps,
-                                                              slot_ptr, nbr_idx, nbr_val, nbr_cnt, w.scratch, nbr_capacity, ovf);
+                                                              slot_ptr, nbr_idx, nbr_val, nbr_cnt, w.scratch, nbr_capacity, ovf, half_precision);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
 
 int reid_jaccard_dense(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
                        const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin, int64_t row_end,
-                       float* out, int64_t ld, void* stream) {
+                       float* out, int64_t ld, int half_precision, void* stream) {
   using namespace reid;
   REID_CHECK_ARG(Q_ptr && Q_idx && Q_val && C_ptr && C_idx && C_val && out, "reid_jaccard_dense: NULL pointer");
   REID_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= N && ld >= N, "reid_jaccard_dense: bad shape");
@@ -633,10 +647,10 @@ int reid_jaccard_dense(const int64_t* Q_ptr, const int32_t* Q_idx, const float* 
   if (smem <= 200 * 1024) {
     REID_CUDA(cudaFuncSetAttribute(jaccard_dense_kernel<true>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     jaccard_dense_kernel<true><<<(unsigned)n, 256, smem, st>>>(Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin,
-                                                              out, ld);
+                                                              out, ld, half_precision);
   } else {
     jaccard_dense_kernel<false><<<(unsigned)n, 256, 0, st>>>(Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin,
-                                                            out, ld);
+                                                            out, ld, half_precision);
   }
   REID_LAUNCH_CHECK();
   return REID_OK;
@@ -653,7 +667,7 @@ int reid_jaccard_neighbors_heavy(const int64_t* Q_ptr, const int32_t* Q_idx, con
   if (n_list == 0) return REID_OK;
   jaccard_neighbors_heavy_kernel<<<(unsigned)n_list, 256, 0, (cudaStream_t)stream>>>(
       Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin, rows_list, n_list, nullptr, eps, slot_ptr, nbr_idx, nbr_val,
-      nbr_cnt, scratch, INT64_MAX, nullptr);
+      nbr_cnt, scratch, INT64_MAX, nullptr, 0);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

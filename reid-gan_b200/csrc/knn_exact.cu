@@ -10,9 +10,12 @@ namespace reid {
 constexpr int TM = 64, TN = 64, TK = 32;
 
 // keys[r][j] = fp32( sum_d (double)x[q_r][d] * (double)x[j][d] ), q_r = rows ? rows[r] : row_begin + r
+// half_sqnorm (optional, fp64[N]): the squared-L2 form of the key, fp32( dot - ||x_j||^2 / 2 ) -- L2 ascending with the
+// per-query constant dropped (rows of different norms; for unit-norm rows both keys order alike).
 __global__ void __launch_bounds__(256) dot64_tile_kernel(const float* __restrict__ x, int64_t N, int64_t D,
                                                          const int32_t* __restrict__ rows, int64_t row_begin,
-                                                         int64_t n_rows, float* __restrict__ keys) {
+                                                         int64_t n_rows, const double* __restrict__ half_sqnorm,
+                                                         float* __restrict__ keys) {
   __shared__ float As[TM][TK + 1];
   __shared__ float Bs[TN][TK + 1];
   const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
@@ -63,8 +66,39 @@ __global__ void __launch_bounds__(256) dot64_tile_kernel(const float* __restrict
 #pragma unroll
     for (int j = 0; j < 4; ++j) {
       int64_t c = c0 + tx + 16 * j;
-      if (c < N) keys[r * N + c] = (float)acc[i][j];
+      if (c < N) keys[r * N + c] = (float)(half_sqnorm ? acc[i][j] - half_sqnorm[c] : acc[i][j]);
     }
+  }
+}
+
+// half_sqnorm[j] = 0.5 * sum_d x[j,d]^2 in fp64; one warp per row
+__global__ void __launch_bounds__(256) half_sqnorm64_kernel(const float* __restrict__ x, int64_t N, int64_t D,
+                                                            double* __restrict__ out) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  double s = 0.0;
+  for (int64_t d = lane_id(); d < D; d += 32) {
+    const double v = (double)x[row * D + d];
+    s = fma(v, v, s);
+  }
+  s = warp_sum(s);
+  if (lane_id() == 0) out[row] = 0.5 * s;
+}
+
+// { max_i ||x_i||^2, min_i ||x_i||^2 } in fp32 (what reid_features_to_half reports on the tensor-core path)
+__global__ void __launch_bounds__(256) sqnorm_range_kernel(const float* __restrict__ x, int64_t N, int64_t D,
+                                                           float* __restrict__ range) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  float ss = 0.f;
+  for (int64_t d = lane_id(); d < D; d += 32) {
+    const float v = x[row * D + d];
+    ss = fmaf(v, v, ss);
+  }
+  ss = warp_sum(ss);
+  if (lane_id() == 0) {
+    atomicMax((unsigned*)range, __float_as_uint(ss));
+    atomicMin((unsigned*)range + 1, __float_as_uint(ss));
   }
 }
 
@@ -146,6 +180,56 @@ size_t reid_knn_exact_scratch_bytes(int64_t N, int64_t n_rows) {
   return (size_t)N * (size_t)n_rows * sizeof(float);
 }
 
+static int knn_exact_impl(const float* x, int64_t N, int64_t D, const int32_t* rows_list, int64_t row_begin,
+                          int64_t n_rows, int k, int32_t* out_idx, float* out_key, const double* half_sqnorm, float* keys,
+                          int64_t chunk, cudaStream_t st) {
+  using namespace reid;
+  for (int64_t s = 0; s < n_rows; s += chunk) {
+    int64_t m = n_rows - s < chunk ? n_rows - s : chunk;
+    dim3 grid((unsigned)((N + TN - 1) / TN), (unsigned)((m + TM - 1) / TM));
+    dot64_tile_kernel<<<grid, 256, 0, st>>>(x, N, D, rows_list ? rows_list + s : nullptr, row_begin + s, m, half_sqnorm,
+                                           keys);
+    REID_LAUNCH_CHECK();
+    select_topk_kernel<false><<<(unsigned)m, kSelThreads, 0, st>>>(keys, N, k, out_idx + s * k,
+                                                           out_key ? out_key + s * k : nullptr);
+    REID_LAUNCH_CHECK();
+  }
+  return REID_OK;
+}
+
+int reid_sqnorm_range(const float* x, int64_t N, int64_t D, float* sqnorm_range, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(x && sqnorm_range && N >= 0 && D > 0, "reid_sqnorm_range: bad arguments");
+  cudaStream_t st = (cudaStream_t)stream;
+  REID_CUDA(cudaMemsetAsync(sqnorm_range, 0, sizeof(float), st));
+  REID_CUDA(cudaMemsetAsync(sqnorm_range + 1, 0x7f, sizeof(float), st));
+  if (N == 0) return REID_OK;
+  sqnorm_range_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(x, N, D, sqnorm_range);
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+
+int reid_knn_exact_l2(const float* x, int64_t N, int64_t D, const int32_t* rows_list, int64_t row_begin,
+                      int64_t n_rows, int k, int32_t* out_idx, float* out_key, void* scratch, size_t scratch_bytes,
+                      void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(x && out_idx && scratch, "reid_knn_exact_l2: NULL pointer");
+  REID_CHECK_ARG(N > 0 && D > 0 && n_rows >= 0, "reid_knn_exact_l2: bad shape N=%lld D=%lld", (long long)N, (long long)D);
+  REID_CHECK_ARG(k >= 1 && k <= kMaxK && k <= N, "reid_knn_exact_l2: k=%d out of range (1..min(%d,N))", k, kMaxK);
+  REID_CHECK_ARG(N < (1ll << 31), "reid_knn_exact_l2: N too large for int32 indices");
+  const size_t head = ((size_t)N * sizeof(double) + 255) / 256 * 256;      // fp64 half norms, then the key rows
+  REID_CHECK_ARG(scratch_bytes > head && (scratch_bytes - head) / (sizeof(float) * (size_t)N) >= 1,
+                 "reid_knn_exact_l2: scratch too small (%zu bytes, need >= %zu)", scratch_bytes,
+                 head + (size_t)N * sizeof(float));
+  const int64_t chunk = (int64_t)((scratch_bytes - head) / (sizeof(float) * (size_t)N));
+  cudaStream_t st = (cudaStream_t)stream;
+  double* hn = (double*)scratch;
+  half_sqnorm64_kernel<<<(unsigned)((N + 7) / 8), 256, 0, st>>>(x, N, D, hn);
+  REID_LAUNCH_CHECK();
+  return knn_exact_impl(x, N, D, rows_list, row_begin, n_rows, k, out_idx, out_key, hn, (float*)((unsigned char*)scratch + head),
+                        chunk, st);
+}
+
 int reid_knn_exact(const float* x, int64_t N, int64_t D, const int32_t* rows_list, int64_t row_begin,
                    int64_t n_rows, int k, int32_t* out_idx, float* out_key, void* scratch, size_t scratch_bytes,
                    void* stream) {
@@ -157,18 +241,8 @@ int reid_knn_exact(const float* x, int64_t N, int64_t D, const int32_t* rows_lis
   int64_t chunk = (int64_t)(scratch_bytes / (sizeof(float) * (size_t)N));
   REID_CHECK_ARG(chunk >= 1, "reid_knn_exact: scratch too small (%zu bytes, need >= %zu)", scratch_bytes,
                  (size_t)N * sizeof(float));
-  cudaStream_t st = (cudaStream_t)stream;
-  float* keys = (float*)scratch;
-  for (int64_t s = 0; s < n_rows; s += chunk) {
-    int64_t m = n_rows - s < chunk ? n_rows - s : chunk;
-    dim3 grid((unsigned)((N + TN - 1) / TN), (unsigned)((m + TM - 1) / TM));
-    dot64_tile_kernel<<<grid, 256, 0, st>>>(x, N, D, rows_list ? rows_list + s : nullptr, row_begin + s, m, keys);
-    REID_LAUNCH_CHECK();
-    select_topk_kernel<false><<<(unsigned)m, kSelThreads, 0, st>>>(keys, N, k, out_idx + s * k,
-                                                           out_key ? out_key + s * k : nullptr);
-    REID_LAUNCH_CHECK();
-  }
-  return REID_OK;
+  return knn_exact_impl(x, N, D, rows_list, row_begin, n_rows, k, out_idx, out_key, nullptr, (float*)scratch, chunk,
+                        (cudaStream_t)stream);
 }
 
 int reid_select_rows(const float* keys, int64_t N, int64_t n_rows, int k, int ascending, int32_t* out_idx, float* out_key,

@@ -496,7 +496,8 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
                : "d"(a), "d"(b));
 }
 
-__global__ void __launch_bounds__(kMThreads) rescore_mma_kernel(
+template <int kUnroll, int kMinBlocks>
+__global__ void __launch_bounds__(kMThreads, kMinBlocks) rescore_mma_kernel(
     const float* __restrict__ x, int64_t D, int64_t row_begin, int64_t n_rows, const int32_t* __restrict__ perm,
     const int32_t* __restrict__ win_cnt, const int32_t* __restrict__ win_idx, const float* __restrict__ win_a, int k,
     float eps_in, const float* __restrict__ max_sqnorm, int32_t* __restrict__ out_idx, float* __restrict__ out_key,
@@ -574,7 +575,7 @@ __global__ void __launch_bounds__(kMThreads) rescore_mma_kernel(
     double acc[kMTiles][2];
 #pragma unroll
     for (int t = 0; t < kMTiles; ++t) acc[t][0] = acc[t][1] = 0.0;
-#pragma unroll 2
+#pragma unroll kUnroll
     for (int kb = 0; kb < n_blocks; ++kb) {
       const float4 a = qp[kb * 4];
       float4 b[kMTiles];
@@ -747,11 +748,21 @@ int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, in
                                                            (unsigned long long*)uncertified_count)
   const bool aligned = (((uintptr_t)x) & 15) == 0;
   static const bool no_group = dev_env("REID_RESCORE_GROUP", 1) == 0;
-  static const int rescore_variant = dev_env("REID_RESCORE_VARIANT", 2);   // developer builds: 1 = CUDA-core grouped kernel
-  if (aligned && D % 64 == 0 && !no_group && rescore_variant == 2) {
-    rescore_mma_kernel<<<(unsigned)((n + kMq - 1) / kMq), kMThreads, 0, st>>>(
-        x, D, row_begin, n, locality_order ? w.perm : nullptr, w.win_cnt, w.win_idx, w.win_a, k, err_bound, max_sqnorm,
-        out_idx, out_key, uncertified_flag, (unsigned*)max_err_out, (unsigned long long*)uncertified_count);
+  const int rescore_variant = dev_env("REID_RESCORE_VARIANT", 2);   // developer builds: 1 = CUDA-core grouped kernel
+#define REID_MMA_LAUNCH(U, B)                                                                                       \
+  rescore_mma_kernel<U, B><<<(unsigned)((n + kMq - 1) / kMq), kMThreads, 0, st>>>(                                   \
+      x, D, row_begin, n, locality_order ? w.perm : nullptr, w.win_cnt, w.win_idx, w.win_a, k, err_bound, max_sqnorm, \
+      out_idx, out_key, uncertified_flag, (unsigned*)max_err_out, (unsigned long long*)uncertified_count)
+  if (aligned && D % 64 == 0 && !no_group && rescore_variant >= 2) {
+#ifdef REID_DEV
+    if (rescore_variant == 3) REID_MMA_LAUNCH(1, 4);
+    else if (rescore_variant == 4) REID_MMA_LAUNCH(1, 5);
+    else if (rescore_variant == 5) REID_MMA_LAUNCH(2, 5);
+    else if (rescore_variant == 6) REID_MMA_LAUNCH(1, 6);
+    else if (rescore_variant == 7) REID_MMA_LAUNCH(4, 3);
+    else
+#endif
+      REID_MMA_LAUNCH(2, 4);
   } else if (aligned && D % 64 == 0 && D <= 2048 && !no_group) {
     const size_t smem = rescore_group_smem(D);
     REID_CUDA(cudaFuncSetAttribute(rescore_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

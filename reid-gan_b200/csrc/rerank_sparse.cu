@@ -1,5 +1,7 @@
 // a4-a6 -- CSR kernels: Gaussian weights V, k2 query expansion V_qe and the inverted index
 // (utils/faiss_rerank.py:81-85, 89-94, 98-100).  No dense N x N matrix is ever formed.
+#include <cuda_fp16.h>
+
 #include "common.cuh"
 
 namespace reid {
@@ -19,7 +21,7 @@ __global__ void __launch_bounds__(kVWarps * 32) v_weights_kernel(
     const float* __restrict__ x, int64_t D, const int32_t* __restrict__ E_pad, int stride,
     const int64_t* __restrict__ E_ptr, int64_t row_begin, int64_t row_end, const int32_t* __restrict__ rank_local,
     const float* __restrict__ key_local, int ncols, const int32_t* __restrict__ perm, int32_t* __restrict__ E_idx,
-    float* __restrict__ V_val) {
+    float* __restrict__ V_val, int half) {
   __shared__ float s_val[kVWarps][kVMaxRow];
   const int w = threadIdx.x >> 5, lane = lane_id();
   const int64_t slot = (int64_t)blockIdx.x * kVWarps + w;
@@ -119,7 +121,11 @@ __global__ void __launch_bounds__(kVWarps * 32) v_weights_kernel(
     sum += ex;
   }
   sum = warp_sum(sum);
-  for (int e = lane; e < n; e += 32) V_val[p0 + e] = __fdiv_rn(sv[e], sum);
+  // use_float16=True (faiss_rerank.py:82-83): the fp32 softmax is stored as float16
+  for (int e = lane; e < n; e += 32) {
+    const float v = __fdiv_rn(sv[e], sum);
+    V_val[p0 + e] = half ? __half2float(__float2half_rn(v)) : v;
+  }
 }
 
 // ---------------------------------------------------------------------------------------
@@ -161,7 +167,7 @@ __global__ void __launch_bounds__(kQWarps * 32) query_expand_kernel(
     const int32_t* __restrict__ rank, int ncols, int k2, const int64_t* __restrict__ V_ptr,
     const int32_t* __restrict__ V_idx, const float* __restrict__ V_val, int cap, int64_t row_begin, int64_t row_end,
     int32_t* __restrict__ Q_cnt, int32_t* __restrict__ Q_idx, float* __restrict__ Q_val,
-    unsigned long long* __restrict__ overflow_rows) {
+    unsigned long long* __restrict__ overflow_rows, int half) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = lane_id();
   uint32_t* key = reinterpret_cast<uint32_t*>(smem_raw) + (size_t)w * cap;              // table keys, then sort keys
@@ -212,12 +218,16 @@ __global__ void __launch_bounds__(kQWarps * 32) query_expand_kernel(
     }
     return;
   }
-  // compact the occupied slots to the front (in place: the write position never passes the read position)
+  // compact the occupied slots to the front (in place: the write position never passes the read position); the mean
+  // is taken here: sum / k2 in fp32 (np.mean), stored as float16 when use_float16 -- an entry that rounds to zero is
+  // no longer a structural non-zero of V_qe (the reference's invIndex is np.where(V != 0), :98-100)
+  const float k2f = (float)k2;
   int n = 0;
   for (int base = 0; base < cap; base += 32) {
     const uint32_t c = key[base + lane];
-    const float v = val[base + lane];
-    const bool occ = c != 0xffffffffu;
+    float v = __fdiv_rn(val[base + lane], k2f);
+    if (half) v = __half2float(__float2half_rn(v));
+    const bool occ = c != 0xffffffffu && !(half && v == 0.f);
     const unsigned b = __ballot_sync(kFull, occ);
     __syncwarp();
     if (occ) {
@@ -236,11 +246,10 @@ __global__ void __launch_bounds__(kQWarps * 32) query_expand_kernel(
   }
   __syncwarp();
   warp_bitonic_sort_kv(key, val, n2);
-  const float k2f = (float)k2;
   const int64_t out = (row - row_begin) * (int64_t)cap;   // padded output: `cap` slots per row
   for (int t = lane; t < n; t += 32) {
     Q_idx[out + t] = (int32_t)key[t];
-    Q_val[out + t] = __fdiv_rn(val[t], k2f);
+    Q_val[out + t] = val[t];
   }
   if (lane == 0) Q_cnt[row - row_begin] = n;
 }
@@ -313,11 +322,17 @@ __device__ __forceinline__ int rows_owner(const int64_t* __restrict__ bounds, in
 
 __global__ void __launch_bounds__(256) rows_unpack_counts_kernel(const int32_t* __restrict__ rec, int words, int W,
                                                                  int64_t max_rows, const int64_t* __restrict__ bounds,
-                                                                 int64_t N, int32_t* __restrict__ g_cnt) {
+                                                                 int64_t N, int32_t* __restrict__ g_cnt, int stride,
+                                                                 unsigned long long* __restrict__ overflow_rows) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   if (i >= N) return;
   const int r = rows_owner(bounds, W, i);
-  g_cnt[i] = rec[((int64_t)r * max_rows + (i - bounds[r])) * words];
+  int c = rec[((int64_t)r * max_rows + (i - bounds[r])) * words];
+  if (overflow_rows && c > stride) {      // a caller that does not read sizes back: keep what travelled, report the row
+    atomicAdd(overflow_rows, 1ull);
+    c = stride;
+  }
+  g_cnt[i] = c;
 }
 
 __global__ void __launch_bounds__(256) rows_unpack_fill_kernel(const int32_t* __restrict__ rec, int words, int stride,
@@ -495,7 +510,7 @@ extern "C" {
 
 int reid_v_weights(const float* x, int64_t N, int64_t D, const int32_t* E_pad, int stride, const int64_t* E_ptr,
                    int64_t row_begin, int64_t row_end, const int32_t* rank_local, const float* rank_key_local,
-                   int ncols, const int32_t* visit_order, int32_t* E_idx, float* V_val, void* stream) {
+                   int ncols, const int32_t* visit_order, int32_t* E_idx, float* V_val, int half_precision, void* stream) {
   using namespace reid;
   REID_CHECK_ARG(x && E_pad && E_ptr && E_idx && V_val, "reid_v_weights: NULL pointer");
   REID_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= N && D > 0 && stride >= 1,
@@ -506,7 +521,8 @@ int reid_v_weights(const float* x, int64_t N, int64_t D, const int32_t* E_pad, i
   if (n == 0) return REID_OK;
 #define REID_V_LAUNCH(CH)                                                                                          \
   v_weights_kernel<CH><<<(unsigned)((n + kVWarps - 1) / kVWarps), kVWarps * 32, 0, (cudaStream_t)stream>>>(          \
-      x, D, E_pad, stride, E_ptr, row_begin, row_end, rank_local, rank_key_local, ncols, visit_order, E_idx, V_val)
+      x, D, E_pad, stride, E_ptr, row_begin, row_end, rank_local, rank_key_local, ncols, visit_order, E_idx, V_val,   \
+      half_precision)
   const bool aligned = (((uintptr_t)x) & 15) == 0;
   if (aligned && D == 2048) REID_V_LAUNCH(16);
   else if (aligned && D == 1024) REID_V_LAUNCH(8);
@@ -526,7 +542,7 @@ int reid_query_expand_stride(int k2, int max_row_nnz) {
 
 int reid_query_expand(const int32_t* rank, int64_t N, int ncols, int k2, const int64_t* V_ptr, const int32_t* V_idx,
                       const float* V_val, int max_row_nnz, int64_t row_begin, int64_t row_end, int32_t* Q_cnt,
-                      int32_t* Q_pad_idx, float* Q_pad_val, uint64_t* overflow_rows, void* stream) {
+                      int32_t* Q_pad_idx, float* Q_pad_val, uint64_t* overflow_rows, int half_precision, void* stream) {
   using namespace reid;
   REID_CHECK_ARG(rank && V_ptr && V_idx && V_val && Q_cnt && Q_pad_idx && Q_pad_val, "reid_query_expand: NULL pointer");
   REID_CHECK_ARG(k2 >= 1 && k2 <= ncols && ncols <= REID_MAX_K1, "reid_query_expand: k2=%d ncols=%d", k2, ncols);
@@ -546,7 +562,7 @@ int reid_query_expand(const int32_t* rank, int64_t N, int ncols, int k2, const i
   REID_CUDA(cudaFuncSetAttribute(query_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
   query_expand_kernel<<<grid, warps * 32, smem, (cudaStream_t)stream>>>(
       rank, ncols, k2, V_ptr, V_idx, V_val, cap, row_begin, row_end, Q_cnt, Q_pad_idx, Q_pad_val,
-      (unsigned long long*)overflow_rows);
+      (unsigned long long*)overflow_rows, half_precision);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
@@ -588,13 +604,14 @@ int reid_rows_pack(const int32_t* cnt, const int64_t* ptr, const int32_t* idx, c
 }
 
 int reid_rows_unpack_counts(const int32_t* rec, int stride, int has_val, int world, int64_t max_rows, const int64_t* bounds,
-                            int64_t N, int32_t* g_cnt, void* stream) {
+                            int64_t N, int32_t* g_cnt, uint64_t* overflow_rows, void* stream) {
   using namespace reid;
   REID_CHECK_ARG(rec && bounds && g_cnt && stride >= 1 && world >= 1 && max_rows >= 0 && N >= 0, "reid_rows_unpack_counts: bad arguments");
   if (N == 0) return REID_OK;
   const int words = 1 + stride * (has_val ? 2 : 1);
   rows_unpack_counts_kernel<<<(unsigned)((N + 255) / 256), 256, 0, (cudaStream_t)stream>>>(rec, words, world, max_rows, bounds,
-                                                                                         N, g_cnt);
+                                                                                         N, g_cnt, stride,
+                                                                                         (unsigned long long*)overflow_rows);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

@@ -366,7 +366,10 @@ __global__ void __launch_bounds__(256) to_half_kernel(const float* __restrict__ 
     xh[row * D + d] = __float2half_rn(v * scale);
   }
   ss = warp_sum(ss);
-  if (lane_id() == 0 && max_sqnorm) atomicMax((unsigned*)max_sqnorm, __float_as_uint(ss));
+  if (lane_id() == 0 && max_sqnorm) {                    // sqnorm_range[0] = max, [1] = min (non-negative floats order like
+    atomicMax((unsigned*)max_sqnorm, __float_as_uint(ss));        // their bit patterns)
+    atomicMin((unsigned*)max_sqnorm + 1, __float_as_uint(ss));
+  }
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -446,13 +449,24 @@ int reid_features_to_half_acc(const float* x, int64_t n_rows, int64_t D, int sca
   return REID_OK;
 }
 
+int reid_sqnorm_range_reset(float* sqnorm_range, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(sqnorm_range, "reid_sqnorm_range_reset: NULL pointer");
+  REID_CUDA(cudaMemsetAsync(sqnorm_range, 0, sizeof(float), (cudaStream_t)stream));
+  REID_CUDA(cudaMemsetAsync(sqnorm_range + 1, 0x7f, sizeof(float), (cudaStream_t)stream));
+  return REID_OK;
+}
+
 int reid_features_to_half(const float* x, int64_t n_rows, int64_t D, int scale_log2, void* xh, float* max_sqnorm_out,
                           void* stream) {
   using namespace reid;
   REID_CHECK_ARG(x && xh && n_rows >= 0 && D > 0, "reid_features_to_half: bad arguments");
   REID_CHECK_ARG(scale_log2 >= -8 && scale_log2 <= 12, "reid_features_to_half: scale_log2=%d out of range", scale_log2);
   cudaStream_t st = (cudaStream_t)stream;
-  if (max_sqnorm_out) REID_CUDA(cudaMemsetAsync(max_sqnorm_out, 0, sizeof(float), st));
+  if (max_sqnorm_out) {                                  // [0] = 0, [1] = 0x7f7f7f7f (3.4e38): identities of max / min
+    REID_CUDA(cudaMemsetAsync(max_sqnorm_out, 0, sizeof(float), st));
+    REID_CUDA(cudaMemsetAsync(max_sqnorm_out + 1, 0x7f, sizeof(float), st));
+  }
   if (n_rows == 0) return REID_OK;
   tc::to_half_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(x, n_rows, D, ldexpf(1.0f, scale_log2), (__half*)xh,
                                                                   max_sqnorm_out);

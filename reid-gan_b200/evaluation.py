@@ -90,10 +90,65 @@ def mean_ap(distmat, query_ids=None, gallery_ids=None, query_cams=None, gallery_
 def cmc(distmat, query_ids=None, gallery_ids=None, query_cams=None, gallery_cams=None, topk=100,
         separate_camera_set=False, single_gallery_shot=False, first_match_break=False):
     if single_gallery_shot:
-        raise NotImplementedError("single_gallery_shot samples gallery items with np.random (ranking.py:10-16, 53-66)")
+        return _cmc_single_gallery_shot(distmat, query_ids, gallery_ids, query_cams, gallery_cams, topk,
+                                        separate_camera_set, first_match_break)
     _, has, ret = _rank_metrics(distmat, query_ids, gallery_ids, query_cams, gallery_cams, separate_camera_set, topk,
                                 first_match_break)
     num_valid_queries = int((has > 0).sum())
+    if num_valid_queries == 0:
+        raise RuntimeError("No valid query")
+    return ret.cumsum() / num_valid_queries
+
+
+def _cmc_single_gallery_shot(distmat, query_ids, gallery_ids, query_cams, gallery_cams, topk, separate_camera_set,
+                             first_match_break):
+    """ranking.py:53-66: per valid query, 10 times, ONE gallery instance per identity is drawn with np.random.choice
+    (ranking.py:10-16) and the CMC contribution is computed on that subset.  The draws consume the process-wide
+    np.random state in a fixed protocol -- query ascending, repeat, identities in order of first appearance in the
+    ranking -- so this option is a host-side twin by definition: same seed, same draws, same result as the
+    reference.  Only the ranking itself comes from the device (rows sorted by distance, ties by gallery index; the
+    reference's np.argsort leaves ties unordered)."""
+    from collections import defaultdict
+    dev = _device_of(distmat if isinstance(distmat, torch.Tensor) else None)
+    with torch.cuda.device(dev), torch.no_grad():
+        d = torch.as_tensor(distmat if isinstance(distmat, torch.Tensor) else np.ascontiguousarray(distmat))
+        d = d.to(dev, torch.float32)
+        m, n = d.shape
+        indices = torch.sort(d, dim=1, stable=True).indices.cpu().numpy()
+    query_ids = np.arange(m) if query_ids is None else np.asarray(query_ids)
+    gallery_ids = np.arange(n) if gallery_ids is None else np.asarray(gallery_ids)
+    query_cams = np.zeros(m).astype(np.int32) if query_cams is None else np.asarray(query_cams)
+    gallery_cams = np.ones(n).astype(np.int32) if gallery_cams is None else np.asarray(gallery_cams)
+    matches = (gallery_ids[indices] == query_ids[:, np.newaxis])
+    ret = np.zeros(topk)
+    num_valid_queries = 0
+    repeat = 10
+    for i in range(m):
+        valid = ((gallery_ids[indices[i]] != query_ids[i]) | (gallery_cams[indices[i]] != query_cams[i]))
+        if separate_camera_set:
+            valid &= (gallery_cams[indices[i]] != query_cams[i])
+        if not np.any(matches[i, valid]):
+            continue
+        gids = gallery_ids[indices[i][valid]]
+        inds = np.where(valid)[0]
+        ids_dict = defaultdict(list)
+        for j, x in zip(inds, gids):
+            ids_dict[x].append(j)
+        for _ in range(repeat):
+            mask = np.zeros(len(valid), dtype=bool)
+            for _, idx_list in ids_dict.items():
+                mask[np.random.choice(idx_list)] = True
+            sampled = valid & mask
+            index = np.nonzero(matches[i, sampled])[0]
+            delta = 1. / (len(index) * repeat)
+            for j, k in enumerate(index):
+                if k - j >= topk:
+                    break
+                if first_match_break:
+                    ret[k - j] += 1
+                    break
+                ret[k - j] += delta
+        num_valid_queries += 1
     if num_valid_queries == 0:
         raise RuntimeError("No valid query")
     return ret.cumsum() / num_valid_queries

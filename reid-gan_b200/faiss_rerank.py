@@ -67,7 +67,10 @@ _nbr_cap_hint = {}           # N -> slot total of the last finished pass (the ne
 # report (int64 x 16): [0:3] |E| total/max/sumsq  [3:6] nnz(V_qe) rows  [6:9] column counts: nnz, longest, sum len^2
 #                      [9] uncertified kNN rows  [10] V_qe rows that overflowed the table  [11] rows that overflowed
 #                      their eps-neighbour slots  [12:15] slot total/max/sumsq
-R_E, R_Q, R_C, R_UNCERT, R_QE_OVF, R_NBR_OVF, R_S = 0, 3, 6, 9, 10, 11, 12
+#                      [15] rows that did not fit a fixed-stride exchange record (row-sharded pass)
+R_E, R_Q, R_C, R_UNCERT, R_QE_OVF, R_NBR_OVF, R_S, R_XCHG_OVF = 0, 3, 6, 9, 10, 11, 12, 15
+REC_STRIDE = {"V": 64, "Q": 128, "nbr": 128}     # exchange record strides of the row-sharded pass (entries per row)
+_rec_stride_hint = {}        # (kind, N) -> longest row of the last finished pass
 
 
 class RerankState:
@@ -93,12 +96,20 @@ class RerankState:
         check_nbr: also require that no row overflowed its eps-neighbour slots (-> (state, nbr_ok))."""
         if self.report is None:
             return (self, True) if check_nbr else self
+        if getattr(self, "_comm", None) is not None:
+            # every rank must take the same decision: the flags of the own rows are maximised over the ranks first
+            import torch.distributed as dist
+            dist.all_reduce(self.report, op=dist.ReduceOp.MAX, group=self._comm.group)
         vals = [int(v) for v in self.report.tolist()]
         self.report, self.report_vals = None, vals
+        if getattr(self, "_check_norms", False) and not _one_norm_info(self.knn_info):
+            st = self._redo("l2")
+            self._redo = None
+            return (st, False) if check_nbr else st
         self.knn_info["uncertified_rows"] = vals[R_UNCERT]
         if vals[R_E + 1] > self.e_stride:
             raise RuntimeError("reid_expand: an expansion set exceeded %d entries" % self.e_stride)
-        ok = vals[R_UNCERT] == 0 and vals[R_QE_OVF] == 0
+        ok = vals[R_UNCERT] == 0 and vals[R_QE_OVF] == 0 and vals[R_XCHG_OVF] == 0
         if ok:
             self.e_total, self.e_max = vals[R_E], vals[R_E + 1]
             self.q_total, self.c_max, self.t_total_all = vals[R_C], vals[R_C + 1], vals[R_C + 2]
@@ -111,12 +122,17 @@ class RerankState:
         return (st, False) if check_nbr else st
 
 
-def knn_search(x, k, mode="auto", rows=None, defer=False, uncert_count=None):
+def knn_search(x, k, mode="auto", rows=None, defer=False, uncert_count=None, metric="auto"):
     """a1: exact top-k neighbour lists (faiss_rerank.py:58-62).  Returns (idx int32, key fp32, info).
     mode "exact": CUDA-core fp64 search for every row; "tc": tensor-core candidates + exact
     re-score + certificate, uncertified rows redone exactly; "auto": "tc" when the shape allows.
-    defer: do not read the certificate flags back (info["pending"] holds them and the repair closure);
-    uncert_count: device scalar that receives the number of uncertified rows."""
+    metric: the reference searches by squared L2 (IndexFlatL2).  "auto" = inner-product key when all rows have one norm
+    (then both orders agree; the backbone L2-normalises, models/resnet.py:90-94), squared-L2 key otherwise; "ip" / "l2"
+    force one (get_dist_nbr's IndexFlatIP is "ip").  info["metric"] tells which key `key` holds.
+    defer: do not read anything back: info["pending"] holds the certificate flags and the repair closure,
+    info["max_sqnorm"] the {max, min} squared norms the caller must check (knn_tc.one_norm); uncert_count: device
+    scalar that receives the number of uncertified rows."""
+    from .knn_tc import one_norm
     L = _lib.lib()
     N, D = x.shape
     dev = x.device
@@ -127,29 +143,46 @@ def knn_search(x, k, mode="auto", rows=None, defer=False, uncert_count=None):
     n = r1 - r0
     idx = torch.empty((n, k), dtype=torch.int32, device=dev)
     key = torch.empty((n, k), dtype=torch.float32, device=dev)
-    info = {"mode": mode, "uncertified_rows": 0}
+    info = {"mode": mode, "uncertified_rows": 0, "metric": "ip"}
+    if metric not in ("auto", "ip", "l2"):
+        raise ValueError("unknown metric %r" % (metric,))
     if mode == "auto":
-        mode = "tc" if (TC_AVAILABLE and D % 64 == 0 and N >= 256 and k <= 64) else "exact"
+        mode = "tc" if (TC_AVAILABLE and D % 64 == 0 and N >= 256 and k <= 64 and metric != "l2") else "exact"
         info["mode"] = mode
     if mode == "tc":
+        if metric == "l2":
+            raise ValueError("the tensor-core search ranks by inner product; metric='l2' needs mode 'exact'")
         from .knn_tc import knn_search_tc
-        return knn_search_tc(x, k, r0, r1, idx, key, info, defer=defer, uncert_count=uncert_count)
+        idx, key, info = knn_search_tc(x, k, r0, r1, idx, key, info, defer=defer, uncert_count=uncert_count)
+        info["metric"] = "ip"
+        if metric == "auto" and not defer and not one_norm(info["max_sqnorm"].tolist()):
+            _knn_exact_rows(x, k, None, r0, n, idx, key, metric="l2")      # rows of different norms: squared-L2 key
+            info.update(mode="exact-l2", metric="l2", visit_order=None, uncertified_rows=0)
+        return idx, key, info
     if mode != "exact":
         raise ValueError("unknown kNN mode %r" % (mode,))
-    _knn_exact_rows(x, k, None, r0, n, idx, key)
+    if metric == "auto":
+        rng = torch.empty(2, dtype=torch.float32, device=dev)
+        call("reid_sqnorm_range", ptr(x), N, D, ptr(rng), stream_ptr())
+        metric = "ip" if one_norm(rng.tolist()) else "l2"
+    _knn_exact_rows(x, k, None, r0, n, idx, key, metric=metric)
+    info["metric"] = metric
+    if metric == "l2":
+        info["mode"] = "exact-l2"
     return idx, key, info
 
 
-def _knn_exact_rows(x, k, rows_list, row_begin, n_rows, idx_out, key_out):
+def _knn_exact_rows(x, k, rows_list, row_begin, n_rows, idx_out, key_out, metric="ip"):
     L = _lib.lib()
     N, D = x.shape
     if n_rows == 0:
         return
     budget = 1 << 30                                        # ~1 GiB of key rows per pass
     chunk = max(1, min(n_rows, budget // (4 * N)))
-    scratch = torch.empty(chunk * N, dtype=torch.float32, device=x.device)
-    call("reid_knn_exact", ptr(x), N, D, ptr(rows_list), row_begin, n_rows, k, ptr(idx_out), ptr(key_out),
-                           ptr(scratch), scratch.numel() * 4, stream_ptr())
+    head = (N * 8 + 255) // 256 * 256 if metric == "l2" else 0
+    scratch = torch.empty(head + chunk * N * 4, dtype=torch.uint8, device=x.device)
+    call("reid_knn_exact_l2" if metric == "l2" else "reid_knn_exact", ptr(x), N, D, ptr(rows_list), row_begin, n_rows, k,
+         ptr(idx_out), ptr(key_out), ptr(scratch), scratch.numel(), stream_ptr())
 
 
 def _check_shape(x, k1, k2):
@@ -162,7 +195,8 @@ def _check_shape(x, k1, k2):
         raise ValueError("k2=%d must be in 1..k1" % k2)
 
 
-def rerank_state_async(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_result=None, speculative=None):
+def rerank_state_async(x, k1, k2, knn="auto", rows=None, timers=False, comm=None, knn_result=None, speculative=None,
+                       metric="auto", half=False, report=None):
     """Run a1-a6 on device.  Single GPU: all rows.  Row-sharded (comm = sharded.RowComm): this rank
     computes rows [comm.r0, comm.r1) of every per-row stage and the stages' outputs are all-gathered
     (neighbour lists, V rows, V_qe rows), so the returned state always holds GLOBAL rank / V / V_qe /
@@ -183,11 +217,14 @@ def rerank_state_async(x, k1, k2, knn="auto", rows=None, timers=False, comm=None
     n = r1 - r0
     full = comm is None and r0 == 0 and r1 == N
     if speculative is None:
-        speculative = full
-    if speculative and not full:
-        raise ValueError("the speculative pass covers all rows of one GPU")
+        speculative = full or (comm is not None and knn_result not in (None, "upload") and x.is_cuda)
+    if speculative and not (full or comm is not None):
+        raise ValueError("the speculative pass covers all rows of one GPU, or a communicator's row shard")
     st = RerankState()
+    st._comm = comm
     st.N, st.D, st.k1, st.k2, st.row_begin, st.row_end = N, D, k1, k2, r0, r1
+    st.half = bool(half)                                      # use_float16=True: fp16 roundings of V, V_qe, sums, J
+    hp = 1 if half else 0
     sp = stream_ptr()
     ev = []
 
@@ -197,7 +234,9 @@ def rerank_state_async(x, k1, k2, knn="auto", rows=None, timers=False, comm=None
             e.record()
             ev.append((name, e))
 
-    report = torch.zeros(16, dtype=torch.int64, device=dev)
+    external_knn = knn_result not in (None, "upload")
+    if report is None:                                        # else: shared with the caller's search (sharded.py)
+        report = torch.zeros(16, dtype=torch.int64, device=dev)
     mark("start")
     # a1 ------------------------------------------------------------------
     if knn_result == "upload":                               # x is still on the host: search while it is uploaded
@@ -211,7 +250,7 @@ def rerank_state_async(x, k1, k2, knn="auto", rows=None, timers=False, comm=None
         # unsharded: the certificate flags are not read back here -- their count rides on the pass report (or, in
         # the exact-size flavour, on the first unavoidable read-back); the rare uncertified rows are then repaired
         rank_local, key_local, info = knn_search(x, k1, knn, rows=(r0, r1), defer=comm is None,
-                                                 uncert_count=report[R_UNCERT:])
+                                                 uncert_count=report[R_UNCERT:], metric=metric)
     st.knn_info = info
     st.x = x
     if knn_result is not None:
@@ -247,6 +286,9 @@ def rerank_state_async(x, k1, k2, knn="auto", rows=None, timers=False, comm=None
         e_cap = max(n, 1) * e_stride                          # upper bound: no size needed on the host
     else:
         vals = report.tolist()                                # read-back 1 of 2: |E| sizes + certificate count
+        if pending is not None and metric == "auto" and not _one_norm_info(info):
+            # rows of different norms: the reference's L2 order is not the inner-product order that was searched
+            return rerank_state_async(x, k1, k2, knn="exact", timers=timers, speculative=False, metric="l2", half=half)
         if pending is not None and vals[R_UNCERT]:            # uncertified rows: exact search for them, then redo a2/a3
             pending["repair"]()
             info["visit_order"] = None                        # only valid for the lists it was built from
@@ -265,11 +307,18 @@ def rerank_state_async(x, k1, k2, knn="auto", rows=None, timers=False, comm=None
     order = info.get("visit_order") if knn_result is None else None
     if order is not None and order.numel() != n:
         order = None                                          # only valid for exactly these rows
-    call("reid_v_weights", ptr(x), N, D, ptr(e_pad), e_stride, ptr(e_ptr), r0, r1, ptr(rank_local), ptr(key_local),
-         k1, ptr(order), ptr(e_idx), ptr(v_val), sp)
+    # members that are among the row's k1 neighbours re-use the search key -- when that key IS the dot product
+    reuse = info.get("metric", "ip") == "ip"
+    call("reid_v_weights", ptr(x), N, D, ptr(e_pad), e_stride, ptr(e_ptr), r0, r1, ptr(rank_local) if reuse else None,
+         ptr(key_local) if reuse else None, k1, ptr(order), ptr(e_idx), ptr(v_val), hp, sp)
     mark("v_weights")
-    if comm is not None:                                     # V rows of other shards are read by a5
+    if comm is not None and speculative:                     # V rows of other shards are read by a5
+        sv = _stride_for("V", N)
+        e_ptr, e_idx, v_val = comm.gather_records(e_cnt[:n], e_ptr, e_idx, v_val, sv, overflow=report[R_XCHG_OVF:],
+                                                  stats_out=report[R_E:R_E + 3])[:3]
+    elif comm is not None:
         e_ptr, e_idx, v_val, e_total, e_max = comm.gather_csr(e_cnt[:n], e_idx[:e_total], v_val[:e_total], row_ptr=e_ptr)
+        _rec_stride_hint[("V", N)] = max(_rec_stride_hint.get(("V", N), 0), int(e_max))
     elif not full:                                           # a row shard without a communicator (tests): a5 cannot run
         st.E_ptr, st.E_idx, st.V_val, st.e_total, st.e_max = e_ptr, e_idx, v_val, e_total, e_max
         return st
@@ -287,11 +336,11 @@ def rerank_state_async(x, k1, k2, knn="auto", rows=None, timers=False, comm=None
         qp_idx = torch.empty(max(n, 1) * q_stride, dtype=torch.int32, device=dev)
         qp_val = torch.empty(max(n, 1) * q_stride, dtype=torch.float32, device=dev)
         call("reid_query_expand", ptr(rank), N, k1, k2, ptr(e_ptr), ptr(e_idx), ptr(v_val), nnz_guess, r0, r1,
-             ptr(q_cnt), ptr(qp_idx), ptr(qp_val), ptr(report[R_QE_OVF:]), sp)
-        if comm is None:
-            # unsharded: no read-back here -- the CSR is compacted into upper-bound storage and nnz stays on the
-            # device (the exact-size flavour reads it with the inverted index's sizes: one read-back for a5 + a6)
-            q_ptr, q_stats = _scan_async(q_cnt, n, dev, stats=report[R_Q:R_Q + 3])
+             ptr(q_cnt), ptr(qp_idx), ptr(qp_val), ptr(report[R_QE_OVF:]), hp, sp)
+        if comm is None or speculative:
+            # no read-back here -- the CSR is compacted into upper-bound storage and nnz stays on the device (the
+            # exact-size flavour reads it with the inverted index's sizes: one read-back for a5 + a6)
+            q_ptr, q_stats = _scan_async(q_cnt, n, dev, stats=report[R_Q:R_Q + 3] if comm is None else None)
             q_idx = torch.empty(max(n, 1) * q_stride, dtype=torch.int32, device=dev)
             q_val = torch.empty(max(n, 1) * q_stride, dtype=torch.float32, device=dev)
             q_total = None
@@ -300,8 +349,13 @@ def rerank_state_async(x, k1, k2, knn="auto", rows=None, timers=False, comm=None
             q_idx = torch.empty(max(q_total, 1), dtype=torch.int32, device=dev)
             q_val = torch.empty(max(q_total, 1), dtype=torch.float32, device=dev)
         call("reid_csr_compact", ptr(qp_idx), ptr(qp_val), q_stride, ptr(q_cnt), ptr(q_ptr), n, ptr(q_idx), ptr(q_val), sp)
-        if comm is not None:
-            q_ptr, q_idx, q_val, q_total, _ = comm.gather_csr(q_cnt[:n], q_idx[:q_total], q_val[:q_total], row_ptr=q_ptr)
+        if comm is not None and speculative:
+            sq = _stride_for("Q", N)
+            q_ptr, q_idx, q_val = comm.gather_records(q_cnt[:n], q_ptr, q_idx, q_val, sq, overflow=report[R_XCHG_OVF:],
+                                                      stats_out=report[R_Q:R_Q + 3])[:3]
+        elif comm is not None:
+            q_ptr, q_idx, q_val, q_total, q_mx = comm.gather_csr(q_cnt[:n], q_idx[:q_total], q_val[:q_total], row_ptr=q_ptr)
+            _rec_stride_hint[("Q", N)] = max(_rec_stride_hint.get(("Q", N), 0), int(q_mx))
     else:                                                    # faiss_rerank.py:89: skipped when k2 == 1
         q_ptr, q_idx, q_val, q_total = e_ptr, e_idx, v_val, e_total
     st.Q_ptr, st.Q_idx, st.Q_val = q_ptr, q_idx, q_val        # global CSR (N + 1)
@@ -309,7 +363,7 @@ def rerank_state_async(x, k1, k2, knn="auto", rows=None, timers=False, comm=None
     # a6 (replicated on every rank: it needs every row of V_qe and is tiny) ---------------------
     c_cnt = torch.empty(N, dtype=torch.int32, device=dev)
     if q_total is None:
-        call("reid_transpose_count", ptr(q_idx), q_idx.numel(), ptr(q_ptr[n:]), N, ptr(c_cnt), sp)
+        call("reid_transpose_count", ptr(q_idx), q_idx.numel(), ptr(q_ptr[q_ptr.numel() - 1:]), N, ptr(c_cnt), sp)
     else:
         call("reid_transpose_count", ptr(q_idx), q_total, None, N, ptr(c_cnt), sp)
     c_ptr, c_stats = _scan_async(c_cnt, N, dev, stats=report[R_C:R_C + 3])
@@ -328,15 +382,22 @@ def rerank_state_async(x, k1, k2, knn="auto", rows=None, timers=False, comm=None
     if speculative:
         st.report = report
 
+        st._check_norms = (pending is not None or info.get("max_sqnorm") is not None) and metric == "auto" \
+            and info.get("metric", "ip") == "ip"
+
         def redo(vals):
             # a guess did not hold (or rows were uncertified): exact sizes, read back where they are needed
+            if comm is not None or external_knn:              # the search ran elsewhere (sharded.py): the caller redoes the
+                return None                                   # whole pass, search included, with sizes read back
+            if vals == "l2":                                  # rows of different norms: search again with the L2 key
+                return rerank_state_async(x, k1, k2, knn="exact", timers=timers, speculative=False, metric="l2", half=half)
             if vals[R_UNCERT] and pending is not None:
                 pending["repair"]()
                 info["visit_order"] = None
             info["uncertified_rows"] = int(vals[R_UNCERT])
             info["speculation_failed"] = dict(uncertified=int(vals[R_UNCERT]), qe_overflow_rows=int(vals[R_QE_OVF]))
             return rerank_state_async(x, k1, k2, knn=knn, timers=timers, knn_result=(rank_local, key_local, info),
-                                      speculative=False)
+                                      speculative=False, half=half)
 
         st._redo = redo
     if timers:
@@ -350,6 +411,18 @@ def rerank_state(x, k1, k2, **kw):
     """a1-a6 on device, finished: `rerank_state_async(...).finish()` (the pass itself does not synchronise; finish()
     reads its report once and redoes the pass with exact sizes in the rare case a guessed size did not hold)."""
     return rerank_state_async(x, k1, k2, **kw).finish()
+
+
+def _stride_for(kind, N):
+    """Record stride of a row-sharded exchange: the default, or 1.25 x the longest row the last pass saw."""
+    hint = _rec_stride_hint.get((kind, N), 0)
+    return max(REC_STRIDE[kind], -(-int(hint * 1.25) // 32) * 32)
+
+
+def _one_norm_info(info):
+    from .knn_tc import one_norm
+    rng = info.get("max_sqnorm")
+    return True if rng is None else one_norm(rng.tolist())
 
 
 def rank_digest(st):
@@ -371,7 +444,7 @@ def query_expand_rows(st, row_begin, row_end):
     qp_idx = torch.empty(max(n, 1) * q_stride, dtype=torch.int32, device=dev)
     qp_val = torch.empty(max(n, 1) * q_stride, dtype=torch.float32, device=dev)
     call("reid_query_expand", ptr(st.rank), st.N, st.k1, st.k2, ptr(st.E_ptr), ptr(st.E_idx), ptr(st.V_val), max(e_max, 1),
-         row_begin, row_end, ptr(q_cnt), ptr(qp_idx), ptr(qp_val), None, sp)
+         row_begin, row_end, ptr(q_cnt), ptr(qp_idx), ptr(qp_val), None, 1 if st.half else 0, sp)
     q_ptr, q_total, _ = _scan(q_cnt, n, dev)
     q_idx = torch.empty(max(q_total, 1), dtype=torch.int32, device=dev)
     q_val = torch.empty(max(q_total, 1), dtype=torch.float32, device=dev)
@@ -409,7 +482,7 @@ def jaccard_neighbors(st, eps, with_values=False, speculative=None):
         nbr_cnt = torch.empty(n, dtype=torch.int32, device=dev)
         call("reid_jaccard_eps_graph", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
              ptr(st.C_val), st.N, r0, r1, eps32, ptr(t_cnt), ptr(slot_ptr), ptr(nbr_idx), ptr(nbr_val), ptr(nbr_cnt),
-             cap, ptr(report[R_NBR_OVF:]), ptr(ws), sp)
+             cap, ptr(report[R_NBR_OVF:]), 1 if st.half else 0, ptr(ws), sp)
         return slot_ptr, nbr_idx, nbr_cnt, nbr_val
     call("reid_jaccard_bounds", ptr(st.Q_ptr), ptr(st.Q_idx), None, ptr(st.C_ptr), r0, r1, eps32, ptr(t_cnt), None, sp)
     if r0 == 0 and r1 == st.N and getattr(st, "t_total_all", None) is not None:
@@ -422,7 +495,7 @@ def jaccard_neighbors(st, eps, with_values=False, speculative=None):
     nbr_cnt = torch.empty(n, dtype=torch.int32, device=dev)
     call("reid_jaccard_eps_graph", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
                                    ptr(st.C_val), st.N, r0, r1, eps32, ptr(t_cnt), ptr(slot_ptr), ptr(nbr_idx),
-                                   ptr(nbr_val), ptr(nbr_cnt), 0, None, ptr(ws), sp)
+                                   ptr(nbr_val), ptr(nbr_cnt), 0, None, 1 if st.half else 0, ptr(ws), sp)
     return slot_ptr, nbr_idx, nbr_cnt, nbr_val
 
 
@@ -430,7 +503,8 @@ def jaccard_dense_rows(st, out, row_begin, row_end):
     """a7 (dense form): rows [row_begin,row_end) of the reference's return value into `out` (device, (rows, N))."""
     L = _lib.lib()
     call("reid_jaccard_dense", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
-                               ptr(st.C_val), st.N, row_begin, row_end, ptr(out), out.stride(0), stream_ptr())
+                               ptr(st.C_val), st.N, row_begin, row_end, ptr(out), out.stride(0),
+                               1 if getattr(st, "half", False) else 0, stream_ptr())
 
 
 class JaccardDistance:
@@ -442,7 +516,8 @@ class JaccardDistance:
         self._state = state
         self._dense = None
         self.shape = (state.N, state.N)
-        self.dtype = np.dtype(np.float32)
+        # use_float16=True returns a float16 matrix (faiss_rerank.py:36,101); the device rows hold fp16-representable fp32
+        self.dtype = np.dtype(np.float16 if getattr(state, "half", False) else np.float32)
         self.ndim = 2
 
     # -- device-side consumers -------------------------------------------------
@@ -463,11 +538,11 @@ class JaccardDistance:
         if self._dense is None:
             st = self._state
             N = st.N
-            host = np.empty((N, N), dtype=np.float32)
+            host = np.empty((N, N), dtype=self.dtype)
             block = max(1, min(N, (256 << 20) // (4 * N)))
             for a in range(0, N, block):
                 b = min(N, a + block)
-                host[a:b] = self.dense_device(a, b).cpu().numpy()
+                host[a:b] = self.dense_device(a, b).cpu().numpy()      # exact: the values are float16 numbers already
             self._dense = host
         return self._dense
 
@@ -516,8 +591,6 @@ def compute_jaccard_distance(target_features, k1=20, k2=6, print_flag=True, sear
         print('Computing jaccard distance...')
     if search_option not in (0, 1, 2, 3):
         raise ValueError("search_option must be 0..3 (faiss_rerank.py:39-62), got %r" % (search_option,))
-    if use_float16:
-        raise NotImplementedError("use_float16=True (fp16 storage of V, faiss_rerank.py:37) is not implemented")
     if isinstance(target_features, np.ndarray):
         target_features = torch.from_numpy(target_features)
     if target_features.dim() != 2:
@@ -528,10 +601,10 @@ def compute_jaccard_distance(target_features, k1=20, k2=6, print_flag=True, sear
         N, D = target_features.shape
         if (not target_features.is_cuda and target_features.dtype == torch.float32 and target_features.is_contiguous()
                 and knn in ("auto", "tc") and sym_eligible(N, D, k1) and 1 <= k2 <= k1 <= N):
-            st = rerank_state(target_features, k1, k2, knn=knn, knn_result="upload")   # search overlaps the upload
+            st = rerank_state(target_features, k1, k2, knn=knn, knn_result="upload", half=bool(use_float16))   # search overlaps the upload
         else:
             x = target_features.to(device=dev, dtype=torch.float32, non_blocking=True).contiguous()
-            st = rerank_state(x, k1, k2, knn=knn)               # finish(): the one host synchronisation of the call
+            st = rerank_state(x, k1, k2, knn=knn, half=bool(use_float16))   # finish(): the one host synchronisation of the call
         out = JaccardDistance(st)
     if print_flag:
         print("Jaccard distance computing time cost: {}".format(time.time() - end))

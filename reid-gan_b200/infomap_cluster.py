@@ -26,7 +26,7 @@ def get_dist_nbr(features, k=80, knn_method='faiss-cpu', return_device=False):
         x = features.to(device=dev, dtype=torch.float32).contiguous()
         if k > x.shape[0]:
             raise ValueError("k=%d exceeds the number of samples N=%d" % (k, x.shape[0]))
-        nbrs, sims, _ = knn_search(x, k, "auto")
+        nbrs, sims, _ = knn_search(x, k, "auto", metric="ip")      # faiss.IndexFlatIP (:70-73): inner product whatever the norms
         dists = 1.0 - sims                                   # :75, fp32
         if return_device:
             return dists, nbrs

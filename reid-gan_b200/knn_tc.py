@@ -20,6 +20,25 @@ ORDER_ROWS = __import__("os").environ.get("REID_RESCORE_ORDER", "1") != "0"   # 
 SLACK = 34              # K = k + SLACK candidates are kept per (row, column range)
 
 
+UNIT_NORM_TOL = 1e-4    # rows count as "one norm" when max ||x||^2 <= (1 + tol) min ||x||^2 (see one_norm)
+
+
+def one_norm(sqnorm_range):
+    """sqnorm_range = [max ||x||^2, min ||x||^2] (reid_features_to_half).  faiss IndexFlatL2 ranks by squared L2, which
+    is the inner-product order the tensor-core search produces iff all rows have the same norm.  Rows normalised in
+    fp32 by the backbone (models/resnet.py:90-94) differ by ~1e-7 -- below what the reference's own fp32 search
+    resolves; beyond UNIT_NORM_TOL the search is redone with the squared-L2 key (reid_knn_exact_l2)."""
+    mx, mn = float(sqnorm_range[0]), float(sqnorm_range[1])
+    return mx <= mn * (1.0 + UNIT_NORM_TOL)
+
+
+def new_sqnorm_range(dev):
+    """{max, min} accumulator for reid_features_to_half_acc: identities {0, 3.4e38}."""
+    r = torch.empty(2, dtype=torch.float32, device=dev)
+    call("reid_sqnorm_range_reset", ptr(r), stream_ptr())
+    return r
+
+
 def err_bound(max_sqnorm):
     """|fp16-GEMM score - exact dot| <= 2^-10 ||x_i|| ||x_j|| (both operands rounded to 11 significant
     bits, Cauchy-Schwarz) + fp32 accumulation allowance."""
@@ -30,7 +49,20 @@ SYM = __import__("os").environ.get("REID_TC_SYM", "1") != "0"     # symmetric se
 SYM_MIN_N = 8192        # below this the sample cannot give a tight threshold; the one-sided kernel is used
 SYM_CAP = 1024          # list capacity per row in the symmetric search
 SYM_RANK = 16           # tau_i = SYM_RANK-th best sample score ...
-SYM_TARGET = 256        # ... with the sample sized so that about SYM_TARGET columns beat it
+SYM_TARGET = 256        # ... with the sample sized so that about SYM_TARGET columns beat it (k <= 32; twice that above)
+SYM_MAX_K = 64          # rank positions live in one 64-bit mask (REID_MAX_K1)
+
+
+def sym_rank(k):
+    """tau_i is the sym_rank(k)-th best of the m sample scores of row i, so about sym_rank / m * N columns beat it:
+    SYM_TARGET for k <= 32 and twice that for 32 < k <= 64 (the lists must hold the k best with room for the
+    certificate's window) -- the sample itself stays the same size."""
+    return SYM_RANK * (1 if k <= 32 else 2)
+
+
+def sample_size(N, k=30):
+    """Rows in the threshold sample (see sym_rank)."""
+    return min(N, max(1024, -(-(SYM_RANK * N // SYM_TARGET) // 256) * 256))
 _tile_cache = {}
 
 
@@ -59,19 +91,19 @@ def _sample_stride(N):
     return a
 
 
-def _candidates_sym(xh, N, D, sp, dev):
+def _candidates_sym(xh, N, D, sp, dev, k=30):
     """Prepass (sample thresholds) + symmetric main pass.  Returns (cand, cand_cnt, tau_ord, cap, stats)."""
-    m = min(N, max(1024, -(-(SYM_RANK * N // SYM_TARGET) // 256) * 256))
+    m = sample_size(N, k)
     xs = torch.empty((m, D), dtype=torch.float16, device=dev)
     call("reid_features_sample", ptr(xh), N, D, m, _sample_stride(N), ptr(xs), sp)
     cand = torch.empty(N * max(2 * TC_CAP, SYM_CAP), dtype=torch.int64, device=dev)     # prepass lists, then main lists
     pre_cnt = torch.zeros(N * 2, dtype=torch.int32, device=dev)
     pre_tau = torch.empty(N, dtype=torch.int32, device=dev)
-    call("reid_knn_candidates_tc_ab", ptr(xh), N, ptr(xs), m, D, SCALE_LOG2, 0, N, -SYM_RANK, 1, 2, ptr(cand), ptr(pre_cnt),
+    call("reid_knn_candidates_tc_ab", ptr(xh), N, ptr(xs), m, D, SCALE_LOG2, 0, N, -sym_rank(k), 1, 2, ptr(cand), ptr(pre_cnt),
          ptr(pre_tau), sp)
     tau = torch.empty(N, dtype=torch.float32, device=dev)
     tau_ord = torch.empty(N, dtype=torch.int32, device=dev)
-    call("reid_knn_sample_tau", ptr(cand), ptr(pre_cnt), ptr(pre_tau), 2, N, SYM_RANK, ptr(tau), ptr(tau_ord), sp)
+    call("reid_knn_sample_tau", ptr(cand), ptr(pre_cnt), ptr(pre_tau), 2, N, sym_rank(k), ptr(tau), ptr(tau_ord), sp)
     tiles = _tile_order((N + 255) // 256, dev)
     cnt = torch.empty(N, dtype=torch.int32, device=dev)
     call("reid_knn_candidates_sym", ptr(xh), N, D, SCALE_LOG2, ptr(tau), ptr(tiles), tiles.shape[0], SYM_CAP, ptr(cand),
@@ -80,7 +112,7 @@ def _candidates_sym(xh, N, D, sp, dev):
 
 
 def sym_eligible(N, D, k):
-    return SYM and N >= SYM_MIN_N and k <= 32 and D % 64 == 0
+    return SYM and N >= SYM_MIN_N and k <= SYM_MAX_K and D % 64 == 0
 
 
 UPLOAD_CHUNKS = int(__import__("os").environ.get("REID_UPLOAD_CHUNKS", "12"))
@@ -102,9 +134,9 @@ def knn_search_upload(x_host, k, dev, idx=None, key=None, info=None, defer=False
     sp = stream_ptr()
     x = torch.empty((N, D), dtype=torch.float32, device=dev)
     xh = torch.empty((N, D), dtype=torch.float16, device=dev)
-    msq = torch.zeros(1, dtype=torch.float32, device=dev)
+    msq = new_sqnorm_range(dev)
     # sample: two interleaved regular strides (odd, different) so that no single period of the row order can bias it
-    m = min(N, max(1024, -(-(SYM_RANK * N // SYM_TARGET) // 256) * 256))
+    m = sample_size(N, k)
     s = max(2, N // m)
     halves = [(0, 2 * s - 1), (s // 2, 2 * s - 3 if s > 2 else 2 * s - 1)]
     rows_h = [min(m // 2, (N - 1 - o) // st + 1) for o, st in halves]
@@ -132,7 +164,7 @@ def knn_search_upload(x_host, k, dev, idx=None, key=None, info=None, defer=False
             e.record(copy)
             events.append(e)
     main.wait_event(ev_s)
-    msq_s = torch.zeros(1, dtype=torch.float32, device=dev)
+    msq_s = torch.zeros(2, dtype=torch.float32, device=dev)
     call("reid_features_to_half", ptr(xs32), m, D, SCALE_LOG2, ptr(xs), ptr(msq_s), sp)
     cand = torch.empty(N * SYM_CAP, dtype=torch.int64, device=dev)
     cnt = torch.zeros(N, dtype=torch.int32, device=dev)
@@ -151,9 +183,9 @@ def knn_search_upload(x_host, k, dev, idx=None, key=None, info=None, defer=False
             continue
         call("reid_features_to_half_acc", ptr(x[a:]), b - a, D, SCALE_LOG2, ptr(xh[a:]), ptr(msq), sp)
         pre_cnt.zero_()
-        call("reid_knn_candidates_tc_ab", ptr(xh), N, ptr(xs), m, D, SCALE_LOG2, a, b, -SYM_RANK, 1, 2, ptr(pre), ptr(pre_cnt),
+        call("reid_knn_candidates_tc_ab", ptr(xh), N, ptr(xs), m, D, SCALE_LOG2, a, b, -sym_rank(k), 1, 2, ptr(pre), ptr(pre_cnt),
              ptr(pre_tau), sp)
-        call("reid_knn_sample_tau", ptr(pre), ptr(pre_cnt), ptr(pre_tau), 2, b - a, SYM_RANK, ptr(tau[a:]), ptr(tau_ord[a:]), sp)
+        call("reid_knn_sample_tau", ptr(pre), ptr(pre_cnt), ptr(pre_tau), 2, b - a, sym_rank(k), ptr(tau[a:]), ptr(tau_ord[a:]), sp)
         key_ = ("chunk", n_t, chunks, c, str(dev))
         if key_ not in _tile_cache:                            # tiles whose larger block index falls into this chunk
             t0, t1 = a // 256, (b + 255) // 256
@@ -185,18 +217,18 @@ def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None, defer=
         max_sqnorm = None
     elif xh is None:
         xh = torch.empty((N, D), dtype=torch.float16, device=dev)
-        msq = torch.zeros(1, dtype=torch.float32, device=dev)
+        msq = torch.zeros(2, dtype=torch.float32, device=dev)
         call("reid_features_to_half", ptr(x), N, D, SCALE_LOG2, ptr(xh), ptr(msq), sp)
         max_sqnorm = None
     else:
         msq = None
-    sym = SYM and r0 == 0 and r1 == N and N >= SYM_MIN_N and k <= 32
+    sym = SYM and r0 == 0 and r1 == N and N >= SYM_MIN_N and k <= SYM_MAX_K
     keep = max(k, min(k + SLACK, KEEP_MAX))
     if cands is not None:
         cand, cand_cnt, row_tau, list_cap, sym_info = cands[:5]
         n_lists, s, sym = 1, 0, True
     elif sym:
-        cand, cand_cnt, row_tau, list_cap, sym_info = _candidates_sym(xh, N, D, sp, dev)
+        cand, cand_cnt, row_tau, list_cap, sym_info = _candidates_sym(xh, N, D, sp, dev, k)
         n_lists, s = 1, 0
     else:
         n_splits = ctypes.c_int(1)

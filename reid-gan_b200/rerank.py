@@ -72,7 +72,7 @@ def re_ranking(q_g_dist, q_q_dist, g_g_dist, k1=20, k2=6, lambda_value=0.3, retu
             qp_idx = torch.empty(M * q_stride, dtype=torch.int32, device=dev)
             qp_val = torch.empty(M * q_stride, dtype=torch.float32, device=dev)
             call("reid_query_expand", ptr(rank), M, cols, k2, ptr(e_ptr), ptr(e_idx), ptr(v_val), max(e_max, 1), 0, M,
-                 ptr(q_cnt), ptr(qp_idx), ptr(qp_val), None, sp)
+                 ptr(q_cnt), ptr(qp_idx), ptr(qp_val), None, 0, sp)
             q_ptr, q_total, _ = _scan(q_cnt, M, dev)
             q_idx = torch.empty(max(q_total, 1), dtype=torch.int32, device=dev)
             q_val = torch.empty(max(q_total, 1), dtype=torch.float32, device=dev)
@@ -96,7 +96,7 @@ def re_ranking(q_g_dist, q_q_dist, g_g_dist, k1=20, k2=6, lambda_value=0.3, retu
             r1 = min(Q, r0 + block)
             J = torch.empty((r1 - r0, M), dtype=torch.float32, device=dev)
             call("reid_jaccard_dense", ptr(q_ptr), ptr(q_idx), ptr(q_val), ptr(c_ptr), ptr(c_idx), ptr(c_val), M, r0, r1, ptr(J),
-                 M, sp)
+                 M, 0, sp)
             call("reid_rr_final", ptr(J), M, ptr(dist[r0:]), r1 - r0, G, a_, b_, ptr(out[r0:]), sp)
         if return_device:
             return out

@@ -26,6 +26,9 @@ RECORD_GATHER = __import__("os").environ.get("REID_RECORD_GATHER", "1") != "0"  
 ROWS_PLAN_MIN_N = 65536     # from this N on the sparse stages are row-sharded too (see pseudo_labels)
 
 
+_bounds_cache = {}
+
+
 def partition(N, world, rank):
     """Contiguous row block of `rank`: [N*rank//world, N*(rank+1)//world)."""
     return (N * rank) // world, (N * (rank + 1)) // world
@@ -83,7 +86,7 @@ class RowComm:
         out = self._all_gather_padded(t, length, max(max(lens), 1))
         return torch.cat([out[r, :l] for r, l in enumerate(lens)], dim=0), lens
 
-    def gather_records(self, cnt, row_ptr, idx, val, stride):
+    def gather_records(self, cnt, row_ptr, idx, val, stride, overflow=None, stats_out=None):
         """CUDA only: ragged rows (cnt, row starts `row_ptr` into idx / val) -> global CSR through ONE all-gather of
         fixed-stride records (csrc/rerank_sparse.cu rows_pack / rows_unpack).  Returns (g_ptr, g_idx, g_val, total,
         max, g_cnt), or None when some row is longer than `stride` (every rank sees the same gathered counts, so
@@ -97,11 +100,23 @@ class RowComm:
         call("reid_rows_pack", p_(cnt), p_(row_ptr), p_(idx), p_(val), n, self.max_rows, stride, p_(rec), stream_ptr())
         out = torch.empty((self.world, self.max_rows, words), dtype=torch.int32, device=dev)
         dist.all_gather_into_tensor(out, rec, group=self.group)
-        if getattr(self, "_bounds_dev", None) is None or self._bounds_dev.device != dev:
-            self._bounds_dev = torch.tensor([a for a, _ in self.bounds] + [self.N], dtype=torch.int64, device=dev)
+        key_ = (self.N, self.world, str(dev))
+        if key_ not in _bounds_cache:                         # cached across passes: no H2D copy inside a captured pass
+            _bounds_cache[key_] = torch.tensor([a for a, _ in self.bounds] + [self.N], dtype=torch.int64, device=dev)
+        self._bounds_dev = _bounds_cache[key_]
         g_cnt = torch.empty(self.N, dtype=torch.int32, device=dev)
+        if overflow is not None:
+            # sync-free flavour: upper-bound storage, rows that did not fit are counted in `overflow` (device scalar)
+            call("reid_rows_unpack_counts", p_(out), stride, 1 if val is not None else 0, self.world, self.max_rows,
+                 p_(self._bounds_dev), self.N, p_(g_cnt), p_(overflow), stream_ptr())
+            g_ptr, stats = _scan_async(g_cnt, self.N, dev, stats=stats_out)
+            g_idx = torch.empty(self.N * stride, dtype=torch.int32, device=dev)
+            g_val = torch.empty(self.N * stride, dtype=torch.float32, device=dev) if val is not None else None
+            call("reid_rows_unpack_fill", p_(out), stride, self.world, self.max_rows, p_(self._bounds_dev), self.N, p_(g_ptr),
+                 p_(g_idx), p_(g_val), stream_ptr())
+            return g_ptr, g_idx, g_val, None, None, g_cnt
         call("reid_rows_unpack_counts", p_(out), stride, 1 if val is not None else 0, self.world, self.max_rows,
-             p_(self._bounds_dev), self.N, p_(g_cnt), stream_ptr())
+             p_(self._bounds_dev), self.N, p_(g_cnt), None, stream_ptr())
         g_ptr, stats = _scan_async(g_cnt, self.N, dev)
         total, mx, _ = (int(v) for v in stats.tolist())
         if mx > stride:
@@ -136,10 +151,13 @@ class RowComm:
             g_val = torch.zeros(1, dtype=val.dtype, device=val.device)
         return g_ptr, g_idx, g_val, total, mx
 
-    def gather_neighbors(self, slot_ptr, nbr_idx, nbr_cnt):
+    def gather_neighbors(self, slot_ptr, nbr_idx, nbr_cnt, overflow=None, stride=128):
         """Per-row neighbour lists stored at slot_ptr (upper-bound slots) -> compact global lists:
-        (ptr int64 (N+1), idx, cnt int32 (N))."""
+        (ptr int64 (N+1), idx, cnt int32 (N)).  overflow (device scalar): sync-free flavour, see gather_records."""
         n = self.r1 - self.r0
+        if overflow is not None:
+            got = self.gather_records(nbr_cnt, slot_ptr, nbr_idx, None, stride, overflow=overflow)
+            return got[0], got[1], got[5]
         if nbr_idx.is_cuda and RECORD_GATHER:
             got = self.gather_records(nbr_cnt, slot_ptr, nbr_idx, None, 128)
             if got is not None:
@@ -183,18 +201,37 @@ def block_partition(N, world, rank):
     return min(N, rank * B), min(N, (rank + 1) * B), B
 
 
+_my_tiles_cache = {}
+
+
+def _my_tiles(N, W, me, dev):
+    """Upper-triangle tiles dealt to this rank: tile (I, J) goes to rank (I + J) mod W -- balanced for the rows of
+    block I (J varies) AND for the rows of block J (I varies), so every row's candidates split evenly over the W
+    partial lists.  Cached (the selection is a boolean-mask gather, i.e. a host synchronisation)."""
+    from . import knn_tc as kt
+    key_ = (N, W, me, str(dev))
+    if key_ not in _my_tiles_cache:
+        tiles = kt._tile_order((N + 255) // 256, dev)
+        _my_tiles_cache[key_] = tiles[((tiles[:, 0] + tiles[:, 1]) % W) == me].contiguous()
+    return _my_tiles_cache[key_]
+
+
 @torch.no_grad()
-def knn_search_tiles(x, k, group=None):
+def knn_search_tiles(x, k, group=None, report=None):
     """a1 on W GPUs, symmetric form: every rank holds all N feature rows; the sampling prepass is split by rows
     (all-gather of the N thresholds), the upper-triangle tiles of the similarity are dealt round-robin to the
     ranks, each rank appends the survivors of ITS tiles to per-row partial lists, one all-to-all hands every
     row's W partial lists to the row's owner, the owner re-scores and certifies its rows, and the final lists
     are all-gathered.  Returns (rank (N, k) int32, key (N, k) fp32, info) -- identical on every rank and
     bit-identical to the single-GPU search (the exact key and the (key desc, index asc) order decide, not
-    the candidate sets)."""
+    the candidate sets).
+
+    report (the int64 pass report of faiss_rerank.py): sync-free flavour -- nothing is read back here; the number of
+    uncertified rows is accumulated in report[R_UNCERT] and info["max_sqnorm"] carries the {max, min} squared norms,
+    both checked by RerankState.finish(), which has the whole pass redone (with the repairs below) if needed."""
     from . import knn_tc as kt
     from ._lib import call, lib, ptr, stream_ptr
-    from .faiss_rerank import _knn_exact_rows
+    from .faiss_rerank import R_UNCERT, _knn_exact_rows
     L = lib()
     W, me = dist.get_world_size(group), dist.get_rank(group)
     N, D = x.shape
@@ -212,41 +249,36 @@ def knn_search_tiles(x, k, group=None):
     b0, b1, B = block_partition(N, W, me)
     nb = b1 - b0
     xh = torch.empty((N, D), dtype=torch.float16, device=dev)
-    msq = torch.zeros(1, dtype=torch.float32, device=dev)
+    msq = torch.empty(2, dtype=torch.float32, device=dev)
     call("reid_features_to_half", ptr(x), N, D, kt.SCALE_LOG2, ptr(xh), ptr(msq), sp)
-    # 1. thresholds of my rows from the sample, all-gathered (tau as float and as order-preserving image)
-    m = min(N, max(1024, -(-(kt.SYM_RANK * N // kt.SYM_TARGET) // 256) * 256))
+    # 1. thresholds of my rows from the sample; the float thresholds are all-gathered (the main pass compares the rows
+    #    AND the columns of a tile), their order-preserving images stay with the owner (certificate)
+    m = kt.sample_size(N, k)
     xs = torch.empty((m, D), dtype=torch.float16, device=dev)
     call("reid_features_sample", ptr(xh), N, D, m, kt._sample_stride(N), ptr(xs), sp)
-    tau2 = torch.zeros((B, 2), dtype=torch.int32, device=dev)          # [:, 0] float bits, [:, 1] ordered image
+    t_f = torch.empty(B, dtype=torch.float32, device=dev)
+    t_o = torch.empty(B, dtype=torch.int32, device=dev)
     if nb:
         pre = torch.empty(nb * 2 * kt.TC_CAP, dtype=torch.int64, device=dev)
         pre_cnt = torch.zeros(nb * 2, dtype=torch.int32, device=dev)
         pre_tau = torch.empty(nb, dtype=torch.int32, device=dev)
-        call("reid_knn_candidates_tc_ab", ptr(xh), N, ptr(xs), m, D, kt.SCALE_LOG2, b0, b1, -kt.SYM_RANK, 1, 2, ptr(pre),
+        call("reid_knn_candidates_tc_ab", ptr(xh), N, ptr(xs), m, D, kt.SCALE_LOG2, b0, b1, -kt.sym_rank(k), 1, 2, ptr(pre),
              ptr(pre_cnt), ptr(pre_tau), sp)
-        t_f = torch.empty(nb, dtype=torch.float32, device=dev)
-        t_o = torch.empty(nb, dtype=torch.int32, device=dev)
-        call("reid_knn_sample_tau", ptr(pre), ptr(pre_cnt), ptr(pre_tau), 2, nb, kt.SYM_RANK, ptr(t_f), ptr(t_o), sp)
-        tau2[:nb, 0] = t_f.view(torch.int32)
-        tau2[:nb, 1] = t_o
+        call("reid_knn_sample_tau", ptr(pre), ptr(pre_cnt), ptr(pre_tau), 2, nb, kt.sym_rank(k), ptr(t_f), ptr(t_o), sp)
     mark("prepass")
-    tau_all = torch.empty((W * B, 2), dtype=torch.int32, device=dev)
-    dist.all_gather_into_tensor(tau_all, tau2, group=group)
-    tau = tau_all[:, 0].contiguous().view(torch.float32)              # rows >= N are padding (never read)
-    tau_ord = tau_all[:, 1].contiguous()
+    tau = torch.empty(W * B, dtype=torch.float32, device=dev)          # rows >= N are padding (never read)
+    dist.all_gather_into_tensor(tau, t_f, group=group)
     mark("gather_tau")
     # 2. my share of the tiles -> partial lists of ALL rows (W * B row slots so that slot == row)
-    # tile (I, J) goes to rank (I + J) mod W: balanced for the rows of block I (J varies) AND for the rows of block J
-    # (I varies), so every row's candidates split evenly over the W partial lists
-    tiles = kt._tile_order((N + 255) // 256, dev)
-    tiles = tiles[((tiles[:, 0] + tiles[:, 1]) % W) == me].contiguous()
+    tiles = _my_tiles(N, W, me, dev)
     cap = max(128, kt.SYM_CAP // W)
     part = torch.empty((W * B, cap), dtype=torch.int64, device=dev)
-    part_cnt = torch.zeros(W * B, dtype=torch.int32, device=dev)
+    part_cnt = torch.empty(W * B, dtype=torch.int32, device=dev)
     if tiles.shape[0]:
         call("reid_knn_candidates_sym", ptr(xh), N, D, kt.SCALE_LOG2, ptr(tau), ptr(tiles), tiles.shape[0], cap, ptr(part),
              ptr(part_cnt), 1, sp)
+    else:
+        part_cnt.zero_()
     mark("tiles")
     # 3. all-to-all: block w of `part` (rows owned by rank w) goes to rank w; I receive W partial lists per own row
     recv = torch.empty_like(part)
@@ -255,25 +287,33 @@ def knn_search_tiles(x, k, group=None):
     dist.all_to_all_single(recv_cnt, part_cnt, group=group)
     mark("all_to_all")
     # 4. exact re-score + certificate of my rows (list q of local row r at q * B + r)
-    idx = torch.zeros((B, k), dtype=torch.int32, device=dev)
-    key = torch.zeros((B, k), dtype=torch.float32, device=dev)
+    idx = torch.empty((B, k), dtype=torch.int32, device=dev)
+    key = torch.empty((B, k), dtype=torch.float32, device=dev)
     n_bad = 0
+    metric = "ip"
     max_err = torch.zeros(1, dtype=torch.float32, device=dev)
     if nb:
         flag = torch.empty(nb, dtype=torch.int32, device=dev)
         ws = torch.empty(L.reid_knn_rescore_workspace_bytes(N, nb), dtype=torch.uint8, device=dev)
-        my_tau = tau_ord[b0:b1].contiguous()
-        call("reid_knn_rescore", ptr(x), N, D, b0, b1, ptr(recv), ptr(recv_cnt), ptr(my_tau), W, cap, B, k, 0.0, ptr(msq),
-             1 if kt.ORDER_ROWS else 0, ptr(idx), ptr(key), ptr(flag), ptr(max_err), ptr(ws), None, sp)
-        bad = torch.nonzero(flag).flatten().to(torch.int32)
-        n_bad = bad.numel()
-        if n_bad:                                          # uncertified rows: exact CUDA-core search
-            rows = (bad + b0).contiguous()
-            bi = torch.empty((n_bad, k), dtype=torch.int32, device=dev)
-            bk = torch.empty((n_bad, k), dtype=torch.float32, device=dev)
-            _knn_exact_rows(x, k, rows, 0, n_bad, bi, bk)
-            idx[bad.long()] = bi
-            key[bad.long()] = bk
+        call("reid_knn_rescore", ptr(x), N, D, b0, b1, ptr(recv), ptr(recv_cnt), ptr(t_o), W, cap, B, k, 0.0, ptr(msq),
+             1 if kt.ORDER_ROWS else 0, ptr(idx), ptr(key), ptr(flag), ptr(max_err), ptr(ws),
+             ptr(report[R_UNCERT:]) if report is not None else None, sp)
+        if report is None:
+            bad = torch.nonzero(flag).flatten().to(torch.int32)
+            n_bad = bad.numel()
+            if not kt.one_norm(msq.tolist()):              # rows of different norms (every rank sees the same features):
+                metric = "l2"                              # the reference's L2 order needs the squared-L2 key
+                _knn_exact_rows(x, k, None, b0, nb, idx[:nb], key[:nb], metric="l2")
+                n_bad = 0
+            elif n_bad:                                    # uncertified rows: exact CUDA-core search
+                rows = (bad + b0).contiguous()
+                bi = torch.empty((n_bad, k), dtype=torch.int32, device=dev)
+                bk = torch.empty((n_bad, k), dtype=torch.float32, device=dev)
+                _knn_exact_rows(x, k, rows, 0, n_bad, bi, bk)
+                idx[bad.long()] = bi
+                key[bad.long()] = bk
+    elif report is None and not kt.one_norm(msq.tolist()):
+        metric = "l2"
     mark("rescore")
     # 5. final lists of all rows on every rank
     g_idx = torch.empty((W * B, k), dtype=torch.int32, device=dev)
@@ -285,14 +325,16 @@ def knn_search_tiles(x, k, group=None):
     if TRACE_STEPS:
         torch.cuda.synchronize()
         steps = {b[0]: round(a[1].elapsed_time(b[1]), 3) for a, b in zip(marks[:-1], marks[1:])}
-    info = dict(mode="tc-sym-tiles", steps_ms=steps, world=W, sym=dict(sample=m, tiles=int(tiles.shape[0])), n_splits=0, keep=cap,
-                uncertified_rows=int(n_bad), max_abs_err=max_err, xh=xh, cand_cnt=recv_cnt)
+    info = dict(mode="tc-sym-tiles" if metric == "ip" else "exact-l2", metric=metric, steps_ms=steps, world=W,
+                sym=dict(sample=m, tiles=int(tiles.shape[0])), n_splits=0, keep=cap,
+                uncertified_rows=int(n_bad), max_abs_err=max_err, xh=xh, cand_cnt=recv_cnt,
+                max_sqnorm=msq if report is not None else None)
     return g_idx[:N], g_key[:N], info
 
 
 @torch.no_grad()
 def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=False, group=None, N=None,
-                  timers=False, plan="auto"):
+                  timers=False, plan="auto", speculative=True, graph=False):
     """Row-sharded pass.  `x`: either all N rows (every rank holds a replica) or this rank's row block
     (then N must be given and the blocks are all-gathered first).  Returns the same dict as
     pipeline.pseudo_labels with GLOBAL labels on every rank."""
@@ -315,65 +357,67 @@ def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=
         # GPUs their exchange steps cost more than sharding saves); plan "tiles+rows" / "rows" shards every per-row
         # stage with the all-gathers listed in the module docstring (default from 4 GPUs or ROWS_PLAN_MIN_N rows on).
         from . import knn_tc as kt
-        sym_ok = (knn in ("auto", "tc") and kt.SYM and N >= kt.SYM_MIN_N and k1 <= 32 and x.shape[1] % 64 == 0)
+        sym_ok = (knn in ("auto", "tc") and kt.SYM and N >= kt.SYM_MIN_N and k1 <= kt.SYM_MAX_K and x.shape[1] % 64 == 0)
         if plan == "auto":
             # measured at N = 32,621: 2 GPUs 3.6 (tiles) vs 4.1 ms (tiles+rows); 8 GPUs 2.9 vs 2.6 ms
             replicate = N < ROWS_PLAN_MIN_N and comm.world <= 2
             plan = ("tiles" if replicate else "tiles+rows") if sym_ok else "rows"
         if plan in ("tiles", "tiles+rows") and not sym_ok:
-            raise ValueError("plan %r needs the symmetric tensor-core search (N >= %d, k1 <= 32, D %% 64 == 0)" % (plan, kt.SYM_MIN_N))
-        res = None
-        if plan in ("tiles", "tiles+rows"):
-            if timers:
-                ek = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
-                ek[0].record()
-            res = knn_search_tiles(x.contiguous(), k1, group)
-            if timers:
-                ek[1].record()
-        if plan == "tiles":
-            # every rank runs the (replicated) sparse stages as the sync-free speculative pass of pipeline.py
-            from .pipeline import _labels_from_state
-            st = rerank_state_async(x.contiguous(), k1, k2, knn_result=res, timers=timers)
-            if timers:
-                st.timings["knn_tiles"] = ek[0].elapsed_time(ek[1]) * 1e-3
-            labels, core, ncl, nbr_cnt = _labels_from_state(st, eps, min_samples, timers)
-            st2, nbr_ok = st.finish(check_nbr=True)
-            if st2 is not st or not nbr_ok:
-                st = st2
+            raise ValueError("plan %r needs the symmetric tensor-core search (N >= %d, k1 <= %d, D %% 64 == 0)" % (plan, kt.SYM_MIN_N, kt.SYM_MAX_K))
+        from .faiss_rerank import R_XCHG_OVF, _stride_for, _rec_stride_hint
+        from .pipeline import _labels_from_state
+        x = x.contiguous()
+        dev = x.device
+
+        def run(spec):
+            """One pass.  spec: the sync-free flavour (no host read-back between the stages: upper-bound / guessed sizes,
+            fixed-stride exchange records, every kernel reports what did not fit); else sizes are read back where needed."""
+            report = torch.zeros(16, dtype=torch.int64, device=dev) if spec else None
+            res = None
+            if plan in ("tiles", "tiles+rows"):
+                res = knn_search_tiles(x, k1, group, report=report)
+            if plan == "tiles":
+                # every rank runs the (replicated) sparse stages like pipeline.pseudo_labels
+                st = rerank_state_async(x, k1, k2, knn_result=res, timers=timers, report=report, speculative=spec)
                 labels, core, ncl, nbr_cnt = _labels_from_state(st, eps, min_samples, timers)
-            out = dict(labels=labels, core=core, num_clusters=ncl, state=st, nbr_cnt=nbr_cnt)
+            else:
+                st = rerank_state_async(x, k1, k2, knn=knn, comm=comm, timers=timers, knn_result=res, report=report,
+                                        speculative=spec and res is not None)
+                slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, eps)
+                if st.report is not None:
+                    g_ptr, g_idx, g_cnt = comm.gather_neighbors(slot_ptr, nbr_idx, nbr_cnt, overflow=st.report[R_XCHG_OVF:],
+                                                                stride=_stride_for("nbr", N))
+                else:
+                    g_ptr, g_idx, g_cnt = comm.gather_neighbors(slot_ptr, nbr_idx, nbr_cnt)
+                    _rec_stride_hint[("nbr", N)] = max(_rec_stride_hint.get(("nbr", N), 0), int(g_cnt.max().item()) if N else 0)
+                labels, core, ncl = dbscan_from_neighbors(N, g_ptr, g_idx, g_cnt, min_samples)
+            cen = None
             if centroids:
-                C = int(ncl.item())
-                cen = torch.empty((C, x.shape[1]), dtype=torch.float32, device=x.device)
-                if C:
-                    call("reid_centroids", ptr(x), N, x.shape[1], ptr(labels), C, 1, ptr(cen), None, stream_ptr())
-                out["centroids"] = cen
-            return out
-        st = rerank_state_async(x.contiguous(), k1, k2, knn=knn, comm=comm, timers=timers, knn_result=res)
-        if timers and res is not None:
-            st.timings["knn_tiles"] = ek[0].elapsed_time(ek[1]) * 1e-3
-        ev = [torch.cuda.Event(enable_timing=True) for _ in range(4)] if timers else None
-        if timers:
-            ev[0].record()
-        slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, eps)
-        if timers:
-            ev[1].record()
-        g_ptr, g_idx, g_cnt = comm.gather_neighbors(slot_ptr, nbr_idx, nbr_cnt)
-        if timers:
-            ev[2].record()
-        labels, core, ncl = dbscan_from_neighbors(N, g_ptr, g_idx, g_cnt, min_samples)
-        if timers:
-            ev[3].record()
-            torch.cuda.synchronize()
-            for nm, a, b in (("jaccard", 0, 1), ("gather_neighbors", 1, 2), ("dbscan", 2, 3)):
-                st.timings[nm] = ev[a].elapsed_time(ev[b]) * 1e-3
+                cen = torch.empty((max(N, 1), x.shape[1]), dtype=torch.float32, device=dev)
+                call("reid_centroids_dev", ptr(x), N, x.shape[1], ptr(labels), ptr(ncl), max(N, 1), 1, ptr(cen), stream_ptr())
+            return st, labels, core, ncl, nbr_cnt, cen
+
+        if graph and speculative and not timers:
+            # the whole pass, collectives included, replayed from one CUDA graph (pipeline.PassGraph)
+            from .pipeline import PassGraph, _graph_key
+            g = PassGraph.get(_graph_key(x, k1, k2, float(eps), min_samples, knn, bool(centroids), plan, comm.world, N),
+                              lambda: run(True) + (None,))
+            if getattr(g, "report", None) is None:
+                g.report = g.result[0].report
+            g.graph.replay()
+            st, labels, core, ncl, nbr_cnt, cen = g.result[:6]
+            st.report = g.report
+        else:
+            st, labels, core, ncl, nbr_cnt, cen = run(speculative)
+        st2, nbr_ok = st.finish(check_nbr=True)
+        if st2 is None or st2 is not st or not nbr_ok:               # a guess did not hold / rows uncertified / other norms
+            info = st.knn_info
+            st, labels, core, ncl, nbr_cnt, cen = run(False)
+            st.finish()
+            st.knn_info["speculation_failed"] = dict(report=getattr(st2 or st, "report_vals", None), first=info.get("mode"))
         out = dict(labels=labels, core=core, num_clusters=ncl, state=st, nbr_cnt=nbr_cnt)
         if centroids:
-            C = int(ncl.item())
-            cen = torch.empty((C, x.shape[1]), dtype=torch.float32, device=x.device)
-            if C:
-                call("reid_centroids", ptr(x), N, x.shape[1], ptr(labels), C, 1, ptr(cen), None, stream_ptr())
-            out["centroids"] = cen
+            out["centroids"] = cen[: int(ncl.item())]
         return out
 
 

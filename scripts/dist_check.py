@@ -1,42 +1,87 @@
-"""Multi-GPU check (run under torchrun): the row-sharded pass must be byte-identical to the single-GPU pass."""
-import os, sys, time
+"""Multi-GPU check (run under torchrun): the row-sharded pass must be byte-identical to the single-GPU pass -- in the
+sync-free flavour (eager and replayed from a CUDA graph), in the exact-size flavour, from pre-sharded features (f4),
+and when the speculative sizes are forced to fail.  Prints one digest line per configuration.
+    python -m torch.distributed.run --nproc-per-node W --master-addr 127.0.0.1 scripts/dist_check.py"""
+import hashlib, os, sys, time, itertools
+import numpy as np
 import torch, torch.distributed as dist
 sys.path.insert(0, ".")
 import reid_gan_b200 as rg
-from reid_gan_b200 import pipeline, sharded
+from reid_gan_b200 import pipeline, sharded, faiss_rerank as fr
 
 rank = int(os.environ["RANK"]); world = int(os.environ["WORLD_SIZE"]); lr = int(os.environ["LOCAL_RANK"])
 torch.cuda.set_device(lr)
 dist.init_process_group("nccl", device_id=torch.device("cuda", lr))
 ok = True
-import itertools
-cfgs = [(3000, 256, 100, 20, 6, 0.6), (12936, 2048, 751, 30, 6, 0.6), (32621, 2048, 1041, 30, 6, 0.6)]
+
+
+def sha(t):
+    return hashlib.sha256(np.ascontiguousarray(t.cpu().numpy()).tobytes()).hexdigest()[:16]
+
+
+def same_as(ref, out):
+    nq = ref["state"].q_total
+    return (torch.equal(out["labels"], ref["labels"]) and torch.equal(out["state"].rank, ref["state"].rank)
+            and torch.equal(out["state"].Q_ptr, ref["state"].Q_ptr)
+            and torch.equal(out["state"].Q_idx[:nq], ref["state"].Q_idx[:nq])
+            and torch.equal(out["state"].Q_val[:nq], ref["state"].Q_val[:nq])
+            and ("centroids" not in ref or torch.equal(out["centroids"], ref["centroids"])))
+
+
+def agree(flag):
+    t = torch.tensor([1 if flag else 0], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MIN)
+    return bool(t.item())
+
+
+def timed(fn, n=10):
+    for _ in range(3): fn()
+    dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
+    for _ in range(n): fn()
+    dist.barrier(); torch.cuda.synchronize()
+    return (time.perf_counter() - t0) / n * 1e3
+
+
+cfgs = [("synth", dict(N=3000, D=256, n_ids=100, noise=0.8, seed=0), 20, 6, 0.6),
+        ("synth", dict(N=12936, D=2048, n_ids=751, noise=0.8, seed=0), 30, 6, 0.6),
+        ("synth_hard", dict(N=20480, D=2048, seed=0), 30, 6, 0.6),
+        ("synth", dict(N=32621, D=2048, n_ids=1041, noise=0.8, seed=0), 30, 6, 0.6)]
 if os.environ.get("ONLY_BIG"): cfgs = cfgs[-1:]
-for (N, D, n_ids, k1, k2, eps), plan in itertools.product(cfgs, ("rows", "tiles", "tiles+rows")):
+for (gen, kw, k1, k2, eps), plan in itertools.product(cfgs, ("rows", "tiles", "tiles+rows")):
+    N = kw["N"]
     if plan != "rows" and N < 8192:
         continue
-    x, _ = rg.synth(N, D, n_ids, 0.8, 0)
+    if plan == "rows" and N > 13000:
+        continue
+    x, _ = getattr(rg, gen)(**kw)
     xd = x.cuda()
     ref = pipeline.pseudo_labels(xd, k1, k2, eps, 4, centroids=True)
     r0, r1 = sharded.partition(N, world, rank)
-    out = sharded.pseudo_labels(xd[r0:r1].contiguous(), k1, k2, eps, 4, centroids=True, N=N, plan=plan)
-    same = (torch.equal(out["labels"], ref["labels"]) and torch.equal(out["state"].rank, ref["state"].rank)
-            and torch.equal(out["state"].Q_ptr, ref["state"].Q_ptr)
-            and torch.equal(out["state"].Q_val[:ref["state"].q_total], ref["state"].Q_val[:ref["state"].q_total])
-            and torch.equal(out["centroids"], ref["centroids"]))
-    t = torch.tensor([1 if same else 0], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MIN)
-    # timing
-    for _ in range(3): sharded.pseudo_labels(xd, k1, k2, eps, 4, plan=plan)
-    dist.barrier(); torch.cuda.synchronize(); t0 = time.perf_counter()
-    for _ in range(5): sharded.pseudo_labels(xd, k1, k2, eps, 4, plan=plan)
-    dist.barrier(); torch.cuda.synchronize(); dt = (time.perf_counter() - t0) / 5
-    o = sharded.pseudo_labels(xd, k1, k2, eps, 4, timers=True, plan=plan)
-    print("   [rank %d] uncertified %s steps %s" % (rank, o["state"].knn_info.get("uncertified_rows"), o["state"].knn_info.get("steps_ms")), flush=True)
+    x_local = xd[r0:r1].contiguous()                      # f4: every rank starts from ITS rows only
+    res = {}
+    out = sharded.pseudo_labels(x_local, k1, k2, eps, 4, centroids=True, N=N, plan=plan)
+    res["sync-free, pre-sharded rows"] = same_as(ref, out)
+    res["sync-free, replicated rows"] = same_as(ref, sharded.pseudo_labels(xd, k1, k2, eps, 4, centroids=True, plan=plan))
+    res["exact sizes"] = same_as(ref, sharded.pseudo_labels(xd, k1, k2, eps, 4, centroids=True, plan=plan, speculative=False))
+    if plan != "rows":
+        o = sharded.pseudo_labels(xd, k1, k2, eps, 4, centroids=True, plan=plan, graph=True)
+        o = sharded.pseudo_labels(xd, k1, k2, eps, 4, centroids=True, plan=plan, graph=True)
+        res["graph replay"] = same_as(ref, o)
+        keep = dict(fr.REC_STRIDE), fr.QE_SPEC_SLOTS
+        fr.REC_STRIDE.update(V=8, Q=8, nbr=8); fr._rec_stride_hint.clear()
+        o = sharded.pseudo_labels(xd, k1, k2, eps, 4, centroids=True, plan=plan)
+        res["forced record overflow -> redo"] = same_as(ref, o) and ("speculation_failed" in o["state"].knn_info or plan == "tiles")
+        fr.REC_STRIDE.update(keep[0]); fr._rec_stride_hint.clear()
+    good = all(agree(v) for v in res.values())
+    ok &= good
+    t_e = timed(lambda: sharded.pseudo_labels(xd, k1, k2, eps, 4, plan=plan))
+    t_g = timed(lambda: sharded.pseudo_labels(xd, k1, k2, eps, 4, plan=plan, graph=True)) if plan != "rows" else float("nan")
+    if os.environ.get("REID_TRACE_STEPS", "0") != "0":
+        o = sharded.pseudo_labels(xd, k1, k2, eps, 4, plan=plan)
+        print("   [rank %d] steps %s" % (rank, o["state"].knn_info.get("steps_ms")), flush=True)
     if rank == 0:
-        print("   stages(ms):", {k: round(v * 1e3, 3) for k, v in o["state"].timings.items()}, o["state"].knn_info.get("steps_ms"), flush=True)
-    if rank == 0:
-        print("N=%d world=%d plan=%s identical=%s clusters=%d  %.2f ms/pass" % (N, world, plan, bool(t.item()), int(out["num_clusters"]), dt * 1e3), flush=True)
-    ok &= bool(t.item())
+        print("%s N=%d world=%d plan=%-10s identical=%s %s labels=%s rank=%s clusters=%d noise=%d  eager %.2f ms  graph %.2f ms"
+              % (gen, N, world, plan, good, {k: v for k, v in res.items() if not v} or "", sha(out["labels"]), sha(out["state"].rank),
+                 int(out["num_clusters"]), int((out["labels"] < 0).sum()), t_e, t_g), flush=True)
 if rank == 0:
     print("DIST OK" if ok else "DIST MISMATCH")
 dist.destroy_process_group()

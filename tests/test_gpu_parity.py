@@ -199,6 +199,8 @@ def _sym_case(N, D, n_ids, noise, seed, order=None, dup=0):
     (8192, 128, 40, 0.5, 6, None, 0, 30),          # ~200 rows per identity: the k-th neighbour sits inside a dense cluster
     (10000, 192, 300, 0.8, 7, "sorted", 0, 20),    # identity-sorted rows: the threshold sample must not depend on row order
     (8500, 128, 280, 0.8, 8, None, 500, 30),       # 500 duplicated rows: ties broken by index
+    (9000, 128, 100, 0.8, 12, None, 0, 64),        # k1 at the 64-bit mask limit: twice the candidates per row
+    (8192, 256, 8192, 1.0, 13, None, 0, 48),       # isotropic, 32 < k <= 64
 ])
 def test_symmetric_search_is_exact(N, D, n_ids, noise, seed, order, dup, k):
     from reid_gan_b200 import faiss_rerank as fr
@@ -346,8 +348,19 @@ def test_evaluation_metrics(N, Q, D, n_ids):
         b = orank.cmc(d, qi, gi, qc, gc, topk=50, **kw)
         assert np.abs(a - b).max() <= 1e-12
     assert abs(ev.mean_ap(d[:, :Q]) - orank.mean_ap(d[:, :Q])) <= 1e-12          # default ids / cameras
-    with pytest.raises(NotImplementedError):
-        ev.cmc(d, qi, gi, qc, gc, single_gallery_shot=True)
+
+
+def test_cmc_single_gallery_shot_follows_the_reference_rng_protocol():
+    """ranking.py:53-66 draws one gallery instance per identity with np.random.choice, 10 times per query: with the same
+    seed the drop-in consumes the generator in the same order and returns the reference's numbers."""
+    from reid_gan_b200 import evaluation as ev
+    g = np.load(os.path.join(GOLD, "ranking_q120_g380.npz"))
+    s = np.load(os.path.join(GOLD, "ranking_sgs_q120_g380.npz"))
+    args = (g["distmat"], g["q_ids"], g["g_ids"], g["q_cams"], g["g_cams"])
+    for name, kw in (("sgs", dict()), ("sgs_fmb", dict(first_match_break=True)), ("sgs_sep", dict(separate_camera_set=True))):
+        np.random.seed(1234)
+        got = ev.cmc(*args, topk=50, single_gallery_shot=True, **kw)
+        assert np.abs(got - s["cmc_" + name + "_seed1234"]).max() <= 1e-12
 
 
 @pytest.mark.parametrize("ci,N,D,n_ids,noise", [
@@ -366,10 +379,39 @@ def test_symmetric_search_random_shapes(ci, N, D, n_ids, noise):
         g = torch.Generator().manual_seed(ci)
         x = x * (0.5 + torch.rand(N, 1, generator=g))
     xd = x.cuda()
-    ie, ke, _ = fr.knn_search(xd, k, "exact")
-    it, kt, info = fr.knn_search(xd, k, "tc")
+    ie, ke, _ = fr.knn_search(xd, k, "exact", metric="ip")        # the inner-product key on both sides (the tensor-core
+    it, kt, info = fr.knn_search(xd, k, "tc", metric="ip")         # kernel under test), whatever the norms
     assert info["mode"] == "tc-sym"
     assert torch.equal(ie, it) and torch.equal(ke, kt)
+
+
+@pytest.mark.parametrize("N,D,k,mode", [(3000, 128, 20, "auto"), (9000, 64, 30, "auto"), (2500, 96, 10, "exact")])
+def test_rows_of_different_norms_are_ranked_by_l2_like_the_reference(N, D, k, mode):
+    """faiss IndexFlatL2 (faiss_rerank.py:58-62) ranks by squared L2.  For rows that do not share one norm that is NOT the
+    inner-product order: the search must notice (device-side min / max of the squared norms) and rank by the L2 key;
+    the whole pass then matches the oracle, which takes the same decision (oracle.rerank.exact_knn metric='auto')."""
+    import reid_gan_b200 as rg
+    from reid_gan_b200 import faiss_rerank as fr, pipeline
+    from oracle import rerank as orr, cluster as ocl
+    x, _ = rg.synth(N, D, max(1, N // 25), 0.8, 11)
+    g = torch.Generator().manual_seed(5)
+    x = (x * (0.6 + 0.8 * torch.rand(N, 1, generator=g))).contiguous()
+    ref_l2, ref_key = orr.exact_knn(x.numpy(), k, return_keys=True, metric="l2")
+    ref_ip = orr.exact_knn(x.numpy(), k, metric="ip")
+    assert not np.array_equal(ref_l2, ref_ip), "the fixture must tell the two orders apart"
+    idx, key, info = fr.knn_search(x.cuda(), k, mode)
+    assert info["metric"] == "l2" and info["mode"] == "exact-l2"
+    assert np.array_equal(idx.cpu().numpy(), ref_l2)
+    assert np.array_equal(key.cpu().numpy(), ref_key)
+    idx_ip, _, info_ip = fr.knn_search(x.cuda(), k, mode, metric="ip")        # what get_dist_nbr (IndexFlatIP) asks for
+    assert info_ip["metric"] == "ip" and np.array_equal(idx_ip.cpu().numpy(), ref_ip)
+    # the whole pass: speculative single-GPU flavour (finish() notices the norms), the drop-in call, and the oracle
+    out = pipeline.pseudo_labels(x.cuda(), k, 6 if k >= 6 else 1, 0.6, 4)
+    assert out["state"].knn_info["metric"] == "l2"
+    assert np.array_equal(out["state"].rank.cpu().numpy(), ref_l2)
+    J_ref = orr.compute_jaccard_distance_oracle(x.numpy(), k, 6 if k >= 6 else 1, rank=ref_l2)
+    J = np.asarray(rg.compute_jaccard_distance(x, k1=k, k2=6 if k >= 6 else 1, print_flag=False))
+    assert np.abs(J - J_ref).max() <= 1e-5
 
 
 # ---- CUDA path against the golden vectors of the "next" rows (outputs of the unmodified reference) -----------
@@ -404,3 +446,75 @@ def test_golden_ranking_metrics_cuda():
     assert np.abs(ev.cmc(*args, topk=50, first_match_break=True) - g["cmc_market"]).max() <= 1e-12
     assert np.abs(ev.cmc(*args, topk=50) - g["cmc_allshots"]).max() <= 1e-12
     assert np.abs(ev.cmc(*args, topk=50, separate_camera_set=True, first_match_break=True) - g["cmc_sepcam"]).max() <= 1e-12
+
+
+HALF = sorted(glob.glob(os.path.join(GOLD, "halfrerank_*.npz")))
+
+
+@pytest.mark.parametrize("path", HALF, ids=[os.path.basename(p)[:-4] for p in HALF])
+def test_use_float16_against_reference(path):
+    """compute_jaccard_distance(..., use_float16=True) (faiss_rerank.py:37): float16 matrix, the reference's float16
+    rounding points.  Bars as in tests/test_oracle.py: identical sparsity, >= 99.9 % of the entries identical to the
+    unmodified reference's, the rest within a few float16 ulps; labels equal sklearn's on the reference's matrix."""
+    import reid_gan_b200 as rg
+    from oracle import cluster as ocl
+    g = np.load(path)
+    x, k1, k2 = torch.from_numpy(g["x"]), int(g["k1"]), int(g["k2"])
+    N = x.shape[0]
+    J_ref = np.ones((N, N), dtype=np.float16)
+    J_ref[g["J_rows"], g["J_cols"]] = g["J_vals"]
+    d = rg.compute_jaccard_distance(x, k1=k1, k2=k2, print_flag=False, search_option=3, use_float16=True)
+    assert d.dtype == np.float16
+    J = np.asarray(d)
+    assert J.dtype == np.float16 and J.shape == (N, N)
+    assert np.array_equal(J == 1.0, J_ref == 1.0)
+    assert (J != J_ref).mean() <= 1e-3
+    assert np.abs(J.astype(np.float32) - J_ref.astype(np.float32)).max() <= 2e-3
+    assert np.array_equal(J, J.T)
+    # the sparse DBSCAN path applies the same float16 roundings as the dense matrix it never builds
+    lab_sparse = rg.DBSCAN(eps=0.6, min_samples=4, metric="precomputed").fit_predict(d)
+    lab_dense = ocl.sklearn_dbscan(J.astype(np.float64), 0.6, 4)
+    assert np.array_equal(lab_sparse, lab_dense)
+
+
+def test_device_resident_feature_hand_off():
+    """f4 (clustercontrast/evaluators.py:16-68 + train_usl.py:152-153): the same extract_features call, but the rows never
+    visit the host; features.matrix(sorted names) equals the reference flow's host-side torch.cat bit for bit, and
+    the pass started from it gives the same labels as the pass started from the host matrix."""
+    import reid_gan_b200 as rg
+    from reid_gan_b200 import pipeline
+    torch.manual_seed(0)
+    N, Din, D, B = 9000, 48, 256, 512
+    model = torch.nn.Sequential(torch.nn.Linear(Din, D)).cuda()
+
+    class Net(torch.nn.Module):
+        def __init__(self):
+            super().__init__()
+            self.body = model
+
+        def forward(self, x):
+            return torch.nn.functional.normalize(self.body(x), dim=1)
+
+    net = Net().cuda()
+    centres = torch.randn(300, Din)
+    ids = torch.randint(0, 300, (N,))
+    imgs = centres[ids] + 0.35 * torch.randn(N, Din)
+    names = ["img_%05d.jpg" % i for i in torch.randperm(N).tolist()]           # loader order != sorted order
+    loader = [(imgs[a:a + B], names[a:a + B], ids[a:a + B].tolist(), None, None) for a in range(0, N, B)]
+    feats, labels = rg.extract_features(net, loader, print_freq=10 ** 9)
+    assert len(feats) == N and list(labels.keys()) == names and feats[names[3]].is_cuda
+    order = sorted(names)
+    x_dev = feats.matrix(order)
+    # the reference flow: per-batch .cpu(), dict of rows, N-way cat on the host
+    ref = {}
+    with torch.no_grad():
+        for im, fn, _, _, _ in loader:
+            out = net(im.cuda()).data.cpu()
+            for f, o in zip(fn, out):
+                ref[f] = o
+    x_ref = torch.cat([ref[f].unsqueeze(0) for f in order], 0)
+    assert x_dev.is_cuda and torch.equal(x_dev.cpu(), x_ref)
+    a = pipeline.pseudo_labels(x_dev, 20, 6, 0.6, 4)["labels"].cpu().numpy()
+    b = rg.DBSCAN(eps=0.6, min_samples=4, metric="precomputed").fit_predict(
+        rg.compute_jaccard_distance(x_ref, k1=20, k2=6, print_flag=False))
+    assert np.array_equal(a, b) and a.max() > 10

@@ -227,3 +227,26 @@ def test_golden_ranking_metrics():
     assert np.abs(orank.cmc(*args, topk=50, first_match_break=True) - g["cmc_market"]).max() <= 1e-12
     assert np.abs(orank.cmc(*args, topk=50) - g["cmc_allshots"]).max() <= 1e-12
     assert np.abs(orank.cmc(*args, topk=50, separate_camera_set=True, first_match_break=True) - g["cmc_sepcam"]).max() <= 1e-12
+
+
+HALF = sorted(glob.glob(os.path.join(GOLD, "halfrerank_*.npz")))
+HALF_ATOL = 2e-3          # a few float16 ulps: one V entry rounded the other way moves a sum by an ulp
+
+
+@pytest.mark.parametrize("path", HALF, ids=[os.path.basename(p)[:-4] for p in HALF])
+def test_oracle_use_float16_against_reference(path):
+    """use_float16=True (faiss_rerank.py:37,82-83,102-104): the oracle's float16 restatement against the unmodified
+    reference's float16 matrix.  The fp32 softmax feeding V differs in the last bit between implementations, so a
+    handful of float16 roundings fall the other way: identical sparsity, >= 99.9 % identical entries, the rest within
+    a few float16 ulps."""
+    from oracle import rerank as orr
+    g = np.load(path)
+    x, k1, k2 = g["x"], int(g["k1"]), int(g["k2"])
+    N = x.shape[0]
+    J_ref = np.ones((N, N), dtype=np.float16)
+    J_ref[g["J_rows"], g["J_cols"]] = g["J_vals"]
+    J = orr.compute_jaccard_distance_oracle(x, k1, k2, use_float16=True)
+    assert J.dtype == np.float16
+    assert np.array_equal(J == 1.0, J_ref == 1.0)
+    assert (J != J_ref).mean() <= 1e-3
+    assert np.abs(J.astype(np.float32) - J_ref.astype(np.float32)).max() <= HALF_ATOL

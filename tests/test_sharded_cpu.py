@@ -106,3 +106,18 @@ def test_tile_dealing_is_balanced_and_complete():
         assert all(0 <= b[1] - b[0] <= B for b in blocks)
         rows = np.arange(N)
         assert np.array_equal(np.minimum(rows // B, W - 1), np.concatenate([np.full(b[1] - b[0], r) for r, b in enumerate(blocks)]))
+
+
+def test_shard_items_matches_the_row_partition():
+    """f4: the share of the sorted training list a rank extracts features for is exactly the row block RowComm gives it
+    (so `sharded.pseudo_labels(x_local, N=N)` receives the rows it expects), for every world size, with no row lost."""
+    from reid_gan_b200.evaluators import shard_items
+    from reid_gan_b200.sharded import partition
+    items = [("img_%05d.jpg" % i, i % 7, i % 3) for i in range(1003)]
+    for world in (1, 2, 3, 4, 8):
+        seen = []
+        for rank in range(world):
+            share, r0, r1, n = shard_items(items, world=world, rank=rank)
+            assert (r0, r1) == partition(len(items), world, rank) and n == len(items) and share == items[r0:r1]
+            seen += share
+        assert seen == items
