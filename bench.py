@@ -667,9 +667,21 @@ def main():
         e2e = {"value": e2e_s, "unit": "s", "h2d_bytes_per_step": int(W["N"] * W["D"] * 4 // world) + extra,
                "d2h_bytes_per_step": int(W["N"] * 9)}
 
+    def shutdown():
+        """Graphs that hold NCCL kernels must be released before the communicator (destroying it with live graphs can
+        hang); a watchdog ends the process if the teardown still does not return."""
+        if dist is None:
+            return
+        sys.stdout.flush()
+        threading.Timer(20.0, lambda: os._exit(0)).start()
+        pipeline.PassGraph._cache.clear()
+        torch.cuda.synchronize()
+        dist.barrier()
+        dist.destroy_process_group()
+        os._exit(0)
+
     if rank != 0:
-        if dist is not None:
-            dist.destroy_process_group()
+        shutdown()
         return
 
     # ---- roofline of the dominant kernel (tcgen05 similarity GEMM + fused top-K) -------------
@@ -734,8 +746,7 @@ def main():
             "clocks": clocks, "e2e": e2e, "gpu_launches": int(launches), "roofline": roof, "cpu_baseline": cpu,
             "stage_ms": stage_ms, "stages": stages}
     print(json.dumps(line))
-    if dist is not None:
-        dist.destroy_process_group()
+    shutdown()
 
 
 if __name__ == "__main__":

@@ -367,6 +367,17 @@ int reid_centroids(const float* x, int64_t N, int64_t D, const int64_t* labels, 
 int reid_centroids_dev(const float* x, int64_t N, int64_t D, const int64_t* labels, const int64_t* num_clusters_dev,
                        int64_t capacity, int normalize, float* out, void* stream);
 
+/* ---- multi-GPU exchange over NVLink peer memory (the reference has no multi-GPU hot path) --------
+ * reid_peer_push_lists: the all-to-all of the tile-sharded search as plain peer stores.  part / part_cnt: this rank's
+ * partial candidate lists of ALL rows (world blocks of block_rows rows, cap entries each).  peer_base[w] (device array
+ * of `world` addresses): base of rank w's receive buffer, mapped into this process -- world * block_rows * cap
+ * entries (list q of local row r at (q * block_rows + r) * cap), followed at cnt_offset_bytes by the
+ * world * block_rows int32 counts.  Block w of `part` is stored as list `me` of rank w; only the valid entries
+ * travel, the true count travels with them.  The caller separates the push from the consumers with a barrier
+ * across the ranks. */
+int reid_peer_push_lists(const uint64_t* part, const int32_t* part_cnt, int world, int64_t block_rows, int cap, int me,
+                         const uint64_t* peer_base, int64_t cnt_offset_bytes, void* stream);
+
 /* ---- f4: feature hand-off  (clustercontrast/evaluators.py:16-68, train_usl.py:152-153) ----------------
  * dst[r] = src[idx[r]] for r < n (rows of D floats, D % 4 == 0): re-orders a device-resident feature store into the
  * sorted-file-name order the pseudo-label pass expects, replacing the per-row `.cpu()` (evaluators.py:19) and the

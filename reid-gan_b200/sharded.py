@@ -202,6 +202,39 @@ def block_partition(N, world, rank):
 
 
 _my_tiles_cache = {}
+_peer_cache = {}
+PEER_EXCHANGE = True      # False: the NCCL all-to-all carries the exchange (tests flip it to compare the two)
+
+
+class PeerLists:
+    """Receive buffer of the tile-sharded search in symmetric (peer-mapped) memory: W * B * cap candidate entries
+    + W * B counts on every rank, each rank holding the base addresses of all of them (torch.distributed.
+    _symmetric_memory does the mapping; the stores are csrc/peer_exchange.cu).  One per (N, W, cap, device)."""
+
+    def __init__(self, W, B, cap, dev, group):
+        import torch.distributed._symmetric_memory as symm
+        self.cnt_off = W * B * cap * 8
+        nbytes = self.cnt_off + W * B * 4
+        self.buf = symm.empty((nbytes + 7) // 8, dtype=torch.int64, device=dev)
+        self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.peer_base = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=dev)
+        self.recv = self.buf[: W * B * cap].view(W * B, cap)
+        self.recv_cnt = self.buf.view(torch.int32)[self.cnt_off // 4: self.cnt_off // 4 + W * B]
+
+    def barrier(self):
+        self.handle.barrier(channel=0)
+
+
+def _peer_lists(W, B, cap, dev, group):
+    key_ = (W, B, cap, str(dev), id(group))
+    if key_ not in _peer_cache:
+        try:
+            _peer_cache[key_] = PeerLists(W, B, cap, dev, group)
+        except Exception as e:                              # no peer mapping on this box: NCCL carries the exchange
+            import warnings
+            warnings.warn("peer-memory exchange unavailable (%r): using the NCCL all-to-all" % (e,))
+            _peer_cache[key_] = None
+    return _peer_cache[key_]
 
 
 def _my_tiles(N, W, me, dev):
@@ -280,11 +313,21 @@ def knn_search_tiles(x, k, group=None, report=None):
     else:
         part_cnt.zero_()
     mark("tiles")
-    # 3. all-to-all: block w of `part` (rows owned by rank w) goes to rank w; I receive W partial lists per own row
-    recv = torch.empty_like(part)
-    recv_cnt = torch.empty_like(part_cnt)
-    dist.all_to_all_single(recv, part, group=group)
-    dist.all_to_all_single(recv_cnt, part_cnt, group=group)
+    # 3. all-to-all: block w of `part` (rows owned by rank w) goes to rank w; I receive W partial lists per own row.
+    #    Over NVLink peer memory when the box maps it: every rank STORES the valid entries of its lists straight into
+    #    the owners' receive buffers (csrc/peer_exchange.cu), a barrier separates the stores from the readers.  The
+    #    buffer is reused by the next pass: its readers (the re-score below) are done on every rank before anyone
+    #    can reach the next push, because the all-gather of the final lists (step 5) needs every rank's re-score.
+    peer = _peer_lists(W, B, cap, dev, group) if PEER_EXCHANGE else None
+    if peer is not None:
+        call("reid_peer_push_lists", ptr(part), ptr(part_cnt), W, B, cap, me, ptr(peer.peer_base), peer.cnt_off, sp)
+        peer.barrier()
+        recv, recv_cnt = peer.recv, peer.recv_cnt
+    else:
+        recv = torch.empty_like(part)
+        recv_cnt = torch.empty_like(part_cnt)
+        dist.all_to_all_single(recv, part, group=group)
+        dist.all_to_all_single(recv_cnt, part_cnt, group=group)
     mark("all_to_all")
     # 4. exact re-score + certificate of my rows (list q of local row r at q * B + r)
     idx = torch.empty((B, k), dtype=torch.int32, device=dev)
