@@ -261,7 +261,10 @@ int reid_transpose_fill(const int64_t* ptr, const int32_t* idx, const float* val
  * B = sum_c Vq[row,c] |col(c)| >= sum_j t_ij and t_min the smallest t with J(t) <= eps (Markov); scanning S_cnt
  * instead of T_cnt gives slots of about twice the edge count instead of sum_c |col(c)|^2. */
 int reid_jaccard_bounds(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
-                        int64_t row_begin, int64_t row_end, float eps, int32_t* T_cnt, int32_t* S_cnt, void* stream);
+                        int64_t row_begin, int64_t row_end, float eps, int32_t* T_cnt, int32_t* S_cnt, int32_t* P_cnt,
+                        void* stream);
+/* P_cnt (optional): a GUESS of the row's number of distinct partners, min(T-based, 3 x longest column + nnz(row)); it
+ * only picks the hash-table class of the row's first attempt in reid_jaccard_eps_graph (NULL there: the T-based guess). */
 /* eps-neighbourhoods { j : J_ij <= eps } (what DBSCAN consumes), written at slot_ptr (local, from a
  * scan of T_cnt); nbr_cnt[row-row_begin] = size, or -1 when the row overflowed the shared-memory
  * table (redo those rows with a larger table_slots).  J values optional (nbr_val may be NULL).
@@ -289,7 +292,7 @@ int reid_jaccard_neighbors_heavy(const int64_t* Q_ptr, const int32_t* Q_idx, con
 size_t reid_jaccard_eps_graph_workspace_bytes(int64_t N, int64_t n_rows);
 int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
                            const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin,
-                           int64_t row_end, float eps, const int32_t* T_cnt, const int64_t* slot_ptr,
+                           int64_t row_end, float eps, const int32_t* T_cnt, const int32_t* P_cnt, const int64_t* slot_ptr,
                            int32_t* nbr_idx, float* nbr_val, int32_t* nbr_cnt, int64_t nbr_capacity,
                            uint64_t* slot_overflow, int half_precision, void* workspace, void* stream);
 /* dense rows: out[(row-row_begin)*ld + j] for all j < N  (the reference's return value). */
@@ -377,6 +380,16 @@ int reid_centroids_dev(const float* x, int64_t N, int64_t D, const int64_t* labe
  * across the ranks. */
 int reid_peer_push_lists(const uint64_t* part, const int32_t* part_cnt, int world, int64_t block_rows, int cap, int me,
                          const uint64_t* peer_base, int64_t cnt_offset_bytes, void* stream);
+/* reid_peer_push_records: the ragged all-gathers of the row-sharded sparse stages (V rows, V_qe rows, eps-neighbour
+ * lists) without a staging copy and without NCCL: the record of local row r -- { count, idx[stride], (val[stride]) }, the
+ * format of reid_rows_pack -- is written as record (me * max_rows + r) into EVERY rank's receive buffer
+ * (peer_base[w] + rec_offset_bytes); only the valid entries travel.  reid_rows_unpack_* then read the local buffer.
+ * reid_peer_allgather: a fixed-size block (block_bytes, multiple of 4) to slot `me` of every rank's buffer. */
+int reid_peer_push_records(const int32_t* cnt, const int64_t* ptr, const int32_t* idx, const float* val, int64_t n_rows,
+                           int64_t max_rows, int stride, int me, int world, const uint64_t* peer_base,
+                           int64_t rec_offset_bytes, void* stream);
+int reid_peer_allgather(const void* src, int64_t block_bytes, int me, int world, const uint64_t* peer_base,
+                        int64_t dst_offset_bytes, void* stream);
 
 /* ---- f4: feature hand-off  (clustercontrast/evaluators.py:16-68, train_usl.py:152-153) ----------------
  * dst[r] = src[idx[r]] for r < n (rows of D floats, D % 4 == 0): re-orders a device-resident feature store into the

@@ -20,22 +20,36 @@ __global__ void __launch_bounds__(256) jaccard_bounds_kernel(const int64_t* __re
                                                              const float* __restrict__ Q_val,
                                                              const int64_t* __restrict__ C_ptr, int64_t row_begin,
                                                              int64_t row_end, float t_min, int32_t* __restrict__ T_cnt,
-                                                             int32_t* __restrict__ S_cnt) {
+                                                             int32_t* __restrict__ S_cnt, int32_t* __restrict__ P_cnt) {
   const int64_t row = row_begin + (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
   if (row >= row_end) return;
   int64_t s = 0;
+  int64_t longest = 0;
   double b = 0.0;
-  for (int64_t p = Q_ptr[row] + lane_id(); p < Q_ptr[row + 1]; p += 32) {
+  const int64_t qa = Q_ptr[row], qb = Q_ptr[row + 1];
+  for (int64_t p = qa + lane_id(); p < qb; p += 32) {
     const int32_t c = Q_idx[p];
     const int64_t len = C_ptr[c + 1] - C_ptr[c];
     s += len;
+    longest = len > longest ? len : longest;
     if (S_cnt) b += (double)Q_val[p] * (double)len;
   }
   s = warp_sum(s);
+  longest = warp_max(longest);
   b = warp_sum(b);
   if (lane_id() == 0) {
     const int32_t t = (int32_t)(s > 0x7fffffff ? 0x7fffffff : s);
     T_cnt[row - row_begin] = t;
+    if (P_cnt) {
+      // GUESS of the number of distinct partners (sizes the hash table of the first attempt; a wrong guess only moves
+      // the row to a bigger table).  T counts every (column, partner) pair and over-estimates the partners ~14x on
+      // clustered data (a partner shares most of the row's columns).  A row inside an identity cluster of size m has
+      // columns of length ~m and ~m..2m partners, so 3 x the longest column + the row's own nnz is a much closer
+      // guess; it is never taken above the T-based one.
+      const int64_t by_t = t < 2048 ? t >> 2 : t >> 1;
+      const int64_t by_col = 3 * longest + (qb - qa);
+      P_cnt[row - row_begin] = (int32_t)(by_col < by_t ? by_col : by_t);
+    }
     if (S_cnt) {
       double need = t_min > 0.f ? b / (double)t_min + 2.0 : (double)t;
       if (need > (double)t) need = (double)t;
@@ -90,7 +104,8 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
     int32_t* __restrict__ next_queue, int32_t* __restrict__ next_len, float eps,
     const int64_t* __restrict__ slot_ptr, int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_val,
     int32_t* __restrict__ nbr_cnt, int slots, int64_t nbr_capacity, unsigned long long* __restrict__ slot_overflow,
-    int half) {
+    int half, const int32_t* __restrict__ T_cnt, int32_t* __restrict__ queues, int32_t* __restrict__ qlen, int64_t q_stride,
+    int cur_class, int direct_from) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = lane_id();
   int32_t* tkey = reinterpret_cast<int32_t*>(smem_raw) + (size_t)w * slots;
@@ -206,8 +221,19 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
     }
     if (overflow) {
       if (lane == 0) {
-        if (next_queue) next_queue[atomicAdd(next_len, 1)] = (int32_t)lr;
-        else nbr_cnt[lr] = -1;
+        if (queues) {
+          const int t = T_cnt[lr];
+          const int need = t < 2048 ? t >> 2 : t >> 1;
+          int c2 = 0;
+          while (c2 < kJClasses && need > ((jclass_slots(c2) >> 1) + (jclass_slots(c2) >> 2))) ++c2;
+          if (c2 <= cur_class) c2 = cur_class + 1;
+          if (c2 >= direct_from) c2 = direct_from <= kJClasses ? kJClasses + 1 : (c2 > kJClasses ? kJClasses : c2);
+          queues[(int64_t)c2 * q_stride + atomicAdd(&qlen[c2], 1)] = (int32_t)lr;
+        } else if (next_queue) {
+          next_queue[atomicAdd(next_len, 1)] = (int32_t)lr;
+        } else {
+          nbr_cnt[lr] = -1;
+        }
       }
       __syncwarp();
       continue;
@@ -351,14 +377,16 @@ __global__ void __launch_bounds__(kJDThreads) jaccard_direct_kernel(
 // do overflow move up one class at a time.
 // direct_from: rows that would need class >= direct_from go to the direct-indexed kernel instead (queue kJClasses + 1);
 // kJClasses + 1 when that kernel is not available for this N.
-__global__ void __launch_bounds__(256) jaccard_classify_kernel(const int32_t* __restrict__ T_cnt, int64_t n_rows,
+__global__ void __launch_bounds__(256) jaccard_classify_kernel(const int32_t* __restrict__ T_cnt,
+                                                               const int32_t* __restrict__ P_cnt, int64_t n_rows,
                                                                int direct_from, int32_t* __restrict__ queues,
                                                                int32_t* __restrict__ qlen) {
   const int64_t lr = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
   int c = -1;
   if (lr < n_rows) {
     const int t = T_cnt[lr];
-    const int need = t < 2048 ? t >> 2 : t >> 1;         // a retry of a long row is expensive: less optimism there
+    // a retry of a long row is expensive: less optimism there; P_cnt (reid_jaccard_bounds) refines the guess
+    const int need = P_cnt ? P_cnt[lr] : (t < 2048 ? t >> 2 : t >> 1);
     c = 0;
     while (c < kJClasses && need > ((jclass_slots(c) >> 1) + (jclass_slots(c) >> 2))) ++c;   // c == kJClasses: heavy
     if (c >= direct_from) c = kJClasses + 1;
@@ -484,6 +512,10 @@ struct JnArgs {
   const int64_t* C_ptr; const int32_t* C_idx; const float* C_val;
   int64_t row_begin; float eps; const int64_t* slot_ptr; int32_t* nbr_idx; float* nbr_val; int32_t* nbr_cnt;
   int64_t nbr_capacity; unsigned long long* slot_overflow; int half;
+  // escalation of a row that overflowed its table (reid_jaccard_eps_graph only; all NULL / 0 otherwise): the row goes to
+  // the class its T-based (pessimistic) size asks for -- at least one class up -- so a wrong optimistic first guess
+  // costs one attempt, not a climb through every class
+  const int32_t* T_cnt; int32_t* queues; int32_t* qlen; int64_t q_stride; int cur_class; int direct_from;
 };
 
 // one launch of the table kernel: `n_max` bounds the grid, the real row count is *queue_len when given
@@ -500,7 +532,8 @@ static int launch_jn(const JnArgs& a, int slots, int64_t n_max, const int32_t* q
   if (grid > cap) grid = cap;
   jaccard_neighbors_kernel<kWarps><<<(unsigned)grid, kWarps * 32, smem, st>>>(
       a.Q_ptr, a.Q_idx, a.Q_val, a.C_ptr, a.C_idx, a.C_val, a.row_begin, n_max, queue, queue_len, next_queue, next_len,
-      a.eps, a.slot_ptr, a.nbr_idx, a.nbr_val, a.nbr_cnt, slots, a.nbr_capacity, a.slot_overflow, a.half);
+      a.eps, a.slot_ptr, a.nbr_idx, a.nbr_val, a.nbr_cnt, slots, a.nbr_capacity, a.slot_overflow, a.half, a.T_cnt,
+      a.queues, a.qlen, a.q_stride, a.cur_class, a.direct_from);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
@@ -539,7 +572,8 @@ static size_t jws_carve(void* base, int64_t N, int64_t n, JWs* w) {
 extern "C" {
 
 int reid_jaccard_bounds(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
-                        int64_t row_begin, int64_t row_end, float eps, int32_t* T_cnt, int32_t* S_cnt, void* stream) {
+                        int64_t row_begin, int64_t row_end, float eps, int32_t* T_cnt, int32_t* S_cnt, int32_t* P_cnt,
+                        void* stream) {
   using namespace reid;
   REID_CHECK_ARG(Q_ptr && Q_idx && C_ptr && T_cnt, "reid_jaccard_bounds: NULL pointer");
   REID_CHECK_ARG(!S_cnt || Q_val, "reid_jaccard_bounds: S_cnt needs Q_val");
@@ -550,7 +584,7 @@ int reid_jaccard_bounds(const int64_t* Q_ptr, const int32_t* Q_idx, const float*
   float t_min = 0.f;
   if (eps < 1.f) t_min = (float)(2.0 * (1.0 - (double)eps) / (2.0 - (double)eps) * 0.999);
   jaccard_bounds_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(Q_ptr, Q_idx, Q_val, C_ptr, row_begin,
-                                                                                  row_end, t_min, T_cnt, S_cnt);
+                                                                                  row_end, t_min, T_cnt, S_cnt, P_cnt);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
@@ -571,7 +605,7 @@ int reid_jaccard_neighbors(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
   const int64_t n = rows_list ? n_list : row_end - row_begin;
   if (n == 0) return REID_OK;
   const JnArgs a{Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, row_begin, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt,
-                 INT64_MAX, nullptr, 0};
+                 INT64_MAX, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, 0};
   return launch_jn_slots(a, table_slots, n, rows_list, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
@@ -582,7 +616,7 @@ size_t reid_jaccard_eps_graph_workspace_bytes(int64_t N, int64_t n_rows) {
 
 int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
                            const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin, int64_t row_end,
-                           float eps, const int32_t* T_cnt, const int64_t* slot_ptr, int32_t* nbr_idx, float* nbr_val,
+                           float eps, const int32_t* T_cnt, const int32_t* P_cnt, const int64_t* slot_ptr, int32_t* nbr_idx, float* nbr_val,
                            int32_t* nbr_cnt, int64_t nbr_capacity, uint64_t* slot_overflow, int half_precision,
                            void* workspace, void* stream) {
   using namespace reid;
@@ -601,17 +635,16 @@ int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
   const int direct_from = row_bytes * 2 <= 220u * 1024u ? 3 : kJClasses + 1;
   int32_t* direct_q = w.queues + (int64_t)(kJClasses + 1) * n;
   int32_t* direct_len = w.qlen + kJClasses + 1;
-  jaccard_classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(T_cnt, n, direct_from, w.queues, w.qlen);
+  jaccard_classify_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(T_cnt, P_cnt, n, direct_from, w.queues, w.qlen);
   REID_LAUNCH_CHECK();
   if (nbr_capacity <= 0) nbr_capacity = INT64_MAX;           // slots sized by the caller from T_cnt: nothing to guard
   unsigned long long* ovf = (unsigned long long*)slot_overflow;
-  const JnArgs a{Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, row_begin, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt,
-                 nbr_capacity, ovf, half_precision};
+  JnArgs a{Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, row_begin, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt,
+           nbr_capacity, ovf, half_precision, T_cnt, w.queues, w.qlen, n, 0, direct_from};
   const int n_hash = direct_from < kJClasses ? direct_from : kJClasses;
   for (int c = 0; c < n_hash; ++c) {
-    const bool last = c + 1 == n_hash && direct_from <= kJClasses;
-    int rc = launch_jn_slots(a, jclass_slots(c), n, w.queues + (int64_t)c * n, w.qlen + c,
-                             last ? direct_q : w.queues + (int64_t)(c + 1) * n, last ? direct_len : w.qlen + c + 1, st);
+    a.cur_class = c;
+    int rc = launch_jn_slots(a, jclass_slots(c), n, w.queues + (int64_t)c * n, w.qlen + c, nullptr, nullptr, st);
     if (rc != REID_OK) return rc;
   }
   if (direct_from <= kJClasses) {

@@ -62,6 +62,7 @@ def _scan(cnt, n, dev):
 # REPORT what did not fit instead of trusting the guess, and reads one small report at the END of the pass
 # (RerankState.finish): a pass whose guesses held never synchronised in between, any other is redone with exact sizes.
 QE_SPEC_SLOTS = 512          # query-expansion table / padded V_qe row (distinct columns <= 3/4 of it)
+PARTNER_GUESS = True         # size each row's first Jaccard hash table from 3 x longest column + nnz (reid_jaccard_bounds P_cnt)
 NBR_SPEC_PER_ROW = 256       # eps-neighbour slots per row on average (slots are dealt by the Markov bound S_i)
 _nbr_cap_hint = {}           # N -> slot total of the last finished pass (the next pass allocates 1.25 x that)
 # report (int64 x 16): [0:3] |E| total/max/sumsq  [3:6] nnz(V_qe) rows  [6:9] column counts: nnz, longest, sum len^2
@@ -315,7 +316,7 @@ def rerank_state_async(x, k1, k2, knn="auto", rows=None, timers=False, comm=None
     if comm is not None and speculative:                     # V rows of other shards are read by a5
         sv = _stride_for("V", N)
         e_ptr, e_idx, v_val = comm.gather_records(e_cnt[:n], e_ptr, e_idx, v_val, sv, overflow=report[R_XCHG_OVF:],
-                                                  stats_out=report[R_E:R_E + 3])[:3]
+                                                  stats_out=report[R_E:R_E + 3], tag="V")[:3]
     elif comm is not None:
         e_ptr, e_idx, v_val, e_total, e_max = comm.gather_csr(e_cnt[:n], e_idx[:e_total], v_val[:e_total], row_ptr=e_ptr)
         _rec_stride_hint[("V", N)] = max(_rec_stride_hint.get(("V", N), 0), int(e_max))
@@ -352,7 +353,7 @@ def rerank_state_async(x, k1, k2, knn="auto", rows=None, timers=False, comm=None
         if comm is not None and speculative:
             sq = _stride_for("Q", N)
             q_ptr, q_idx, q_val = comm.gather_records(q_cnt[:n], q_ptr, q_idx, q_val, sq, overflow=report[R_XCHG_OVF:],
-                                                      stats_out=report[R_Q:R_Q + 3])[:3]
+                                                      stats_out=report[R_Q:R_Q + 3], tag="Q")[:3]
         elif comm is not None:
             q_ptr, q_idx, q_val, q_total, q_mx = comm.gather_csr(q_cnt[:n], q_idx[:q_total], q_val[:q_total], row_ptr=q_ptr)
             _rec_stride_hint[("Q", N)] = max(_rec_stride_hint.get(("Q", N), 0), int(q_mx))
@@ -469,22 +470,23 @@ def jaccard_neighbors(st, eps, with_values=False, speculative=None):
         speculative = st.report is not None
     eps32 = float(np.float32(eps))
     t_cnt = torch.empty(n, dtype=torch.int32, device=dev)
+    p_cnt = torch.empty(n, dtype=torch.int32, device=dev)       # partner-count guess: picks each row's first table class
     ws = torch.empty(L.reid_jaccard_eps_graph_workspace_bytes(st.N, n), dtype=torch.uint8, device=dev)
     if speculative:
         report = st.report
         s_cnt = torch.empty(n, dtype=torch.int32, device=dev)
         call("reid_jaccard_bounds", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), r0, r1, eps32, ptr(t_cnt),
-             ptr(s_cnt), sp)
+             ptr(s_cnt), ptr(p_cnt), sp)
         slot_ptr, _ = _scan_async(s_cnt, n, dev, stats=report[R_S:R_S + 3])
         cap = max(n * NBR_SPEC_PER_ROW, int(_nbr_cap_hint.get(st.N, 0) * 1.25), 1)
         nbr_idx = torch.empty(cap, dtype=torch.int32, device=dev)
         nbr_val = torch.empty(cap, dtype=torch.float32, device=dev) if with_values else None
         nbr_cnt = torch.empty(n, dtype=torch.int32, device=dev)
         call("reid_jaccard_eps_graph", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
-             ptr(st.C_val), st.N, r0, r1, eps32, ptr(t_cnt), ptr(slot_ptr), ptr(nbr_idx), ptr(nbr_val), ptr(nbr_cnt),
-             cap, ptr(report[R_NBR_OVF:]), 1 if st.half else 0, ptr(ws), sp)
+             ptr(st.C_val), st.N, r0, r1, eps32, ptr(t_cnt), ptr(p_cnt) if PARTNER_GUESS else None, ptr(slot_ptr), ptr(nbr_idx),
+             ptr(nbr_val), ptr(nbr_cnt), cap, ptr(report[R_NBR_OVF:]), 1 if st.half else 0, ptr(ws), sp)
         return slot_ptr, nbr_idx, nbr_cnt, nbr_val
-    call("reid_jaccard_bounds", ptr(st.Q_ptr), ptr(st.Q_idx), None, ptr(st.C_ptr), r0, r1, eps32, ptr(t_cnt), None, sp)
+    call("reid_jaccard_bounds", ptr(st.Q_ptr), ptr(st.Q_idx), None, ptr(st.C_ptr), r0, r1, eps32, ptr(t_cnt), None, ptr(p_cnt), sp)
     if r0 == 0 and r1 == st.N and getattr(st, "t_total_all", None) is not None:
         slot_ptr, _ = _scan_async(t_cnt, n, dev)              # the total is already known (rerank_state, a6)
         t_total = st.t_total_all
@@ -494,8 +496,8 @@ def jaccard_neighbors(st, eps, with_values=False, speculative=None):
     nbr_val = torch.empty(max(t_total, 1), dtype=torch.float32, device=dev) if with_values else None
     nbr_cnt = torch.empty(n, dtype=torch.int32, device=dev)
     call("reid_jaccard_eps_graph", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
-                                   ptr(st.C_val), st.N, r0, r1, eps32, ptr(t_cnt), ptr(slot_ptr), ptr(nbr_idx),
-                                   ptr(nbr_val), ptr(nbr_cnt), 0, None, 1 if st.half else 0, ptr(ws), sp)
+                                   ptr(st.C_val), st.N, r0, r1, eps32, ptr(t_cnt), ptr(p_cnt) if PARTNER_GUESS else None,
+                                   ptr(slot_ptr), ptr(nbr_idx), ptr(nbr_val), ptr(nbr_cnt), 0, None, 1 if st.half else 0, ptr(ws), sp)
     return slot_ptr, nbr_idx, nbr_cnt, nbr_val
 
 

@@ -86,7 +86,7 @@ class RowComm:
         out = self._all_gather_padded(t, length, max(max(lens), 1))
         return torch.cat([out[r, :l] for r, l in enumerate(lens)], dim=0), lens
 
-    def gather_records(self, cnt, row_ptr, idx, val, stride, overflow=None, stats_out=None):
+    def gather_records(self, cnt, row_ptr, idx, val, stride, overflow=None, stats_out=None, tag="rec"):
         """CUDA only: ragged rows (cnt, row starts `row_ptr` into idx / val) -> global CSR through ONE all-gather of
         fixed-stride records (csrc/rerank_sparse.cu rows_pack / rows_unpack).  Returns (g_ptr, g_idx, g_val, total,
         max, g_cnt), or None when some row is longer than `stride` (every rank sees the same gathered counts, so
@@ -96,10 +96,21 @@ class RowComm:
         dev = idx.device
         n = self.r1 - self.r0
         words = 1 + stride * (2 if val is not None else 1)
-        rec = torch.empty((self.max_rows, words), dtype=torch.int32, device=dev)
-        call("reid_rows_pack", p_(cnt), p_(row_ptr), p_(idx), p_(val), n, self.max_rows, stride, p_(rec), stream_ptr())
-        out = torch.empty((self.world, self.max_rows, words), dtype=torch.int32, device=dev)
-        dist.all_gather_into_tensor(out, rec, group=self.group)
+        pb = None
+        if overflow is not None:                             # sync-free pass: peer stores instead of pack + NCCL all-gather
+            # one buffer per exchange (tag): two exchanges of one pass must never share a receive buffer -- a fast rank
+            # could push the second while a slow one still unpacks the first
+            pb = _peer_buffer("rec:" + tag, self.world * self.max_rows * words * 4, dev, self.group)
+        if pb is not None:
+            call("reid_peer_push_records", p_(cnt), p_(row_ptr), p_(idx), p_(val), n, self.max_rows, stride, self.rank,
+                 self.world, p_(pb.peer_base), 0, stream_ptr())
+            pb.barrier()
+            out = pb.buf.view(torch.int32)[: self.world * self.max_rows * words]
+        else:
+            rec = torch.empty((self.max_rows, words), dtype=torch.int32, device=dev)
+            call("reid_rows_pack", p_(cnt), p_(row_ptr), p_(idx), p_(val), n, self.max_rows, stride, p_(rec), stream_ptr())
+            out = torch.empty((self.world, self.max_rows, words), dtype=torch.int32, device=dev)
+            dist.all_gather_into_tensor(out, rec, group=self.group)
         key_ = (self.N, self.world, str(dev))
         if key_ not in _bounds_cache:                         # cached across passes: no H2D copy inside a captured pass
             _bounds_cache[key_] = torch.tensor([a for a, _ in self.bounds] + [self.N], dtype=torch.int64, device=dev)
@@ -156,7 +167,7 @@ class RowComm:
         (ptr int64 (N+1), idx, cnt int32 (N)).  overflow (device scalar): sync-free flavour, see gather_records."""
         n = self.r1 - self.r0
         if overflow is not None:
-            got = self.gather_records(nbr_cnt, slot_ptr, nbr_idx, None, stride, overflow=overflow)
+            got = self.gather_records(nbr_cnt, slot_ptr, nbr_idx, None, stride, overflow=overflow, tag="nbr")
             return got[0], got[1], got[5]
         if nbr_idx.is_cuda and RECORD_GATHER:
             got = self.gather_records(nbr_cnt, slot_ptr, nbr_idx, None, 128)
@@ -223,6 +234,52 @@ class PeerLists:
 
     def barrier(self):
         self.handle.barrier(channel=0)
+
+
+class PeerBuffer:
+    """nbytes of symmetric (peer-mapped) memory on every rank + the device array of all ranks' base addresses."""
+
+    def __init__(self, nbytes, dev, group):
+        import torch.distributed._symmetric_memory as symm
+        self.buf = symm.empty((nbytes + 7) // 8, dtype=torch.int64, device=dev)
+        self.handle = symm.rendezvous(self.buf, group if group is not None else dist.group.WORLD)
+        self.peer_base = torch.tensor([int(p) for p in self.handle.buffer_ptrs], dtype=torch.int64, device=dev)
+
+    def barrier(self):
+        self.handle.barrier(channel=0)
+
+
+def _peer_buffer(name, nbytes, dev, group):
+    """Cached per (name, size): creating one is a collective (rendezvous) and must not happen inside a captured pass.
+    None when the box cannot map peer memory (NCCL then carries the exchange)."""
+    if not PEER_EXCHANGE:
+        return None
+    key_ = (name, nbytes, str(dev), id(group))
+    if key_ not in _peer_cache:
+        try:
+            _peer_cache[key_] = PeerBuffer(nbytes, dev, group)
+        except Exception as e:
+            import warnings
+            warnings.warn("peer-memory exchange unavailable (%r): using NCCL collectives" % (e,))
+            _peer_cache[key_] = None
+    return _peer_cache[key_]
+
+
+def peer_all_gather(name, block, group=None):
+    """all_gather_into_tensor over peer stores: `block` (contiguous, same shape on every rank) -> (W * len(block), ...)
+    on every rank, in rank order.  Falls back to NCCL when peer memory is unavailable."""
+    from ._lib import call, ptr, stream_ptr
+    W, me = dist.get_world_size(group), dist.get_rank(group)
+    nbytes = block.numel() * block.element_size()
+    pb = _peer_buffer(name, W * nbytes, block.device, group) if nbytes % 4 == 0 else None
+    shape = (W * block.shape[0],) + tuple(block.shape[1:])
+    if pb is None:
+        out = torch.empty(shape, dtype=block.dtype, device=block.device)
+        dist.all_gather_into_tensor(out, block, group=group)
+        return out
+    call("reid_peer_allgather", ptr(block), nbytes, me, W, ptr(pb.peer_base), 0, stream_ptr())
+    pb.barrier()
+    return pb.buf.view(torch.uint8)[: W * nbytes].view(block.dtype).view(shape)
 
 
 def _peer_lists(W, B, cap, dev, group):
@@ -299,8 +356,11 @@ def knn_search_tiles(x, k, group=None, report=None):
              ptr(pre_cnt), ptr(pre_tau), sp)
         call("reid_knn_sample_tau", ptr(pre), ptr(pre_cnt), ptr(pre_tau), 2, nb, kt.sym_rank(k), ptr(t_f), ptr(t_o), sp)
     mark("prepass")
-    tau = torch.empty(W * B, dtype=torch.float32, device=dev)          # rows >= N are padding (never read)
-    dist.all_gather_into_tensor(tau, t_f, group=group)
+    if report is not None:
+        tau = peer_all_gather("tau", t_f, group)                       # rows >= N are padding (never read)
+    else:
+        tau = torch.empty(W * B, dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(tau, t_f, group=group)
     mark("gather_tau")
     # 2. my share of the tiles -> partial lists of ALL rows (W * B row slots so that slot == row)
     tiles = _my_tiles(N, W, me, dev)
@@ -359,10 +419,14 @@ def knn_search_tiles(x, k, group=None, report=None):
         metric = "l2"
     mark("rescore")
     # 5. final lists of all rows on every rank
-    g_idx = torch.empty((W * B, k), dtype=torch.int32, device=dev)
-    g_key = torch.empty((W * B, k), dtype=torch.float32, device=dev)
-    dist.all_gather_into_tensor(g_idx, idx, group=group)
-    dist.all_gather_into_tensor(g_key, key, group=group)
+    if report is not None:
+        g_idx = peer_all_gather("rank", idx, group)
+        g_key = peer_all_gather("rkey", key, group)
+    else:
+        g_idx = torch.empty((W * B, k), dtype=torch.int32, device=dev)
+        g_key = torch.empty((W * B, k), dtype=torch.float32, device=dev)
+        dist.all_gather_into_tensor(g_idx, idx, group=group)
+        dist.all_gather_into_tensor(g_key, key, group=group)
     mark("gather_lists")
     steps = None
     if TRACE_STEPS:
@@ -402,9 +466,9 @@ def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=
         from . import knn_tc as kt
         sym_ok = (knn in ("auto", "tc") and kt.SYM and N >= kt.SYM_MIN_N and k1 <= kt.SYM_MAX_K and x.shape[1] % 64 == 0)
         if plan == "auto":
-            # measured at N = 32,621: 2 GPUs 3.6 (tiles) vs 4.1 ms (tiles+rows); 8 GPUs 2.9 vs 2.6 ms
-            replicate = N < ROWS_PLAN_MIN_N and comm.world <= 2
-            plan = ("tiles" if replicate else "tiles+rows") if sym_ok else "rows"
+            # measured at N = 32,621 with the peer-store exchanges and graph replay (profiles/): 2 GPUs 2.81 ms (tiles)
+            # vs 2.57 ms (tiles+rows), 8 GPUs 2.16 vs 1.78 ms: the per-row stages are sharded from 2 GPUs on
+            plan = "tiles+rows" if sym_ok else "rows"
         if plan in ("tiles", "tiles+rows") and not sym_ok:
             raise ValueError("plan %r needs the symmetric tensor-core search (N >= %d, k1 <= %d, D %% 64 == 0)" % (plan, kt.SYM_MIN_N, kt.SYM_MAX_K))
         from .faiss_rerank import R_XCHG_OVF, _stride_for, _rec_stride_hint
