@@ -484,11 +484,9 @@ __global__ void __launch_bounds__(kGThreads, 2) rescore_group_kernel(
 //     added in warp order: the summation order of a dot is fixed by the kernel alone, not by the group or the slot
 //     the pair landed in -- keys are identical for every sharding;
 //   * accumulators: 2 doubles per tile and lane -- 16 registers for 64 candidates per pass.
-constexpr int kMq = 8;                      // queries per group (= MMA M)
 constexpr int kMThreads = 128;              // 4 warps = 4 quarters of K
 constexpr int kMTiles = 8;                  // candidate tiles (8 candidates each) per pass
 constexpr int kMChunk = kMTiles * 8;        // 64 candidates per pass
-constexpr int kMSlots = 2048;               // union hash table (|union| <= kMq * kWinMax = 1024)
 
 __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, double b) {
   asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0, %1}, {%2}, {%3}, {%0, %1};"
@@ -496,41 +494,62 @@ __device__ __forceinline__ void dmma_8x8x4(double& c0, double& c1, double a, dou
                : "d"(a), "d"(b));
 }
 
-template <int kUnroll, int kMinBlocks>
+// kMT = M tiles per group: a group is 8 * kMT locality-ordered rows.  With kMT = 2 every candidate value that is
+// loaded and converted feeds 16 queries instead of 8 (half the XU work and half the L2 -> SM bytes per FMA) at the
+// price of 64 accumulator registers; the union of 16 cluster mates is barely larger than that of 8.
+template <int kMT>
+struct MmaSmem {
+  static constexpr int kQ = 8 * kMT;                       // queries per group
+  static constexpr int kSlots = 2 * kQ * kWinMax;          // union hash table (|union| <= kQ * kWinMax)
+  static constexpr int kSlotBits = kMT == 1 ? 11 : 12;
+  // region 0: the hash table (setup) and, afterwards, the per-quarter partial dots of a pass -- never live together
+  static constexpr size_t kTabBytes = (size_t)kSlots * 4 + (size_t)kSlots * 2;
+  static constexpr size_t kDotBytes = (size_t)4 * kQ * kMChunk * 8;
+  static constexpr size_t kRegion0 = kTabBytes > kDotBytes ? kTabBytes : kDotBytes;
+  static constexpr size_t kUlist = kRegion0;                                    // int32 [kQ * kWinMax]
+  static constexpr size_t kPid = kUlist + (size_t)kQ * kWinMax * 4;             // uint16 [kQ * kWinMax]
+  static constexpr size_t kKey = kPid + (size_t)kQ * kWinMax * 2;               // uint64 [kQ * kWinMax]
+  static constexpr size_t kBytes = kKey + (size_t)kQ * kWinMax * 8;
+};
+
+template <int kMT, int kUnroll, int kMinBlocks>
 __global__ void __launch_bounds__(kMThreads, kMinBlocks) rescore_mma_kernel(
     const float* __restrict__ x, int64_t D, int64_t row_begin, int64_t n_rows, const int32_t* __restrict__ perm,
     const int32_t* __restrict__ win_cnt, const int32_t* __restrict__ win_idx, const float* __restrict__ win_a, int k,
     float eps_in, const float* __restrict__ max_sqnorm, int32_t* __restrict__ out_idx, float* __restrict__ out_key,
     int32_t* __restrict__ uncert, unsigned* __restrict__ max_err_bits, unsigned long long* __restrict__ uncert_count) {
-  __shared__ int32_t s_tab[kMSlots];                   // union hash table: column ids
-  __shared__ uint16_t s_tid[kMSlots];                  // slot -> position in the union
-  __shared__ int32_t s_ulist[kMq * kWinMax];           // the union
-  __shared__ uint16_t s_pid[kMq * kWinMax];            // window entry -> position in the union
-  __shared__ uint64_t s_key[kMq * kWinMax];            // window entry -> final sort key
-  __shared__ double s_dot[4][kMq][kMChunk];            // per K-quarter partial dots of one pass
+  using L = MmaSmem<kMT>;
+  constexpr int kQ = L::kQ;
+  extern __shared__ __align__(16) unsigned char mma_smem[];
+  int32_t* s_tab = reinterpret_cast<int32_t*>(mma_smem);                              // union hash table: column ids
+  uint16_t* s_tid = reinterpret_cast<uint16_t*>(mma_smem + (size_t)L::kSlots * 4);    // slot -> position in the union
+  double* s_dot = reinterpret_cast<double*>(mma_smem);                                // [4][kQ][kMChunk], after the setup
+  int32_t* s_ulist = reinterpret_cast<int32_t*>(mma_smem + L::kUlist);                // the union
+  uint16_t* s_pid = reinterpret_cast<uint16_t*>(mma_smem + L::kPid);                  // window entry -> union position
+  uint64_t* s_key = reinterpret_cast<uint64_t*>(mma_smem + L::kKey);                  // window entry -> final sort key
   __shared__ int s_U;
-  __shared__ int s_nw[kMq];
-  __shared__ int64_t s_lr[kMq];
-  __shared__ unsigned s_worst[kMq];
+  __shared__ int s_nw[kQ];
+  __shared__ int64_t s_lr[kQ];
+  __shared__ unsigned s_worst[kQ];
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float eps = max_sqnorm ? reid_tc_err_bound(*max_sqnorm) : eps_in;
 
-  if (tid < kMq) {
-    const int64_t slot = (int64_t)blockIdx.x * kMq + tid;
+  if (tid < kQ) {
+    const int64_t slot = (int64_t)blockIdx.x * kQ + tid;
     const int64_t lr = slot < n_rows ? (perm ? perm[slot] : slot) : -1;
     s_lr[tid] = lr;
     s_nw[tid] = lr >= 0 ? win_cnt[lr] : 0;
     s_worst[tid] = 0u;
   }
   if (tid == 0) s_U = 0;
-  for (int h = tid; h < kMSlots; h += kMThreads) s_tab[h] = -1;
+  for (int h = tid; h < L::kSlots; h += kMThreads) s_tab[h] = -1;
   __syncthreads();
   // union of the windows
-  for (int it = tid; it < kMq * kWinMax; it += kMThreads) {
+  for (int it = tid; it < kQ * kWinMax; it += kMThreads) {
     const int q = it / kWinMax, t = it % kWinMax;
     if (t < s_nw[q]) {
       const int32_t j = win_idx[s_lr[q] * kWinMax + t];
-      uint32_t h = ((uint32_t)j * 0x9e3779b1u) >> 21;          // 11 bits
+      uint32_t h = ((uint32_t)j * 0x9e3779b1u) >> (32 - L::kSlotBits);
       while (true) {
         const int32_t old = atomicCAS(&s_tab[h], -1, j);
         if (old == -1) {
@@ -540,28 +559,32 @@ __global__ void __launch_bounds__(kMThreads, kMinBlocks) rescore_mma_kernel(
           break;
         }
         if (old == j) break;
-        h = (h + 1) & (kMSlots - 1);
+        h = (h + 1) & (L::kSlots - 1);
       }
     }
   }
   __syncthreads();
-  for (int it = tid; it < kMq * kWinMax; it += kMThreads) {
+  for (int it = tid; it < kQ * kWinMax; it += kMThreads) {
     const int q = it / kWinMax, t = it % kWinMax;
     if (t < s_nw[q]) {
       const int32_t j = win_idx[s_lr[q] * kWinMax + t];
-      uint32_t h = ((uint32_t)j * 0x9e3779b1u) >> 21;
-      while (s_tab[h] != j) h = (h + 1) & (kMSlots - 1);
+      uint32_t h = ((uint32_t)j * 0x9e3779b1u) >> (32 - L::kSlotBits);
+      while (s_tab[h] != j) h = (h + 1) & (L::kSlots - 1);
       s_pid[it] = s_tid[h];
     }
   }
-  __syncthreads();
+  __syncthreads();                                              // the table is dead from here on: region 0 becomes s_dot
   const int U = s_U;
 
   const int g = lane >> 2, tg = lane & 3;
   const int64_t quarter = D >> 2;                               // D % 64 == 0: 16-wide K blocks, four quarters
-  const int64_t lr_g = s_lr[g];
   // a group that is not full multiplies by row 0's values for the missing queries; those dots are never read
-  const float4* qp = reinterpret_cast<const float4*>(x + (row_begin + (lr_g >= 0 ? lr_g : 0)) * D + warp * quarter) + tg;
+  const float4* qp[kMT];
+#pragma unroll
+  for (int m = 0; m < kMT; ++m) {
+    const int64_t lr_g = s_lr[m * 8 + g];
+    qp[m] = reinterpret_cast<const float4*>(x + (row_begin + (lr_g >= 0 ? lr_g : 0)) * D + warp * quarter) + tg;
+  }
   const int n_blocks = (int)(quarter >> 4);
 
   for (int c0 = 0; c0 < U; c0 += kMChunk) {
@@ -572,44 +595,63 @@ __global__ void __launch_bounds__(kMThreads, kMinBlocks) rescore_mma_kernel(
       const int id = c0 + t * 8 + g;
       cp[t] = reinterpret_cast<const float4*>(x + (int64_t)s_ulist[id < U ? id : U - 1] * D + warp * quarter) + tg;
     }
-    double acc[kMTiles][2];
+    double acc[kMT][kMTiles][2];
 #pragma unroll
-    for (int t = 0; t < kMTiles; ++t) acc[t][0] = acc[t][1] = 0.0;
+    for (int m = 0; m < kMT; ++m)
+#pragma unroll
+      for (int t = 0; t < kMTiles; ++t) acc[m][t][0] = acc[m][t][1] = 0.0;
 #pragma unroll kUnroll
     for (int kb = 0; kb < n_blocks; ++kb) {
-      const float4 a = qp[kb * 4];
+      float4 a[kMT];
+#pragma unroll
+      for (int m = 0; m < kMT; ++m) a[m] = qp[m][kb * 4];
       float4 b[kMTiles];
 #pragma unroll
       for (int t = 0; t < kMTiles; ++t)
         if (t < nt) b[t] = cp[t][kb * 4];
-      const double a0 = (double)a.x, a1 = (double)a.y, a2 = (double)a.z, a3 = (double)a.w;
+      double ad[kMT][4];
+#pragma unroll
+      for (int m = 0; m < kMT; ++m) {
+        ad[m][0] = (double)a[m].x;
+        ad[m][1] = (double)a[m].y;
+        ad[m][2] = (double)a[m].z;
+        ad[m][3] = (double)a[m].w;
+      }
 #pragma unroll
       for (int t = 0; t < kMTiles; ++t) {
         if (t < nt) {
-          dmma_8x8x4(acc[t][0], acc[t][1], a0, (double)b[t].x);
-          dmma_8x8x4(acc[t][0], acc[t][1], a1, (double)b[t].y);
-          dmma_8x8x4(acc[t][0], acc[t][1], a2, (double)b[t].z);
-          dmma_8x8x4(acc[t][0], acc[t][1], a3, (double)b[t].w);
+          const double b0 = (double)b[t].x, b1 = (double)b[t].y, b2 = (double)b[t].z, b3 = (double)b[t].w;
+#pragma unroll
+          for (int m = 0; m < kMT; ++m) {
+            dmma_8x8x4(acc[m][t][0], acc[m][t][1], ad[m][0], b0);
+            dmma_8x8x4(acc[m][t][0], acc[m][t][1], ad[m][1], b1);
+            dmma_8x8x4(acc[m][t][0], acc[m][t][1], ad[m][2], b2);
+            dmma_8x8x4(acc[m][t][0], acc[m][t][1], ad[m][3], b3);
+          }
         }
       }
     }
-    // C fragment: row = g (query), columns 2 tg, 2 tg + 1 of the tile
+    // C fragment: row = g (query within the M tile), columns 2 tg, 2 tg + 1 of the N tile
 #pragma unroll
-    for (int t = 0; t < kMTiles; ++t) {
-      if (t < nt) {
-        s_dot[warp][g][t * 8 + 2 * tg] = acc[t][0];
-        s_dot[warp][g][t * 8 + 2 * tg + 1] = acc[t][1];
+    for (int m = 0; m < kMT; ++m)
+#pragma unroll
+      for (int t = 0; t < kMTiles; ++t) {
+        if (t < nt) {
+          double* d = s_dot + ((size_t)warp * kQ + m * 8 + g) * kMChunk + t * 8 + 2 * tg;
+          d[0] = acc[m][t][0];
+          d[1] = acc[m][t][1];
+        }
       }
-    }
     __syncthreads();
-    for (int it = tid; it < kMq * kWinMax; it += kMThreads) {
+    for (int it = tid; it < kQ * kWinMax; it += kMThreads) {
       const int q = it / kWinMax, t = it % kWinMax;
       if (t < s_nw[q]) {
         const int id = (int)s_pid[it] - c0;
         if (id >= 0 && id < kMChunk) {
           const int64_t lr = s_lr[q];
-          const double d = ((s_dot[0][q][id] + s_dot[1][q][id]) + s_dot[2][q][id]) + s_dot[3][q][id];   // fixed order
-          const float sc = (float)d;
+          const double* d = s_dot + (size_t)q * kMChunk + id;
+          const double dd = ((d[0] + d[(size_t)kQ * kMChunk]) + d[(size_t)2 * kQ * kMChunk]) + d[(size_t)3 * kQ * kMChunk];  // fixed order
+          const float sc = (float)dd;
           const float err = fabsf(sc - win_a[lr * kWinMax + t]);
           atomicMax(&s_worst[q], __float_as_uint(err == err ? err : INFINITY));
           s_key[it] = sel_key(sc, win_idx[lr * kWinMax + t]);
@@ -620,7 +662,7 @@ __global__ void __launch_bounds__(kMThreads, kMinBlocks) rescore_mma_kernel(
   }
 
   // per row: audit, then order by (key desc, idx asc); the first k go out
-  for (int q = warp; q < kMq; q += kMThreads / 32) {
+  for (int q = warp; q < kQ; q += kMThreads / 32) {
     const int64_t lr = s_lr[q];
     if (lr < 0) continue;
     const int n_w = s_nw[q];
@@ -749,20 +791,25 @@ int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, in
   const bool aligned = (((uintptr_t)x) & 15) == 0;
   static const bool no_group = dev_env("REID_RESCORE_GROUP", 1) == 0;
   const int rescore_variant = dev_env("REID_RESCORE_VARIANT", 2);   // developer builds: 1 = CUDA-core grouped kernel
-#define REID_MMA_LAUNCH(U, B)                                                                                       \
-  rescore_mma_kernel<U, B><<<(unsigned)((n + kMq - 1) / kMq), kMThreads, 0, st>>>(                                   \
-      x, D, row_begin, n, locality_order ? w.perm : nullptr, w.win_cnt, w.win_idx, w.win_a, k, err_bound, max_sqnorm, \
-      out_idx, out_key, uncertified_flag, (unsigned*)max_err_out, (unsigned long long*)uncertified_count)
+#define REID_MMA_LAUNCH(MT, U, B)                                                                                   \
+  do {                                                                                                              \
+    const size_t sm_ = MmaSmem<MT>::kBytes;                                                                         \
+    REID_CUDA(cudaFuncSetAttribute(rescore_mma_kernel<MT, U, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_)); \
+    rescore_mma_kernel<MT, U, B><<<(unsigned)((n + 8 * MT - 1) / (8 * MT)), kMThreads, sm_, st>>>(                   \
+        x, D, row_begin, n, locality_order ? w.perm : nullptr, w.win_cnt, w.win_idx, w.win_a, k, err_bound,         \
+        max_sqnorm, out_idx, out_key, uncertified_flag, (unsigned*)max_err_out,                                     \
+        (unsigned long long*)uncertified_count);                                                                    \
+  } while (0)
   if (aligned && D % 64 == 0 && !no_group && rescore_variant >= 2) {
 #ifdef REID_DEV
-    if (rescore_variant == 3) REID_MMA_LAUNCH(1, 4);
-    else if (rescore_variant == 4) REID_MMA_LAUNCH(1, 5);
-    else if (rescore_variant == 5) REID_MMA_LAUNCH(2, 5);
-    else if (rescore_variant == 6) REID_MMA_LAUNCH(1, 6);
-    else if (rescore_variant == 7) REID_MMA_LAUNCH(4, 3);
+    if (rescore_variant == 3) REID_MMA_LAUNCH(1, 1, 4);
+    else if (rescore_variant == 4) REID_MMA_LAUNCH(2, 1, 3);
+    else if (rescore_variant == 5) REID_MMA_LAUNCH(2, 2, 2);
+    else if (rescore_variant == 6) REID_MMA_LAUNCH(2, 1, 2);
+    else if (rescore_variant == 7) REID_MMA_LAUNCH(1, 2, 4);
     else
 #endif
-      REID_MMA_LAUNCH(2, 4);
+      REID_MMA_LAUNCH(1, 2, 4);
   } else if (aligned && D % 64 == 0 && D <= 2048 && !no_group) {
     const size_t smem = rescore_group_smem(D);
     REID_CUDA(cudaFuncSetAttribute(rescore_group_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
