@@ -1,8 +1,8 @@
 // a10-a12 -- ClusterMemory (clustercontrast/models/cm.py:9-76, 110-137).
 // The problem is latency bound (B=256, C~700, D=2048: 1.5 GFLOP, 16 MB), so the design goal is
 // few launches and no host synchronisation -- the reference's CM_Hard.backward performs 256
-// .cpu() round trips (cm.py:66).  fp32 CUDA-core arithmetic keeps loss and centroids within
-// 1e-4 of the reference's fp32 cuBLAS path; tensor-core formats would not.
+// .cpu() round trips (cm.py:66).  The two GEMMs run on the tensor cores as 3-product TF32 splits (fp32-accurate:
+// loss and centroids stay within 1e-4 of the reference's fp32 cuBLAS path), everything else in fp32.
 //   forward : split-K GEMM (raw inputs . F^T)  ->  per-row kernel: norm, xhat, z, logsumexp, loss
 //   backward: per-row softmax-grad  ->  GEMM (gz . F)  ->  per-row normalize-backward
 //   update  : one CTA per distinct label (sequential chain for CM, first-argmin for CM_Hard)
@@ -12,15 +12,43 @@ namespace reid {
 
 constexpr int GM = 64, GN = 64, GK = 16;
 
+// The two contractions (logits = x . F^T, grad = gz . F; 0.73 GFLOP each) run on the tensor cores in TF32 with the
+// 3-product split that keeps fp32 accuracy: a = a_hi + a_lo with a_hi = tf32(a), a_lo = tf32(a - a_hi), and
+// a.b ~ a_lo.b_hi + a_hi.b_lo + a_hi.b_hi (the dropped a_lo.b_lo term and the representation error are ~2^-22 per
+// product; fp32 accumulators).  After the x20 of 1/temp the logits still agree with the reference's fp32 cuBLAS result
+// far inside the 1e-4 bar (tests/test_gpu_cm.py: rtol 1e-4, atol 2e-6 on loss, gradient and centroids).  The tiles are
+// small (B = 256, C ~ 700: 44 CTAs per split) and the operands need no layout change, so this is the register-operand
+// mma.sync.m16n8k8 path rather than a tcgen05 / TMEM pipeline: the stage is latency bound (1.5 GFLOP per step).
+__device__ __forceinline__ uint32_t to_tf32(float x) {
+  uint32_t r;
+  asm("cvt.rna.tf32.f32 %0, %1;" : "=r"(r) : "f"(x));
+  return r;
+}
+__device__ __forceinline__ void split_tf32(float x, uint32_t& hi, uint32_t& lo) {
+  hi = to_tf32(x);
+  lo = to_tf32(x - __uint_as_float(hi));
+}
+__device__ __forceinline__ void mma_tf32(float (&c)[4], const uint32_t (&a)[4], const uint32_t (&b)[2]) {
+  asm volatile(
+      "mma.sync.aligned.m16n8k8.row.col.f32.tf32.tf32.f32 {%0, %1, %2, %3}, {%4, %5, %6, %7}, {%8, %9}, {%0, %1, %2, %3};"
+      : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3])
+      : "r"(a[0]), "r"(a[1]), "r"(a[2]), "r"(a[3]), "r"(b[0]), "r"(b[1]));
+}
+
 // out[z][m][n] = sum_{k in slice z} A[m][k] * Bop[k][n]
 //   kBT = true : B is [Nn x K] row-major (out = A . B^T);  false: B is [K x Nn] row-major (out = A . B)
+// 8 warps = 4 (M) x 2 (N); a warp owns a 16 x 32 piece of the 64 x 64 tile = one A fragment x four B fragments per
+// 8-wide K step.  Shared-memory rows are padded to 72 floats: the fragment loads (k = t or t + 4, m / n = g) then hit
+// 32 different banks.
 template <bool kBT>
 __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__ A, const float* __restrict__ B,
                                                        int64_t M, int64_t Nn, int64_t K, int64_t k_per_split,
                                                        float* __restrict__ out) {
-  __shared__ float As[GK][GM + 4];
-  __shared__ float Bs[GK][GN + 4];
-  const int tx = threadIdx.x & 15, ty = threadIdx.x >> 4;
+  __shared__ float As[GK][GM + 8];
+  __shared__ float Bs[GK][GN + 8];
+  const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
+  const int g = lane >> 2, t = lane & 3;
+  const int wm = warp >> 1, wn = warp & 1;
   const int64_t m0 = (int64_t)blockIdx.y * GM, n0 = (int64_t)blockIdx.x * GN;
   const int64_t kb = (int64_t)blockIdx.z * k_per_split;
   const int64_t ke = kb + k_per_split < K ? kb + k_per_split : K;
@@ -50,28 +78,33 @@ __global__ void __launch_bounds__(256) gemm_f32_kernel(const float* __restrict__
     }
     __syncthreads();
 #pragma unroll
-    for (int kk = 0; kk < GK; ++kk) {
-      float a[4], b[4];
+    for (int ks = 0; ks < GK; ks += 8) {
+      uint32_t ah[4], al[4];
+      split_tf32(As[ks + t][wm * 16 + g], ah[0], al[0]);
+      split_tf32(As[ks + t][wm * 16 + g + 8], ah[1], al[1]);
+      split_tf32(As[ks + t + 4][wm * 16 + g], ah[2], al[2]);
+      split_tf32(As[ks + t + 4][wm * 16 + g + 8], ah[3], al[3]);
 #pragma unroll
-      for (int i = 0; i < 4; ++i) a[i] = As[kk][ty + 16 * i];
-#pragma unroll
-      for (int j = 0; j < 4; ++j) b[j] = Bs[kk][tx + 16 * j];
-#pragma unroll
-      for (int i = 0; i < 4; ++i)
-#pragma unroll
-        for (int j = 0; j < 4; ++j) acc[i][j] = fmaf(a[i], b[j], acc[i][j]);
+      for (int nf = 0; nf < 4; ++nf) {
+        uint32_t bh[2], bl[2];
+        split_tf32(Bs[ks + t][wn * 32 + nf * 8 + g], bh[0], bl[0]);
+        split_tf32(Bs[ks + t + 4][wn * 32 + nf * 8 + g], bh[1], bl[1]);
+        mma_tf32(acc[nf], al, bh);        // the small terms first
+        mma_tf32(acc[nf], ah, bl);
+        mma_tf32(acc[nf], ah, bh);
+      }
     }
     __syncthreads();
   }
+  // C fragment: (g, 2t), (g, 2t + 1), (g + 8, 2t), (g + 8, 2t + 1) of the 16 x 8 piece
   float* o = out + (int64_t)blockIdx.z * M * Nn;
 #pragma unroll
-  for (int i = 0; i < 4; ++i) {
-    const int64_t m = m0 + ty + 16 * i;
-    if (m >= M) continue;
+  for (int nf = 0; nf < 4; ++nf) {
 #pragma unroll
-    for (int j = 0; j < 4; ++j) {
-      const int64_t n = n0 + tx + 16 * j;
-      if (n < Nn) o[m * Nn + n] = acc[i][j];
+    for (int e = 0; e < 4; ++e) {
+      const int64_t m = m0 + wm * 16 + g + (e >> 1) * 8;
+      const int64_t n = n0 + wn * 32 + nf * 8 + 2 * t + (e & 1);
+      if (m < M && n < Nn) o[m * Nn + n] = acc[nf][e];
     }
   }
 }

@@ -517,7 +517,8 @@ __global__ void __launch_bounds__(kMThreads, kMinBlocks) rescore_mma_kernel(
     const float* __restrict__ x, int64_t D, int64_t row_begin, int64_t n_rows, const int32_t* __restrict__ perm,
     const int32_t* __restrict__ win_cnt, const int32_t* __restrict__ win_idx, const float* __restrict__ win_a, int k,
     float eps_in, const float* __restrict__ max_sqnorm, int32_t* __restrict__ out_idx, float* __restrict__ out_key,
-    int32_t* __restrict__ uncert, unsigned* __restrict__ max_err_bits, unsigned long long* __restrict__ uncert_count) {
+    int32_t* __restrict__ uncert, unsigned* __restrict__ max_err_bits, unsigned long long* __restrict__ uncert_count,
+    int groups_per_cta) {
   using L = MmaSmem<kMT>;
   constexpr int kQ = L::kQ;
   extern __shared__ __align__(16) unsigned char mma_smem[];
@@ -534,8 +535,16 @@ __global__ void __launch_bounds__(kMThreads, kMinBlocks) rescore_mma_kernel(
   const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
   const float eps = max_sqnorm ? reid_tc_err_bound(*max_sqnorm) : eps_in;
 
+  // groups_per_cta > 1: a CTA takes a CONTIGUOUS run of groups (cluster mates re-score against nearly the same
+  // candidate rows, so a run re-uses what its first group pulled into L2).  Measured: it does not pay -- 0.62 ms with
+  // one group per CTA against 0.74 / 0.87 / 0.89 ms with runs sized for 4 / 2 / 1 waves (the stage is short of
+  // independent work per SM, not of L2 hits); the launch below uses groups_per_cta = 1.
+  const int64_t n_groups = (n_rows + kQ - 1) / kQ;
+  const int64_t grp_end = min(n_groups, ((int64_t)blockIdx.x + 1) * groups_per_cta);
+  for (int64_t grp = (int64_t)blockIdx.x * groups_per_cta; grp < grp_end; ++grp) {
+  __syncthreads();                                              // the previous group's shared-memory readers are done
   if (tid < kQ) {
-    const int64_t slot = (int64_t)blockIdx.x * kQ + tid;
+    const int64_t slot = grp * kQ + tid;
     const int64_t lr = slot < n_rows ? (perm ? perm[slot] : slot) : -1;
     s_lr[tid] = lr;
     s_nw[tid] = lr >= 0 ? win_cnt[lr] : 0;
@@ -687,6 +696,7 @@ __global__ void __launch_bounds__(kMThreads, kMinBlocks) rescore_mma_kernel(
       if (out_key) out_key[lr * k + t] = -INFINITY;
     }
   }
+  }  // groups of this CTA
 }
 
 inline size_t rescore_group_smem(int64_t D) {
@@ -791,14 +801,18 @@ int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, in
   const bool aligned = (((uintptr_t)x) & 15) == 0;
   static const bool no_group = dev_env("REID_RESCORE_GROUP", 1) == 0;
   const int rescore_variant = dev_env("REID_RESCORE_VARIANT", 2);   // developer builds: 1 = CUDA-core grouped kernel
+  const int mma_waves = dev_env("REID_MMA_WAVES", 0);               // developer builds: > 0 = contiguous runs of groups per CTA
 #define REID_MMA_LAUNCH(MT, U, B)                                                                                   \
   do {                                                                                                              \
     const size_t sm_ = MmaSmem<MT>::kBytes;                                                                         \
     REID_CUDA(cudaFuncSetAttribute(rescore_mma_kernel<MT, U, B>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)sm_)); \
-    rescore_mma_kernel<MT, U, B><<<(unsigned)((n + 8 * MT - 1) / (8 * MT)), kMThreads, sm_, st>>>(                   \
+    const int64_t groups_ = (n + 8 * MT - 1) / (8 * MT);                                                            \
+    int per_ = mma_waves > 0 ? (int)((groups_ + (int64_t)num_sms() * B * mma_waves - 1) / ((int64_t)num_sms() * B * mma_waves)) : 1; \
+    if (per_ < 1) per_ = 1;                                                                                         \
+    rescore_mma_kernel<MT, U, B><<<(unsigned)((groups_ + per_ - 1) / per_), kMThreads, sm_, st>>>(                   \
         x, D, row_begin, n, locality_order ? w.perm : nullptr, w.win_cnt, w.win_idx, w.win_a, k, err_bound,         \
         max_sqnorm, out_idx, out_key, uncertified_flag, (unsigned*)max_err_out,                                     \
-        (unsigned long long*)uncertified_count);                                                                    \
+        (unsigned long long*)uncertified_count, per_);                                                              \
   } while (0)
   if (aligned && D % 64 == 0 && !no_group && rescore_variant >= 2) {
 #ifdef REID_DEV

@@ -106,7 +106,6 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(
   const int lane = lane_id();
   const unsigned lt = (1u << lane) - 1u;
 
-  for (int s = lane; s < L.set_slots; s += 32) set[s] = -1;
   for (int s = lane; s < 128; s += 32) hr[s] = -1;
   for (int s = lane; s < 64; s += 32) s_cnt[s] = 0;
   // R(row) in rank order
@@ -189,20 +188,31 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(
     if (in) atomicAdd(&s_cnt[ci], 1);
   }
   __syncwarp();
+  // The de-duplication table is carved for the worst case (every candidate passes: k1 + k1 (h + 1) entries), but a row
+  // only uses what its passing candidates can contribute: |R| + sum of the passing |R_half(c)| entries.  Clearing and
+  // sweeping the table are a large part of this kernel's instructions, so only a power of two >= twice that is used.
+  int contrib = 0;
   for (int ci = lane; ci < nR; ci += 32) {
-    s_pass[ci] = 3 * s_cnt[ci] > 2 * s_m[ci];    // == len(intersect1d) > 2/3*len  (faiss_rerank.py:77)
-    insert(set, L.set_slots, rlist[ci]);
+    const int pass = 3 * s_cnt[ci] > 2 * s_m[ci];    // == len(intersect1d) > 2/3*len  (faiss_rerank.py:77)
+    s_pass[ci] = pass;
+    contrib += 1 + (pass ? s_m[ci] : 0);
   }
+  contrib = warp_sum(contrib);
+  int slots_row = 64;
+  while (slots_row < 2 * contrib && slots_row < L.set_slots) slots_row <<= 1;
+  for (int s = lane; s < slots_row; s += 32) set[s] = -1;
+  __syncwarp();
+  for (int ci = lane; ci < nR; ci += 32) insert(set, slots_row, rlist[ci]);
   __syncwarp();
   for (int p = lane; p < P; p += 32)
-    if (s_pass[s_ci[p]]) insert(set, L.set_slots, s_g[p]);
+    if (s_pass[s_ci[p]]) insert(set, slots_row, s_g[p]);
   __syncwarp();
 
   // compact the set into the list (re-using the pair buffer), count
   int32_t* list = s_g;
   const int list_cap = list_ints < kListCap ? list_ints : kListCap;
   int nE = 0;
-  for (int b0 = 0; b0 < L.set_slots; b0 += 32) {
+  for (int b0 = 0; b0 < slots_row; b0 += 32) {
     const int32_t v = set[b0 + lane];
     const unsigned b = __ballot_sync(kFull, v >= 0);
     if (v >= 0) {

@@ -13,8 +13,9 @@ N = int(sys.argv[1]) if len(sys.argv) > 1 else 32621
 x, _ = rg.synth(N, 2048, max(1, N // 31), 0.8, 0)
 x = x.cuda()
 ref = None
-for variant in (1, 2, 3, 4, 5, 6, 7):
+for variant, waves in ((1, 2), (2, 1000), (2, 8), (2, 4), (2, 2), (2, 1), (3, 2), (3, 1), (2, 1000), (2, 2)):
     os.environ["REID_RESCORE_VARIANT"] = str(variant)
+    os.environ["REID_MMA_WAVES"] = str(waves)
     for _ in range(2):
         idx, key, info = fr.knn_search(x, 30, "tc")
     torch.cuda.synchronize()
@@ -27,4 +28,4 @@ for variant in (1, 2, 3, 4, 5, 6, 7):
     if ref is None:
         ref = (idx.clone(), key.clone())
     same = torch.equal(idx, ref[0]) and torch.equal(key, ref[1])
-    print("variant %d: reid_knn_rescore %.4f ms  identical_to_variant_1=%s uncertified=%d" % (variant, ms[1] / ms[0], same, info["uncertified_rows"]), flush=True)
+    print("variant %d waves %d: reid_knn_rescore %.4f ms  identical_to_variant_1=%s uncertified=%d" % (variant, waves, ms[1] / ms[0], same, info["uncertified_rows"]), flush=True)
