@@ -178,6 +178,10 @@ size_t reid_knn_rescore_order_offset(int64_t N, int64_t n_rows);
  * R_k(row) = { rank[row, r] : bit r set }, in rank order. */
 int reid_reciprocal_masks(const int32_t* rank, int64_t N, int ncols, int k, int64_t row_begin,
                           int64_t row_end, uint64_t* mask_out, void* stream);
+/* Both sets of the loop at :65-69 in one pass: R_out[row - row_begin] = mask for k_full (rows [row_begin, row_end) only),
+ * Rhalf_out[row] = mask for k_half (ALL N rows: a row-sharded pass needs R_half of every row, R only of its own). */
+int reid_reciprocal_masks2(const int32_t* rank, int64_t N, int ncols, int k_full, int k_half, int64_t row_begin,
+                           int64_t row_end, uint64_t* R_out, uint64_t* Rhalf_out, void* stream);
 
 /* ---- a3: expansion  (faiss_rerank.py:72-80) ------------------------------------
  * E(row) = sort_unique( R(row) + all R_half(c), c in R(row), 3*|R_half(c) & R(row)| > 2*|R_half(c)| ).

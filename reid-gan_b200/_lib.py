@@ -48,6 +48,7 @@ SIGNATURES = {
     "reid_features_sample": (_I, [_P, _L, _L, _L, _L, _P, _P]),
     "reid_knn_sample_tau": (_I, [_P, _P, _P, _I, _L, _I, _P, _P, _P]),
     "reid_reciprocal_masks": (_I, [_P, _L, _I, _I, _L, _L, _P, _P]),
+    "reid_reciprocal_masks2": (_I, [_P, _L, _I, _I, _I, _L, _L, _P, _P, _P]),
     "reid_expand": (_I, [_P, _L, _I, _I, _P, _P, _L, _L, _I, _P, _P, _P]),
     "reid_v_weights": (_I, [_P, _L, _L, _P, _I, _P, _L, _L, _P, _P, _I, _P, _P, _P, _I, _P]),
     "reid_knn_rescore_order_offset": (_Z, [_L, _L]),

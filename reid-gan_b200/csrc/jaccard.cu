@@ -91,7 +91,7 @@ __device__ __forceinline__ float jaccard_from_t(float t, int half = 0) {
 // class is one persistent launch that reads its queue length from device memory: no host round trip.
 constexpr int kJWarps = 4;
 constexpr int kJClasses = 5;                 // 512, 1024, 2048, 4096, 8192 slots
-constexpr int kJE = 1;                       // entries of a column per lane and step, table kernel (registers = occupancy)
+constexpr int kJPF = 3;                      // steps the column loads run ahead of the table updates (table kernel)
 constexpr int kJHeavyCtas = 64;              // dense-accumulator rows processed at a time by the last resort
 
 __host__ __device__ constexpr int jclass_slots(int c) { return 512 << c; }
@@ -124,98 +124,92 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
     int used = 0;
     bool overflow = false;
     const int64_t qa = Q_ptr[row], qb = Q_ptr[row + 1];
-    for (int64_t pc = qa; pc < qb && !overflow; pc += 32) {   // up to 32 columns of the row at a time
+    // metadata of up to 32 columns at a time (lane-parallel: column id, V_ic, start, length); the NEXT block's metadata
+    // is requested before the current block is walked, so its three dependent loads are off the critical path
+    auto load_meta = [&](int64_t pc, float& vic, int64_t& ca, int& len) {
       const int64_t p = pc + lane;
       const bool has = p < qb;
       const int32_t c = has ? Q_idx[p] : 0;
-      const float vic = has ? Q_val[p] : 0.f;
-      const int64_t ca = has ? C_ptr[c] : 0;
-      const int len = has ? (int)(C_ptr[c + 1] - ca) : 0;
+      vic = has ? Q_val[p] : 0.f;
+      ca = has ? C_ptr[c] : 0;
+      len = has ? (int)(C_ptr[c + 1] - ca) : 0;
+    };
+    float vic_n = 0.f;
+    int64_t ca_n = 0;
+    int len_n = 0;
+    load_meta(qa, vic_n, ca_n, len_n);
+    for (int64_t pc = qa; pc < qb && !overflow; pc += 32) {   // up to 32 columns of the row at a time
+      const float vic = vic_n;
+      const int64_t ca = ca_n;
+      const int len = len_n;
+      if (pc + 32 < qb) load_meta(pc + 32, vic_n, ca_n, len_n);
       const int ncol = (int)min((int64_t)32, qb - pc);
       // Walk the columns in ascending order, 32 entries of ONE column per step: inside a column every j is
       // distinct, so a step needs no ordering between its lanes, and the step sequence is the reference's
-      // accumulation order.  The loads of the next step are issued before the current one goes through the table.
-      // kJE entries per lane and step (128 entries of ONE column per step): most columns are a single step, and
-      // with the next step's loads issued ahead a lane keeps 2 * kJE independent loads in flight
-      int k = 0, base = 0;
-      int64_t cak = __shfl_sync(kFull, ca, 0);
-      int lenk = __shfl_sync(kFull, len, 0);
-      float vk = __shfl_sync(kFull, vic, 0);
-      int32_t j[kJE];
-      float m[kJE];
-#pragma unroll
-      for (int u = 0; u < kJE; ++u) {
-        const int e = u * 32 + lane;
-        j[u] = -1;
-        m[u] = 0.f;
-        if (e < lenk) {
-          j[u] = C_idx[cak + e];
-          m[u] = fminf(vk, C_val[cak + e]);
+      // accumulation order.  The kernel is bound by the latency of the column loads (L2), so the loads run kJPF steps
+      // ahead of the table updates: a software pipeline over the warp-uniform (column, offset) cursor.
+      int ck = 0, cbase = 0;                                    // cursor of the next step to FETCH
+      int clen = __shfl_sync(kFull, len, 0);
+      int32_t jq[kJPF];
+      float mq[kJPF];
+      auto fetch = [&](int32_t& j, float& m) {
+        j = -1;
+        m = 0.f;
+        if (ck < ncol) {                                        // warp-uniform
+          const int64_t cak = __shfl_sync(kFull, ca, ck);
+          const float vk = __shfl_sync(kFull, vic, ck);
+          const int e = cbase + lane;
+          if (e < clen) {
+            j = C_idx[cak + e];
+            m = fminf(vk, C_val[cak + e]);
+          }
+          cbase += 32;
+          if (cbase >= clen) {
+            ++ck;
+            cbase = 0;
+            if (ck < ncol) clen = __shfl_sync(kFull, len, ck);
+          }
         }
+      };
+      // number of steps of this block = sum over its columns of ceil(len / 32) (columns of length 0 cannot occur)
+      int steps = 0;
+      {
+        const int mine = lane < ncol ? (len + 31) >> 5 : 0;
+        steps = __reduce_add_sync(kFull, mine);
       }
-      while (k < ncol) {
-        int nk = k, nbase = base + 32 * kJE;
-        int64_t ncak = cak;
-        int nlen = lenk;
-        float nv = vk;
-        if (nbase >= lenk) {                                   // warp-uniform: next column
-          nk = k + 1;
-          nbase = 0;
-          if (nk < ncol) {
-            ncak = __shfl_sync(kFull, ca, nk);
-            nlen = __shfl_sync(kFull, len, nk);
-            nv = __shfl_sync(kFull, vic, nk);
-          }
-        }
-        int32_t jn[kJE];
-        float mn[kJE];
 #pragma unroll
-        for (int u = 0; u < kJE; ++u) {
-          const int e = nbase + u * 32 + lane;
-          jn[u] = -1;
-          mn[u] = 0.f;
-          if (nk < ncol && e < nlen) {
-            jn[u] = C_idx[ncak + e];
-            mn[u] = fminf(nv, C_val[ncak + e]);
-          }
-        }
-        int fresh_n = 0;
+      for (int u = 0; u < kJPF; ++u) fetch(jq[u], mq[u]);
+      for (int st = 0; st < steps; ++st) {
+        const int32_t j = jq[0];
+        const float m = mq[0];
 #pragma unroll
-        for (int u = 0; u < kJE; ++u) {
-          bool fresh = false;
-          if (j[u] >= 0) {
-            uint32_t h = jhash((uint32_t)j[u]) & smask;
-            while (true) {
-              const int32_t old = atomicCAS(&tkey[h], -1, j[u]);
-              if (old == -1) {
-                tval[h] = m[u];                                // 0 + m
-                fresh = true;
-                break;
-              }
-              if (old == j[u]) {
-                tval[h] = acc_add(tval[h], m[u], half);
-                break;
-              }
-              h = (h + 1) & smask;
+        for (int u = 0; u + 1 < kJPF; ++u) {
+          jq[u] = jq[u + 1];
+          mq[u] = mq[u + 1];
+        }
+        fetch(jq[kJPF - 1], mq[kJPF - 1]);
+        bool fresh = false;
+        if (j >= 0) {
+          uint32_t h = jhash((uint32_t)j) & smask;
+          while (true) {
+            const int32_t old = atomicCAS(&tkey[h], -1, j);
+            if (old == -1) {
+              tval[h] = m;                                     // 0 + m
+              fresh = true;
+              break;
             }
+            if (old == j) {
+              tval[h] = acc_add(tval[h], m, half);
+              break;
+            }
+            h = (h + 1) & smask;
           }
-          fresh_n += __popc(__ballot_sync(kFull, fresh));
         }
-        used += fresh_n;
+        used += __popc(__ballot_sync(kFull, fresh));
         __syncwarp();                                          // this step's adds land before the next step's
         if (used > limit) {
           overflow = true;
           break;
-        }
-        k = nk;
-        base = nbase;
-        cak = ncak;
-        lenk = nlen;
-        vk = nv;
-#pragma unroll
-        for (int u = 0; u < kJE; ++u) {
-          j[u] = jn[u];
-          m[u] = mn[u];
         }
       }
     }

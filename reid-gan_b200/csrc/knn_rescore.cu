@@ -11,6 +11,8 @@
 // redone by the caller with reid_knn_exact, so the result never depends on eps being right.
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "common.cuh"
 
 namespace reid {
@@ -79,24 +81,36 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_select_kernel(
     __syncwarp();
     return cnt;
   };
-  auto kth_largest = [&](int m) {
-    uint32_t o[kRsPer];
+  // k-th largest of a[0..m): bitwise binary search on the order-preserving image, every lane holding m / 32 values in
+  // registers.  Two savings against the plain 32-step / 16-register form (the kernel is ALU bound): only as many
+  // registers as m needs take part (kPer = 4, 8, 12 or 16), and the lowest 8 bits are not resolved -- the result is
+  // then at most 2^8 ulp (1.5e-5 on scores below 1) BELOW the true k-th largest, which can only widen the window
+  // [a_k - 2 eps, inf) by a hair and make the certificate `bound < a_k - 2 eps` stricter: both safe.
+  auto kth_impl = [&](int m, auto per_tag) {
+    constexpr int kPer = decltype(per_tag)::value;
+    uint32_t o[kPer];
 #pragma unroll
-    for (int u = 0; u < kRsPer; ++u) {
+    for (int u = 0; u < kPer; ++u) {
       const int t = u * 32 + lane;
       o[u] = t < m ? float_ord(a[t]) : 0u;
     }
     uint32_t T = 0;
 #pragma unroll 1
-    for (int bit = 31; bit >= 0; --bit) {
+    for (int bit = 31; bit >= 8; --bit) {
       const uint32_t c2 = T | (1u << bit);
       int c = 0;
 #pragma unroll
-      for (int u = 0; u < kRsPer; ++u) c += o[u] >= c2;
+      for (int u = 0; u < kPer; ++u) c += o[u] >= c2;
       c = __reduce_add_sync(kFull, c);
       if (c >= k) T = c2;
     }
     return m >= k ? ord_float(T) : -INFINITY;
+  };
+  auto kth_largest = [&](int m) {
+    if (m <= 128) return kth_impl(m, std::integral_constant<int, 4>{});
+    if (m <= 256) return kth_impl(m, std::integral_constant<int, 8>{});
+    if (m <= 384) return kth_impl(m, std::integral_constant<int, 12>{});
+    return kth_impl(m, std::integral_constant<int, kRsPer>{});
   };
 
   bool list_overflow = false;                       // an overflowed list lost columns above the threshold

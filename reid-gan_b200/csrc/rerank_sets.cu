@@ -26,6 +26,38 @@ __global__ void __launch_bounds__(256) reciprocal_kernel(const int32_t* __restri
   if (lane == 0) mask_out[row - row_begin] = mask;
 }
 
+// Both masks of a row in one pass over its neighbours' lists: R uses the first `cols_full` columns of every list it
+// looks into, R_half the first `cols_half` -- the same lists, read once.  Rows outside [row_begin, row_end) only get
+// their R_half bit mask (every rank of a row-sharded pass needs R_half of ALL rows, R only of its own).
+__global__ void __launch_bounds__(256) reciprocal2_kernel(const int32_t* __restrict__ rank, int64_t N, int ncols, int cols_full,
+                                                          int cols_half, int64_t row_begin, int64_t row_end,
+                                                          uint64_t* __restrict__ R_out, uint64_t* __restrict__ Rh_out) {
+  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (row >= N) return;
+  const int lane = lane_id();
+  const bool own = row >= row_begin && row < row_end;
+  const int cols = own ? cols_full : cols_half;
+  uint64_t mf = 0, mh = 0;
+  for (int base = 0; base < cols; base += 32) {
+    const int r = base + lane;
+    bool in_full = false, in_half = false;
+    if (r < cols) {
+      const int32_t* nb = rank + (int64_t)rank[row * ncols + r] * ncols;
+      for (int q = 0; q < cols; ++q) {
+        const bool hit = nb[q] == (int32_t)row;
+        in_full |= hit;
+        in_half |= hit && q < cols_half;
+      }
+    }
+    mf |= (uint64_t)__ballot_sync(kFull, in_full) << base;
+    mh |= (uint64_t)__ballot_sync(kFull, in_half && r < cols_half) << base;
+  }
+  if (lane == 0) {
+    if (own) R_out[row - row_begin] = mf;
+    Rh_out[row] = mh;
+  }
+}
+
 constexpr int kListCap = 1024;    // max |E| handled (theoretical max for k1=30 is 30 + 30*16 = 510)
 constexpr int kExpandWarps = 8;
 
@@ -36,6 +68,20 @@ __device__ __forceinline__ uint32_t hash32(uint32_t v) {
   v *= 0x846ca68bu;
   v ^= v >> 16;
   return v;
+}
+
+// position of the (n + 1)-th set bit of m (n < popc(m)): five popc steps instead of the software loop behind __fns
+__device__ __forceinline__ int nth_set_bit(uint32_t m, int n) {
+  int pos = 0;
+#pragma unroll
+  for (int w = 16; w >= 1; w >>= 1) {
+    const int c = __popc((m >> pos) & ((1u << w) - 1u));
+    if (n >= c) {
+      n -= c;
+      pos += w;
+    }
+  }
+  return pos;
 }
 
 // ascending bitonic sort of n2 (power of two) ints held in shared memory, by one warp
@@ -170,7 +216,7 @@ __global__ void __launch_bounds__(kExpandWarps * 32) expand_kernel(
     const uint64_t hm = s_hm[ci];
     const uint32_t mlo = (uint32_t)hm, mhi = (uint32_t)(hm >> 32);
     const int nlo = __popc(mlo);
-    const int pos = kth < nlo ? (int)__fns(mlo, 0, kth + 1) : 32 + (int)__fns(mhi, 0, kth - nlo + 1);
+    const int pos = kth < nlo ? nth_set_bit(mlo, kth) : 32 + nth_set_bit(mhi, kth - nlo);
     const int32_t g = rank[(int64_t)rlist[ci] * ncols + pos];
     s_g[p] = g;
     s_ci[p] = (uint8_t)ci;
@@ -250,6 +296,22 @@ int reid_reciprocal_masks(const int32_t* rank, int64_t N, int ncols, int k, int6
   if (n == 0) return REID_OK;
   reciprocal_kernel<<<(unsigned)((n + 7) / 8), 256, 0, (cudaStream_t)stream>>>(rank, ncols, cols, row_begin, row_end,
                                                                               mask_out);
+  REID_LAUNCH_CHECK();
+  return REID_OK;
+}
+
+int reid_reciprocal_masks2(const int32_t* rank, int64_t N, int ncols, int k_full, int k_half, int64_t row_begin,
+                           int64_t row_end, uint64_t* R_out, uint64_t* Rhalf_out, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(rank && R_out && Rhalf_out, "reid_reciprocal_masks2: NULL pointer");
+  REID_CHECK_ARG(ncols >= 1 && ncols <= REID_MAX_K1, "reid_reciprocal_masks2: ncols=%d not in 1..%d", ncols, REID_MAX_K1);
+  REID_CHECK_ARG(k_full >= 0 && k_half >= 0 && k_half <= k_full, "reid_reciprocal_masks2: k_full=%d k_half=%d", k_full, k_half);
+  REID_CHECK_ARG(0 <= row_begin && row_begin <= row_end && row_end <= N, "reid_reciprocal_masks2: bad row range");
+  if (N == 0) return REID_OK;
+  const int cf = k_full + 1 < ncols ? k_full + 1 : ncols;    // rank[i, :k+1] clamps to the stored columns
+  const int ch = k_half + 1 < ncols ? k_half + 1 : ncols;
+  reciprocal2_kernel<<<(unsigned)((N + 7) / 8), 256, 0, (cudaStream_t)stream>>>(rank, N, ncols, cf, ch, row_begin, row_end,
+                                                                              R_out, Rhalf_out);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

@@ -178,8 +178,10 @@ __global__ void __launch_bounds__(kQWarps * 32) query_expand_kernel(
   const uint32_t smask = (uint32_t)cap - 1u;
   for (int t = lane; t < cap; t += 32) key[t] = 0xffffffffu;
   __syncwarp();
-  // A speculatively sized table (the caller did not know the longest V row) can fill up: probing is bounded, the
-  // row then reports Q_cnt = 0 and is counted in *overflow_rows (the caller redoes the stage with the exact size).
+  // A speculatively sized table (the caller did not know the longest V row) can fill up.  Before a V row is folded
+  // in, its length is checked against the free slots (warp-uniform, conservative: every entry could be a new column),
+  // so the probing below always finds a free slot; a row that might not fit reports Q_cnt = 0 and is counted in
+  // *overflow_rows (the caller redoes the stage with the exact size).
   bool lost = false;
   int used = 0;
   const int limit = cap - (cap >> 2);
@@ -187,13 +189,16 @@ __global__ void __launch_bounds__(kQWarps * 32) query_expand_kernel(
     const int64_t j = rank[row * ncols + r];
     const int64_t a = V_ptr[j];
     const int m = (int)(V_ptr[j + 1] - a);
+    if (used + m > limit) {                          // same on every lane
+      lost = true;
+      break;
+    }
     int fresh = 0;
     for (int e = lane; e < m; e += 32) {
       const uint32_t c = (uint32_t)V_idx[a + e];
       const float v = V_val[a + e];
       uint32_t h = (c * 0x9e3779b1u) >> 7 & smask;
-      int probe = 0;
-      for (; probe < cap; ++probe) {
+      while (true) {
         const uint32_t old = atomicCAS(&key[h], 0xffffffffu, c);
         if (old == 0xffffffffu) {
           val[h] = v;
@@ -206,10 +211,8 @@ __global__ void __launch_bounds__(kQWarps * 32) query_expand_kernel(
         }
         h = (h + 1) & smask;
       }
-      if (probe == cap) lost = true;
     }
-    used += __reduce_add_sync(kFull, fresh);
-    lost = __any_sync(kFull, lost) || used > limit;   // also: row r is folded before row r + 1 starts
+    used += __reduce_add_sync(kFull, fresh);          // also: row r is folded before row r + 1 starts
   }
   if (lost) {
     if (lane == 0) {
@@ -535,8 +538,10 @@ int reid_v_weights(const float* x, int64_t N, int64_t D, const int32_t* E_pad, i
 }
 
 int reid_query_expand_stride(int k2, int max_row_nnz) {
+  // 3/4 of the slots must hold k2 rows of max_row_nnz entries: with the TRUE maximum the kernel's (conservative)
+  // free-slot check can then never reject a row
   int cap = 32;
-  while (cap < k2 * max_row_nnz) cap <<= 1;
+  while (cap - (cap >> 2) < k2 * max_row_nnz) cap <<= 1;
   return cap;
 }
 

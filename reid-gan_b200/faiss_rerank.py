@@ -272,8 +272,7 @@ def rerank_state_async(x, k1, k2, knn="auto", rows=None, timers=False, comm=None
 
     def sets():
         # a2 ------------------------------------------------------------------
-        call("reid_reciprocal_masks", ptr(rank), N, k1, k1, r0, r1, ptr(R), sp)
-        call("reid_reciprocal_masks", ptr(rank), N, k1, h, 0, N, ptr(Rh), sp)
+        call("reid_reciprocal_masks2", ptr(rank), N, k1, k1, h, r0, r1, ptr(R), ptr(Rh), sp)
         # a3 ------------------------------------------------------------------
         call("reid_expand", ptr(rank), N, k1, min(h + 1, k1), ptr(R), ptr(Rh), r0, r1, e_stride, ptr(e_pad), ptr(e_cnt), sp)
         return _scan_async(e_cnt, n, dev, stats=report[R_E:R_E + 3])
@@ -329,7 +328,7 @@ def rerank_state_async(x, k1, k2, knn="auto", rows=None, timers=False, comm=None
     if k2 != 1:
         if speculative:
             q_stride = QE_SPEC_SLOTS
-            nnz_guess = max(1, QE_SPEC_SLOTS // k2)
+            nnz_guess = max(1, (QE_SPEC_SLOTS - QE_SPEC_SLOTS // 4) // k2)    # reid_query_expand_stride(k2, guess) == 512
         else:
             q_stride = L.reid_query_expand_stride(k2, max(e_max, 1))
             nnz_guess = max(e_max, 1)
