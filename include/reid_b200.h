@@ -298,7 +298,11 @@ int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
                            const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin,
                            int64_t row_end, float eps, const int32_t* T_cnt, const int32_t* P_cnt, const int64_t* slot_ptr,
                            int32_t* nbr_idx, float* nbr_val, int32_t* nbr_cnt, int64_t nbr_capacity,
-                           uint64_t* slot_overflow, int half_precision, void* workspace, void* stream);
+                           uint64_t* slot_overflow, int half_precision, int owned_pairs_only, void* workspace,
+                           void* stream);
+/* owned_pairs_only: J is bit-symmetric, so each unordered pair {i, j} may be accumulated and listed by only ONE of its
+ * rows -- i owns (i, j) iff i == j, or i < j with i + j even, or i > j with i + j odd (every row keeps about half of its
+ * partners).  Half the table updates; reid_dbscan_labels(owned_pairs = 1) consumes such lists. */
 /* dense rows: out[(row-row_begin)*ld + j] for all j < N  (the reference's return value). */
 int reid_jaccard_dense(const int64_t* Q_ptr, const int32_t* Q_idx, const float* Q_val, const int64_t* C_ptr,
                        const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin,
@@ -318,7 +322,10 @@ int reid_dbscan_dense_fill(const float* dist, int64_t N, int64_t ld, float eps, 
 size_t reid_dbscan_workspace_bytes(int64_t N);
 int reid_dbscan_labels(int64_t N, const int64_t* nbr_ptr, const int32_t* nbr_idx, const int32_t* nbr_cnt,
                        int min_samples, int64_t* labels, uint8_t* core_mask, int64_t* num_clusters_out,
-                       void* workspace, void* stream);
+                       void* workspace, int owned_pairs, void* stream);
+/* owned_pairs != 0: the lists name every edge {i, j} ONCE (reid_jaccard_eps_graph with owned_pairs_only; the self pair
+ * (i, i) is in i's list when d_ii <= eps): degrees are counted from both ends, the union-find needs each edge once
+ * anyway, border points take the smallest adjacent core label from whichever end lists the edge. */
 
 /* ---- f1 (next row): edge filter of the Infomap variant  (utils/infomap_cluster.py:129-144) ----
  * nbrs / dists: (N, k) neighbour lists in ascending distance 1 - sim (reid_knn_* keys give sim).  Row i links to

@@ -91,6 +91,55 @@ __global__ void __launch_bounds__(256) union_kernel(int64_t N, const int64_t* __
   }
 }
 
+// ---- owned-pair lists (csrc/jaccard.cu pair_owned): every edge {i, j} is listed by ONE of its rows ----------------
+// degree = own entries (the self pair (i, i) is i's own entry when J_ii <= eps) + one per foreign list that names i
+__global__ void __launch_bounds__(256) degree_kernel(int64_t N, const int64_t* __restrict__ ptr, const int32_t* __restrict__ idx,
+                                                     const int32_t* __restrict__ cnt, int32_t* __restrict__ deg) {
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= N) return;
+  const int64_t a = ptr[i];
+  const int n = cnt[i];
+  for (int e = lane_id(); e < n; e += 32) {
+    const int32_t j = idx[a + e];
+    if (j != (int32_t)i) atomicAdd(&deg[j], 1);
+  }
+  if (lane_id() == 0 && n) atomicAdd(&deg[i], n);
+}
+
+// cores take their component's number, everything else "no label yet" (INT64_MAX)
+__global__ void label_core_kernel(int64_t N, const uint8_t* __restrict__ core, const int32_t* __restrict__ parent,
+                                  const int64_t* __restrict__ root_rank, int64_t* __restrict__ labels) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i >= N) return;
+  labels[i] = core[i] ? root_rank[parent[i]] : INT64_MAX;
+}
+
+// border points: smallest label among adjacent cores -- an edge is seen once, so it reports in both directions
+__global__ void __launch_bounds__(256) label_border_kernel(int64_t N, const int64_t* __restrict__ ptr,
+                                                           const int32_t* __restrict__ idx, const int32_t* __restrict__ cnt,
+                                                           const uint8_t* __restrict__ core,
+                                                           const int32_t* __restrict__ parent,
+                                                           const int64_t* __restrict__ root_rank, int64_t* __restrict__ labels) {
+  const int64_t i = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
+  if (i >= N) return;
+  const int64_t a = ptr[i];
+  const int n = cnt[i];
+  const bool ci = core[i];
+  const long long li = ci ? (long long)root_rank[parent[i]] : 0;
+  for (int e = lane_id(); e < n; e += 32) {
+    const int32_t j = idx[a + e];
+    if (j == (int32_t)i) continue;
+    const bool cj = core[j];
+    if (cj && !ci) atomicMin(reinterpret_cast<long long*>(&labels[i]), (long long)root_rank[parent[j]]);
+    if (ci && !cj) atomicMin(reinterpret_cast<long long*>(&labels[j]), li);
+  }
+}
+
+__global__ void label_noise_kernel(int64_t N, int64_t* __restrict__ labels) {
+  const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+  if (i < N && labels[i] == INT64_MAX) labels[i] = -1;
+}
+
 __global__ void flatten_kernel(int64_t N, const uint8_t* __restrict__ core, int32_t* __restrict__ parent,
                                int32_t* __restrict__ is_root) {
   const int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
@@ -193,7 +242,7 @@ size_t reid_dbscan_workspace_bytes(int64_t N) {
 
 int reid_dbscan_labels(int64_t N, const int64_t* nbr_ptr, const int32_t* nbr_idx, const int32_t* nbr_cnt,
                        int min_samples, int64_t* labels, uint8_t* core_mask, int64_t* num_clusters_out,
-                       void* workspace, void* stream) {
+                       void* workspace, int owned_pairs, void* stream) {
   using namespace reid;
   REID_CHECK_ARG(nbr_ptr && nbr_cnt && labels && workspace, "reid_dbscan_labels: NULL pointer");
   REID_CHECK_ARG(N >= 0 && N < (1ll << 31), "reid_dbscan_labels: bad N");
@@ -201,7 +250,14 @@ int reid_dbscan_labels(int64_t N, const int64_t* nbr_ptr, const int32_t* nbr_idx
   cudaStream_t st = (cudaStream_t)stream;
   DbscanWs w = carve(workspace, N);
   const unsigned gt = (unsigned)((N + 255) / 256), gw = (unsigned)((N + 7) / 8);
-  init_kernel<<<gt, 256, 0, st>>>(N, nbr_cnt, min_samples, w.parent, w.core);
+  const int32_t* degree = nbr_cnt;
+  if (owned_pairs) {                                   // every edge is listed once: degrees first (is_root is free until flatten)
+    REID_CUDA(cudaMemsetAsync(w.is_root, 0, sizeof(int32_t) * (size_t)N, st));
+    degree_kernel<<<gw, 256, 0, st>>>(N, nbr_ptr, nbr_idx, nbr_cnt, w.is_root);
+    REID_LAUNCH_CHECK();
+    degree = w.is_root;
+  }
+  init_kernel<<<gt, 256, 0, st>>>(N, degree, min_samples, w.parent, w.core);
   REID_LAUNCH_CHECK();
   union_kernel<<<gw, 256, 0, st>>>(N, nbr_ptr, nbr_idx, nbr_cnt, w.core, w.parent);
   REID_LAUNCH_CHECK();
@@ -209,8 +265,17 @@ int reid_dbscan_labels(int64_t N, const int64_t* nbr_ptr, const int32_t* nbr_idx
   REID_LAUNCH_CHECK();
   int rc = reid_scan_counts(w.is_root, N, w.root_rank, nullptr, stream);
   if (rc != REID_OK) return rc;
-  label_kernel<<<gw, 256, 0, st>>>(N, nbr_ptr, nbr_idx, nbr_cnt, w.core, w.parent, w.root_rank, labels);
-  REID_LAUNCH_CHECK();
+  if (owned_pairs) {
+    label_core_kernel<<<gt, 256, 0, st>>>(N, w.core, w.parent, w.root_rank, labels);
+    REID_LAUNCH_CHECK();
+    label_border_kernel<<<gw, 256, 0, st>>>(N, nbr_ptr, nbr_idx, nbr_cnt, w.core, w.parent, w.root_rank, labels);
+    REID_LAUNCH_CHECK();
+    label_noise_kernel<<<gt, 256, 0, st>>>(N, labels);
+    REID_LAUNCH_CHECK();
+  } else {
+    label_kernel<<<gw, 256, 0, st>>>(N, nbr_ptr, nbr_idx, nbr_cnt, w.core, w.parent, w.root_rank, labels);
+    REID_LAUNCH_CHECK();
+  }
   if (core_mask) REID_CUDA(cudaMemcpyAsync(core_mask, w.core, (size_t)N, cudaMemcpyDeviceToDevice, st));
   if (num_clusters_out)
     REID_CUDA(cudaMemcpyAsync(num_clusters_out, w.root_rank + N, sizeof(int64_t), cudaMemcpyDeviceToDevice, st));

@@ -46,9 +46,12 @@ __global__ void __launch_bounds__(256) jaccard_bounds_kernel(const int64_t* __re
       // clustered data (a partner shares most of the row's columns).  A row inside an identity cluster of size m has
       // columns of length ~m and ~m..2m partners, so 3 x the longest column + the row's own nnz is a much closer
       // guess; it is never taken above the T-based one.
+      // When the column-based guess is MUCH smaller than the T-based one (8x), the row's columns do not overlap the
+      // way an identity cluster's do (Market shape: k1 larger than the identities, every row's neighbourhood spans
+      // several of them and its partners run into the thousands): the guess is then not trusted.
       const int64_t by_t = t < 2048 ? t >> 2 : t >> 1;
       const int64_t by_col = 3 * longest + (qb - qa);
-      P_cnt[row - row_begin] = (int32_t)(by_col < by_t ? by_col : by_t);
+      P_cnt[row - row_begin] = (int32_t)((by_col * 8 < by_t || by_col > by_t) ? by_t : by_col);
     }
     if (S_cnt) {
       double need = t_min > 0.f ? b / (double)t_min + 2.0 : (double)t;
@@ -71,6 +74,15 @@ __device__ __forceinline__ float acc_add(float a, float b, int half) {
   const float s = __fadd_rn(a, b);
   return half ? round_h(s) : s;
 }
+// J is symmetric bit for bit (both rows add the same minima over the same shared columns in the same ascending
+// order), so an eps-graph consumer that only needs every EDGE once (union-find, degree counting: csrc/dbscan.cu) lets
+// each unordered pair {i, j} be accumulated by exactly one of its two rows -- half the table updates.  The owner is
+// chosen by the parity of i + j, which splits every row's partners evenly whatever its index (a plain "j > i" rule
+// would leave the low rows with all the work, and the first rank of a row-sharded pass with it).  (i, i) is i's own.
+__device__ __forceinline__ bool pair_owned(int32_t i, int32_t j) {
+  return i == j ? true : ((i < j) == (((i + j) & 1) == 0));
+}
+
 __device__ __forceinline__ float jaccard_from_t(float t, int half = 0) {
   float j;
   if (half) j = round_h(__fsub_rn(1.0f, round_h(__fdiv_rn(t, round_h(__fsub_rn(2.0f, t))))));
@@ -91,7 +103,7 @@ __device__ __forceinline__ float jaccard_from_t(float t, int half = 0) {
 // class is one persistent launch that reads its queue length from device memory: no host round trip.
 constexpr int kJWarps = 4;
 constexpr int kJClasses = 5;                 // 512, 1024, 2048, 4096, 8192 slots
-constexpr int kJPF = 3;                      // steps the column loads run ahead of the table updates (table kernel)
+constexpr int kJE = 1;                       // entries of a column per lane and step, table kernel (registers = occupancy)
 constexpr int kJHeavyCtas = 64;              // dense-accumulator rows processed at a time by the last resort
 
 __host__ __device__ constexpr int jclass_slots(int c) { return 512 << c; }
@@ -105,7 +117,7 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
     const int64_t* __restrict__ slot_ptr, int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_val,
     int32_t* __restrict__ nbr_cnt, int slots, int64_t nbr_capacity, unsigned long long* __restrict__ slot_overflow,
     int half, const int32_t* __restrict__ T_cnt, int32_t* __restrict__ queues, int32_t* __restrict__ qlen, int64_t q_stride,
-    int cur_class, int direct_from) {
+    int cur_class, int direct_from, int owned_only) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = lane_id();
   int32_t* tkey = reinterpret_cast<int32_t*>(smem_raw) + (size_t)w * slots;
@@ -124,92 +136,98 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
     int used = 0;
     bool overflow = false;
     const int64_t qa = Q_ptr[row], qb = Q_ptr[row + 1];
-    // metadata of up to 32 columns at a time (lane-parallel: column id, V_ic, start, length); the NEXT block's metadata
-    // is requested before the current block is walked, so its three dependent loads are off the critical path
-    auto load_meta = [&](int64_t pc, float& vic, int64_t& ca, int& len) {
+    for (int64_t pc = qa; pc < qb && !overflow; pc += 32) {   // up to 32 columns of the row at a time
       const int64_t p = pc + lane;
       const bool has = p < qb;
       const int32_t c = has ? Q_idx[p] : 0;
-      vic = has ? Q_val[p] : 0.f;
-      ca = has ? C_ptr[c] : 0;
-      len = has ? (int)(C_ptr[c + 1] - ca) : 0;
-    };
-    float vic_n = 0.f;
-    int64_t ca_n = 0;
-    int len_n = 0;
-    load_meta(qa, vic_n, ca_n, len_n);
-    for (int64_t pc = qa; pc < qb && !overflow; pc += 32) {   // up to 32 columns of the row at a time
-      const float vic = vic_n;
-      const int64_t ca = ca_n;
-      const int len = len_n;
-      if (pc + 32 < qb) load_meta(pc + 32, vic_n, ca_n, len_n);
+      const float vic = has ? Q_val[p] : 0.f;
+      const int64_t ca = has ? C_ptr[c] : 0;
+      const int len = has ? (int)(C_ptr[c + 1] - ca) : 0;
       const int ncol = (int)min((int64_t)32, qb - pc);
       // Walk the columns in ascending order, 32 entries of ONE column per step: inside a column every j is
       // distinct, so a step needs no ordering between its lanes, and the step sequence is the reference's
-      // accumulation order.  The kernel is bound by the latency of the column loads (L2), so the loads run kJPF steps
-      // ahead of the table updates: a software pipeline over the warp-uniform (column, offset) cursor.
-      int ck = 0, cbase = 0;                                    // cursor of the next step to FETCH
-      int clen = __shfl_sync(kFull, len, 0);
-      int32_t jq[kJPF];
-      float mq[kJPF];
-      auto fetch = [&](int32_t& j, float& m) {
-        j = -1;
-        m = 0.f;
-        if (ck < ncol) {                                        // warp-uniform
-          const int64_t cak = __shfl_sync(kFull, ca, ck);
-          const float vk = __shfl_sync(kFull, vic, ck);
-          const int e = cbase + lane;
-          if (e < clen) {
-            j = C_idx[cak + e];
-            m = fminf(vk, C_val[cak + e]);
-          }
-          cbase += 32;
-          if (cbase >= clen) {
-            ++ck;
-            cbase = 0;
-            if (ck < ncol) clen = __shfl_sync(kFull, len, ck);
-          }
+      // accumulation order.  The loads of the next step are issued before the current one goes through the table.
+      // kJE entries per lane and step (128 entries of ONE column per step): most columns are a single step, and
+      // with the next step's loads issued ahead a lane keeps 2 * kJE independent loads in flight
+      int k = 0, base = 0;
+      int64_t cak = __shfl_sync(kFull, ca, 0);
+      int lenk = __shfl_sync(kFull, len, 0);
+      float vk = __shfl_sync(kFull, vic, 0);
+      int32_t j[kJE];
+      float m[kJE];
+#pragma unroll
+      for (int u = 0; u < kJE; ++u) {
+        const int e = u * 32 + lane;
+        j[u] = -1;
+        m[u] = 0.f;
+        if (e < lenk) {
+          j[u] = C_idx[cak + e];
+          m[u] = fminf(vk, C_val[cak + e]);
         }
-      };
-      // number of steps of this block = sum over its columns of ceil(len / 32) (columns of length 0 cannot occur)
-      int steps = 0;
-      {
-        const int mine = lane < ncol ? (len + 31) >> 5 : 0;
-        steps = __reduce_add_sync(kFull, mine);
       }
-#pragma unroll
-      for (int u = 0; u < kJPF; ++u) fetch(jq[u], mq[u]);
-      for (int st = 0; st < steps; ++st) {
-        const int32_t j = jq[0];
-        const float m = mq[0];
-#pragma unroll
-        for (int u = 0; u + 1 < kJPF; ++u) {
-          jq[u] = jq[u + 1];
-          mq[u] = mq[u + 1];
-        }
-        fetch(jq[kJPF - 1], mq[kJPF - 1]);
-        bool fresh = false;
-        if (j >= 0) {
-          uint32_t h = jhash((uint32_t)j) & smask;
-          while (true) {
-            const int32_t old = atomicCAS(&tkey[h], -1, j);
-            if (old == -1) {
-              tval[h] = m;                                     // 0 + m
-              fresh = true;
-              break;
-            }
-            if (old == j) {
-              tval[h] = acc_add(tval[h], m, half);
-              break;
-            }
-            h = (h + 1) & smask;
+      while (k < ncol) {
+        int nk = k, nbase = base + 32 * kJE;
+        int64_t ncak = cak;
+        int nlen = lenk;
+        float nv = vk;
+        if (nbase >= lenk) {                                   // warp-uniform: next column
+          nk = k + 1;
+          nbase = 0;
+          if (nk < ncol) {
+            ncak = __shfl_sync(kFull, ca, nk);
+            nlen = __shfl_sync(kFull, len, nk);
+            nv = __shfl_sync(kFull, vic, nk);
           }
         }
-        used += __popc(__ballot_sync(kFull, fresh));
+        int32_t jn[kJE];
+        float mn[kJE];
+#pragma unroll
+        for (int u = 0; u < kJE; ++u) {
+          const int e = nbase + u * 32 + lane;
+          jn[u] = -1;
+          mn[u] = 0.f;
+          if (nk < ncol && e < nlen) {
+            jn[u] = C_idx[ncak + e];
+            mn[u] = fminf(nv, C_val[ncak + e]);
+          }
+        }
+        int fresh_n = 0;
+#pragma unroll
+        for (int u = 0; u < kJE; ++u) {
+          bool fresh = false;
+          if (j[u] >= 0 && (!owned_only || pair_owned((int32_t)row, j[u]))) {
+            uint32_t h = jhash((uint32_t)j[u]) & smask;
+            while (true) {
+              const int32_t old = atomicCAS(&tkey[h], -1, j[u]);
+              if (old == -1) {
+                tval[h] = m[u];                                // 0 + m
+                fresh = true;
+                break;
+              }
+              if (old == j[u]) {
+                tval[h] = acc_add(tval[h], m[u], half);
+                break;
+              }
+              h = (h + 1) & smask;
+            }
+          }
+          fresh_n += __popc(__ballot_sync(kFull, fresh));
+        }
+        used += fresh_n;
         __syncwarp();                                          // this step's adds land before the next step's
         if (used > limit) {
           overflow = true;
           break;
+        }
+        k = nk;
+        base = nbase;
+        cak = ncak;
+        lenk = nlen;
+        vk = nv;
+#pragma unroll
+        for (int u = 0; u < kJE; ++u) {
+          j[u] = jn[u];
+          m[u] = mn[u];
         }
       }
     }
@@ -273,7 +291,8 @@ __global__ void __launch_bounds__(kJDThreads) jaccard_direct_kernel(
     const int64_t* __restrict__ C_ptr, const int32_t* __restrict__ C_idx, const float* __restrict__ C_val, int64_t N,
     int64_t row_begin, const int32_t* __restrict__ queue, const int32_t* __restrict__ queue_len, float eps,
     const int64_t* __restrict__ slot_ptr, int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_val,
-    int32_t* __restrict__ nbr_cnt, int64_t nbr_capacity, unsigned long long* __restrict__ slot_overflow, int half) {
+    int32_t* __restrict__ nbr_cnt, int64_t nbr_capacity, unsigned long long* __restrict__ slot_overflow, int half,
+    int owned_only) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   float* acc = reinterpret_cast<float*>(smem_raw);
   __shared__ int64_t s_ca[32];
@@ -313,11 +332,11 @@ __global__ void __launch_bounds__(kJDThreads) jaccard_direct_kernel(
           jn = C_idx[s_ca[k + 1] + t];
           mn = fminf(s_v[k + 1], C_val[s_ca[k + 1] + t]);
         }
-        if (j >= 0) acc[j] = acc_add(acc[j], m, half);
+        if (j >= 0 && (!owned_only || pair_owned((int32_t)row, j))) acc[j] = acc_add(acc[j], m, half);
         const int len = s_len[k];
         for (int e = t + kJDThreads; e < len; e += kJDThreads) {   // columns longer than the CTA (rare)
           const int32_t j2 = C_idx[s_ca[k] + e];
-          acc[j2] = acc_add(acc[j2], fminf(s_v[k], C_val[s_ca[k] + e]), half);
+          if (!owned_only || pair_owned((int32_t)row, j2)) acc[j2] = acc_add(acc[j2], fminf(s_v[k], C_val[s_ca[k] + e]), half);
         }
         __syncthreads();                                       // column k is in before column k + 1 starts
         j = jn;
@@ -441,7 +460,8 @@ __global__ void __launch_bounds__(256) jaccard_neighbors_heavy_kernel(
     int64_t row_begin, const int32_t* __restrict__ rows_list, int64_t n_list_host,
     const int32_t* __restrict__ list_len, float eps, const int64_t* __restrict__ slot_ptr,
     int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_val, int32_t* __restrict__ nbr_cnt,
-    float* __restrict__ scratch, int64_t nbr_capacity, unsigned long long* __restrict__ slot_overflow, int half) {
+    float* __restrict__ scratch, int64_t nbr_capacity, unsigned long long* __restrict__ slot_overflow, int half,
+    int owned_only) {
   __shared__ int s_warp[8];
   __shared__ int s_base;
   const int64_t n_list = list_len ? (int64_t)*list_len : n_list_host;
@@ -458,7 +478,7 @@ __global__ void __launch_bounds__(256) jaccard_neighbors_heavy_kernel(
     const float vic = Q_val[p];
     for (int64_t q = C_ptr[c] + threadIdx.x; q < C_ptr[c + 1]; q += blockDim.x) {
       const int32_t j = C_idx[q];
-      __stcg(&acc[j], acc_add(__ldcg(&acc[j]), fminf(vic, C_val[q]), half));
+      if (!owned_only || pair_owned((int32_t)row, j)) __stcg(&acc[j], acc_add(__ldcg(&acc[j]), fminf(vic, C_val[q]), half));
     }
     __syncthreads();
   }
@@ -510,6 +530,7 @@ struct JnArgs {
   // the class its T-based (pessimistic) size asks for -- at least one class up -- so a wrong optimistic first guess
   // costs one attempt, not a climb through every class
   const int32_t* T_cnt; int32_t* queues; int32_t* qlen; int64_t q_stride; int cur_class; int direct_from;
+  int owned_only;
 };
 
 // one launch of the table kernel: `n_max` bounds the grid, the real row count is *queue_len when given
@@ -527,7 +548,7 @@ static int launch_jn(const JnArgs& a, int slots, int64_t n_max, const int32_t* q
   jaccard_neighbors_kernel<kWarps><<<(unsigned)grid, kWarps * 32, smem, st>>>(
       a.Q_ptr, a.Q_idx, a.Q_val, a.C_ptr, a.C_idx, a.C_val, a.row_begin, n_max, queue, queue_len, next_queue, next_len,
       a.eps, a.slot_ptr, a.nbr_idx, a.nbr_val, a.nbr_cnt, slots, a.nbr_capacity, a.slot_overflow, a.half, a.T_cnt,
-      a.queues, a.qlen, a.q_stride, a.cur_class, a.direct_from);
+      a.queues, a.qlen, a.q_stride, a.cur_class, a.direct_from, a.owned_only);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
@@ -599,7 +620,7 @@ int reid_jaccard_neighbors(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
   const int64_t n = rows_list ? n_list : row_end - row_begin;
   if (n == 0) return REID_OK;
   const JnArgs a{Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, row_begin, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt,
-                 INT64_MAX, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, 0};
+                 INT64_MAX, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, 0, 0};
   return launch_jn_slots(a, table_slots, n, rows_list, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
@@ -612,7 +633,7 @@ int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
                            const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin, int64_t row_end,
                            float eps, const int32_t* T_cnt, const int32_t* P_cnt, const int64_t* slot_ptr, int32_t* nbr_idx, float* nbr_val,
                            int32_t* nbr_cnt, int64_t nbr_capacity, uint64_t* slot_overflow, int half_precision,
-                           void* workspace, void* stream) {
+                           int owned_pairs_only, void* workspace, void* stream) {
   using namespace reid;
   REID_CHECK_ARG(Q_ptr && Q_idx && Q_val && C_ptr && C_idx && C_val && T_cnt && slot_ptr && nbr_idx && nbr_cnt && workspace,
                  "reid_jaccard_eps_graph: NULL pointer");
@@ -634,7 +655,7 @@ int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
   if (nbr_capacity <= 0) nbr_capacity = INT64_MAX;           // slots sized by the caller from T_cnt: nothing to guard
   unsigned long long* ovf = (unsigned long long*)slot_overflow;
   JnArgs a{Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, row_begin, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt,
-           nbr_capacity, ovf, half_precision, T_cnt, w.queues, w.qlen, n, 0, direct_from};
+           nbr_capacity, ovf, half_precision, T_cnt, w.queues, w.qlen, n, 0, direct_from, owned_pairs_only};
   const int n_hash = direct_from < kJClasses ? direct_from : kJClasses;
   for (int c = 0; c < n_hash; ++c) {
     a.cur_class = c;
@@ -650,13 +671,15 @@ int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
     if (grid > n) grid = n;
     jaccard_direct_kernel<<<(unsigned)grid, kJDThreads, row_bytes, st>>>(Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin,
                                                                         direct_q, direct_len, eps, slot_ptr, nbr_idx, nbr_val,
-                                                                        nbr_cnt, nbr_capacity, ovf, half_precision);
+                                                                        nbr_cnt, nbr_capacity, ovf, half_precision,
+                                                                        owned_pairs_only);
     REID_LAUNCH_CHECK();
   }
   const int64_t hg = n < kJHeavyCtas ? n : kJHeavyCtas;
   jaccard_neighbors_heavy_kernel<<<(unsigned)hg, 256, 0, st>>>(Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin,
                                                               w.queues + (int64_t)kJClasses * n, 0, w.qlen + kJClasses, eps,
-                                                              slot_ptr, nbr_idx, nbr_val, nbr_cnt, w.scratch, nbr_capacity, ovf, half_precision);
+                                                              slot_ptr, nbr_idx, nbr_val, nbr_cnt, w.scratch, nbr_capacity, ovf, half_precision,
+                                                              owned_pairs_only);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
@@ -694,7 +717,7 @@ int reid_jaccard_neighbors_heavy(const int64_t* Q_ptr, const int32_t* Q_idx, con
   if (n_list == 0) return REID_OK;
   jaccard_neighbors_heavy_kernel<<<(unsigned)n_list, 256, 0, (cudaStream_t)stream>>>(
       Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, N, row_begin, rows_list, n_list, nullptr, eps, slot_ptr, nbr_idx, nbr_val,
-      nbr_cnt, scratch, INT64_MAX, nullptr, 0);
+      nbr_cnt, scratch, INT64_MAX, nullptr, 0, 0);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

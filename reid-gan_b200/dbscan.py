@@ -19,8 +19,9 @@ from ._lib import call, check, ptr, stream_ptr
 from .faiss_rerank import JaccardDistance, R_NBR_OVF, R_S, _device_of, _nbr_cap_hint, _scan, jaccard_neighbors
 
 
-def dbscan_from_neighbors(N, nbr_ptr, nbr_idx, nbr_cnt, min_samples):
-    """Device labelling from eps-neighbour lists of all N rows -> (labels int64 cuda, core uint8 cuda, n_clusters)."""
+def dbscan_from_neighbors(N, nbr_ptr, nbr_idx, nbr_cnt, min_samples, owned=False):
+    """Device labelling from eps-neighbour lists of all N rows -> (labels int64 cuda, core uint8 cuda, n_clusters).
+    owned: the lists name every edge once (jaccard_neighbors(owned=True))."""
     L = _lib.lib()
     dev = nbr_ptr.device
     labels = torch.empty(N, dtype=torch.int64, device=dev)
@@ -28,7 +29,7 @@ def dbscan_from_neighbors(N, nbr_ptr, nbr_idx, nbr_cnt, min_samples):
     ncl = torch.zeros(1, dtype=torch.int64, device=dev)
     ws = torch.empty(max(1, L.reid_dbscan_workspace_bytes(N)), dtype=torch.uint8, device=dev)
     call("reid_dbscan_labels", N, ptr(nbr_ptr), ptr(nbr_idx), ptr(nbr_cnt), int(min_samples), ptr(labels), ptr(core),
-                               ptr(ncl), ptr(ws), stream_ptr())
+                               ptr(ncl), ptr(ws), 1 if owned else 0, stream_ptr())
     return labels, core, ncl
 
 
@@ -82,14 +83,14 @@ class DBSCAN:
             report = torch.zeros(16, dtype=torch.int64, device=st.Q_ptr.device)
             st.report = report
             try:
-                slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, self.eps, speculative=True)
+                slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, self.eps, speculative=True, owned=True)
             finally:
                 st.report = None
-            labels, core, _ = dbscan_from_neighbors(st.N, slot_ptr, nbr_idx, nbr_cnt, self.min_samples)
+            labels, core, _ = dbscan_from_neighbors(st.N, slot_ptr, nbr_idx, nbr_cnt, self.min_samples, owned=True)
             vals = report.tolist()
             if vals[R_NBR_OVF]:
-                slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, self.eps, speculative=False)
-                labels, core, _ = dbscan_from_neighbors(st.N, slot_ptr, nbr_idx, nbr_cnt, self.min_samples)
+                slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, self.eps, speculative=False, owned=True)
+                labels, core, _ = dbscan_from_neighbors(st.N, slot_ptr, nbr_idx, nbr_cnt, self.min_samples, owned=True)
             elif vals[R_S]:
                 _nbr_cap_hint[st.N] = int(vals[R_S])
         return labels, core

@@ -452,14 +452,16 @@ def query_expand_rows(st, row_begin, row_end):
     return q_cnt[:n], q_idx, q_val
 
 
-def jaccard_neighbors(st, eps, with_values=False, speculative=None):
+def jaccard_neighbors(st, eps, with_values=False, speculative=None, owned=False):
     """a7 (sparse form): eps-neighbourhoods of the shard's rows.  Returns (slot_ptr int64 (n+1),
     nbr_idx int32, nbr_cnt int32 (n), nbr_val or None): row r's list is nbr_idx[slot_ptr[r] : +nbr_cnt[r]].
 
     Exact-size flavour: slots from T_i = sum_c |col(c)| (an upper bound of the partner count), total read back.
     Speculative flavour (default while the state's report is pending, i.e. inside a sync-free pass): slots from the
     Markov bound S_i (reid_jaccard_bounds), storage guessed, every kernel guarded; rows that did not fit are counted
-    in the report (finish(check_nbr=True) tells)."""
+    in the report (finish(check_nbr=True) tells).
+    owned: every unordered pair {i, j} is accumulated and listed by ONE of its rows only (csrc/jaccard.cu pair_owned;
+    J is bit-symmetric) -- half the table updates; dbscan_from_neighbors(owned=True) consumes such lists."""
     L = _lib.lib()
     dev = st.Q_ptr.device
     r0, r1 = st.row_begin, st.row_end
@@ -483,7 +485,7 @@ def jaccard_neighbors(st, eps, with_values=False, speculative=None):
         nbr_cnt = torch.empty(n, dtype=torch.int32, device=dev)
         call("reid_jaccard_eps_graph", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
              ptr(st.C_val), st.N, r0, r1, eps32, ptr(t_cnt), ptr(p_cnt) if PARTNER_GUESS else None, ptr(slot_ptr), ptr(nbr_idx),
-             ptr(nbr_val), ptr(nbr_cnt), cap, ptr(report[R_NBR_OVF:]), 1 if st.half else 0, ptr(ws), sp)
+             ptr(nbr_val), ptr(nbr_cnt), cap, ptr(report[R_NBR_OVF:]), 1 if st.half else 0, 1 if owned else 0, ptr(ws), sp)
         return slot_ptr, nbr_idx, nbr_cnt, nbr_val
     call("reid_jaccard_bounds", ptr(st.Q_ptr), ptr(st.Q_idx), None, ptr(st.C_ptr), r0, r1, eps32, ptr(t_cnt), None, ptr(p_cnt), sp)
     if r0 == 0 and r1 == st.N and getattr(st, "t_total_all", None) is not None:
@@ -496,7 +498,8 @@ def jaccard_neighbors(st, eps, with_values=False, speculative=None):
     nbr_cnt = torch.empty(n, dtype=torch.int32, device=dev)
     call("reid_jaccard_eps_graph", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
                                    ptr(st.C_val), st.N, r0, r1, eps32, ptr(t_cnt), ptr(p_cnt) if PARTNER_GUESS else None,
-                                   ptr(slot_ptr), ptr(nbr_idx), ptr(nbr_val), ptr(nbr_cnt), 0, None, 1 if st.half else 0, ptr(ws), sp)
+                                   ptr(slot_ptr), ptr(nbr_idx), ptr(nbr_val), ptr(nbr_cnt), 0, None, 1 if st.half else 0,
+                                   1 if owned else 0, ptr(ws), sp)
     return slot_ptr, nbr_idx, nbr_cnt, nbr_val
 
 

@@ -24,11 +24,12 @@ def _labels_from_state(st, eps, min_samples, timers=False):
     if timers:
         ev0 = torch.cuda.Event(enable_timing=True)
         ev0.record()
-    slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, eps)
+    # owned pairs: every edge of the eps-graph is accumulated and listed once (J is bit-symmetric)
+    slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, eps, owned=True)
     if timers:
         ev1 = torch.cuda.Event(enable_timing=True)
         ev1.record()
-    labels, core, ncl = dbscan_from_neighbors(st.N, slot_ptr, nbr_idx, nbr_cnt, min_samples)
+    labels, core, ncl = dbscan_from_neighbors(st.N, slot_ptr, nbr_idx, nbr_cnt, min_samples, owned=True)
     if timers:
         ev2 = torch.cuda.Event(enable_timing=True)
         ev2.record()

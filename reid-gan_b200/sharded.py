@@ -490,14 +490,14 @@ def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=
             else:
                 st = rerank_state_async(x, k1, k2, knn=knn, comm=comm, timers=timers, knn_result=res, report=report,
                                         speculative=spec and res is not None)
-                slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, eps)
+                slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, eps, owned=True)
                 if st.report is not None:
                     g_ptr, g_idx, g_cnt = comm.gather_neighbors(slot_ptr, nbr_idx, nbr_cnt, overflow=st.report[R_XCHG_OVF:],
                                                                 stride=_stride_for("nbr", N))
                 else:
                     g_ptr, g_idx, g_cnt = comm.gather_neighbors(slot_ptr, nbr_idx, nbr_cnt)
                     _rec_stride_hint[("nbr", N)] = max(_rec_stride_hint.get(("nbr", N), 0), int(g_cnt.max().item()) if N else 0)
-                labels, core, ncl = dbscan_from_neighbors(N, g_ptr, g_idx, g_cnt, min_samples)
+                labels, core, ncl = dbscan_from_neighbors(N, g_ptr, g_idx, g_cnt, min_samples, owned=True)
             cen = None
             if centroids:
                 cen = torch.empty((max(N, 1), x.shape[1]), dtype=torch.float32, device=dev)

@@ -175,3 +175,34 @@ def test_speculative_sizes_that_do_not_hold_only_cost_time(monkeypatch):
     assert out["state"].knn_info["uncertified_rows"] > 0
     assert np.array_equal(out["labels"].cpu().numpy(), g["labels"])
     assert fr.rank_digest(out["state"]) == str(g["rank_sha256"])
+
+
+@pytest.mark.parametrize("name", ["hard", "c1"])
+def test_owned_pair_lists_are_the_full_lists_once(name):
+    """The pass accumulates every unordered pair {i, j} in ONE of its two rows (J is bit-symmetric; csrc/jaccard.cu
+    pair_owned).  Mirrored, the owned lists must be exactly the full eps-neighbourhoods (= the reference's, by the digest
+    test above), no pair may be listed twice, and DBSCAN on them gives the same labels and core points."""
+    from reid_gan_b200.dbscan import dbscan_from_neighbors
+    from reid_gan_b200.faiss_rerank import jaccard_neighbors, rerank_state
+    g = np.load(os.path.join(GOLD, "full_%s.npz" % name))
+    x = inputs(name).cuda()
+    k1, k2, eps, ms = int(g["k1"]), int(g["k2"]), float(g["eps"]), int(g["min_samples"])
+    N = x.shape[0]
+    st = rerank_state(x, k1, k2)
+    f_ptr, f_idx, f_cnt, _ = jaccard_neighbors(st, eps)
+    o_ptr, o_idx, o_cnt, _ = jaccard_neighbors(st, eps, owned=True)
+    full = sorted_lists(f_ptr, f_idx, f_cnt)
+    full_rows = np.repeat(np.arange(N), f_cnt.cpu().numpy().astype(np.int64))
+    own = sorted_lists(o_ptr, o_idx, o_cnt).astype(np.int64)
+    own_rows = np.repeat(np.arange(N), o_cnt.cpu().numpy().astype(np.int64))
+    off = own != own_rows
+    a = np.concatenate([own_rows, own[off]])
+    b = np.concatenate([own, own_rows[off]])
+    keys = a * N + b
+    assert np.unique(keys).size == keys.size, "a pair is listed by both of its rows"
+    assert np.array_equal(np.sort(keys), np.sort(full_rows * N + full.astype(np.int64)))
+    assert abs(int(off.sum()) * 2 - int((full != full_rows).sum())) == 0
+    lf, cf, nf = dbscan_from_neighbors(N, f_ptr, f_idx, f_cnt, ms)
+    lo, co, no = dbscan_from_neighbors(N, o_ptr, o_idx, o_cnt, ms, owned=True)
+    assert torch.equal(lf, lo) and torch.equal(cf, co) and int(nf) == int(no)
+    assert np.array_equal(lo.cpu().numpy(), g["labels"])
