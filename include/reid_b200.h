@@ -298,8 +298,10 @@ int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
                            const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin,
                            int64_t row_end, float eps, const int32_t* T_cnt, const int32_t* P_cnt, const int64_t* slot_ptr,
                            int32_t* nbr_idx, float* nbr_val, int32_t* nbr_cnt, int64_t nbr_capacity,
-                           uint64_t* slot_overflow, int half_precision, int owned_pairs_only, void* workspace,
-                           void* stream);
+                           uint64_t* slot_overflow, int half_precision, int owned_pairs_only, uint64_t* escalated_rows,
+                           void* workspace, void* stream);
+/* escalated_rows (optional device scalar, accumulates): rows whose first table was too small and that were moved to a
+ * bigger class -- tells the caller whether the P_cnt guess suits the data. */
 /* owned_pairs_only: J is bit-symmetric, so each unordered pair {i, j} may be accumulated and listed by only ONE of its
  * rows -- i owns (i, j) iff i == j, or i < j with i + j even, or i > j with i + j odd (every row keeps about half of its
  * partners).  Half the table updates; reid_dbscan_labels(owned_pairs = 1) consumes such lists. */

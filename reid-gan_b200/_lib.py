@@ -65,7 +65,7 @@ SIGNATURES = {
     "reid_jaccard_neighbors": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _P, _L, _F, _P, _P, _P, _P, _I, _P]),
     "reid_jaccard_neighbors_heavy": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _P, _L, _F, _P, _P, _P, _P, _P, _P]),
     "reid_jaccard_eps_graph_workspace_bytes": (ctypes.c_size_t, [_L, _L]),
-    "reid_jaccard_eps_graph": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _F, _P, _P, _P, _P, _P, _P, _L, _P, _I, _I, _P, _P]),
+    "reid_jaccard_eps_graph": (_I, [_P, _P, _P, _P, _P, _P, _L, _L, _L, _F, _P, _P, _P, _P, _P, _P, _L, _P, _I, _I, _P, _P, _P]),
     "reid_rr_normalised_distance": (_I, [_P, _P, _P, _L, _L, _P, _P, _P, _P]),
     "reid_rr_weights": (_I, [_P, _L, _P, _I, _P, _L, _P, _P, _P]),
     "reid_rr_final": (_I, [_P, _L, _P, _L, _L, _F, _F, _P, _P]),

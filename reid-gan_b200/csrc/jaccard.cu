@@ -46,12 +46,12 @@ __global__ void __launch_bounds__(256) jaccard_bounds_kernel(const int64_t* __re
       // clustered data (a partner shares most of the row's columns).  A row inside an identity cluster of size m has
       // columns of length ~m and ~m..2m partners, so 3 x the longest column + the row's own nnz is a much closer
       // guess; it is never taken above the T-based one.
-      // When the column-based guess is MUCH smaller than the T-based one (8x), the row's columns do not overlap the
-      // way an identity cluster's do (Market shape: k1 larger than the identities, every row's neighbourhood spans
-      // several of them and its partners run into the thousands): the guess is then not trusted.
+      // It is the wrong guess on shapes whose neighbourhoods span several identities (Market shape: partners ~ T / 2,
+      // 98 % of the rows then waste their first attempt): the eps-graph entry counts the rows it had to move up, and the
+      // host layer stops asking for this guess on a data set where more than three quarters of the rows needed it.
       const int64_t by_t = t < 2048 ? t >> 2 : t >> 1;
       const int64_t by_col = 3 * longest + (qb - qa);
-      P_cnt[row - row_begin] = (int32_t)((by_col * 8 < by_t || by_col > by_t) ? by_t : by_col);
+      P_cnt[row - row_begin] = (int32_t)(by_col < by_t ? by_col : by_t);
     }
     if (S_cnt) {
       double need = t_min > 0.f ? b / (double)t_min + 2.0 : (double)t;
@@ -117,7 +117,7 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
     const int64_t* __restrict__ slot_ptr, int32_t* __restrict__ nbr_idx, float* __restrict__ nbr_val,
     int32_t* __restrict__ nbr_cnt, int slots, int64_t nbr_capacity, unsigned long long* __restrict__ slot_overflow,
     int half, const int32_t* __restrict__ T_cnt, int32_t* __restrict__ queues, int32_t* __restrict__ qlen, int64_t q_stride,
-    int cur_class, int direct_from, int owned_only) {
+    int cur_class, int direct_from, int owned_only, unsigned long long* __restrict__ escalated) {
   extern __shared__ __align__(16) unsigned char smem_raw[];
   const int w = threadIdx.x >> 5, lane = lane_id();
   int32_t* tkey = reinterpret_cast<int32_t*>(smem_raw) + (size_t)w * slots;
@@ -241,6 +241,7 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
           if (c2 <= cur_class) c2 = cur_class + 1;
           if (c2 >= direct_from) c2 = direct_from <= kJClasses ? kJClasses + 1 : (c2 > kJClasses ? kJClasses : c2);
           queues[(int64_t)c2 * q_stride + atomicAdd(&qlen[c2], 1)] = (int32_t)lr;
+          if (escalated) atomicAdd(escalated, 1ull);
         } else if (next_queue) {
           next_queue[atomicAdd(next_len, 1)] = (int32_t)lr;
         } else {
@@ -530,7 +531,7 @@ struct JnArgs {
   // the class its T-based (pessimistic) size asks for -- at least one class up -- so a wrong optimistic first guess
   // costs one attempt, not a climb through every class
   const int32_t* T_cnt; int32_t* queues; int32_t* qlen; int64_t q_stride; int cur_class; int direct_from;
-  int owned_only;
+  int owned_only; unsigned long long* escalated;
 };
 
 // one launch of the table kernel: `n_max` bounds the grid, the real row count is *queue_len when given
@@ -548,7 +549,7 @@ static int launch_jn(const JnArgs& a, int slots, int64_t n_max, const int32_t* q
   jaccard_neighbors_kernel<kWarps><<<(unsigned)grid, kWarps * 32, smem, st>>>(
       a.Q_ptr, a.Q_idx, a.Q_val, a.C_ptr, a.C_idx, a.C_val, a.row_begin, n_max, queue, queue_len, next_queue, next_len,
       a.eps, a.slot_ptr, a.nbr_idx, a.nbr_val, a.nbr_cnt, slots, a.nbr_capacity, a.slot_overflow, a.half, a.T_cnt,
-      a.queues, a.qlen, a.q_stride, a.cur_class, a.direct_from, a.owned_only);
+      a.queues, a.qlen, a.q_stride, a.cur_class, a.direct_from, a.owned_only, a.escalated);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
@@ -620,7 +621,7 @@ int reid_jaccard_neighbors(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
   const int64_t n = rows_list ? n_list : row_end - row_begin;
   if (n == 0) return REID_OK;
   const JnArgs a{Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, row_begin, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt,
-                 INT64_MAX, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, 0, 0};
+                 INT64_MAX, nullptr, 0, nullptr, nullptr, nullptr, 0, 0, 0, 0, nullptr};
   return launch_jn_slots(a, table_slots, n, rows_list, nullptr, nullptr, nullptr, (cudaStream_t)stream);
 }
 
@@ -633,7 +634,7 @@ int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
                            const int32_t* C_idx, const float* C_val, int64_t N, int64_t row_begin, int64_t row_end,
                            float eps, const int32_t* T_cnt, const int32_t* P_cnt, const int64_t* slot_ptr, int32_t* nbr_idx, float* nbr_val,
                            int32_t* nbr_cnt, int64_t nbr_capacity, uint64_t* slot_overflow, int half_precision,
-                           int owned_pairs_only, void* workspace, void* stream) {
+                           int owned_pairs_only, uint64_t* escalated_rows, void* workspace, void* stream) {
   using namespace reid;
   REID_CHECK_ARG(Q_ptr && Q_idx && Q_val && C_ptr && C_idx && C_val && T_cnt && slot_ptr && nbr_idx && nbr_cnt && workspace,
                  "reid_jaccard_eps_graph: NULL pointer");
@@ -655,7 +656,8 @@ int reid_jaccard_eps_graph(const int64_t* Q_ptr, const int32_t* Q_idx, const flo
   if (nbr_capacity <= 0) nbr_capacity = INT64_MAX;           // slots sized by the caller from T_cnt: nothing to guard
   unsigned long long* ovf = (unsigned long long*)slot_overflow;
   JnArgs a{Q_ptr, Q_idx, Q_val, C_ptr, C_idx, C_val, row_begin, eps, slot_ptr, nbr_idx, nbr_val, nbr_cnt,
-           nbr_capacity, ovf, half_precision, T_cnt, w.queues, w.qlen, n, 0, direct_from, owned_pairs_only};
+           nbr_capacity, ovf, half_precision, T_cnt, w.queues, w.qlen, n, 0, direct_from, owned_pairs_only,
+           (unsigned long long*)escalated_rows};
   const int n_hash = direct_from < kJClasses ? direct_from : kJClasses;
   for (int c = 0; c < n_hash; ++c) {
     a.cur_class = c;

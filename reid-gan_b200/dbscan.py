@@ -16,7 +16,7 @@ import torch
 
 from . import _lib
 from ._lib import call, check, ptr, stream_ptr
-from .faiss_rerank import JaccardDistance, R_NBR_OVF, R_S, _device_of, _nbr_cap_hint, _scan, jaccard_neighbors
+from .faiss_rerank import JaccardDistance, REPORT_WORDS, R_ESC, R_NBR_OVF, R_S, _guess_hint, _device_of, _nbr_cap_hint, _scan, jaccard_neighbors
 
 
 def dbscan_from_neighbors(N, nbr_ptr, nbr_idx, nbr_cnt, min_samples, owned=False):
@@ -80,7 +80,7 @@ class DBSCAN:
                 return self._fit_dense(dist.dense_device())
             # speculative slot sizes first (no host round trip before the labels); the overflow count comes back
             # with the same synchronisation that fetches the labels, and a pass that did not fit is redone exactly
-            report = torch.zeros(16, dtype=torch.int64, device=st.Q_ptr.device)
+            report = torch.zeros(REPORT_WORDS, dtype=torch.int64, device=st.Q_ptr.device)
             st.report = report
             try:
                 slot_ptr, nbr_idx, nbr_cnt, _ = jaccard_neighbors(st, self.eps, speculative=True, owned=True)
@@ -93,6 +93,8 @@ class DBSCAN:
                 labels, core, _ = dbscan_from_neighbors(st.N, slot_ptr, nbr_idx, nbr_cnt, self.min_samples, owned=True)
             elif vals[R_S]:
                 _nbr_cap_hint[st.N] = int(vals[R_S])
+                if st.N not in _guess_hint and vals[R_ESC] * 4 > 3 * st.N:
+                    _guess_hint[st.N] = False
         return labels, core
 
     def _fit_dense(self, X):

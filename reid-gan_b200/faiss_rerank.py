@@ -69,7 +69,15 @@ _nbr_cap_hint = {}           # N -> slot total of the last finished pass (the ne
 #                      [9] uncertified kNN rows  [10] V_qe rows that overflowed the table  [11] rows that overflowed
 #                      their eps-neighbour slots  [12:15] slot total/max/sumsq
 #                      [15] rows that did not fit a fixed-stride exchange record (row-sharded pass)
-R_E, R_Q, R_C, R_UNCERT, R_QE_OVF, R_NBR_OVF, R_S, R_XCHG_OVF = 0, 3, 6, 9, 10, 11, 12, 15
+#                      [16] rows the eps-graph stage had to move to a bigger hash table (the partner guess was too small)
+R_E, R_Q, R_C, R_UNCERT, R_QE_OVF, R_NBR_OVF, R_S, R_XCHG_OVF, R_ESC = 0, 3, 6, 9, 10, 11, 12, 15, 16
+REPORT_WORDS = 24
+_guess_hint = {}             # N -> False once more than 3/4 of the rows outgrew the partner guess (Market-like shapes: 98 %;
+                             # the hard set, where the guess still pays, 55 %)
+
+
+def partner_guess_on(N):
+    return PARTNER_GUESS and _guess_hint.get(N, True)
 REC_STRIDE = {"V": 64, "Q": 128, "nbr": 128}     # exchange record strides of the row-sharded pass (entries per row)
 _rec_stride_hint = {}        # (kind, N) -> longest row of the last finished pass
 
@@ -116,6 +124,8 @@ class RerankState:
             self.q_total, self.c_max, self.t_total_all = vals[R_C], vals[R_C + 1], vals[R_C + 2]
             if vals[R_S]:
                 _nbr_cap_hint[self.N] = vals[R_S]
+                if PARTNER_GUESS and self.N not in _guess_hint and vals[R_ESC] * 4 > 3 * (self.row_end - self.row_begin):
+                    _guess_hint[self.N] = False
             nbr_ok = vals[R_NBR_OVF] == 0
             return (self, nbr_ok) if check_nbr else self
         st = self._redo(vals)
@@ -237,7 +247,7 @@ def rerank_state_async(x, k1, k2, knn="auto", rows=None, timers=False, comm=None
 
     external_knn = knn_result not in (None, "upload")
     if report is None:                                        # else: shared with the caller's search (sharded.py)
-        report = torch.zeros(16, dtype=torch.int64, device=dev)
+        report = torch.zeros(REPORT_WORDS, dtype=torch.int64, device=dev)
     mark("start")
     # a1 ------------------------------------------------------------------
     if knn_result == "upload":                               # x is still on the host: search while it is uploaded
@@ -484,8 +494,9 @@ def jaccard_neighbors(st, eps, with_values=False, speculative=None, owned=False)
         nbr_val = torch.empty(cap, dtype=torch.float32, device=dev) if with_values else None
         nbr_cnt = torch.empty(n, dtype=torch.int32, device=dev)
         call("reid_jaccard_eps_graph", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
-             ptr(st.C_val), st.N, r0, r1, eps32, ptr(t_cnt), ptr(p_cnt) if PARTNER_GUESS else None, ptr(slot_ptr), ptr(nbr_idx),
-             ptr(nbr_val), ptr(nbr_cnt), cap, ptr(report[R_NBR_OVF:]), 1 if st.half else 0, 1 if owned else 0, ptr(ws), sp)
+             ptr(st.C_val), st.N, r0, r1, eps32, ptr(t_cnt), ptr(p_cnt) if partner_guess_on(st.N) else None, ptr(slot_ptr),
+             ptr(nbr_idx), ptr(nbr_val), ptr(nbr_cnt), cap, ptr(report[R_NBR_OVF:]), 1 if st.half else 0, 1 if owned else 0,
+             ptr(report[R_ESC:]) if report.numel() > R_ESC else None, ptr(ws), sp)
         return slot_ptr, nbr_idx, nbr_cnt, nbr_val
     call("reid_jaccard_bounds", ptr(st.Q_ptr), ptr(st.Q_idx), None, ptr(st.C_ptr), r0, r1, eps32, ptr(t_cnt), None, ptr(p_cnt), sp)
     if r0 == 0 and r1 == st.N and getattr(st, "t_total_all", None) is not None:
@@ -497,9 +508,9 @@ def jaccard_neighbors(st, eps, with_values=False, speculative=None, owned=False)
     nbr_val = torch.empty(max(t_total, 1), dtype=torch.float32, device=dev) if with_values else None
     nbr_cnt = torch.empty(n, dtype=torch.int32, device=dev)
     call("reid_jaccard_eps_graph", ptr(st.Q_ptr), ptr(st.Q_idx), ptr(st.Q_val), ptr(st.C_ptr), ptr(st.C_idx),
-                                   ptr(st.C_val), st.N, r0, r1, eps32, ptr(t_cnt), ptr(p_cnt) if PARTNER_GUESS else None,
+                                   ptr(st.C_val), st.N, r0, r1, eps32, ptr(t_cnt), ptr(p_cnt) if partner_guess_on(st.N) else None,
                                    ptr(slot_ptr), ptr(nbr_idx), ptr(nbr_val), ptr(nbr_cnt), 0, None, 1 if st.half else 0,
-                                   1 if owned else 0, ptr(ws), sp)
+                                   1 if owned else 0, None, ptr(ws), sp)
     return slot_ptr, nbr_idx, nbr_cnt, nbr_val
 
 

@@ -102,7 +102,9 @@ def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=
             return st, labels, core, ncl, nbr_cnt, cen, st.report
 
         if graph and not timers:
-            g = PassGraph.get(_graph_key(x, k1, k2, float(eps), min_samples, knn, bool(centroids)), enqueue)
+            from .faiss_rerank import partner_guess_on          # a changed hint changes the launch sequence: new graph
+            g = PassGraph.get(_graph_key(x, k1, k2, float(eps), min_samples, knn, bool(centroids), partner_guess_on(x.shape[0])),
+                              enqueue)
             g.graph.replay()
             st, labels, core, ncl, nbr_cnt, cen, report = g.result
             st.report = report                              # finish() consumes it: hand the (refilled) tensor back

@@ -471,7 +471,7 @@ def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=
             plan = "tiles+rows" if sym_ok else "rows"
         if plan in ("tiles", "tiles+rows") and not sym_ok:
             raise ValueError("plan %r needs the symmetric tensor-core search (N >= %d, k1 <= %d, D %% 64 == 0)" % (plan, kt.SYM_MIN_N, kt.SYM_MAX_K))
-        from .faiss_rerank import R_XCHG_OVF, _stride_for, _rec_stride_hint
+        from .faiss_rerank import REPORT_WORDS, R_XCHG_OVF, _stride_for, _rec_stride_hint, partner_guess_on
         from .pipeline import _labels_from_state
         x = x.contiguous()
         dev = x.device
@@ -479,7 +479,7 @@ def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=
         def run(spec):
             """One pass.  spec: the sync-free flavour (no host read-back between the stages: upper-bound / guessed sizes,
             fixed-stride exchange records, every kernel reports what did not fit); else sizes are read back where needed."""
-            report = torch.zeros(16, dtype=torch.int64, device=dev) if spec else None
+            report = torch.zeros(REPORT_WORDS, dtype=torch.int64, device=dev) if spec else None
             res = None
             if plan in ("tiles", "tiles+rows"):
                 res = knn_search_tiles(x, k1, group, report=report)
@@ -507,7 +507,8 @@ def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=
         if graph and speculative and not timers:
             # the whole pass, collectives included, replayed from one CUDA graph (pipeline.PassGraph)
             from .pipeline import PassGraph, _graph_key
-            g = PassGraph.get(_graph_key(x, k1, k2, float(eps), min_samples, knn, bool(centroids), plan, comm.world, N),
+            g = PassGraph.get(_graph_key(x, k1, k2, float(eps), min_samples, knn, bool(centroids), plan, comm.world, N,
+                                         partner_guess_on(N)),
                               lambda: run(True) + (None,))
             if getattr(g, "report", None) is None:
                 g.report = g.result[0].report

@@ -13,6 +13,7 @@ for name, gen, kw in (("c2", "synth", dict(N=32621, D=2048, n_ids=1041, noise=0.
     ref = None
     for guess in (False, True):
         fr.PARTNER_GUESS = guess
+        fr._guess_hint.clear()
         for _ in range(3):
             out = pipeline.pseudo_labels(x, 30, 6, 0.6, 4)
         torch.cuda.synchronize()
@@ -25,5 +26,5 @@ for name, gen, kw in (("c2", "synth", dict(N=32621, D=2048, n_ids=1041, noise=0.
         lab = out["labels"].cpu()
         if ref is None:
             ref = lab
-        print("%-7s guess=%-5s eps_graph %.3f ms  pass(sum of calls) %.3f ms  same_labels=%s" % (
-            name, guess, p["reid_jaccard_eps_graph"][1] / 5, sum(v[1] for v in p.values()) / 5, torch.equal(lab, ref)), flush=True)
+        print("%-7s guess=%-5s (adaptive hint: %s) eps_graph %.3f ms  pass(sum of calls) %.3f ms  same_labels=%s" % (
+            name, guess, fr._guess_hint.get(x.shape[0], True), p["reid_jaccard_eps_graph"][1] / 5, sum(v[1] for v in p.values()) / 5, torch.equal(lab, ref)), flush=True)
