@@ -286,6 +286,7 @@ __global__ void __launch_bounds__(kWarps * 32) jaccard_neighbors_kernel(
 // every j once, so no two threads meet), with the next column's loads in flight.  An update is one load-add-store,
 // nothing can overflow, and the ordered emit pass clears the row on the way.
 constexpr int kJDThreads = 128;
+constexpr int kJDPF = 4;                     // columns whose loads are in flight ahead of the accumulation
 
 __global__ void __launch_bounds__(kJDThreads) jaccard_direct_kernel(
     const int64_t* __restrict__ Q_ptr, const int32_t* __restrict__ Q_idx, const float* __restrict__ Q_val,
@@ -320,18 +321,32 @@ __global__ void __launch_bounds__(kJDThreads) jaccard_direct_kernel(
         s_v[t] = Q_val[pc + t];
       }
       __syncthreads();
-      int32_t j = -1;
-      float m = 0.f;
-      if (t < s_len[0]) {
-        j = C_idx[s_ca[0] + t];
-        m = fminf(s_v[0], C_val[s_ca[0] + t]);
+      // The first kJDThreads entries of the next kJDPF columns are requested ahead of time: a column step is then one
+      // shared-memory add and a barrier instead of a round trip to L2 (the kernel was bound by that latency).
+      int32_t jq[kJDPF];
+      float mq[kJDPF];
+#pragma unroll
+      for (int u = 0; u < kJDPF; ++u) {
+        jq[u] = -1;
+        mq[u] = 0.f;
+        if (u < ncol && t < s_len[u]) {
+          jq[u] = C_idx[s_ca[u] + t];
+          mq[u] = fminf(s_v[u], C_val[s_ca[u] + t]);
+        }
       }
       for (int k = 0; k < ncol; ++k) {
-        int32_t jn = -1;
-        float mn = 0.f;
-        if (k + 1 < ncol && t < s_len[k + 1]) {               // first entry of the next column, ahead of time
-          jn = C_idx[s_ca[k + 1] + t];
-          mn = fminf(s_v[k + 1], C_val[s_ca[k + 1] + t]);
+        const int32_t j = jq[0];
+        const float m = mq[0];
+#pragma unroll
+        for (int u = 0; u + 1 < kJDPF; ++u) {
+          jq[u] = jq[u + 1];
+          mq[u] = mq[u + 1];
+        }
+        jq[kJDPF - 1] = -1;
+        mq[kJDPF - 1] = 0.f;
+        if (k + kJDPF < ncol && t < s_len[k + kJDPF]) {
+          jq[kJDPF - 1] = C_idx[s_ca[k + kJDPF] + t];
+          mq[kJDPF - 1] = fminf(s_v[k + kJDPF], C_val[s_ca[k + kJDPF] + t]);
         }
         if (j >= 0 && (!owned_only || pair_owned((int32_t)row, j))) acc[j] = acc_add(acc[j], m, half);
         const int len = s_len[k];
@@ -340,47 +355,36 @@ __global__ void __launch_bounds__(kJDThreads) jaccard_direct_kernel(
           if (!owned_only || pair_owned((int32_t)row, j2)) acc[j2] = acc_add(acc[j2], fminf(s_v[k], C_val[s_ca[k] + e]), half);
         }
         __syncthreads();                                       // column k is in before column k + 1 starts
-        j = jn;
-        m = mn;
       }
     }
-    // ordered emit of { j : J <= eps }; the accumulator is cleared on the way
+    // emit { j : J <= eps }; the accumulator is cleared on the way.  The order of a row's list does not matter to any
+    // consumer (union-find, degree counts, min over adjacent labels; the tests sort), so every thread appends its own
+    // finds through a shared-memory counter: no ballots and no barriers inside the sweep over the N slots, which was
+    // more than half of this kernel's instructions when it compacted in order.
     const int64_t o = slot_ptr[lr];
     const int64_t o_end = min(slot_ptr[lr + 1], nbr_capacity);
+    const int64_t room = o_end > o ? o_end - o : 0;
     if (t == 0) s_base = 0;
     __syncthreads();
-    for (int64_t b0 = 0; b0 < n_pad; b0 += kJDThreads) {
-      const float tv = acc[b0 + t];
-      acc[b0 + t] = 0.f;
-      float jd = 2.f;
-      if (tv > 0.f) jd = jaccard_from_t(tv, half);
-      const bool keep = tv > 0.f && jd <= eps;
-      const unsigned b = __ballot_sync(kFull, keep);
-      if (__syncthreads_or(b != 0)) {                          // most 128-wide windows hold no neighbour at all
-        if (lane == 0) s_warp[w] = __popc(b);
-        __syncthreads();
-        int before = s_base;
-        for (int ww = 0; ww < w; ++ww) before += s_warp[ww];
-        if (keep) {
-          const int64_t dst = o + before + __popc(b & ((1u << lane) - 1u));
-          if (dst < o_end) {
-            nbr_idx[dst] = (int32_t)(b0 + t);
-            if (nbr_val) nbr_val[dst] = jd;
+    for (int64_t s0 = t; s0 < n_pad; s0 += kJDThreads) {
+      const float tv = acc[s0];
+      if (tv > 0.f) {
+        acc[s0] = 0.f;
+        const float jd = jaccard_from_t(tv, half);
+        if (jd <= eps) {
+          const int pos = atomicAdd(&s_base, 1);
+          if (pos < room) {
+            nbr_idx[o + pos] = (int32_t)s0;
+            if (nbr_val) nbr_val[o + pos] = jd;
           }
-        }
-        __syncthreads();
-        if (t == 0) {
-          int tot = 0;
-          for (int ww = 0; ww < kJDThreads / 32; ++ww) tot += s_warp[ww];
-          s_base += tot;
         }
       }
     }
     __syncthreads();
     if (t == 0) {
-      const int64_t room = o_end > o ? o_end - o : 0;
-      nbr_cnt[lr] = s_base <= room ? s_base : (int)room;
-      if (s_base > room && slot_overflow) atomicAdd(slot_overflow, 1ull);
+      const int found = s_base;
+      nbr_cnt[lr] = found <= room ? found : (int)room;
+      if (found > room && slot_overflow) atomicAdd(slot_overflow, 1ull);
     }
   }
 }
