@@ -381,7 +381,10 @@ int reid_centroids(const float* x, int64_t N, int64_t D, const int64_t* labels, 
  * `capacity` clusters (<= N: every cluster holds a core point), rows >= *num_clusters_dev of `out` are not written.
  * Lets the whole pseudo-label pass run without a host round trip (train_usl.py:163-191 back to back). */
 int reid_centroids_dev(const float* x, int64_t N, int64_t D, const int64_t* labels, const int64_t* num_clusters_dev,
-                       int64_t capacity, int normalize, float* out, void* stream);
+                       int64_t capacity, int normalize, float* out, void* workspace, void* stream);
+/* workspace (both entries; reid_centroids_workspace_bytes(N, C or capacity); NULL = none): with it the labels are binned
+ * ONCE into per-cluster member lists (count, scan, scatter; each CTA sorts its short list ascending and adds the rows
+ * four at a time) instead of every cluster's CTA streaming the whole label vector. */
 
 /* ---- multi-GPU exchange over NVLink peer memory (the reference has no multi-GPU hot path) --------
  * reid_peer_push_lists: the all-to-all of the tile-sharded search as plain peer stores.  part / part_cnt: this rank's

@@ -36,5 +36,6 @@ def generate_cluster_features(labels, features, normalize=False, num_clusters=No
             raise RuntimeError("generate_cluster_features: no clusters (all labels are -1); "
                                "the reference fails at torch.stack of an empty list here too")
         out = torch.empty((C, D), dtype=torch.float32, device=dev)
-        call("reid_centroids", ptr(x), N, D, ptr(lab), C, 1 if normalize else 0, ptr(out), None, stream_ptr())
+        ws = torch.empty(max(1, L.reid_centroids_workspace_bytes(N, C)), dtype=torch.uint8, device=dev)
+        call("reid_centroids", ptr(x), N, D, ptr(lab), C, 1 if normalize else 0, ptr(out), ptr(ws), stream_ptr())
         return out

@@ -98,7 +98,8 @@ def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=
                 # C is not known on the host yet (at most N: every cluster holds a core point): the kernel takes the
                 # capacity and the device-side count, rows beyond the count are never written (nor their memory touched)
                 cen = torch.empty((cap, x.shape[1]), dtype=torch.float32, device=x.device)
-                call("reid_centroids_dev", ptr(x), x.shape[0], x.shape[1], ptr(labels), ptr(ncl), cap, 1, ptr(cen), stream_ptr())
+                cws = torch.empty(max(1, _lib.lib().reid_centroids_workspace_bytes(x.shape[0], cap)), dtype=torch.uint8, device=x.device)
+                call("reid_centroids_dev", ptr(x), x.shape[0], x.shape[1], ptr(labels), ptr(ncl), cap, 1, ptr(cen), ptr(cws), stream_ptr())
             return st, labels, core, ncl, nbr_cnt, cen, st.report
 
         if graph and not timers:
@@ -116,7 +117,8 @@ def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=
             labels, core, ncl, nbr_cnt = _labels_from_state(st, eps, min_samples, timers)
             if centroids:
                 cen = torch.empty((cap, x.shape[1]), dtype=torch.float32, device=x.device)
-                call("reid_centroids_dev", ptr(x), x.shape[0], x.shape[1], ptr(labels), ptr(ncl), cap, 1, ptr(cen), stream_ptr())
+                cws = torch.empty(max(1, _lib.lib().reid_centroids_workspace_bytes(x.shape[0], cap)), dtype=torch.uint8, device=x.device)
+                call("reid_centroids_dev", ptr(x), x.shape[0], x.shape[1], ptr(labels), ptr(ncl), cap, 1, ptr(cen), ptr(cws), stream_ptr())
         out = dict(labels=labels, core=core, num_clusters=ncl, state=st, nbr_cnt=nbr_cnt)
         if centroids:
             out["centroids"] = cen[: int(ncl.item())]

@@ -501,7 +501,9 @@ def pseudo_labels(x, k1=30, k2=6, eps=0.6, min_samples=4, knn="auto", centroids=
             cen = None
             if centroids:
                 cen = torch.empty((max(N, 1), x.shape[1]), dtype=torch.float32, device=dev)
-                call("reid_centroids_dev", ptr(x), N, x.shape[1], ptr(labels), ptr(ncl), max(N, 1), 1, ptr(cen), stream_ptr())
+                from ._lib import lib as _L
+                cws = torch.empty(max(1, _L().reid_centroids_workspace_bytes(N, max(N, 1))), dtype=torch.uint8, device=dev)
+                call("reid_centroids_dev", ptr(x), N, x.shape[1], ptr(labels), ptr(ncl), max(N, 1), 1, ptr(cen), ptr(cws), stream_ptr())
             return st, labels, core, ncl, nbr_cnt, cen
 
         if graph and speculative and not timers:
