@@ -107,7 +107,9 @@ __device__ __forceinline__ void warp_bitonic_sort(int32_t* a, int n2) {
 
 // Per-warp shared memory, carved by the host for the call's (ncols, half_cols):
 //   pairs_cap = ncols * half_cols (rounded up to 32): every (candidate c in R(i), member g of R_half(c)) pair
-//   set_slots = power of two >= 2 * (ncols + pairs_cap): de-duplication table of E(i)
+//   set_slots = power of two >= ncols + pairs_cap: de-duplication table of E(i).  It can never fill up (|E| <= ncols +
+//               pairs), and real rows leave it mostly empty (|E| ~ 2 k1 of 512 slots for k1 = 30); the table used to be
+//               twice as big, which cost a quarter of the kernel's occupancy for rows that do not exist
 struct ExpandLayout {
   int pairs_cap, set_slots, bytes;
 };
@@ -115,7 +117,7 @@ __host__ __device__ inline ExpandLayout expand_layout(int ncols, int half_cols) 
   ExpandLayout l;
   l.pairs_cap = (ncols * half_cols + 31) / 32 * 32;
   int s = 64;
-  while (s < 2 * (ncols + l.pairs_cap)) s <<= 1;
+  while (s < ncols + l.pairs_cap) s <<= 1;
   l.set_slots = s;
   // rlist[64] hr[128] off[65 -> 68] m[64] cnt[64] pass[64] hm[64 x u64] | g[pairs_cap] (later: list) | ci[pairs_cap x u8] | set[]
   const int list_ints = l.pairs_cap + 64;                 // |E| <= ncols + pairs

@@ -518,3 +518,32 @@ def test_device_resident_feature_hand_off():
     b = rg.DBSCAN(eps=0.6, min_samples=4, metric="precomputed").fit_predict(
         rg.compute_jaccard_distance(x_ref, k1=20, k2=6, print_flag=False))
     assert np.array_equal(a, b) and a.max() > 10
+
+
+def test_scan_counts_is_64_bit_and_multi_tile():
+    """reid_scan_counts: decoupled look-back over many CTAs, sums in 64 bits -- counts that add up to more than 2^31 inside
+    one 2048-element tile (the slot bounds of reid_jaccard_bounds can) must not wrap; ragged sizes; repeated use of the
+    self-resetting state."""
+    from reid_gan_b200.faiss_rerank import _scan_async
+    g = torch.Generator().manual_seed(0)
+    for n, hi in ((1, 5), (2047, 100), (2048, 100), (2049, 100), (70001, 3_000_000), (300000, 40)):
+        cnt = torch.randint(0, hi, (n,), generator=g, dtype=torch.int32)
+        if n == 70001:
+            cnt[:2048] = 2_000_000                      # 4.1e9 inside the first tile alone
+        ptr, stats = _scan_async(cnt.cuda(), n, torch.device("cuda"))
+        ref = torch.zeros(n + 1, dtype=torch.int64)
+        ref[1:] = torch.cumsum(cnt.to(torch.int64), 0)
+        assert torch.equal(ptr.cpu(), ref)
+        assert stats.tolist() == [int(ref[-1]), int(cnt.max()), int((cnt.to(torch.int64) ** 2).sum())]
+
+
+def test_centroids_of_very_large_clusters():
+    """train_usl.py:169-191 with clusters far beyond the shared-memory member list (the kernel then streams the labels):
+    same means as the oracle, outliers (-1) skipped, empty label ids give zero rows."""
+    import reid_gan_b200 as rg
+    from oracle import cluster as ocl
+    g = torch.Generator().manual_seed(3)
+    x = torch.randn(15000, 192, generator=g)
+    labels = torch.randint(-1, 3, (15000,), generator=g).numpy()        # three clusters of ~3750 rows + outliers
+    cen = rg.generate_cluster_features(labels, x, normalize=True).cpu().numpy()
+    np.testing.assert_allclose(cen, ocl.cluster_centroids(x.numpy(), labels), rtol=1e-4, atol=1e-6)
