@@ -66,6 +66,16 @@ def sample_size(N, k=30):
 _tile_cache = {}
 
 
+def prepass_splits(n_rows, m, pair_slots=74):
+    """Column splits of the sampling prepass over `n_rows` rows: as many (<= 4, <= sample tiles) as keep the
+    (256-row unit x split) count within one wave of the CTA-pair slots."""
+    units = (n_rows + 255) // 256
+    s = 1
+    while s < 4 and units * s * 2 <= pair_slots and s * 2 <= m // 256:
+        s *= 2
+    return s
+
+
 def _tile_order(n_t, dev, sb=16):
     """Upper-triangle 256 x 256 tiles in super-blocks of sb x sb: the ~74 tiles in flight share a few dozen operand
     blocks, so they stream out of L2.  Cached per (n_t, device)."""

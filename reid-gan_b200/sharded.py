@@ -349,12 +349,16 @@ def knn_search_tiles(x, k, group=None, report=None):
     t_f = torch.empty(B, dtype=torch.float32, device=dev)
     t_o = torch.empty(B, dtype=torch.int32, device=dev)
     if nb:
-        pre = torch.empty(nb * 2 * kt.TC_CAP, dtype=torch.int64, device=dev)
-        pre_cnt = torch.zeros(nb * 2, dtype=torch.int32, device=dev)
+        # A rank's block is a few 256-row units (16 at W = 8) for 74 CTA-pair slots: the prepass then runs at the
+        # latency of ONE unit.  The sample columns of a unit are split over up to 4 CTA pairs (every (row, split,
+        # epilogue group) keeps its own list; the threshold is the r-th best over all of a row's lists).
+        splits = kt.prepass_splits(nb, m)
+        pre = torch.empty(nb * 2 * splits * kt.TC_CAP, dtype=torch.int64, device=dev)
+        pre_cnt = torch.zeros(nb * 2 * splits, dtype=torch.int32, device=dev)
         pre_tau = torch.empty(nb, dtype=torch.int32, device=dev)
-        call("reid_knn_candidates_tc_ab", ptr(xh), N, ptr(xs), m, D, kt.SCALE_LOG2, b0, b1, -kt.sym_rank(k), 1, 2, ptr(pre),
+        call("reid_knn_candidates_tc_ab", ptr(xh), N, ptr(xs), m, D, kt.SCALE_LOG2, b0, b1, -kt.sym_rank(k), splits, 2, ptr(pre),
              ptr(pre_cnt), ptr(pre_tau), sp)
-        call("reid_knn_sample_tau", ptr(pre), ptr(pre_cnt), ptr(pre_tau), 2, nb, kt.sym_rank(k), ptr(t_f), ptr(t_o), sp)
+        call("reid_knn_sample_tau", ptr(pre), ptr(pre_cnt), ptr(pre_tau), 2 * splits, nb, kt.sym_rank(k), ptr(t_f), ptr(t_o), sp)
     mark("prepass")
     if report is not None:
         tau = peer_all_gather("tau", t_f, group)                       # rows >= N are padding (never read)

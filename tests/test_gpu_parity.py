@@ -547,3 +547,43 @@ def test_centroids_of_very_large_clusters():
     labels = torch.randint(-1, 3, (15000,), generator=g).numpy()        # three clusters of ~3750 rows + outliers
     cen = rg.generate_cluster_features(labels, x, normalize=True).cpu().numpy()
     np.testing.assert_allclose(cen, ocl.cluster_centroids(x.numpy(), labels), rtol=1e-4, atol=1e-6)
+
+
+@pytest.mark.parametrize("splits", [2, 4])
+def test_prepass_thresholds_with_column_splits(splits):
+    """The sampling prepass of a row block whose 256-row units do not fill the CTA-pair slots is split over the sample
+    columns (sharded.knn_search_tiles at W >= 4).  tau_i = r-th best sample score over all of a row's lists: never above
+    the exact r-th best (a threshold can only err towards more candidates) and equal to it (to the 16 resolved bits) on
+    practically every row, for the unsplit and the split prepass alike."""
+    import ctypes
+    import reid_gan_b200 as rg
+    from reid_gan_b200 import knn_tc as kt
+    from reid_gan_b200._lib import call, ptr, stream_ptr
+    N, D, k = 8192, 512, 30
+    x = rg.synth(N, D, 300, 0.8, 1)[0].cuda()
+    dev, sp = x.device, stream_ptr()
+    xh = torch.empty((N, D), dtype=torch.float16, device=dev)
+    call("reid_features_to_half", ptr(x), N, D, kt.SCALE_LOG2, ptr(xh), None, sp)
+    m = kt.sample_size(N, k)
+    xs = torch.empty((m, D), dtype=torch.float16, device=dev)
+    call("reid_features_sample", ptr(xh), N, D, m, kt._sample_stride(N), ptr(xs), sp)
+    r = kt.sym_rank(k)
+    b0, b1 = 1024, 1024 + 2560 + 77                      # a ragged block in the middle
+    nb = b1 - b0
+    assert kt.prepass_splits(4096, 2048) == 4 and kt.prepass_splits(8192, 2048) == 2 and kt.prepass_splits(16384, 2048) == 1
+    # exact r-th best sample score of every row, from the same fp16 operands (fp32 accumulation like the tensor core)
+    s = (xh[b0:b1].float() @ xs.float().T) * 2.0 ** (-2 * kt.SCALE_LOG2)
+    exact = torch.sort(s, dim=1, descending=True).values[:, r - 1]
+    pre = torch.empty(nb * 2 * splits * kt.TC_CAP, dtype=torch.int64, device=dev)
+    pre_cnt = torch.zeros(nb * 2 * splits, dtype=torch.int32, device=dev)
+    pre_tau = torch.empty(nb, dtype=torch.int32, device=dev)
+    call("reid_knn_candidates_tc_ab", ptr(xh), N, ptr(xs), m, D, kt.SCALE_LOG2, b0, b1, -r, splits, 2, ptr(pre), ptr(pre_cnt),
+         ptr(pre_tau), sp)
+    tau = torch.empty(nb, dtype=torch.float32, device=dev)
+    tau_ord = torch.empty(nb, dtype=torch.int32, device=dev)
+    call("reid_knn_sample_tau", ptr(pre), ptr(pre_cnt), ptr(pre_tau), 2 * splits, nb, r, ptr(tau), ptr(tau_ord), sp)
+    torch.cuda.synchronize()
+    assert bool(torch.isfinite(tau).all())
+    assert bool((tau <= exact + 1e-6).all())
+    close = (exact - tau) <= 2.0 ** -7 * exact.abs().clamp_min(1e-3)      # 16 resolved bits of the fp32 image = 8 mantissa bits
+    assert float(close.float().mean()) > 0.99
