@@ -703,8 +703,8 @@ def main():
         roof = {"kernel": "simsym_kernel (reid_knn_candidates_sym)", "bound": "tensor", "achieved": ach,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full` capture of this
-                # workload on one GPU (profiles/r02_v2_summary.txt: 517 MB read + 66 MB written); the fp16 operand alone is 134 MB
-                "traffic": 583.0e6 if (world == 1 and W["N"] == WORKLOAD["N"]) else None,
+                # workload on one GPU (profiles/r02_v3_summary.txt: 523 MB read + 65 MB written); the fp16 operand alone is 134 MB
+                "traffic": 587.6e6 if (world == 1 and W["N"] == WORKLOAD["N"]) else None,
                 "ms_per_launch": k_ms, "flops_per_launch": exec_flops,
                 "algorithmic_flops": flops, "algorithmic_tflops": flops / ((k_ms + pre_ms) * 1e-3) / 1e12,
                 "prepass_ms": pre_ms,

@@ -15,8 +15,8 @@ from ._lib import call, check, ptr, stream_ptr
 TC_CAP = 512
 KEEP_MAX = 64
 SCALE_LOG2 = 4          # features are scaled by 2^4 before rounding to fp16 (keeps them out of the subnormals)
-CTA_GROUP = int(__import__("os").environ.get("REID_TC_CTA_GROUP", "2"))   # 2 = CTA pairs (tcgen05 cta_group::2)
-ORDER_ROWS = __import__("os").environ.get("REID_RESCORE_ORDER", "1") != "0"   # cluster-locality visiting order
+CTA_GROUP = 2                 # 2 = CTA pairs (tcgen05 cta_group::2); 1 = single CTAs (developer comparison: set the attribute)
+ORDER_ROWS = True             # cluster-locality visiting order of the re-score stage
 SLACK = 34              # K = k + SLACK candidates are kept per (row, column range)
 
 
@@ -45,7 +45,7 @@ def err_bound(max_sqnorm):
     return float(max_sqnorm) * (2.0 ** -10) * 1.02 + 2.0 ** -14
 
 
-SYM = __import__("os").environ.get("REID_TC_SYM", "1") != "0"     # symmetric search when the shard is the whole matrix
+SYM = True                    # symmetric search when the shard is the whole matrix
 SYM_MIN_N = 8192        # below this the sample cannot give a tight threshold; the one-sided kernel is used
 SYM_CAP = 1024          # list capacity per row in the symmetric search
 SYM_RANK = 16           # tau_i = SYM_RANK-th best sample score ...
@@ -125,7 +125,17 @@ def sym_eligible(N, D, k):
     return SYM and N >= SYM_MIN_N and k <= SYM_MAX_K and D % 64 == 0
 
 
-UPLOAD_CHUNKS = int(__import__("os").environ.get("REID_UPLOAD_CHUNKS", "12"))
+UPLOAD_CHUNKS = None          # None: about five 256-row blocks per chunk, 4..24 chunks (measured: scripts/dev_e2e_ab.py --
+                              # N = 32,621: 12 -> 7.51, 24 -> 7.45, 32 -> 7.64, 48 -> 8.6 ms; N = 12,936: 8-12 best)
+
+
+def upload_bounds(n_t, chunks):
+    """Block boundaries (in 256-row tile blocks, chunks + 1 of them) of the chunked upload: equal chunks.  Chunks that
+    shrink towards the end (so that less tensor work is left when the last byte lands) were measured and are slower
+    (7.80 vs 7.58 ms end to end, scripts/dev_e2e_ab.py): every chunk carries ~0.15 ms of fixed latency -- conversion,
+    a prepass that runs at the latency of one row unit, the thresholds, a partial wave of tiles -- and the small last
+    chunks put that, not their tiles, behind the copy."""
+    return [n_t * c // chunks for c in range(chunks)] + [n_t]
 
 
 def knn_search_upload(x_host, k, dev, idx=None, key=None, info=None, defer=False, chunks=None, uncert_count=None):
@@ -135,8 +145,9 @@ def knn_search_upload(x_host, k, dev, idx=None, key=None, info=None, defer=False
     lands only its own share of the tiles is left.  The threshold sample (rows at two interleaved regular strides,
     one cudaMemcpy2DAsync each) goes up first.  Returns (x_dev, idx, key, info); same results as knn_search."""
     L = _lib.lib()
-    chunks = UPLOAD_CHUNKS if chunks is None else chunks
     N, D = x_host.shape
+    if chunks is None:
+        chunks = UPLOAD_CHUNKS if UPLOAD_CHUNKS else max(4, min(24, ((N + 255) // 256) // 5))
     assert x_host.dtype == torch.float32 and x_host.is_contiguous() and not x_host.is_cuda
     info = {} if info is None else info
     main = torch.cuda.current_stream()
@@ -154,7 +165,7 @@ def knn_search_upload(x_host, k, dev, idx=None, key=None, info=None, defer=False
     xs32 = torch.empty((m, D), dtype=torch.float32, device=dev)
     xs = torch.empty((m, D), dtype=torch.float16, device=dev)
     n_t = (N + 255) // 256
-    bounds = [min(N, 256 * (n_t * c // chunks)) for c in range(chunks)] + [N]
+    bounds = [min(N, 256 * t) for t in upload_bounds(n_t, chunks)[:-1]] + [N]
     copy.wait_stream(main)                       # the destination buffers were just allocated on `main`
     events = []
     with torch.cuda.stream(copy):
@@ -180,9 +191,11 @@ def knn_search_upload(x_host, k, dev, idx=None, key=None, info=None, defer=False
     cnt = torch.zeros(N, dtype=torch.int32, device=dev)
     tau = torch.empty(N, dtype=torch.float32, device=dev)
     tau_ord = torch.empty(N, dtype=torch.int32, device=dev)
+    chunks = len(bounds) - 1
     max_rows = max(bounds[c + 1] - bounds[c] for c in range(chunks))
-    pre = torch.empty(max_rows * 2 * TC_CAP, dtype=torch.int64, device=dev)
-    pre_cnt = torch.empty(max_rows * 2, dtype=torch.int32, device=dev)
+    splits = prepass_splits(max_rows, m)         # a chunk is ~11 row units for 74 CTA-pair slots: split its sample columns
+    pre = torch.empty(max_rows * 2 * splits * TC_CAP, dtype=torch.int64, device=dev)
+    pre_cnt = torch.empty(max_rows * 2 * splits, dtype=torch.int32, device=dev)
     pre_tau = torch.empty(max_rows, dtype=torch.int32, device=dev)
     order = _tile_order(n_t, dev)
     n_tiles = 0
@@ -193,9 +206,9 @@ def knn_search_upload(x_host, k, dev, idx=None, key=None, info=None, defer=False
             continue
         call("reid_features_to_half_acc", ptr(x[a:]), b - a, D, SCALE_LOG2, ptr(xh[a:]), ptr(msq), sp)
         pre_cnt.zero_()
-        call("reid_knn_candidates_tc_ab", ptr(xh), N, ptr(xs), m, D, SCALE_LOG2, a, b, -sym_rank(k), 1, 2, ptr(pre), ptr(pre_cnt),
+        call("reid_knn_candidates_tc_ab", ptr(xh), N, ptr(xs), m, D, SCALE_LOG2, a, b, -sym_rank(k), splits, 2, ptr(pre), ptr(pre_cnt),
              ptr(pre_tau), sp)
-        call("reid_knn_sample_tau", ptr(pre), ptr(pre_cnt), ptr(pre_tau), 2, b - a, sym_rank(k), ptr(tau[a:]), ptr(tau_ord[a:]), sp)
+        call("reid_knn_sample_tau", ptr(pre), ptr(pre_cnt), ptr(pre_tau), 2 * splits, b - a, sym_rank(k), ptr(tau[a:]), ptr(tau_ord[a:]), sp)
         key_ = ("chunk", n_t, chunks, c, str(dev))
         if key_ not in _tile_cache:                            # tiles whose larger block index falls into this chunk
             t0, t1 = a // 256, (b + 255) // 256

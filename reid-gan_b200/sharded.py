@@ -21,8 +21,8 @@ import torch
 import torch.distributed as dist
 
 
-TRACE_STEPS = __import__("os").environ.get("REID_TRACE_STEPS", "0") != "0"
-RECORD_GATHER = __import__("os").environ.get("REID_RECORD_GATHER", "1") != "0"   # one-collective ragged gathers
+TRACE_STEPS = False           # developer switch (scripts set the attribute): per-step CUDA-event times in knn_info["steps_ms"]
+RECORD_GATHER = True          # one-collective ragged gathers
 ROWS_PLAN_MIN_N = 65536     # from this N on the sparse stages are row-sharded too (see pseudo_labels)
 
 

@@ -75,8 +75,10 @@ for (gen, kw, k1, k2, eps), plan in itertools.product(cfgs, ("rows", "tiles", "t
     ok &= good
     t_e = timed(lambda: sharded.pseudo_labels(xd, k1, k2, eps, 4, plan=plan))
     t_g = timed(lambda: sharded.pseudo_labels(xd, k1, k2, eps, 4, plan=plan, graph=True)) if plan != "rows" else float("nan")
-    if os.environ.get("REID_TRACE_STEPS", "0") != "0":
+    if os.environ.get("REID_TRACE_STEPS", "0") != "0":             # this script's own switch; the package reads no environment
+        sharded.TRACE_STEPS = True
         o = sharded.pseudo_labels(xd, k1, k2, eps, 4, plan=plan)
+        sharded.TRACE_STEPS = False
         print("   [rank %d] steps %s" % (rank, o["state"].knn_info.get("steps_ms")), flush=True)
     if rank == 0:
         print("%s N=%d world=%d plan=%-10s identical=%s %s labels=%s rank=%s clusters=%d noise=%d  eager %.2f ms  graph %.2f ms"
