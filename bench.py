@@ -689,18 +689,19 @@ def main():
     n_rows = W["N"] // world + (1 if W["N"] % world else 0)
     flops = 2.0 * n_rows * W["N"] * W["D"]               # algorithmic: 2*N^2*D, symmetry not credited
     roof = None
-    if "reid_knn_candidates_sym" in prof:
+    sym_key = next((k_ for k_ in ("reid_knn_candidates_sym_wide", "reid_knn_candidates_sym") if k_ in prof), None)
+    if sym_key:
         # symmetric search: the dominant kernel executes only the tiles (I <= J); `achieved` counts the flops it
         # really issues (tiles * 2*256*256*D, padding included), `algorithmic_tflops` credits the 2*N^2*D of SURVEY 8(d)
         # to the whole candidate stage (prepass + main pass).
-        calls, tot_ms = prof["reid_knn_candidates_sym"]
+        calls, tot_ms = prof[sym_key]
         k_ms = tot_ms / calls
         n_tiles = (info.get("sym") or {}).get("tiles", 0)
         exec_flops = 2.0 * 256 * 256 * W["D"] * n_tiles
         pre_ms = prof.get("reid_knn_candidates_tc_ab", (1, 0.0))
         pre_ms = pre_ms[1] / max(pre_ms[0], 1)
         ach = exec_flops / (k_ms * 1e-3) / 1e12
-        roof = {"kernel": "simsym_kernel (reid_knn_candidates_sym)", "bound": "tensor", "achieved": ach,
+        roof = {"kernel": "simsym_kernel<%d> (%s)" % (2 if sym_key.endswith("wide") else 1, sym_key), "bound": "tensor", "achieved": ach,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full` capture of this
                 # workload on one GPU (profiles/r02_v3_summary.txt: 523 MB read + 65 MB written); the fp16 operand alone is 134 MB

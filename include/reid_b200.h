@@ -114,6 +114,14 @@ int reid_knn_candidates_sym(const void* xh, int64_t N, int64_t D, int scale_log2
                             int reset_counts, void* stream);
 /* reset_counts = 0 keeps appending to the lists of earlier launches: the tiles may be issued in several launches
  * as the feature rows arrive from the host (tiles whose rows are all resident), see knn_tc.knn_search_upload. */
+/* The same search over 256 x 512 strips: units = n_units int32 triples (I, J0, J1), the tiles (I, J0) and (I, J1) of
+ * one row block (J1 = -1: a single tile), both accumulated from ONE A slice per K step -- 48 KB instead of 64 KB of
+ * operands per pair of tiles through the L2 -> shared-memory feed that bounds the kernel.  Same lists (as sets; the
+ * order inside a list is the order of the atomics in either flavour).  knn_tc.pair_units builds the triples from the
+ * tile order.  (replaces the same lines as reid_knn_candidates_sym: utils/faiss_rerank.py:39-62) */
+int reid_knn_candidates_sym_wide(const void* xh, int64_t N, int64_t D, int scale_log2, const float* tau,
+                                 const int32_t* units, int64_t n_units, int cap, uint64_t* cand, int32_t* cand_cnt,
+                                 int reset_counts, void* stream);
 /* n_rows rows of row_bytes each, src_pitch_bytes apart in (pinned) HOST memory -> packed on the device
  * (cudaMemcpy2DAsync): the regularly strided threshold sample goes up before the bulk of the features. */
 int reid_upload_rows_strided(void* dst, const void* src_host, size_t row_bytes, size_t src_pitch_bytes,

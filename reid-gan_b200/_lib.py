@@ -43,6 +43,7 @@ SIGNATURES = {
     "reid_knn_rescore": (_I, [_P, _L, _L, _L, _L, _P, _P, _P, _I, _I, _L, _I, _F, _P, _I, _P, _P, _P, _P, _P, _P, _P]),
     "reid_knn_candidates_tc_ab": (_I, [_P, _L, _P, _L, _L, _I, _L, _L, _I, _I, _I, _P, _P, _P, _P]),
     "reid_knn_candidates_sym": (_I, [_P, _L, _L, _I, _P, _P, _L, _I, _P, _P, _I, _P]),
+    "reid_knn_candidates_sym_wide": (_I, [_P, _L, _L, _I, _P, _P, _L, _I, _P, _P, _I, _P]),
     "reid_upload_rows_strided": (_I, [_P, _P, _Z, _Z, _L, _P]),
     "reid_features_to_half_acc": (_I, [_P, _L, _L, _I, _P, _P, _P]),
     "reid_features_sample": (_I, [_P, _L, _L, _L, _L, _P, _P]),

@@ -35,18 +35,29 @@ int make_tmap_rows128(CUtensorMap* tmap, const void* base, int64_t n_rows, int64
 // favours the highest warp id among the eligible ones, and the single-thread MMA / TMA roles are the ones that
 // must never wait for an issue slot behind an epilogue warp.
 constexpr int kTmaWarp = 8, kMmaWarp = 9;
-constexpr int kSymStages = 6;
-constexpr int kSymStage = kATileBytes + 128 * BK * 2;     // 16 KB of A + this CTA's half (128 rows) of B
+// NB = column blocks per work unit.  NB = 1: one 256 x 256 tile per unit, the two TMEM accumulators alternate between
+// units (drain of one under the MMAs of the next).  NB = 2 ("wide"): a unit is the 256 x 512 strip (I, J0), (I, J1): both
+// accumulators are filled from ONE A slice per K step, i.e. 48 KB instead of 64 KB of operands per 2 x 256 x 256 x 64
+// MACs.  The main loop runs against the L2 -> shared-memory throughput of the chip (2 MB per tile x 8,256 tiles in
+// 1.5 ms = 11.5 TB/s), so the wide strip buys 25 % of it; the price is that the drain is no longer under the MMAs of
+// the next unit -- the TMA producer keeps refilling the ring meanwhile, so the operand feed never pauses.
+template <int NB>
+struct SymCfg {
+  static constexpr int kStages = NB == 2 ? 4 : 6;
+  static constexpr int kBHalf = 128 * BK * 2;                         // this CTA's half (128 rows) of one B block
+  static constexpr int kStage = kATileBytes + NB * kBHalf;            // 32 KB / 48 KB
+  static constexpr int kSmem = kStages * kStage + 1024 /*align*/ + 256 /*barriers*/ + 2 * BN * 4 + 8 * 8 * 32 * 8;
+};
 constexpr int kSymTauBytes = 2 * BN * 4;                  // column thresholds, one buffer per epilogue group
 constexpr int kSymHitSlots = 8;                           // staged survivors per lane and tile
 constexpr int kSymHitBytes = 8 * kSymHitSlots * 32 * 8;   // 8 epilogue warps x slots x lanes x 8 B = 16 KB
-constexpr int kSymSmem = kSymStages * kSymStage + 1024 /*align*/ + 256 /*barriers*/ + kSymTauBytes + kSymHitBytes;
 
 struct SymParams {
   int64_t N;
   int num_k_blocks;                // D / 64
-  int n_units;                     // tiles in the list
-  const int32_t* tiles;            // (I, J) pairs, I <= J, in processing order
+  int n_units;                     // units in the list
+  const int32_t* tiles;            // NB = 1: (I, J) pairs, I <= J, in processing order; NB = 2: (I, J0, J1) triples, J1 = -1:
+                                   // a single tile
   const float* tau;                // [N] rejection threshold per row (descaled score units)
   float scale2;                    // 2^(2 s): raw accumulator = score * scale2
   float descale;                   // 2^(-2 s)
@@ -62,7 +73,10 @@ __device__ __forceinline__ void sym_append(const SymParams& p, int64_t row, int 
   if (pos < p.cap) p.cand[row * p.cap + pos] = ((unsigned long long)__float_as_uint(s) << 32) | (uint32_t)col;
 }
 
+template <int NB>
 __global__ void __launch_bounds__(kThreads, 1) simsym_kernel(const __grid_constant__ CUtensorMap tmap, const SymParams p) {
+  constexpr int kSymStages = SymCfg<NB>::kStages, kSymStage = SymCfg<NB>::kStage, US = NB + 1;
+  static_assert(SymCfg<NB>::kSmem <= 227 * 1024, "shared memory");
   extern __shared__ __align__(1024) uint8_t smem_raw[];
   uint8_t* smem = (uint8_t*)(((uintptr_t)smem_raw + 1023) & ~(uintptr_t)1023);
   uint64_t* full_bar = (uint64_t*)(smem + kSymStages * kSymStage);
@@ -106,9 +120,12 @@ __global__ void __launch_bounds__(kThreads, 1) simsym_kernel(const __grid_consta
       int stage = 0;
       uint32_t phase = 0;
       for (int u = unit0; u < p.n_units; u += unit_step) {
-        const int ti = p.tiles[2 * u], tj = p.tiles[2 * u + 1];
+        const int ti = p.tiles[US * u], tj = p.tiles[US * u + 1];
+        const int tj1 = NB == 2 ? p.tiles[US * u + 2] : -1;
         const int a_row = ti * BN + (int)cta_rank * BM;
         const int b_row = tj * BN + (int)cta_rank * 128;
+        const int b1_row = tj1 * BN + (int)cta_rank * 128;
+        const uint32_t tx = 2 * (kATileBytes + (tj1 >= 0 ? 2 : 1) * SymCfg<NB>::kBHalf);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
           mbar_wait(&empty_bar[stage], phase ^ 1);
           uint8_t* a_dst = smem + stage * kSymStage;
@@ -116,10 +133,11 @@ __global__ void __launch_bounds__(kThreads, 1) simsym_kernel(const __grid_consta
           if (REID_DBG(p) & 4) {
             if (leader) mbar_arrive(&full_bar[stage]);
           } else {
-            if (leader) mbar_expect_tx(&full_bar[stage], 2 * kSymStage);   // the pair's bytes land on the leader's barrier
+            if (leader) mbar_expect_tx(&full_bar[stage], tx);   // the pair's bytes land on the leader's barrier
             const uint32_t lbar = mapa_u32(smem_u32(&full_bar[stage]), 0);
             tma_load_2d_pair(a_dst, &tmap, lbar, kb * BK, a_row);
             tma_load_2d_pair(b_dst, &tmap, lbar, kb * BK, b_row);
+            if (NB == 2 && tj1 >= 0) tma_load_2d_pair(b_dst + SymCfg<NB>::kBHalf, &tmap, lbar, kb * BK, b1_row);
           }
           if (++stage == kSymStages) {
             stage = 0;
@@ -137,7 +155,14 @@ __global__ void __launch_bounds__(kThreads, 1) simsym_kernel(const __grid_consta
       int acc = 0;
       uint32_t acc_phase = 0;
       for (int u = unit0; u < p.n_units; u += unit_step) {
-        mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // every epilogue warp of the pair has drained this accumulator
+        bool two = false;
+        if (NB == 2) {                                // the strip takes both accumulators
+          two = p.tiles[US * u + 2] >= 0;
+          mbar_wait(&tempty_bar[0], acc_phase ^ 1);
+          mbar_wait(&tempty_bar[1], acc_phase ^ 1);
+        } else {
+          mbar_wait(&tempty_bar[acc], acc_phase ^ 1);   // every epilogue warp of the pair has drained this accumulator
+        }
         tcgen05_fence_after();
         const uint32_t tmem_c = tmem_base + (uint32_t)(acc * BN);
         for (int kb = 0; kb < p.num_k_blocks; ++kb) {
@@ -151,22 +176,36 @@ __global__ void __launch_bounds__(kThreads, 1) simsym_kernel(const __grid_consta
             const uint64_t db = make_smem_desc(b_addr + k * UMMA_K * 2);
             umma_f16_pair(tmem_c, da, db, idesc, (kb | k) != 0);
           }
+          if (NB == 2 && two) {
+#pragma unroll
+            for (int k = 0; k < BK / UMMA_K; ++k) {
+              const uint64_t da = make_smem_desc(a_addr + k * UMMA_K * 2);
+              const uint64_t db = make_smem_desc(b_addr + SymCfg<NB>::kBHalf + k * UMMA_K * 2);
+              umma_f16_pair(tmem_c + BN, da, db, idesc, (kb | k) != 0);
+            }
+          }
           umma_commit_pair(&empty_bar[stage]);
           if (++stage == kSymStages) {
             stage = 0;
             phase ^= 1;
           }
         }
-        umma_commit_pair(&tfull_bar[acc]);
-        if (++acc == 2) {
-          acc = 0;
+        if (NB == 2) {
+          umma_commit_pair(&tfull_bar[0]);
+          umma_commit_pair(&tfull_bar[1]);
           acc_phase ^= 1;
+        } else {
+          umma_commit_pair(&tfull_bar[acc]);
+          if (++acc == 2) {
+            acc = 0;
+            acc_phase ^= 1;
+          }
         }
       }
     }
   } else {
     // ------------------------------ epilogue: fixed-threshold selection, both directions -------------
-    const int wg = warp >> 2;                           // group g drains accumulator g = every other tile of the CTA
+    const int wg = warp >> 2;                           // group g drains accumulator g: every other tile (NB = 1) / block J_g
     const int quarter = warp & 3;                       // TMEM lanes this warp may read
     const int r_in_tile = (int)cta_rank * BM + quarter * 32 + lane;
     const int gt = (warp - wg * 4) * 32 + lane;         // 0..127 inside the group
@@ -176,8 +215,18 @@ __global__ void __launch_bounds__(kThreads, 1) simsym_kernel(const __grid_consta
     uint32_t acc_phase = 0;
     int tile_ctr = 0;
     for (int u = unit0; u < p.n_units; u += unit_step, ++tile_ctr) {
-      if ((tile_ctr & 1) != wg) continue;
-      const int ti = p.tiles[2 * u], tj = p.tiles[2 * u + 1];
+      if (NB == 1 && (tile_ctr & 1) != wg) continue;
+      const int ti = p.tiles[US * u], tj = p.tiles[US * u + 1 + (NB == 2 ? wg : 0)];
+      if (NB == 2 && tj < 0) {                            // single tile: nothing in this group's accumulator
+        mbar_wait(&tfull_bar[wg], acc_phase);
+        acc_phase ^= 1;
+        __syncwarp();
+        if (lane == 0) {
+          if (leader) mbar_arrive(&tempty_bar[wg]);
+          else mbar_arrive_cluster(tempty_remote);
+        }
+        continue;
+      }
       const int64_t row = (int64_t)ti * BN + r_in_tile;
       const bool row_ok = row < p.N;
       const float tr = row_ok ? p.tau[row] * p.scale2 : INFINITY;          // compare raw accumulators
@@ -379,14 +428,14 @@ int reid_upload_rows_strided(void* dst, const void* src_host, size_t row_bytes, 
   return REID_OK;
 }
 
-int reid_knn_candidates_sym(const void* xh, int64_t N, int64_t D, int scale_log2, const float* tau, const int32_t* tiles,
-                            int64_t n_tiles, int cap, uint64_t* cand, int32_t* cand_cnt, int reset_counts, void* stream) {
+static int launch_sym(int nb, const void* xh, int64_t N, int64_t D, int scale_log2, const float* tau, const int32_t* units,
+                      int64_t n_units, int cap, uint64_t* cand, int32_t* cand_cnt, int reset_counts, void* stream) {
   using namespace reid;
-  REID_CHECK_ARG(xh && tau && tiles && cand && cand_cnt, "reid_knn_candidates_sym: NULL pointer");
+  REID_CHECK_ARG(xh && tau && units && cand && cand_cnt, "reid_knn_candidates_sym: NULL pointer");
   REID_CHECK_ARG(N > 0 && N < (1ll << 31) && D > 0 && D % tc::BK == 0, "reid_knn_candidates_sym: need D %% 64 == 0 (D=%lld)",
                  (long long)D);
   REID_CHECK_ARG(((uintptr_t)xh & 15) == 0, "reid_knn_candidates_sym: xh must be 16-byte aligned");
-  REID_CHECK_ARG(n_tiles > 0 && n_tiles < (1ll << 30) && cap >= 1, "reid_knn_candidates_sym: bad tile list / capacity");
+  REID_CHECK_ARG(n_units > 0 && n_units < (1ll << 30) && cap >= 1, "reid_knn_candidates_sym: bad tile list / capacity");
   REID_CHECK_ARG(num_sms() >= 2, "reid_knn_candidates_sym: needs CTA pairs");
   cudaStream_t st = (cudaStream_t)stream;
   CUtensorMap tmap;
@@ -395,8 +444,8 @@ int reid_knn_candidates_sym(const void* xh, int64_t N, int64_t D, int scale_log2
   tc::SymParams p;
   p.N = N;
   p.num_k_blocks = (int)(D / tc::BK);
-  p.n_units = (int)n_tiles;
-  p.tiles = tiles;
+  p.n_units = (int)n_units;
+  p.tiles = units;
   p.tau = tau;
   p.scale2 = ldexpf(1.0f, 2 * scale_log2);
   p.descale = ldexpf(1.0f, -2 * scale_log2);
@@ -406,12 +455,12 @@ int reid_knn_candidates_sym(const void* xh, int64_t N, int64_t D, int scale_log2
   p.dbg = dev_env("REID_TC_DEBUG", 0);
   if (reset_counts) REID_CUDA(cudaMemsetAsync(cand_cnt, 0, sizeof(int32_t) * (size_t)N, st));
   const int slots = num_sms() / 2;
-  const int grid = (int)(n_tiles < slots ? n_tiles : slots) * 2;
+  const int grid = (int)(n_units < slots ? n_units : slots) * 2;
   cudaLaunchConfig_t cfg = {};
   cfg.gridDim = dim3((unsigned)grid);
   cfg.blockDim = dim3(tc::kThreads);
   cfg.stream = st;
-  cfg.dynamicSmemBytes = tc::kSymSmem;
+  cfg.dynamicSmemBytes = nb == 2 ? tc::SymCfg<2>::kSmem : tc::SymCfg<1>::kSmem;
   cudaLaunchAttribute attr[1];
   attr[0].id = cudaLaunchAttributeClusterDimension;
   attr[0].val.clusterDim.x = 2;
@@ -419,9 +468,24 @@ int reid_knn_candidates_sym(const void* xh, int64_t N, int64_t D, int scale_log2
   attr[0].val.clusterDim.z = 1;
   cfg.attrs = attr;
   cfg.numAttrs = 1;
-  REID_CUDA(cudaFuncSetAttribute(tc::simsym_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::kSymSmem));
-  REID_CUDA(cudaLaunchKernelEx(&cfg, tc::simsym_kernel, tmap, p));
+  if (nb == 2) {
+    REID_CUDA(cudaFuncSetAttribute(tc::simsym_kernel<2>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SymCfg<2>::kSmem));
+    REID_CUDA(cudaLaunchKernelEx(&cfg, tc::simsym_kernel<2>, tmap, p));
+  } else {
+    REID_CUDA(cudaFuncSetAttribute(tc::simsym_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, tc::SymCfg<1>::kSmem));
+    REID_CUDA(cudaLaunchKernelEx(&cfg, tc::simsym_kernel<1>, tmap, p));
+  }
   REID_LAUNCH_CHECK();
   return REID_OK;
+}
+
+int reid_knn_candidates_sym(const void* xh, int64_t N, int64_t D, int scale_log2, const float* tau, const int32_t* tiles,
+                            int64_t n_tiles, int cap, uint64_t* cand, int32_t* cand_cnt, int reset_counts, void* stream) {
+  return launch_sym(1, xh, N, D, scale_log2, tau, tiles, n_tiles, cap, cand, cand_cnt, reset_counts, stream);
+}
+
+int reid_knn_candidates_sym_wide(const void* xh, int64_t N, int64_t D, int scale_log2, const float* tau, const int32_t* units,
+                                 int64_t n_units, int cap, uint64_t* cand, int32_t* cand_cnt, int reset_counts, void* stream) {
+  return launch_sym(2, xh, N, D, scale_log2, tau, units, n_units, cap, cand, cand_cnt, reset_counts, stream);
 }
 }

@@ -372,8 +372,7 @@ def knn_search_tiles(x, k, group=None, report=None):
     part = torch.empty((W * B, cap), dtype=torch.int64, device=dev)
     part_cnt = torch.empty(W * B, dtype=torch.int32, device=dev)
     if tiles.shape[0]:
-        call("reid_knn_candidates_sym", ptr(xh), N, D, kt.SCALE_LOG2, ptr(tau), ptr(tiles), tiles.shape[0], cap, ptr(part),
-             ptr(part_cnt), 1, sp)
+        kt.candidates_sym_launch(xh, N, D, tau, tiles, cap, part, part_cnt, 1, sp)
     else:
         part_cnt.zero_()
     mark("tiles")

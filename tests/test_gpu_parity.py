@@ -214,6 +214,31 @@ def test_symmetric_search_is_exact(N, D, n_ids, noise, seed, order, dup, k):
     assert int(cnt.min()) >= k, "every row must have kept at least k candidates"
 
 
+@pytest.mark.parametrize("N,D,n_ids,k", [(8192 + 77, 128, 300, 30), (9000, 256, 100, 48)])
+def test_symmetric_search_strip_flavour(monkeypatch, N, D, n_ids, k):
+    """reid_knn_candidates_sym_wide (256 x 512 strips, both TMEM accumulators per unit; off by default -- measured
+    slower): same neighbour lists as the exact search, and the pairing keeps every tile exactly once."""
+    from reid_gan_b200 import faiss_rerank as fr, knn_tc
+    t = knn_tc._tile_order(37, "cpu")
+    u = knn_tc.pair_units(t)
+    flat = [(int(a), int(b)) for a, b, c in u.tolist()] + [(int(a), int(c)) for a, b, c in u.tolist() if c >= 0]
+    assert sorted(flat) == sorted(map(tuple, t.tolist()))
+    x = _sym_case(N, D, n_ids, 0.8, 21).cuda()
+    ie, ke, _ = fr.knn_search(x, k, "exact")
+    from reid_gan_b200 import _lib
+    monkeypatch.setattr(knn_tc, "SYM_WIDE", True)
+    _lib.profiler.start()
+    try:
+        it, kt, info = fr.knn_search(x, k, "tc")
+        torch.cuda.synchronize()
+    finally:
+        _lib.profiler.stop()
+    assert info["mode"] == "tc-sym" and info["uncertified_rows"] == 0
+    ran = _lib.profiler.summary()
+    assert "reid_knn_candidates_sym_wide" in ran and "reid_knn_candidates_sym" not in ran, "the strip kernel must be the one that ran"
+    assert torch.equal(ie, it) and torch.equal(ke, kt)
+
+
 def test_symmetric_search_survives_bad_thresholds(monkeypatch):
     """A threshold sample that is far too optimistic (almost no column passes) must only cost time: the rows fail
     their certificate and are redone by the exact search."""
