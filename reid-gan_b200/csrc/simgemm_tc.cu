@@ -364,18 +364,33 @@ __global__ void __launch_bounds__(256) to_half_kernel(const float* __restrict__ 
     // 16-byte loads, 8-byte stores: the stage is a pure stream (4ND bytes in, 2ND out)
     const float4* src = reinterpret_cast<const float4*>(x + row * D);
     uint2* dst = reinterpret_cast<uint2*>(xh + row * D);
-    for (int64_t d4 = lane_id(); d4 < (D >> 2); d4 += 32) {
-      const float4 v = __ldcs(src + d4);                    // streamed once: do not keep it in L2 ahead of the fp16 copy
-      ss = fmaf(v.x, v.x, ss);
-      ss = fmaf(v.y, v.y, ss);
-      ss = fmaf(v.z, v.z, ss);
-      ss = fmaf(v.w, v.w, ss);
-      const __half2 lo = __floats2half2_rn(v.x * scale, v.y * scale);
-      const __half2 hi = __floats2half2_rn(v.z * scale, v.w * scale);
-      uint2 o;
-      o.x = *reinterpret_cast<const uint32_t*>(&lo);
-      o.y = *reinterpret_cast<const uint32_t*>(&hi);
-      dst[d4] = o;
+    // eight independent 16-byte loads per lane in flight (4 KB per warp) before the first use: the stream is bound by
+    // bytes in flight, not by the conversions.  ss is accumulated in ascending element order, batch or not.
+    const int64_t n4 = D >> 2;
+    constexpr int kBatch = 8;
+    for (int64_t base = 0; base < n4; base += 32 * kBatch) {
+      float4 v[kBatch];
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int64_t d4 = base + u * 32 + lane_id();
+        v[u] = d4 < n4 ? __ldcs(src + d4) : make_float4(0.f, 0.f, 0.f, 0.f);   // streamed once: keep it out of L2's way
+      }
+#pragma unroll
+      for (int u = 0; u < kBatch; ++u) {
+        const int64_t d4 = base + u * 32 + lane_id();
+        if (d4 < n4) {
+          ss = fmaf(v[u].x, v[u].x, ss);
+          ss = fmaf(v[u].y, v[u].y, ss);
+          ss = fmaf(v[u].z, v[u].z, ss);
+          ss = fmaf(v[u].w, v[u].w, ss);
+          const __half2 lo = __floats2half2_rn(v[u].x * scale, v[u].y * scale);
+          const __half2 hi = __floats2half2_rn(v[u].z * scale, v[u].w * scale);
+          uint2 o;
+          o.x = *reinterpret_cast<const uint32_t*>(&lo);
+          o.y = *reinterpret_cast<const uint32_t*>(&hi);
+          dst[d4] = o;
+        }
+      }
     }
   } else {
     for (int64_t d = lane_id(); d < D; d += 32) {
