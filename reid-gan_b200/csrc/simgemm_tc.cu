@@ -357,8 +357,9 @@ __global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_const
 
 __global__ void __launch_bounds__(256) to_half_kernel(const float* __restrict__ x, int64_t n_rows, int64_t D, float scale,
                                                       __half* __restrict__ xh, float* __restrict__ max_sqnorm) {
-  const int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5);
-  if (row >= n_rows) return;
+  // warp per row, grid-stride: the launch is sized to the machine (no partial last wave of 8-row CTAs)
+  for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows;
+       row += (int64_t)gridDim.x * (blockDim.x >> 5)) {
   float ss = 0.f;
   if ((D & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)xh)) & 15) == 0) {
     // 16-byte loads, 8-byte stores: the stage is a pure stream (4ND bytes in, 2ND out)
@@ -404,6 +405,18 @@ __global__ void __launch_bounds__(256) to_half_kernel(const float* __restrict__ 
     atomicMax((unsigned*)max_sqnorm, __float_as_uint(ss));        // their bit patterns)
     atomicMin((unsigned*)max_sqnorm + 1, __float_as_uint(ss));
   }
+  }
+}
+
+static unsigned to_half_grid(int64_t n_rows) {
+  static int per_sm = 0;                                    // resident CTAs per SM (registers decide), asked once
+  if (per_sm == 0) {
+    int b = 0;
+    if (cudaOccupancyMaxActiveBlocksPerMultiprocessor(&b, to_half_kernel, 256, 0) != cudaSuccess || b < 1) b = 4;
+    per_sm = b;
+  }
+  const int64_t want = (n_rows + 7) / 8, cap = (int64_t)reid::num_sms() * per_sm;
+  return (unsigned)(want < cap ? want : cap);
 }
 
 typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*,
@@ -477,7 +490,7 @@ int reid_features_to_half_acc(const float* x, int64_t n_rows, int64_t D, int sca
   REID_CHECK_ARG(x && xh && n_rows >= 0 && D > 0, "reid_features_to_half_acc: bad arguments");
   REID_CHECK_ARG(scale_log2 >= -8 && scale_log2 <= 12, "reid_features_to_half_acc: scale_log2=%d out of range", scale_log2);
   if (n_rows == 0) return REID_OK;
-  tc::to_half_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, (cudaStream_t)stream>>>(x, n_rows, D, ldexpf(1.0f, scale_log2),
+  tc::to_half_kernel<<<tc::to_half_grid(n_rows), 256, 0, (cudaStream_t)stream>>>(x, n_rows, D, ldexpf(1.0f, scale_log2),
                                                                                      (__half*)xh, max_sqnorm_inout);
   REID_LAUNCH_CHECK();
   return REID_OK;
@@ -502,7 +515,7 @@ int reid_features_to_half(const float* x, int64_t n_rows, int64_t D, int scale_l
     REID_CUDA(cudaMemsetAsync(max_sqnorm_out + 1, 0x7f, sizeof(float), st));
   }
   if (n_rows == 0) return REID_OK;
-  tc::to_half_kernel<<<(unsigned)((n_rows + 7) / 8), 256, 0, st>>>(x, n_rows, D, ldexpf(1.0f, scale_log2), (__half*)xh,
+  tc::to_half_kernel<<<tc::to_half_grid(n_rows), 256, 0, st>>>(x, n_rows, D, ldexpf(1.0f, scale_log2), (__half*)xh,
                                                                   max_sqnorm_out);
   REID_LAUNCH_CHECK();
   return REID_OK;
