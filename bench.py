@@ -94,7 +94,7 @@ class ClockSampler:
         if self.proc is not None:
             time.sleep(0.15)
             self.proc.terminate()
-        sm, mx, reasons = [], [], set()
+        sm, mx, pw, reasons = [], [], [], set()
         names = ("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap")
         for r in self.rows:
             f = [c.strip() for c in r.split(",")]
@@ -105,13 +105,21 @@ class ClockSampler:
                 mx.append(float(f[2]))
             except ValueError:
                 continue
+            try:
+                pw.append(float(f[3]))
+            except ValueError:
+                pass
             for name, v in zip(names, f[5:9]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
         if not sm:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": [], "samples": 0}
         sm.sort()
-        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm)}
+        pw.sort()
+        # power_w: board power during the timed region -- the symmetric candidate kernel runs into the board's power limit
+        # (sw_power_cap; DESIGN.md 4, profiles/r02_k1_power.txt), which is what `reasons` then reports
+        return {"sm_mhz": sm[len(sm) // 2], "sm_max_mhz": max(mx), "reasons": sorted(reasons), "samples": len(sm),
+                "power_w_median": pw[len(pw) // 2] if pw else None, "power_w_max": pw[-1] if pw else None}
 
 
 def measured_peaks():

@@ -134,6 +134,41 @@ int reid_features_sample(const void* xh, int64_t N, int64_t D, int64_t n_sample,
 int reid_knn_sample_tau(const uint64_t* cand, const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists,
                         int64_t n_rows, int r, float* tau, uint32_t* tau_ord, void* stream);
 
+/* ---- sample-first layout of the symmetric search (knn_tc._candidates_sym_sf; replaces the same lines,
+ * utils/faiss_rerank.py:39-62).  The fp16 operand is written with the threshold sample in its first m rows
+ * (reid_features_to_half_gather), so the prepass -- all rows against rows [0, m) -- computes scores the symmetric
+ * pass needs anyway: the prepass hands them to the main lists in both directions and the symmetric pass runs
+ * only the tiles (I, J) with m / 256 <= I <= J (12 % fewer tcgen05 tiles at N = 32,621, m = 2,048).
+ *   reid_knn_candidates_tc_abt : reid_knn_candidates_tc_ab + the transposed direction -- tau_col[j] is the (already
+ *       known) threshold of column row j; every score above it is appended to cand_col[j * cap_col + ..] with the
+ *       query row as its column (tau_col = NULL: off); publish_final: row_tau additionally receives every list's final
+ *       rejection threshold (the seeds of the prepass mode included), so that it bounds everything any list of the
+ *       row ever rejected;
+ *   reid_knn_sample_tau_emit   : reid_knn_sample_tau + the direct direction -- the listed scores above tau[row] go to
+ *       the main list of row row0 + row (cand_main = NULL: plain reid_knn_sample_tau).  Here tau is raised to the
+ *       published floor of the prepass lists (they are complete only above it; needs publish_final), which is also the
+ *       threshold when fewer than r scores are listed above the floor;
+ *   reid_knn_rescore_mapped    : reid_knn_rescore on lists that live in the permuted row space -- row r's lists and
+ *       threshold are those of position row_pos[r], a listed column p is the original row col_orig[p] (both NULL:
+ *       plain reid_knn_rescore). */
+/* xh[i] = fp16(2^s x[src_row[i]]), i < n_rows; max_sqnorm_inout accumulates like reid_features_to_half_acc */
+int reid_features_to_half_gather(const float* x, const int32_t* src_row, int64_t n_rows, int64_t D, int scale_log2,
+                                 void* xh, float* max_sqnorm_inout, void* stream);
+int reid_knn_candidates_tc_abt(const void* xa, int64_t Na, const void* xb, int64_t N, int64_t D, int scale_log2,
+                               int64_t row_begin, int64_t row_end, int keep, int n_splits, int cta_group,
+                               uint64_t* cand, int32_t* cand_cnt, uint32_t* row_tau, int publish_final,
+                               const float* tau_col, uint64_t* cand_col, int32_t* cand_col_cnt, int cap_col,
+                               void* stream);
+int reid_knn_sample_tau_emit(const uint64_t* cand, const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists,
+                             int64_t n_rows, int r, float* tau, uint32_t* tau_ord, uint64_t* cand_main,
+                             int32_t* cand_main_cnt, int cap_main, int64_t row0, void* stream);
+int reid_knn_rescore_mapped(const float* x, int64_t N, int64_t D, int64_t row_begin, int64_t row_end,
+                            const uint64_t* cand, const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists,
+                            int list_cap, int64_t list_pitch_rows, int k, float err_bound, const float* max_sqnorm,
+                            int locality_order, const int32_t* row_pos, const int32_t* col_orig, int32_t* out_idx,
+                            float* out_key, int32_t* uncertified_flag, float* max_err_out, void* workspace,
+                            uint64_t* uncertified_count, void* stream);
+
 /* fp32 features -> scaled fp16 operand; max_sqnorm_out (optional, TWO floats) = { max_i ||x_i||^2, min_i ||x_i||^2 }:
  * the maximum scales the fp16 rounding bound  |approx - exact| <= 2^-10 ||x_i|| ||x_j||, the pair tells the caller
  * whether all rows have one norm (inner-product order == the reference's L2 order) or reid_knn_exact_l2 is needed. */

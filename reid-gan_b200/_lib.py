@@ -48,6 +48,10 @@ SIGNATURES = {
     "reid_features_to_half_acc": (_I, [_P, _L, _L, _I, _P, _P, _P]),
     "reid_features_sample": (_I, [_P, _L, _L, _L, _L, _P, _P]),
     "reid_knn_sample_tau": (_I, [_P, _P, _P, _I, _L, _I, _P, _P, _P]),
+    "reid_knn_sample_tau_emit": (_I, [_P, _P, _P, _I, _L, _I, _P, _P, _P, _P, _I, _L, _P]),
+    "reid_features_to_half_gather": (_I, [_P, _P, _L, _L, _I, _P, _P, _P]),
+    "reid_knn_candidates_tc_abt": (_I, [_P, _L, _P, _L, _L, _I, _L, _L, _I, _I, _I, _P, _P, _P, _I, _P, _P, _P, _I, _P]),
+    "reid_knn_rescore_mapped": (_I, [_P, _L, _L, _L, _L, _P, _P, _P, _I, _I, _L, _I, _F, _P, _I, _P, _P, _P, _P, _P, _P, _P, _P, _P]),
     "reid_reciprocal_masks": (_I, [_P, _L, _I, _I, _L, _L, _P, _P]),
     "reid_reciprocal_masks2": (_I, [_P, _L, _I, _I, _I, _L, _L, _P, _P, _P]),
     "reid_expand": (_I, [_P, _L, _I, _I, _P, _P, _L, _L, _I, _P, _P, _P]),

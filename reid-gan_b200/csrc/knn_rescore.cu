@@ -37,13 +37,16 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_select_kernel(
     int64_t row_begin, int64_t n_rows, const unsigned long long* __restrict__ cand,
     const int32_t* __restrict__ cand_cnt, const uint32_t* __restrict__ row_tau, int n_lists, int list_cap,
     int64_t list_pitch_rows, int k, float eps_in, const float* __restrict__ max_sqnorm, int32_t* __restrict__ win_cnt, int32_t* __restrict__ win_idx, float* __restrict__ win_a,
-    int32_t* __restrict__ uncert, int32_t* __restrict__ key_out, int32_t* __restrict__ hist) {
+    int32_t* __restrict__ uncert, int32_t* __restrict__ key_out, int32_t* __restrict__ hist,
+    const int32_t* __restrict__ row_pos, const int32_t* __restrict__ col_orig) {
+  // row_pos / col_orig (sample-first symmetric search): the lists live in a permuted row space -- row lr's lists and
+  // threshold are those of position row_pos[lr], and a listed column p is the original row col_orig[p].
   __shared__ float s_a[kRsWarps][kRsMaxC];
   __shared__ int32_t s_j[kRsWarps][kRsMaxC];
   const int w = threadIdx.x >> 5, lane = lane_id();
   const int64_t lr = (int64_t)blockIdx.x * kRsWarps + w;
   if (lr >= n_rows) return;
-  const int32_t self = (int32_t)(row_begin + lr);
+  const int32_t self_orig = (int32_t)(row_begin + lr);
   const float eps = max_sqnorm ? reid_tc_err_bound(*max_sqnorm) : eps_in;
   float* a = s_a[w];
   int32_t* jj = s_j[w];
@@ -51,13 +54,15 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_select_kernel(
   // Every column outside the row's lists scored <= bound.  The window [a_(k) - 2 eps, inf) starts at or
   // above bound - 2 eps (a_(k) >= bound because at least `keep` >= k listed columns score >= bound), so a
   // sweep that collects the entries >= bound - 2 eps finds every window member.
-  const uint32_t tq = row_tau[lr];
+  const int64_t pl = row_pos ? (int64_t)row_pos[lr] : lr;
+  const int32_t self = row_pos ? (int32_t)pl : self_orig;      // the row's own id in the id space of the lists
+  const uint32_t tq = row_tau[pl];
   const float bound = tq ? ord_float(tq) : -INFINITY;
 
   auto collect = [&](float thr) {
     int cnt = 0;
     for (int q = 0; q < n_lists; ++q) {
-      const int64_t li = list_pitch_rows ? q * list_pitch_rows + lr : lr * n_lists + q;   // list-major / row-major
+      const int64_t li = list_pitch_rows ? q * list_pitch_rows + pl : pl * n_lists + q;   // list-major / row-major
       const int c = min(cand_cnt[li], list_cap);
       const unsigned long long* src = cand + li * (int64_t)list_cap;
       for (int base = 0; base < c; base += 32) {
@@ -73,7 +78,7 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_select_kernel(
         const int pos = cnt + __popc(b & ((1u << lane) - 1u));
         if (in && pos < kRsMaxC) {
           a[pos] = v;
-          jj[pos] = (int32_t)(uint32_t)e;
+          jj[pos] = (int32_t)(uint32_t)e;                  // a POSITION when col_orig is given: translated on the way out
         }
         cnt += __popc(b);
       }
@@ -115,7 +120,7 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_select_kernel(
 
   bool list_overflow = false;                       // an overflowed list lost columns above the threshold
   for (int q = 0; q < n_lists; ++q)
-    list_overflow |= cand_cnt[list_pitch_rows ? q * list_pitch_rows + lr : lr * n_lists + q] > list_cap;
+    list_overflow |= cand_cnt[list_pitch_rows ? q * list_pitch_rows + pl : pl * n_lists + q] > list_cap;
   float thr = bound - 2.0f * eps;
   int n = collect(thr);
   if (n > kRsMaxC) {
@@ -144,11 +149,12 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_select_kernel(
     const bool in = t < n && a[t] >= lo;
     const unsigned b = __ballot_sync(kFull, in);
     const int pos = n_w + __popc(b & ((1u << lane) - 1u));
+    const int32_t j_orig = in ? (col_orig ? col_orig[jj[t]] : jj[t]) : 0;     // only window members are translated
     if (in && pos < kWinMax) {
-      win_idx[lr * kWinMax + pos] = jj[t];
+      win_idx[lr * kWinMax + pos] = j_orig;
       win_a[lr * kWinMax + pos] = a[t];
     }
-    if (in && a[t] >= near) kmin = min(kmin, jj[t]);
+    if (in && a[t] >= near) kmin = min(kmin, j_orig);
     n_w += __popc(b);
   }
   kmin = warp_min(kmin);
@@ -157,7 +163,7 @@ __global__ void __launch_bounds__(kRsWarps * 32) rescore_select_kernel(
     win_cnt[lr] = min(n_w, kWinMax);
     uncert[lr] = certified ? 0 : 1;
     if (key_out) {
-      if (kmin == 0x7fffffff) kmin = self;
+      if (kmin == 0x7fffffff) kmin = self_orig;
       key_out[lr] = kmin;
       atomicAdd(&hist[kmin], 1);
     }
@@ -779,7 +785,19 @@ int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, in
                      const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists, int list_cap, int64_t list_pitch_rows,
                      int k, float err_bound, const float* max_sqnorm, int locality_order, int32_t* out_idx, float* out_key, int32_t* uncertified_flag,
                      float* max_err_out, void* workspace, uint64_t* uncertified_count, void* stream) {
+  return reid_knn_rescore_mapped(x, N, D, row_begin, row_end, cand, cand_cnt, row_tau, n_lists, list_cap, list_pitch_rows, k,
+                                 err_bound, max_sqnorm, locality_order, nullptr, nullptr, out_idx, out_key, uncertified_flag,
+                                 max_err_out, workspace, uncertified_count, stream);
+}
+
+int reid_knn_rescore_mapped(const float* x, int64_t N, int64_t D, int64_t row_begin, int64_t row_end, const uint64_t* cand,
+                            const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists, int list_cap, int64_t list_pitch_rows,
+                            int k, float err_bound, const float* max_sqnorm, int locality_order, const int32_t* row_pos,
+                            const int32_t* col_orig, int32_t* out_idx, float* out_key, int32_t* uncertified_flag,
+                            float* max_err_out, void* workspace, uint64_t* uncertified_count, void* stream) {
   using namespace reid;
+  REID_CHECK_ARG((row_pos == nullptr) == (col_orig == nullptr), "reid_knn_rescore_mapped: row_pos and col_orig come together");
+  REID_CHECK_ARG(!row_pos || (row_begin == 0 && row_end == N), "reid_knn_rescore_mapped: the maps cover all N rows");
   REID_CHECK_ARG(x && cand && cand_cnt && row_tau && out_idx && uncertified_flag && max_err_out && workspace,
                  "reid_knn_rescore: NULL pointer");
   REID_CHECK_ARG(N > 0 && D > 0 && 0 <= row_begin && row_begin <= row_end && row_end <= N, "reid_knn_rescore: bad shape");
@@ -799,7 +817,7 @@ int reid_knn_rescore(const float* x, int64_t N, int64_t D, int64_t row_begin, in
   rescore_select_kernel<<<grid, kRsWarps * 32, 0, st>>>(row_begin, n, (const unsigned long long*)cand, cand_cnt, row_tau,
                                                         n_lists, list_cap, list_pitch_rows, k, err_bound, max_sqnorm, w.win_cnt,
                                                         w.win_idx, w.win_a,
-                                                        uncertified_flag, locality_order ? w.key : nullptr, w.hist);
+                                                        uncertified_flag, locality_order ? w.key : nullptr, w.hist, row_pos, col_orig);
   REID_LAUNCH_CHECK();
   if (locality_order) {
     int rc = reid_scan_counts(w.hist, N, w.ptr, nullptr, stream);

@@ -343,8 +343,14 @@ __global__ void __launch_bounds__(kTauWarps * 32) sample_tau_kernel(const unsign
                                                                    const int32_t* __restrict__ cand_cnt,
                                                                    const uint32_t* __restrict__ row_tau, int n_lists,
                                                                    int64_t n_rows, int r, float* __restrict__ tau,
-                                                                   uint32_t* __restrict__ tau_ord) {
+                                                                   uint32_t* __restrict__ tau_ord,
+                                                                   unsigned long long* __restrict__ cand2,
+                                                                   int32_t* __restrict__ cand2_cnt, int cap2, int64_t row0) {
+  // cand2 != nullptr (sample-first symmetric search): the columns of the prepass ARE rows of the matrix, so the listed
+  // scores above tau are this row's candidates among them -- they go straight to the row's main list (row0 + row),
+  // and the symmetric pass skips the sample blocks.
   __shared__ uint32_t s_o[kTauWarps][kTauMax];
+  __shared__ uint32_t s_c[kTauWarps][kTauMax];          // columns of the collected scores (emit mode)
   const int w = threadIdx.x >> 5, lane = lane_id();
   const int64_t row = (int64_t)blockIdx.x * kTauWarps + w;
   if (row >= n_rows) return;
@@ -356,11 +362,18 @@ __global__ void __launch_bounds__(kTauWarps * 32) sample_tau_kernel(const unsign
     for (int base = 0; base < c; base += 32) {
       const int t = base + lane;
       uint32_t o = 0;
-      if (t < c) o = float_ord(__uint_as_float((uint32_t)(src[t] >> 32)));
+      unsigned long long e = 0ull;
+      if (t < c) {
+        e = src[t];
+        o = float_ord(__uint_as_float((uint32_t)(e >> 32)));
+      }
       const bool in = t < c && o >= floor_ord;
       const unsigned b = __ballot_sync(kFull, in);
       const int pos = n + __popc(b & ((1u << lane) - 1u));
-      if (in && pos < kTauMax) s_o[w][pos] = o;
+      if (in && pos < kTauMax) {
+        s_o[w][pos] = o;
+        if (cand2) s_c[w][pos] = (uint32_t)e;
+      }
       n += __popc(b);
     }
   }
@@ -383,8 +396,52 @@ __global__ void __launch_bounds__(kTauWarps * 32) sample_tau_kernel(const unsign
     c = __reduce_add_sync(kFull, c);
     if (c >= r) T = c2;
   }
+  bool ok = m >= r;
+  if (cand2) {
+    // The lists are complete only above the published floor (= the largest threshold any list of the row rejected with,
+    // reid_knn_candidates_tc_abt publish_final), and the 16-bit search rounds T down -- possibly below the floor.
+    // max(T, floor) keeps every score above it in the lists (also when the collection above was truncated): they are
+    // swept once more and everything above the threshold goes to the main list.  (A floor that came from a lucky seed
+    // can exceed the true r-th best: the row then gets fewer candidates than planned, never wrong ones.)
+    T = (ok && T > floor_ord) ? T : floor_ord;
+    ok = ok || floor_ord != 0u;          // fewer than r scores above the floor: the floor itself is the threshold
+    // Nobody else appends to this row's main list while this kernel runs (the transposed appends of the prepass go to
+    // SAMPLE rows and are launched after the sample rows' thresholds; the symmetric pass comes later), so the warp
+    // owns the counter: positions from ballots, one plain update at the end.
+    if (ok && n <= kTauMax) {            // the usual case: everything at or above the floor sits in shared memory
+      const int base0 = cand2_cnt[row0 + row];
+      int n_e = 0;
+      for (int b0 = 0; b0 < m; b0 += 32) {
+        const int t = b0 + lane;
+        const bool hit = t < m && s_o[w][t] > T;
+        const unsigned bal = __ballot_sync(kFull, hit);
+        const int pos = base0 + n_e + __popc(bal & ((1u << lane) - 1u));
+        if (hit && pos < cap2)
+          cand2[(row0 + row) * cap2 + pos] =
+              ((unsigned long long)__float_as_uint(ord_float(s_o[w][t])) << 32) | (unsigned long long)s_c[w][t];
+        n_e += __popc(bal);
+      }
+      if (lane == 0) cand2_cnt[row0 + row] = base0 + n_e;
+    } else if (ok) {
+      const int base0 = cand2_cnt[row0 + row];
+      int n_e = 0;
+      for (int q = 0; q < n_lists; ++q) {
+        const int c = min(cand_cnt[row * n_lists + q], kCap);
+        const unsigned long long* src = cand + (row * n_lists + q) * (int64_t)kCap;
+        for (int b0 = 0; b0 < c; b0 += 32) {
+          const int t = b0 + lane;
+          const unsigned long long e = t < c ? src[t] : 0ull;
+          const bool hit = t < c && float_ord(__uint_as_float((uint32_t)(e >> 32))) > T;
+          const unsigned bal = __ballot_sync(kFull, hit);
+          const int pos = base0 + n_e + __popc(bal & ((1u << lane) - 1u));
+          if (hit && pos < cap2) cand2[(row0 + row) * cap2 + pos] = e;
+          n_e += __popc(bal);
+        }
+      }
+      if (lane == 0) cand2_cnt[row0 + row] = base0 + n_e;
+    }
+  }
   if (lane == 0) {
-    const bool ok = m >= r;
     tau[row] = ok ? ord_float(T) : -INFINITY;
     tau_ord[row] = ok ? T : 0u;
   }
@@ -407,12 +464,20 @@ int reid_features_sample(const void* xh, int64_t N, int64_t D, int64_t n_sample,
 
 int reid_knn_sample_tau(const uint64_t* cand, const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists, int64_t n_rows,
                         int r, float* tau, uint32_t* tau_ord, void* stream) {
+  return reid_knn_sample_tau_emit(cand, cand_cnt, row_tau, n_lists, n_rows, r, tau, tau_ord, nullptr, nullptr, 0, 0, stream);
+}
+
+int reid_knn_sample_tau_emit(const uint64_t* cand, const int32_t* cand_cnt, const uint32_t* row_tau, int n_lists, int64_t n_rows,
+                             int r, float* tau, uint32_t* tau_ord, uint64_t* cand_main, int32_t* cand_main_cnt, int cap_main,
+                             int64_t row0, void* stream) {
   using namespace reid;
+  REID_CHECK_ARG(!cand_main || (cand_main_cnt && cap_main >= 1 && row0 >= 0), "reid_knn_sample_tau_emit: bad main lists");
   REID_CHECK_ARG(cand && cand_cnt && row_tau && tau && tau_ord && n_lists >= 1 && n_rows >= 0 && r >= 1,
                  "reid_knn_sample_tau: bad arguments");
   if (n_rows == 0) return REID_OK;
   tc::sample_tau_kernel<<<(unsigned)((n_rows + tc::kTauWarps - 1) / tc::kTauWarps), tc::kTauWarps * 32, 0, (cudaStream_t)stream>>>(
-      (const unsigned long long*)cand, cand_cnt, row_tau, n_lists, n_rows, r, tau, tau_ord);
+      (const unsigned long long*)cand, cand_cnt, row_tau, n_lists, n_rows, r, tau, tau_ord, (unsigned long long*)cand_main,
+      cand_main_cnt, cap_main, row0);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }

@@ -96,6 +96,17 @@ struct Params {
   unsigned long long* cand;   // [(rows) x n_splits x kCap]
   int32_t* cand_cnt;          // [(rows) x n_splits]
   uint32_t* row_tau;          // [rows] shared rejection threshold per query row (order-preserving image), 0 = none
+  // transposed direction (sample-first symmetric search, knn_tc._candidates_sym_sf): the columns are the SAMPLE rows,
+  // whose own thresholds are known already; every score above its column's threshold is appended to that sample row's
+  // main list (entry column = this query row) -- the tiles (sample block, other block) of the symmetric pass are then
+  // covered by this prepass and skipped there.  tau_col == nullptr: off.
+  const float* tau_col;       // [N] threshold per column (descaled score units)
+  unsigned long long* cand2;  // [N x cap2] main lists of the column rows
+  int32_t* cand2_cnt;         // [N]
+  int cap2;
+  int publish_final;          // every list publishes its FINAL rejection threshold (boot seeds included) in row_tau, so that
+                              // row_tau ends up >= every threshold any list of the row ever rejected with: what
+                              // reid_knn_sample_tau_emit needs to hand the listed scores on as complete candidate sets
   int boot;                   // sampling prepass: seed tau from the first 32 scores of a unit (see the epilogue)
   int dbg;                    // developer switch (REID_TC_DEBUG): 1 = epilogue skips TMEM reads, 2 = reads but no selection, 4 = no TMA
 };
@@ -107,7 +118,10 @@ struct Cfg {
   static constexpr int kBBytes = kBRows * BK * 2;
   static constexpr int kStage = kATileBytes + kBBytes;      // 48 KB (1 CTA) / 32 KB (pair)
   static constexpr int kNumStages = kCtas == 1 ? 4 : 6;
-  static constexpr int kSmem = kNumStages * kStage + 1024 /*align*/ + 256 /*barriers*/;
+  static constexpr int kTauColBytes = 2 * BN * 4;            // column thresholds, one buffer per epilogue group
+  static constexpr int kHitSlots = 8;                        // parked transposed survivors per lane and tile
+  static constexpr int kHitBytes = 8 * kHitSlots * 32 * 8;   // 8 epilogue warps x slots x lanes x 8 B
+  static constexpr int kSmem = kNumStages * kStage + 1024 /*align*/ + 256 /*barriers*/ + kTauColBytes + kHitBytes;
 };
 
 // kCtas = 1: one CTA per 128-row tile (tcgen05.mma.cta_group::1, M = 128).
@@ -127,6 +141,8 @@ __global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_const
   uint64_t* tfull_bar = empty_bar + kNumStages;   // [2] accumulator ready
   uint64_t* tempty_bar = tfull_bar + 2;           // [2] accumulator drained (lives in the leader CTA)
   uint32_t* tmem_slot = (uint32_t*)(tempty_bar + 2);
+  float* s_tauc = (float*)(smem + kNumStages * C::kStage + 256);                                                  // [2][BN]
+  unsigned long long* s_hits = (unsigned long long*)(smem + kNumStages * C::kStage + 256 + C::kTauColBytes);     // [8][slots][32]
 
   const int warp = threadIdx.x >> 5, lane = lane_id();
   const uint32_t cta_rank = kCtas == 2 ? cluster_ctarank() : 0u;
@@ -269,6 +285,21 @@ __global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_const
           const uint32_t g = *my_tau;
           if (g && row_ok) tau = fmaxf(tau, ord_float(g));
         }
+        float* tauc = s_tauc + wg * BN;
+        unsigned long long* hits = s_hits + (size_t)(warp - 2) * C::kHitSlots * 32;
+        int n_hit = 0;
+        if (p.tau_col) {                                  // thresholds of this tile's columns (uniform branch)
+          __syncwarp();
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");        // the previous tile's readers are done
+          const int gt = ((warp - 2) & 3) * 32 + lane;
+#pragma unroll
+          for (int h = 0; h < 2; ++h) {
+            const int c = gt + h * 128;
+            const int64_t col = (int64_t)t * BN + c;
+            tauc[c] = col < p.N ? p.tau_col[col] : INFINITY;
+          }
+          asm volatile("bar.sync %0, 128;" ::"r"(1 + wg) : "memory");
+        }
         mbar_wait(&tfull_bar[wg], acc_phase);
         acc_phase ^= 1;
         tcgen05_fence_after();
@@ -279,6 +310,35 @@ __global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_const
           uint32_t v[32];
           tmem_ld_32x32b_x32(taddr + ch * 32, v);
           const int col0 = t * BN + ch * 32;
+          if (p.tau_col && row_ok) {                      // transposed direction: score against the column's threshold
+            const float4* tc4 = reinterpret_cast<const float4*>(tauc + ch * 32);
+            unsigned hit = 0;
+#pragma unroll
+            for (int q = 0; q < 8; ++q) {
+              const float4 t4 = tc4[q];
+              hit |= (unsigned)(__uint_as_float(v[4 * q]) * p.descale > t4.x) << (4 * q);
+              hit |= (unsigned)(__uint_as_float(v[4 * q + 1]) * p.descale > t4.y) << (4 * q + 1);
+              hit |= (unsigned)(__uint_as_float(v[4 * q + 2]) * p.descale > t4.z) << (4 * q + 2);
+              hit |= (unsigned)(__uint_as_float(v[4 * q + 3]) * p.descale > t4.w) << (4 * q + 3);
+            }
+            while (hit) {                                 // rare: about r / m of the scores
+              const int c = __ffs(hit) - 1;
+              hit &= hit - 1;
+              float a = 0.f;
+#pragma unroll
+              for (int e = 0; e < 32; ++e) a = e == c ? __uint_as_float(v[e]) : a;
+              const float sc = a * p.descale;
+              const int64_t col = col0 + c;               // < N: columns beyond N carry an infinite threshold
+              if (n_hit < C::kHitSlots) {                 // parked; appended after the accumulator has been handed back
+                hits[n_hit * 32 + lane] = ((unsigned long long)__float_as_uint(sc) << 32) | (unsigned long long)(ch * 32 + c);
+                ++n_hit;
+              } else {
+                const int pos = atomicAdd(p.cand2_cnt + col, 1);
+                if (pos < p.cap2)
+                  p.cand2[col * p.cap2 + pos] = ((unsigned long long)__float_as_uint(sc) << 32) | (uint32_t)(p.row_begin + lrow);
+              }
+            }
+          }
           if (p.boot && cnt == 0 && tau == -INFINITY) {
             // Sampling prepass (reid_knn_sample_tau wants the r-th best of a few thousand scores, r ~ 16): instead
             // of appending the first tiles unfiltered -- uncoalesced 8-byte stores that outlast the MMA -- seed the
@@ -323,6 +383,18 @@ __global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_const
           if (kCtas == 1 || leader) mbar_arrive(&tempty_bar[wg]);
           else mbar_arrive_cluster(tempty_remote);
         }
+        if (p.tau_col) {                                  // flush the parked transposed survivors
+          const int max_hit = __reduce_max_sync(kFull, n_hit);
+          for (int h = 0; h < max_hit; ++h) {
+            if (h < n_hit) {
+              const unsigned long long e8 = hits[h * 32 + lane];
+              const int64_t col = (int64_t)t * BN + (int)(e8 & 0xffu);
+              const int pos = atomicAdd(p.cand2_cnt + col, 1);
+              if (pos < p.cap2)
+                p.cand2[col * p.cap2 + pos] = (e8 & 0xffffffff00000000ull) | (uint32_t)(p.row_begin + lrow);
+            }
+          }
+        }
         // a tile appends at most BN entries: lists that could overflow during the next tile are compacted
         // now (coarse threshold), one row at a time, while the tensor core works on the other accumulator
         unsigned need = __ballot_sync(kFull, cnt > kCap - BN);
@@ -343,7 +415,10 @@ __global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_const
       }
       // unit done: publish the count; the list is left untrimmed (<= kCap entries) -- knn_rescore.cu only
       // looks at entries above the row's final threshold
-      if (row_ok) p.cand_cnt[list_id] = cnt;
+      if (row_ok) {
+        p.cand_cnt[list_id] = cnt;
+        if (p.publish_final && tau > -INFINITY) atomicMax(p.row_tau + lrow, float_ord(tau));
+      }
     }
   }
 
@@ -356,14 +431,16 @@ __global__ void __launch_bounds__(kThreads, 1) simtopk_kernel(const __grid_const
 }
 
 __global__ void __launch_bounds__(256) to_half_kernel(const float* __restrict__ x, int64_t n_rows, int64_t D, float scale,
-                                                      __half* __restrict__ xh, float* __restrict__ max_sqnorm) {
+                                                      __half* __restrict__ xh, float* __restrict__ max_sqnorm,
+                                                      const int32_t* __restrict__ src_row) {
   // warp per row, grid-stride: the launch is sized to the machine (no partial last wave of 8-row CTAs)
   for (int64_t row = (int64_t)blockIdx.x * (blockDim.x >> 5) + (threadIdx.x >> 5); row < n_rows;
        row += (int64_t)gridDim.x * (blockDim.x >> 5)) {
   float ss = 0.f;
   if ((D & 3) == 0 && ((((uintptr_t)x) | ((uintptr_t)xh)) & 15) == 0) {
     // 16-byte loads, 8-byte stores: the stage is a pure stream (4ND bytes in, 2ND out)
-    const float4* src = reinterpret_cast<const float4*>(x + row * D);
+    const int64_t srow = src_row ? (int64_t)src_row[row] : row;      // sample-first layout of the symmetric search
+    const float4* src = reinterpret_cast<const float4*>(x + srow * D);
     uint2* dst = reinterpret_cast<uint2*>(xh + row * D);
     // eight independent 16-byte loads per lane in flight (4 KB per warp) before the first use: the stream is bound by
     // bytes in flight, not by the conversions.  ss is accumulated in ascending element order, batch or not.
@@ -395,7 +472,7 @@ __global__ void __launch_bounds__(256) to_half_kernel(const float* __restrict__ 
     }
   } else {
     for (int64_t d = lane_id(); d < D; d += 32) {
-      const float v = x[row * D + d];
+      const float v = x[(src_row ? (int64_t)src_row[row] : row) * D + d];
       ss = fmaf(v, v, ss);
       xh[row * D + d] = __float2half_rn(v * scale);
     }
@@ -491,7 +568,7 @@ int reid_features_to_half_acc(const float* x, int64_t n_rows, int64_t D, int sca
   REID_CHECK_ARG(scale_log2 >= -8 && scale_log2 <= 12, "reid_features_to_half_acc: scale_log2=%d out of range", scale_log2);
   if (n_rows == 0) return REID_OK;
   tc::to_half_kernel<<<tc::to_half_grid(n_rows), 256, 0, (cudaStream_t)stream>>>(x, n_rows, D, ldexpf(1.0f, scale_log2),
-                                                                                     (__half*)xh, max_sqnorm_inout);
+                                                                                     (__half*)xh, max_sqnorm_inout, nullptr);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
@@ -501,6 +578,18 @@ int reid_sqnorm_range_reset(float* sqnorm_range, void* stream) {
   REID_CHECK_ARG(sqnorm_range, "reid_sqnorm_range_reset: NULL pointer");
   REID_CUDA(cudaMemsetAsync(sqnorm_range, 0, sizeof(float), (cudaStream_t)stream));
   REID_CUDA(cudaMemsetAsync(sqnorm_range + 1, 0x7f, sizeof(float), (cudaStream_t)stream));
+  return REID_OK;
+}
+
+int reid_features_to_half_gather(const float* x, const int32_t* src_row, int64_t n_rows, int64_t D, int scale_log2, void* xh,
+                                 float* max_sqnorm_inout, void* stream) {
+  using namespace reid;
+  REID_CHECK_ARG(x && src_row && xh && n_rows >= 0 && D > 0, "reid_features_to_half_gather: bad arguments");
+  REID_CHECK_ARG(scale_log2 >= -8 && scale_log2 <= 12, "reid_features_to_half_gather: scale_log2=%d out of range", scale_log2);
+  if (n_rows == 0) return REID_OK;
+  tc::to_half_kernel<<<tc::to_half_grid(n_rows), 256, 0, (cudaStream_t)stream>>>(x, n_rows, D, ldexpf(1.0f, scale_log2),
+                                                                                     (__half*)xh, max_sqnorm_inout, src_row);
+  REID_LAUNCH_CHECK();
   return REID_OK;
 }
 
@@ -516,7 +605,7 @@ int reid_features_to_half(const float* x, int64_t n_rows, int64_t D, int scale_l
   }
   if (n_rows == 0) return REID_OK;
   tc::to_half_kernel<<<tc::to_half_grid(n_rows), 256, 0, st>>>(x, n_rows, D, ldexpf(1.0f, scale_log2), (__half*)xh,
-                                                                  max_sqnorm_out);
+                                                                  max_sqnorm_out, nullptr);
   REID_LAUNCH_CHECK();
   return REID_OK;
 }
@@ -531,7 +620,16 @@ int reid_knn_candidates_tc(const void* xh, int64_t N, int64_t D, int scale_log2,
 int reid_knn_candidates_tc_ab(const void* xa, int64_t Na, const void* xh, int64_t N, int64_t D, int scale_log2,
                               int64_t row_begin, int64_t row_end, int keep, int n_splits, int cta_group, uint64_t* cand,
                               int32_t* cand_cnt, uint32_t* row_tau, void* stream) {
+  return reid_knn_candidates_tc_abt(xa, Na, xh, N, D, scale_log2, row_begin, row_end, keep, n_splits, cta_group, cand, cand_cnt,
+                                    row_tau, 0, nullptr, nullptr, nullptr, 0, stream);
+}
+
+int reid_knn_candidates_tc_abt(const void* xa, int64_t Na, const void* xh, int64_t N, int64_t D, int scale_log2,
+                               int64_t row_begin, int64_t row_end, int keep, int n_splits, int cta_group, uint64_t* cand,
+                               int32_t* cand_cnt, uint32_t* row_tau, int publish_final, const float* tau_col,
+                               uint64_t* cand_col, int32_t* cand_col_cnt, int cap_col, void* stream) {
   using namespace reid;
+  REID_CHECK_ARG(!tau_col || (cand_col && cand_col_cnt && cap_col >= 1), "reid_knn_candidates_tc_abt: tau_col needs the column lists");
   const int boot = keep < 0;          // keep < 0: sampling prepass, |keep| kept, threshold seeded from the first scores
   if (boot) keep = -keep;
   REID_CHECK_ARG(xa && xh && cand && cand_cnt && row_tau, "reid_knn_candidates_tc: NULL pointer");
@@ -543,7 +641,8 @@ int reid_knn_candidates_tc_ab(const void* xa, int64_t Na, const void* xh, int64_
                  REID_TC_KEEP_MAX);
   REID_CHECK_ARG(cta_group == 1 || cta_group == 2, "reid_knn_candidates_tc: cta_group=%d must be 1 or 2", cta_group);
   const int64_t n_tiles = (N + tc::BN - 1) / tc::BN;
-  REID_CHECK_ARG(n_splits >= 1 && n_splits <= REID_TC_MAX_SPLITS && n_splits <= n_tiles,
+  // the prepass mode may cut its few column tiles finer: its lists are only read by reid_knn_sample_tau
+  REID_CHECK_ARG(n_splits >= 1 && n_splits <= (boot ? 2 * REID_TC_MAX_SPLITS : REID_TC_MAX_SPLITS) && n_splits <= n_tiles,
                  "reid_knn_candidates_tc: n_splits=%d", n_splits);
   CUtensorMap tmap, tmap_b;
   int rc = tc::make_tmap_rows128(&tmap, xa, Na, D);
@@ -564,6 +663,11 @@ int reid_knn_candidates_tc_ab(const void* xa, int64_t Na, const void* xh, int64_
   p.cand = (unsigned long long*)cand;
   p.cand_cnt = cand_cnt;
   p.row_tau = row_tau;
+  p.tau_col = tau_col;
+  p.cand2 = (unsigned long long*)cand_col;
+  p.cand2_cnt = cand_col_cnt;
+  p.cap2 = cap_col;
+  p.publish_final = publish_final;
   REID_CUDA(cudaMemsetAsync(row_tau, 0, sizeof(uint32_t) * (size_t)(row_end - row_begin), (cudaStream_t)stream));
   p.dbg = dev_env("REID_TC_DEBUG", 0);
   const int units = p.n_mblk * n_splits;

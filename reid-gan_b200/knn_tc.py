@@ -66,12 +66,12 @@ def sample_size(N, k=30):
 _tile_cache = {}
 
 
-def prepass_splits(n_rows, m, pair_slots=74):
-    """Column splits of the sampling prepass over `n_rows` rows: as many (<= 4, <= sample tiles) as keep the
+def prepass_splits(n_rows, m, pair_slots=74, max_splits=4):
+    """Column splits of the sampling prepass over `n_rows` rows: as many (<= max_splits, <= sample tiles) as keep the
     (256-row unit x split) count within one wave of the CTA-pair slots."""
     units = (n_rows + 255) // 256
     s = 1
-    while s < 4 and units * s * 2 <= pair_slots and s * 2 <= m // 256:
+    while s < max_splits and units * s * 2 <= pair_slots and s * 2 <= m // 256:
         s *= 2
     return s
 
@@ -156,6 +156,101 @@ def _candidates_sym(xh, N, D, sp, dev, k=30):
     cnt = torch.empty(N, dtype=torch.int32, device=dev)
     candidates_sym_launch(xh, N, D, tau, tiles, SYM_CAP, cand, cnt, 1, sp)
     return cand, cnt, tau_ord, SYM_CAP, dict(sample=m, tiles=int(tiles.shape[0]))
+
+
+SYM_SAMPLE_FIRST = True       # sample-first layout: the prepass scores are handed to the main lists and the symmetric pass
+                              # skips the sample blocks (device-resident single-GPU search; see _candidates_sym_sf)
+_sf_cache = {}
+_side_streams = {}
+
+
+def _side_stream(dev):
+    """One forked stream per device (created once: a stream made under graph capture would not outlive it)."""
+    key_ = str(dev)
+    if key_ not in _side_streams:
+        _side_streams[key_] = torch.cuda.Stream(device=dev)
+    return _side_streams[key_]
+
+
+def _sample_first_maps(N, m, dev):
+    """(pos_of, orig_of) int32 device tensors of the sample-first layout: positions [0, m) hold the low-discrepancy
+    sample rows (p * stride) mod N, positions [m, N) the other rows in their original order.  Cached per (N, m, dev)."""
+    key_ = (N, m, str(dev))
+    if key_ not in _sf_cache:
+        import numpy as np
+        samp = (np.arange(m, dtype=np.int64) * _sample_stride(N)) % N
+        is_s = np.zeros(N, dtype=bool)
+        is_s[samp] = True
+        orig_of = np.concatenate([samp, np.flatnonzero(~is_s)]).astype(np.int32)
+        pos_of = np.empty(N, dtype=np.int32)
+        pos_of[orig_of] = np.arange(N, dtype=np.int32)
+        _sf_cache[key_] = (torch.from_numpy(pos_of).to(dev), torch.from_numpy(orig_of).to(dev))
+    return _sf_cache[key_]
+
+
+def _tile_order_from(n_t, first, dev):
+    """_tile_order over the blocks [first, n_t): the upper triangle without the sample blocks.  Cached."""
+    key_ = ("from", n_t, first, str(dev))
+    if key_ not in _tile_cache:
+        _tile_cache[key_] = (_tile_order(n_t - first, "cpu") + first).to(dev).contiguous()
+    return _tile_cache[key_]
+
+
+def _candidates_sym_sf(x, N, D, sp, dev, k, msq):
+    """Symmetric search in the sample-first layout.  The fp16 operand is written with the m threshold-sample rows first,
+    so `all rows x sample` IS the block column [0, m) of the similarity matrix:
+      A. sample rows x sample  -> thresholds of the sample rows; their listed scores above the threshold are their
+         candidates among the sample (reid_knn_sample_tau_emit);
+      B. other rows x sample   -> thresholds of the other rows + their candidates among the sample (same), and, score
+         by score, the transposed direction against the sample rows' thresholds from A (reid_knn_candidates_tc_abt);
+      C. the symmetric kernel on the tiles (I, J), m / 256 <= I <= J, appending to the same lists.
+    Every pair of rows is scored exactly once; all lists and thresholds are indexed by POSITION (reid_knn_rescore_mapped
+    translates).  Returns (cand, cnt, tau_ord, cap, stats, xh, maps)."""
+    m = sample_size(N, k)
+    pos_of, orig_of = _sample_first_maps(N, m, dev)
+    xh = torch.empty((N, D), dtype=torch.float16, device=dev)
+    r = sym_rank(k)
+    cand = torch.empty(N * SYM_CAP, dtype=torch.int64, device=dev)
+    cnt = torch.zeros(N, dtype=torch.int32, device=dev)
+    tau = torch.empty(N, dtype=torch.float32, device=dev)
+    tau_ord = torch.empty(N, dtype=torch.int32, device=dev)
+    n_rest = N - m
+    splits_a = prepass_splits(m, m, max_splits=8)
+    pre = torch.empty(max(n_rest, 1) * 2 * TC_CAP, dtype=torch.int64, device=dev)
+    pre_cnt = torch.zeros(max(n_rest, 1) * 2, dtype=torch.int32, device=dev)
+    pre_tau = torch.empty(max(n_rest, 1), dtype=torch.int32, device=dev)
+    # fp16 operand, sample rows first.  Phase A needs only those: it runs on a forked stream (64 tile units for 74 CTA
+    # pairs, tensor bound) under the conversion of the other rows (HBM bound); with its own list buffers.
+    call("reid_sqnorm_range_reset", ptr(msq), sp)
+    call("reid_features_to_half_gather", ptr(x), ptr(orig_of), m, D, SCALE_LOG2, ptr(xh), ptr(msq), sp)
+    pre_a = torch.empty(m * 2 * splits_a * TC_CAP, dtype=torch.int64, device=dev)
+    pre_a_cnt = torch.zeros(m * 2 * splits_a, dtype=torch.int32, device=dev)
+    pre_a_tau = torch.empty(m, dtype=torch.int32, device=dev)
+    main = torch.cuda.current_stream()
+    side = _side_stream(dev)
+    side.wait_stream(main)
+    with torch.cuda.stream(side):
+        sp_a = stream_ptr()
+        # A: the sample rows against the sample (a few row units: their columns are split over CTA pairs)
+        call("reid_knn_candidates_tc_abt", ptr(xh), N, ptr(xh), m, D, SCALE_LOG2, 0, m, -r, splits_a, 2, ptr(pre_a), ptr(pre_a_cnt),
+             ptr(pre_a_tau), 1, None, None, None, 0, sp_a)
+        call("reid_knn_sample_tau_emit", ptr(pre_a), ptr(pre_a_cnt), ptr(pre_a_tau), 2 * splits_a, m, r, ptr(tau), ptr(tau_ord),
+             ptr(cand), ptr(cnt), SYM_CAP, 0, sp_a)
+    if n_rest > 0:
+        call("reid_features_to_half_gather", ptr(x), ptr(orig_of[m:]), n_rest, D, SCALE_LOG2, ptr(xh[m:]), ptr(msq), sp)
+    main.wait_stream(side)
+    # B: the other rows against the sample, both directions
+    if n_rest > 0:
+        call("reid_knn_candidates_tc_abt", ptr(xh), N, ptr(xh), m, D, SCALE_LOG2, m, N, -r, 1, 2, ptr(pre), ptr(pre_cnt),
+             ptr(pre_tau), 1, ptr(tau), ptr(cand), ptr(cnt), SYM_CAP, sp)
+        call("reid_knn_sample_tau_emit", ptr(pre), ptr(pre_cnt), ptr(pre_tau), 2, n_rest, r, ptr(tau[m:]), ptr(tau_ord[m:]),
+             ptr(cand), ptr(cnt), SYM_CAP, m, sp)
+    # C: the rest of the upper triangle
+    n_t = (N + 255) // 256
+    tiles = _tile_order_from(n_t, m // 256, dev)
+    if tiles.shape[0]:
+        candidates_sym_launch(xh, N, D, tau, tiles, SYM_CAP, cand, cnt, 0, sp)
+    return cand, cnt, tau_ord, SYM_CAP, dict(sample=m, tiles=int(tiles.shape[0]), layout="sample-first"), xh, (pos_of, orig_of)
 
 
 def sym_eligible(N, D, k):
@@ -271,7 +366,15 @@ def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None, defer=
     dev = x.device
     n = r1 - r0
     sp = stream_ptr()
-    if cands is not None:
+    sym = SYM and r0 == 0 and r1 == N and N >= SYM_MIN_N and k <= SYM_MAX_K
+    maps = None
+    sf = None
+    if cands is None and xh is None and sym and SYM_SAMPLE_FIRST and sample_size(N, k) % 256 == 0 and N - sample_size(N, k) >= 256:
+        msq = torch.zeros(2, dtype=torch.float32, device=dev)
+        sf = _candidates_sym_sf(x, N, D, sp, dev, k, msq)
+        xh, maps = sf[5], sf[6]
+        max_sqnorm = None
+    elif cands is not None:
         msq = cands[5]
         max_sqnorm = None
     elif xh is None:
@@ -281,9 +384,11 @@ def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None, defer=
         max_sqnorm = None
     else:
         msq = None
-    sym = SYM and r0 == 0 and r1 == N and N >= SYM_MIN_N and k <= SYM_MAX_K
     keep = max(k, min(k + SLACK, KEEP_MAX))
-    if cands is not None:
+    if sf is not None:
+        cand, cand_cnt, row_tau, list_cap, sym_info = sf[:5]
+        n_lists, s = 1, 0
+    elif cands is not None:
         cand, cand_cnt, row_tau, list_cap, sym_info = cands[:5]
         n_lists, s, sym = 1, 0, True
     elif sym:
@@ -303,8 +408,13 @@ def knn_search_tc(x, k, r0, r1, idx, key, info, xh=None, max_sqnorm=None, defer=
     flag = torch.empty(n, dtype=torch.int32, device=dev)
     max_err = torch.zeros(1, dtype=torch.float32, device=dev)
     ws = torch.empty(L.reid_knn_rescore_workspace_bytes(N, n), dtype=torch.uint8, device=dev)
-    call("reid_knn_rescore", ptr(x), N, D, r0, r1, ptr(cand), ptr(cand_cnt), ptr(row_tau), n_lists, list_cap, 0, k, eps,
-         ptr(msq), 1 if ORDER_ROWS else 0, ptr(idx), ptr(key), ptr(flag), ptr(max_err), ptr(ws), ptr(uncert_count), sp)
+    if maps is not None:      # the lists live in the sample-first positions
+        call("reid_knn_rescore_mapped", ptr(x), N, D, r0, r1, ptr(cand), ptr(cand_cnt), ptr(row_tau), n_lists, list_cap, 0, k, eps,
+             ptr(msq), 1 if ORDER_ROWS else 0, ptr(maps[0]), ptr(maps[1]), ptr(idx), ptr(key), ptr(flag), ptr(max_err), ptr(ws),
+             ptr(uncert_count), sp)
+    else:
+        call("reid_knn_rescore", ptr(x), N, D, r0, r1, ptr(cand), ptr(cand_cnt), ptr(row_tau), n_lists, list_cap, 0, k, eps,
+             ptr(msq), 1 if ORDER_ROWS else 0, ptr(idx), ptr(key), ptr(flag), ptr(max_err), ptr(ws), ptr(uncert_count), sp)
 
     def repair():
         """Exact CUDA-core search for the rows the certificate rejected (none on typical data)."""

@@ -202,16 +202,28 @@ def _sym_case(N, D, n_ids, noise, seed, order=None, dup=0):
     (9000, 128, 100, 0.8, 12, None, 0, 64),        # k1 at the 64-bit mask limit: twice the candidates per row
     (8192, 256, 8192, 1.0, 13, None, 0, 48),       # isotropic, 32 < k <= 64
 ])
-def test_symmetric_search_is_exact(N, D, n_ids, noise, seed, order, dup, k):
-    from reid_gan_b200 import faiss_rerank as fr
+def test_symmetric_search_is_exact(monkeypatch, N, D, n_ids, noise, seed, order, dup, k):
+    """Both layouts of the symmetric search: sample-first (the default: the prepass scores are handed to the main lists,
+    the symmetric pass skips the sample blocks) and the separate-sample one (what the upload / sharded paths use)."""
+    from reid_gan_b200 import faiss_rerank as fr, knn_tc
     x = _sym_case(N, D, n_ids, noise, seed, order, dup).cuda()
     ie, ke, _ = fr.knn_search(x, k, "exact")
-    it, kt, info = fr.knn_search(x, k, "tc")
-    assert info["mode"] == "tc-sym", "the symmetric kernel must be the one that ran"
-    assert torch.equal(ie, it), "neighbour lists differ from the exact search"
-    assert torch.equal(ke, kt), "keys differ from the exact search"
-    cnt = info["cand_cnt"]
-    assert int(cnt.min()) >= k, "every row must have kept at least k candidates"
+    for sample_first in (True, False):
+        monkeypatch.setattr(knn_tc, "SYM_SAMPLE_FIRST", sample_first)
+        it, kt, info = fr.knn_search(x, k, "tc")
+        assert info["mode"] == "tc-sym", "the symmetric kernel must be the one that ran"
+        assert (info["sym"].get("layout") == "sample-first") == sample_first
+        assert info["uncertified_rows"] == 0
+        assert torch.equal(ie, it), "neighbour lists differ from the exact search"
+        assert torch.equal(ke, kt), "keys differ from the exact search"
+        cnt = info["cand_cnt"]
+        assert int(cnt.min()) >= k, "every row must have kept at least k candidates"
+        if sample_first:         # every pair is scored once: the lists are as long as in the other layout, tile count drops
+            n_t, s_t = (N + 255) // 256, knn_tc.sample_size(N, k) // 256
+            assert info["sym"]["tiles"] == (n_t - s_t) * (n_t - s_t + 1) // 2
+            mean_sf = float(cnt.float().mean())
+        else:
+            assert abs(float(cnt.float().mean()) - mean_sf) <= 0.35 * mean_sf
 
 
 @pytest.mark.parametrize("N,D,n_ids,k", [(8192 + 77, 128, 300, 30), (9000, 256, 100, 48)])
