@@ -332,11 +332,12 @@ def stage_rooflines(out, W, prof, steps, peaks, world):
         gathered += int((~(rank_local[rr] == ee[:, None].long()).any(1)).sum())
     fp64_peak = 148 * 64 * 2 * 1.965e9 / 1e12        # nominal: 64 FP64 FMA / clk / SM x 148 SMs x 1965 MHz = 37.2 TFLOP/s
     rows = [
-        ("features_to_half", ("reid_features_to_half",), "hbm", 6.0 * N * D, "4ND read + 2ND write"),
-        ("K1 sample thresholds", ("reid_features_sample", "reid_knn_candidates_tc_ab", "reid_knn_sample_tau"), "tensor",
+        ("features_to_half", ("reid_features_to_half", "reid_features_to_half_gather", "reid_sqnorm_range_reset"), "hbm", 6.0 * N * D, "4ND read + 2ND write"),
+        ("K1 sample thresholds", ("reid_features_sample", "reid_knn_candidates_tc_ab", "reid_knn_sample_tau", "reid_knn_candidates_tc_abt",
+                                  "reid_knn_sample_tau_emit"), "tensor",
          2.0 * (n if world == 1 else -(-N // world)) * sym.get("sample", 0) * D,
          "2 * rows * sample(%d) * D flops (tcgen05 prepass) + r-th best selection" % sym.get("sample", 0)),
-        ("K2 re-score", ("reid_knn_rescore",), "fp64", 2.0 * D * win,
+        ("K2 re-score", ("reid_knn_rescore", "reid_knn_rescore_mapped"), "fp64", 2.0 * D * win,
          "exact keys: 2*D flops per window member in the FP64 pipe, window total %d (%.1f/row); peak = nominal 64 FMA/clk/SM; "
          "HBM side: every feature row is needed once (4ND = %.0f MB compulsory), the SURVEY gather formula 4D*(window+rows) = "
          "%.2f GB is served by L2 because rows are visited in cluster-locality order" % (win, win / max(n, 1), 4.0 * N * D / 1e6,
@@ -706,14 +707,15 @@ def main():
         k_ms = tot_ms / calls
         n_tiles = (info.get("sym") or {}).get("tiles", 0)
         exec_flops = 2.0 * 256 * 256 * W["D"] * n_tiles
-        pre_ms = prof.get("reid_knn_candidates_tc_ab", (1, 0.0))
-        pre_ms = pre_ms[1] / max(pre_ms[0], 1)
+        pre_ms = sum(prof[k_][1] for k_ in ("reid_knn_candidates_tc_ab", "reid_knn_candidates_tc_abt") if k_ in prof) / max(calls, 1)
         ach = exec_flops / (k_ms * 1e-3) / 1e12
         roof = {"kernel": "simsym_kernel<%d> (%s)" % (2 if sym_key.endswith("wide") else 1, sym_key), "bound": "tensor", "achieved": ach,
                 "peak": peaks["bf16_tflops"], "unit": "TFLOP/s", "frac": ach / peaks["bf16_tflops"],
                 # dram__bytes_read.sum + dram__bytes_write.sum of one launch, `ncu --set full` capture of this
-                # workload on one GPU (profiles/r02_v3_summary.txt: 523 MB read + 65 MB written); the fp16 operand alone is 134 MB
-                "traffic": 587.6e6 if (world == 1 and W["N"] == WORKLOAD["N"]) else None,
+                # workload on one GPU: sample-first layout, 7,260 tiles (profiles/r02_v4_summary.txt: 455 MB read + 57 MB
+                # written); all 8,256 tiles (profiles/r02_v3_summary.txt): 523 + 65 MB; the fp16 operand alone is 134 MB
+                "traffic": ((512.2e6 if (info.get("sym") or {}).get("layout") == "sample-first" else 587.6e6)
+                            if (world == 1 and W["N"] == WORKLOAD["N"]) else None),
                 "ms_per_launch": k_ms, "flops_per_launch": exec_flops,
                 "algorithmic_flops": flops, "algorithmic_tflops": flops / ((k_ms + pre_ms) * 1e-3) / 1e12,
                 "prepass_ms": pre_ms,
