@@ -24,6 +24,8 @@
 // (super-blocks of 8 x 8 tiles so that the ~74 tiles in flight share 16 operand blocks in L2).
 #include <stdlib.h>
 
+#include <type_traits>
+
 #include "tc_ptx.cuh"
 
 namespace reid {
@@ -379,23 +381,31 @@ __global__ void __launch_bounds__(kTauWarps * 32) sample_tau_kernel(const unsign
   }
   __syncwarp();
   const int m = min(n, kTauMax);                        // a truncated set can only lower the result: still valid
-  uint32_t o[kTauMax / 32];
+  // the top 16 bits of the image are plenty: a threshold rounded DOWN only lets a few more columns through.  Only as
+  // many registers as m needs take part (with the published floors of the emit mode a row collects a few dozen scores).
+  auto search = [&](auto per_tag) {
+    constexpr int kPer = decltype(per_tag)::value;
+    uint32_t o[kPer];
 #pragma unroll
-  for (int u = 0; u < kTauMax / 32; ++u) {
-    const int t = u * 32 + lane;
-    o[u] = t < m ? s_o[w][t] : 0u;
-  }
-  // the top 16 bits of the image are plenty: a threshold rounded DOWN only lets a few more columns through
-  uint32_t T = 0;
+    for (int u = 0; u < kPer; ++u) {
+      const int t = u * 32 + lane;
+      o[u] = t < m ? s_o[w][t] : 0u;
+    }
+    uint32_t T_ = 0;
 #pragma unroll 1
-  for (int bit = 31; bit >= 16; --bit) {
-    const uint32_t c2 = T | (1u << bit);
-    int c = 0;
+    for (int bit = 31; bit >= 16; --bit) {
+      const uint32_t c2 = T_ | (1u << bit);
+      int c = 0;
 #pragma unroll
-    for (int u = 0; u < kTauMax / 32; ++u) c += o[u] >= c2;
-    c = __reduce_add_sync(kFull, c);
-    if (c >= r) T = c2;
-  }
+      for (int u = 0; u < kPer; ++u) c += o[u] >= c2;
+      c = __reduce_add_sync(kFull, c);
+      if (c >= r) T_ = c2;
+    }
+    return T_;
+  };
+  uint32_t T = m <= 64    ? search(std::integral_constant<int, 2>{})
+               : m <= 192 ? search(std::integral_constant<int, 6>{})
+                          : search(std::integral_constant<int, kTauMax / 32>{});
   bool ok = m >= r;
   if (cand2) {
     // The lists are complete only above the published floor (= the largest threshold any list of the row rejected with,

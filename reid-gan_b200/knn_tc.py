@@ -130,20 +130,44 @@ def candidates_sym_launch(xh, N, D, tau, tiles, cap, cand, cnt, reset, sp):
          ptr(cnt), reset, sp)
 
 
-def _sample_stride(N):
-    """~N / golden ratio, coprime with N: (m * stride) mod N walks the rows with low discrepancy."""
+_stride_cache = {}
+
+
+def _sample_stride(N, m=None):
+    """~N / golden ratio, coprime with N: (i * stride) mod N, i < m, walks the rows with low discrepancy.  a / N is only
+    close to the golden ratio: past the last Fibonacci denominator below m its continued fraction has large terms and the
+    first m points bunch up (N = 32,621, m = 2,048, a = round(0.618 N): gaps of 4, 65 and 69 rows).  So among the strides
+    within +-64 of round(0.618 N) the one whose first m points leave the smallest largest gap is taken (ties: the
+    closest).  m = None: plain rounding."""
     import math
-    a = max(1, int(round(N * 0.6180339887498949)))
-    while math.gcd(a, N) != 1:
-        a += 1
-    return a
+    a0 = max(1, int(round(N * 0.6180339887498949)))
+    if m is None or m < 2 or m >= N:
+        a = a0
+        while math.gcd(a, N) != 1:
+            a += 1
+        return a
+    key_ = (N, m)
+    if key_ not in _stride_cache:
+        import numpy as np
+        best = None
+        idx = np.arange(m, dtype=np.int64)
+        for d in sorted(range(-64, 65), key=abs):
+            a = a0 + d
+            if a < 1 or a >= N or math.gcd(a, N) != 1:
+                continue
+            p = np.sort((idx * a) % N)
+            gap = int(max(np.diff(p).max(), p[0] + N - p[-1]))
+            if best is None or gap < best[0]:
+                best = (gap, a)
+        _stride_cache[key_] = best[1] if best else _sample_stride(N)
+    return _stride_cache[key_]
 
 
 def _candidates_sym(xh, N, D, sp, dev, k=30):
     """Prepass (sample thresholds) + symmetric main pass.  Returns (cand, cand_cnt, tau_ord, cap, stats)."""
     m = sample_size(N, k)
     xs = torch.empty((m, D), dtype=torch.float16, device=dev)
-    call("reid_features_sample", ptr(xh), N, D, m, _sample_stride(N), ptr(xs), sp)
+    call("reid_features_sample", ptr(xh), N, D, m, _sample_stride(N, m), ptr(xs), sp)
     cand = torch.empty(N * max(2 * TC_CAP, SYM_CAP), dtype=torch.int64, device=dev)     # prepass lists, then main lists
     pre_cnt = torch.zeros(N * 2, dtype=torch.int32, device=dev)
     pre_tau = torch.empty(N, dtype=torch.int32, device=dev)
@@ -178,7 +202,7 @@ def _sample_first_maps(N, m, dev):
     key_ = (N, m, str(dev))
     if key_ not in _sf_cache:
         import numpy as np
-        samp = (np.arange(m, dtype=np.int64) * _sample_stride(N)) % N
+        samp = (np.arange(m, dtype=np.int64) * _sample_stride(N, m)) % N
         is_s = np.zeros(N, dtype=bool)
         is_s[samp] = True
         orig_of = np.concatenate([samp, np.flatnonzero(~is_s)]).astype(np.int32)

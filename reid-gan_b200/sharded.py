@@ -345,7 +345,7 @@ def knn_search_tiles(x, k, group=None, report=None):
     #    AND the columns of a tile), their order-preserving images stay with the owner (certificate)
     m = kt.sample_size(N, k)
     xs = torch.empty((m, D), dtype=torch.float16, device=dev)
-    call("reid_features_sample", ptr(xh), N, D, m, kt._sample_stride(N), ptr(xs), sp)
+    call("reid_features_sample", ptr(xh), N, D, m, kt._sample_stride(N, m), ptr(xs), sp)
     t_f = torch.empty(B, dtype=torch.float32, device=dev)
     t_o = torch.empty(B, dtype=torch.int32, device=dev)
     if nb:

@@ -28,7 +28,7 @@ call("reid_features_to_half", ptr(x), N, D, kt.SCALE_LOG2, ptr(xh), ptr(msq), sp
 cand, cnt, tau_ord, cap, info = kt._candidates_sym(xh, N, D, sp, dev)
 m = kt.sample_size(N)
 xs = torch.empty((m, D), dtype=torch.float16, device=dev)
-call("reid_features_sample", ptr(xh), N, D, m, kt._sample_stride(N), ptr(xs), sp)
+call("reid_features_sample", ptr(xh), N, D, m, kt._sample_stride(N, m), ptr(xs), sp)
 pre = torch.empty(N * 2 * kt.TC_CAP, dtype=torch.int64, device=dev)
 pre_cnt = torch.zeros(N * 2, dtype=torch.int32, device=dev)
 pre_tau = torch.empty(N, dtype=torch.int32, device=dev)

@@ -26,7 +26,7 @@ def run(N, D, n_ids, reps=10):
     # thresholds again (the helper does not return the float ones): same calls as _candidates_sym
     m = kt.sample_size(N)
     xs = torch.empty((m, D), dtype=torch.float16, device=dev)
-    call("reid_features_sample", ptr(xh), N, D, m, kt._sample_stride(N), ptr(xs), sp)
+    call("reid_features_sample", ptr(xh), N, D, m, kt._sample_stride(N, m), ptr(xs), sp)
     pre = torch.empty(N * 2 * kt.TC_CAP, dtype=torch.int64, device=dev)
     pre_cnt = torch.zeros(N * 2, dtype=torch.int32, device=dev)
     pre_tau = torch.empty(N, dtype=torch.int32, device=dev)

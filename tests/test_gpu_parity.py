@@ -603,7 +603,7 @@ def test_prepass_thresholds_with_column_splits(splits):
     call("reid_features_to_half", ptr(x), N, D, kt.SCALE_LOG2, ptr(xh), None, sp)
     m = kt.sample_size(N, k)
     xs = torch.empty((m, D), dtype=torch.float16, device=dev)
-    call("reid_features_sample", ptr(xh), N, D, m, kt._sample_stride(N), ptr(xs), sp)
+    call("reid_features_sample", ptr(xh), N, D, m, kt._sample_stride(N, m), ptr(xs), sp)
     r = kt.sym_rank(k)
     b0, b1 = 1024, 1024 + 2560 + 77                      # a ragged block in the middle
     nb = b1 - b0
