@@ -46,6 +46,31 @@ def test_argument_validation_needs_no_gpu():
     assert rc == _lib.REID_ERR_INVALID_ARG
 
 
+def test_argument_validation_of_the_sample_first_entries():
+    """The entry points of the sample-first symmetric search reject inconsistent optional arguments before any CUDA call."""
+    from reid_gan_b200 import _lib
+    L = _lib.lib()
+    buf = (ctypes.c_int64 * 16)()
+    a = (ctypes.addressof(buf) + 15) & ~15                   # some entries check 16-byte alignment first
+    # position tables come together
+    rc = L.reid_knn_rescore_mapped(a, 8, 64, 0, 8, a, a, a, 1, 16, 0, 4, 0.0, None, 0, a, None, a, a, a, a, a, None, None)
+    assert rc == _lib.REID_ERR_INVALID_ARG and "row_pos" in _lib.last_error()
+    # ... and cover all N rows
+    rc = L.reid_knn_rescore_mapped(a, 8, 64, 0, 4, a, a, a, 1, 16, 0, 4, 0.0, None, 0, a, a, a, a, a, a, a, None, None)
+    assert rc == _lib.REID_ERR_INVALID_ARG and "all N rows" in _lib.last_error()
+    # column thresholds need the column lists
+    rc = L.reid_knn_candidates_tc_abt(a, 512, a, 256, 64, 4, 0, 512, -16, 1, 2, a, a, a, 1, a, None, None, 0, None)
+    assert rc == _lib.REID_ERR_INVALID_ARG and "column lists" in _lib.last_error()
+    # the emission needs a counter array and a capacity
+    rc = L.reid_knn_sample_tau_emit(a, a, a, 2, 8, 16, a, a, a, None, 0, 0, None)
+    assert rc == _lib.REID_ERR_INVALID_ARG and "main lists" in _lib.last_error()
+    rc = L.reid_features_to_half_gather(a, None, 8, 64, 4, a, a, None)
+    assert rc == _lib.REID_ERR_INVALID_ARG
+    # the prepass mode may cut its column tiles up to 8 ways, the top-k mode 4
+    rc = L.reid_knn_candidates_tc_abt(a, 4096, a, 4096, 64, 4, 0, 256, 16, 8, 2, a, a, a, 0, None, None, None, 0, None)
+    assert rc == _lib.REID_ERR_INVALID_ARG and "n_splits" in _lib.last_error()
+
+
 def test_python_surface_matches_reference_signatures():
     import reid_gan_b200 as rg
     sig = inspect.signature(rg.compute_jaccard_distance)
