@@ -8,7 +8,7 @@ rest = args[args.index("--") + 1:] if "--" in args else []
 for a in (args[:args.index("--")] if "--" in args else args):
     name, val = a.split("=")
     assert hasattr(knn_tc, name), name
-    setattr(knn_tc, name, bool(int(val)))
+    setattr(knn_tc, name, bool(int(val)) if isinstance(getattr(knn_tc, name), bool) else int(val))
 sys.argv = [sys.argv[0]] + rest
 import bench
 bench.main()
